@@ -1,0 +1,66 @@
+"""In-tree builds of the native libraries (no JIT cache: the built .so files travel with the repo).
+
+  libbella_b200.so      bella_b200/csrc/bella_b200.cu  -- CUDA kernels (sm_100a) + the C-ABI (include/bella_b200.h)
+  libbella_frontend.so  bella_b200/csrc/frontend.cpp   -- host front end (matrix construction, read simulator)
+"""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB_CUDA = os.path.join(HERE, "libbella_b200.so")
+LIB_FE = os.path.join(HERE, "libbella_frontend.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O3,-fopenmp", "-shared", "--use_fast_math",
+]
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found: cannot build libbella_b200.so (there is no CPU fallback)")
+
+
+def build_cuda(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    srcs.append(os.path.join(ROOT, "include", "bella_b200.h"))
+    if not force and not _stale(LIB_CUDA, srcs):
+        return LIB_CUDA
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", LIB_CUDA,
+                                    os.path.join(CSRC, "bella_b200.cu"), "-lgomp"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.run(cmd, check=True)
+    return LIB_CUDA
+
+
+def build_frontend(force=False):
+    src = os.path.join(CSRC, "frontend.cpp")
+    if not force and not _stale(LIB_FE, [src]):
+        return LIB_FE
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-O3", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-Wall", "-o", LIB_FE, src], check=True)
+    return LIB_FE
+
+
+def build_oracle():
+    """Test infrastructure: oracle/_build/libbella_oracle.so and, when /root/reference exists, oracle/_ref."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"], check=True)
+
+
+if __name__ == "__main__":
+    build_frontend()
+    build_cuda(verbose=True)
+    build_oracle()

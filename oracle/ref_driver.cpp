@@ -1,0 +1,280 @@
+// TEST INFRASTRUCTURE ONLY -- never linked, imported or executed by the product path.
+//
+// Thin C-ABI driver around the UNMODIFIED reference implementation of the overlap SpGEMM.
+// This TU #includes the reference's own headers where they lie under $(BELLA_REF)
+// (= /root/reference); no reference source is copied into this repository.  It is built by
+// oracle/Makefile into oracle/_ref/libbella_ref.so and used
+//   * by tests/ to validate oracle/bella_oracle.c (the C restatement) and to generate
+//     tests/golden/ fixtures (tests/golden/make_golden.py),
+//   * by bench.py as the `cpu_baseline` / `--impl reference` arm (kind = "reference").
+//
+// What it runs (reference file:line):
+//   estimateFLOP        include/overlap.hpp:157-202
+//   prefixsum           include/overlap.hpp:110-146
+//   estimateNNZ_Hash    include/overlap.hpp:205-276
+//   LocalSpGEMM         include/overlap.hpp:281-363
+//   the two lambdas of  src/main.cpp:502-524 (multiop / chainop, include/chain.hpp:74-150)
+//   spmatType_::choose  include/common/common.h:162-170
+//   CSC tuple ctor + MergeDuplicates + Transpose   src/CSC.cpp:289-479, include/common/transpose.h
+#include <iostream>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <istream>
+#include <vector>
+#include <string>
+#include <algorithm>
+#include <utility>
+#include <array>
+#include <typeinfo>
+#include <tuple>
+#include <queue>
+#include <memory>
+#include <stack>
+#include <functional>
+#include <cstring>
+#include <numeric>
+#include <math.h>
+#include <cassert>
+#include <ios>
+#include <chrono>
+#include <thread>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <map>
+#include <unordered_map>
+#include <unistd.h>
+#include <fcntl.h>
+#include <omp.h>
+
+#include "libcuckoo/cuckoohash_map.hh"
+#include "include/kmercount.hpp"
+#include "include/chain.hpp"
+#include "kmercode/hash_funcs.h"
+#include "kmercode/Kmer.hpp"
+#include "kmercode/Buffer.h"
+#include "kmercode/common.h"
+#include "kmercode/fq_reader.h"
+#include "kmercode/ParallelFASTQ.h"
+#include "include/common/utility.h"
+#include "include/common/CSC.h"
+#include "include/common/common.h"
+#include "include/overlap.hpp"
+#include "include/align.hpp"
+
+typedef uint32_t IT;             // KMERINDEX, src/main.cpp:60
+typedef unsigned short NT;
+typedef CSC<IT, NT> Mat;
+
+namespace {
+
+// the reference prints through bare std::cout / printLog(std::cerr); silence fd 1/2 around calls
+struct Quiet {
+	int o1, o2, nul;
+	Quiet() {
+		fflush(stdout); fflush(stderr); std::cout.flush(); std::cerr.flush();
+		nul = open("/dev/null", O_WRONLY);
+		o1 = dup(1); o2 = dup(2);
+		dup2(nul, 1); dup2(nul, 2);
+	}
+	~Quiet() {
+		fflush(stdout); fflush(stderr); std::cout.flush(); std::cerr.flush();
+		dup2(o1, 1); dup2(o2, 2);
+		close(o1); close(o2); close(nul);
+	}
+};
+
+struct RefHandle {
+	Mat* A = nullptr;            // reads x kmers  (spmat,     src/main.cpp:489)
+	Mat* B = nullptr;            // kmers x reads  (transpmat, src/main.cpp:476), possibly a column prefix
+	readVector_ reads;
+	BELLApars bpars;
+	IT* flopC = nullptr;
+	IT* colptrC = nullptr;
+	IT flops = 0;
+	double t_flop = 0, t_nnz = 0, t_numeric = 0;
+	~RefHandle() { delete A; delete B; delete[] flopC; delete[] colptrC; }
+};
+
+Mat* make_csc(IT rows, IT cols, IT nnz, const IT* colptr, const IT* rowids, const NT* values)
+{
+	Mat* M = new Mat(nnz, rows, cols);     // (nnz, m, n) argument order, include/common/CSC.h:25
+	memcpy(M->colptr, colptr, sizeof(IT) * (size_t(cols) + 1));
+	memcpy(M->rowids, rowids, sizeof(IT) * size_t(nnz));
+	memcpy(M->values, values, sizeof(NT) * size_t(nnz));
+	return M;
+}
+
+} // namespace
+
+extern "C" {
+
+// Create: copies the matrices, rebuilds `reads` (sequence strings are what the reference's multiply
+// needs, chain.hpp:35-44), then runs the symbolic phase exactly as HashSpGEMM does
+// (overlap.hpp:667-679).  `ncols_sample` (0 = all) restricts B to its first ncols_sample columns
+// (the bounded CPU-baseline sample: output columns [0, ncols_sample) of the same workload).
+void* bella_ref_create(IT n_reads, IT n_kmers,
+		IT nnzA, const IT* A_colptr, const IT* A_rowids, const NT* A_values,
+		IT nnzB, const IT* B_colptr, const IT* B_rowids, const NT* B_values,
+		const char* seqs, const uint64_t* seq_off,
+		unsigned short kmer_size, unsigned short bin_size,
+		IT ncols_sample, int nthreads)
+{
+	Quiet q;
+	if (nthreads > 0) omp_set_num_threads(nthreads);
+	RefHandle* h = new RefHandle();
+	IT bcols = (ncols_sample && ncols_sample < n_reads) ? ncols_sample : n_reads;
+	IT bnnz = B_colptr[bcols];
+	if (nnzA == 0 || bnnz == 0) { delete h; return nullptr; }
+	h->A = make_csc(n_reads, n_kmers, nnzA, A_colptr, A_rowids, A_values);
+	h->B = make_csc(n_kmers, bcols, bnnz, B_colptr, B_rowids, B_values);
+	h->reads.resize(n_reads);
+	for (IT i = 0; i < n_reads; ++i) {
+		h->reads[i].readid = i;
+		h->reads[i].nametag = std::to_string(i);
+		h->reads[i].seq.assign(seqs + seq_off[i], seqs + seq_off[i + 1]);
+	}
+	h->bpars.kmerSize = kmer_size;
+	h->bpars.binSize = bin_size;
+	h->bpars.skipAlignment = true;
+
+	int numThreads = 1;
+#pragma omp parallel
+	{
+		numThreads = omp_get_num_threads();
+	}
+	double t0 = omp_get_wtime();
+	h->flopC = estimateFLOP(*h->A, *h->B, true);
+	IT* flopptr = prefixsum<IT>(h->flopC, h->B->cols, numThreads);
+	h->flops = flopptr[h->B->cols];
+	double t1 = omp_get_wtime();
+	IT* colnnzC = estimateNNZ_Hash(*h->A, *h->B, h->flopC, true);
+	h->colptrC = prefixsum<IT>(colnnzC, h->B->cols, numThreads);
+	double t2 = omp_get_wtime();
+	delete[] colnnzC;
+	delete[] flopptr;
+	h->t_flop = t1 - t0;
+	h->t_nnz = t2 - t1;
+	return h;
+}
+
+IT bella_ref_cols(void* hv) { return ((RefHandle*)hv)->B->cols; }
+uint64_t bella_ref_flops(void* hv) { return ((RefHandle*)hv)->flops; }
+const IT* bella_ref_flopC(void* hv) { return ((RefHandle*)hv)->flopC; }
+const IT* bella_ref_colptrC(void* hv) { return ((RefHandle*)hv)->colptrC; }
+void bella_ref_times(void* hv, double* out3)
+{
+	RefHandle* h = (RefHandle*)hv;
+	out3[0] = h->t_flop; out3[1] = h->t_nnz; out3[2] = h->t_numeric;
+}
+
+// Numeric phase for output columns [c0, c1): LocalSpGEMM + choose().  Outputs are laid out at
+// colptrC[i]-colptrC[c0]; rows are sorted ascending inside each column (the reference's own order
+// is hash-slot order and already schedule-dependent through Transpose(), so the canonical order
+// for comparisons is (col, row)).  aux (optional, may be NULL) = {nbins, support, overlap} of the
+// chosen bin, 3 x u16 per nonzero.
+int bella_ref_numeric(void* hv, IT c0, IT c1, IT* rowidsC, NT* count, NT* posH, NT* posV, NT* aux)
+{
+	Quiet q;
+	RefHandle* h = (RefHandle*)hv;
+	if (c1 > h->B->cols || c0 > c1) return -1;
+	IT ncols = c1 - c0;
+	std::vector<IT>* RowIdsofC = new std::vector<IT>[ncols];
+	std::vector<spmatPtr_>* ValuesofC = new std::vector<spmatPtr_>[ncols];
+	BELLApars& bpars = h->bpars;
+	readVector_& reads = h->reads;
+
+	IT s0 = c0, e0 = c1;         // LocalSpGEMM takes non-const lvalue refs (overlap.hpp:281)
+	double t0 = omp_get_wtime();
+	LocalSpGEMM(s0, e0, *h->A, *h->B,
+		// src/main.cpp:502-513
+		[&bpars, &reads] (const unsigned short int& begpH, const unsigned short int& begpV,
+			const unsigned int& id1, const unsigned int& id2)
+		{
+			spmatPtr_ value(make_shared<spmatType_>());
+			std::string& read1 = reads[id1].seq;
+			std::string& read2 = reads[id2].seq;
+			multiop(value, read1, read2, begpH, begpV, bpars.kmerSize);
+			return value;
+		},
+		// src/main.cpp:514-524
+		[&bpars, &reads] (spmatPtr_& m1, spmatPtr_& m2, const unsigned int& id1,
+			const unsigned int& id2)
+		{
+			std::string& readname1 = reads[id1].nametag;
+			std::string& readname2 = reads[id2].nametag;
+			chainop(m1, m2, bpars, readname1, readname2);
+			return m1;
+		},
+		RowIdsofC, ValuesofC, h->colptrC, true);
+	h->t_numeric = omp_get_wtime() - t0;
+
+	IT base = h->colptrC[c0];
+	int rc = 0;
+#pragma omp parallel for schedule(dynamic, 64)
+	for (IT i = 0; i < ncols; ++i) {
+		IT off = h->colptrC[c0 + i] - base;
+		IT cnt = RowIdsofC[i].size();
+		if (cnt != h->colptrC[c0 + i + 1] - h->colptrC[c0 + i]) { rc = -2; continue; }
+		std::vector<IT> perm(cnt);
+		std::iota(perm.begin(), perm.end(), 0);
+		std::sort(perm.begin(), perm.end(), [&](IT a, IT b) { return RowIdsofC[i][a] < RowIdsofC[i][b]; });
+		for (IT t = 0; t < cnt; ++t) {
+			IT p = perm[t];
+			spmatPtr_& v = ValuesofC[i][p];
+			rowidsC[off + t] = RowIdsofC[i][p];
+			count[off + t] = v->count;
+			NT nb = v->support.size();
+			auto seed = v->choose();      // mutates the value; call once, last (common.h:162-170)
+			posH[off + t] = seed.first;
+			posV[off + t] = seed.second;
+			if (aux) {
+				aux[3 * size_t(off + t) + 0] = nb;
+				aux[3 * size_t(off + t) + 1] = v->support[v->ids[0]];
+				aux[3 * size_t(off + t) + 2] = v->overlap[v->ids[0]];
+			}
+		}
+	}
+	delete[] RowIdsofC;
+	delete[] ValuesofC;
+	return rc;
+}
+
+void bella_ref_destroy(void* hv) { delete (RefHandle*)hv; }
+
+// Matrix construction exactly as src/main.cpp:476-489: B = CSC(tuples, m, n, keep-p1, needsort=false)
+// (counting sort by column + MergeDuplicates, src/CSC.cpp:301-479) and A = B.Transpose()
+// (include/common/transpose.h:12-52).  Tuples are (kmer_id, read_id, pos).  The caller passes
+// output buffers of capacity ntuples; returns nnz after de-duplication.  A's within-column order
+// is schedule dependent in the reference (atomic cursors) -- run with nthreads = 1 for a
+// reproducible A.
+int64_t bella_ref_build(IT n_kmers, IT n_reads, uint64_t ntuples,
+		const IT* t_kmer, const IT* t_read, const NT* t_pos, int nthreads,
+		IT* B_colptr, IT* B_rowids, NT* B_values,
+		IT* A_colptr, IT* A_rowids, NT* A_values)
+{
+	Quiet q;
+	if (nthreads > 0) omp_set_num_threads(nthreads);
+	std::vector<std::tuple<IT, IT, NT>> tuples(ntuples);
+	for (uint64_t k = 0; k < ntuples; ++k) tuples[k] = std::make_tuple(t_kmer[k], t_read[k], t_pos[k]);
+	Mat transpmat(tuples, n_kmers, n_reads,
+		[] (unsigned short int& p1, unsigned short int& p2) { return p1; }, false);
+	IT nnz = transpmat.nnz;
+	memcpy(B_colptr, transpmat.colptr, sizeof(IT) * (size_t(n_reads) + 1));
+	memcpy(B_rowids, transpmat.rowids, sizeof(IT) * size_t(nnz));
+	memcpy(B_values, transpmat.values, sizeof(NT) * size_t(nnz));
+	// A = B.Transpose() (src/CSC.cpp:289-299) == csr2csc_atomic_nosort(cols, rows, nnz, ...).
+	// transpose.h:35 loops `i <= n` and writes cscColPtr[n+1], one past an (n+1)-entry array;
+	// call the reference routine directly on an output colptr with one spare slot so the
+	// reference code runs unmodified but in bounds.
+	std::vector<IT> acolptr(size_t(n_kmers) + 2);
+	csr2csc_atomic_nosort(transpmat.cols, transpmat.rows, transpmat.nnz,
+		transpmat.colptr, transpmat.rowids, transpmat.values,
+		acolptr.data(), A_rowids, A_values);
+	memcpy(A_colptr, acolptr.data(), sizeof(IT) * (size_t(n_kmers) + 1));
+	return nnz;
+}
+
+int bella_ref_max_threads(void) { return omp_get_max_threads(); }
+
+} // extern "C"

@@ -1,0 +1,144 @@
+"""TEST INFRASTRUCTURE: ctypes loaders for the CPU oracle (oracle/bella_oracle.c) and, when it has
+been built, the unmodified reference (oracle/_ref/libbella_ref.so, see oracle/ref_driver.cpp)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libbella_oracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libbella_ref.so")
+
+_oracle = None
+_ref = None
+u32p, u16p, u8p = (ctypes.c_void_p,) * 3
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True)
+        L = ctypes.CDLL(ORACLE_SO)
+        L.oracle_local_spgemm.restype = ctypes.c_int64
+        L.oracle_build_csc.restype = ctypes.c_int64
+        _oracle = L
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        L = ctypes.CDLL(REF_SO)
+        L.bella_ref_create.restype = ctypes.c_void_p
+        L.bella_ref_flops.restype = ctypes.c_uint64
+        L.bella_ref_flopC.restype = ctypes.c_void_p
+        L.bella_ref_colptrC.restype = ctypes.c_void_p
+        L.bella_ref_cols.restype = ctypes.c_uint32
+        L.bella_ref_build.restype = ctypes.c_int64
+        _ref = L
+    return _ref
+
+
+def _p(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def sort_tuples(cols, rows, *vals):
+    order = np.lexsort((rows, cols))
+    return (cols[order], rows[order]) + tuple(v[order] for v in vals)
+
+
+class Result:
+    """Canonical SpGEMM result: CSC of C with rows ascending in each column."""
+
+    def __init__(self, flopC, colptrC, rowids, count, posH, posV, aux=None, times=None, unpinned=0):
+        self.flopC, self.colptrC, self.rowids = flopC, colptrC, rowids
+        self.count, self.posH, self.posV, self.aux = count, posH, posV, aux
+        self.times, self.unpinned = times, unpinned
+
+    @property
+    def nnz(self):
+        return int(self.colptrC[-1])
+
+
+def oracle_spgemm(inp, ncols=None, nthreads=0, want_aux=True):
+    """oracle/bella_oracle.c on OverlapInputs; ncols restricts to output columns [0, ncols)."""
+    L = oracle()
+    if nthreads:
+        L.oracle_set_threads(nthreads)
+    n = inp.n_reads if ncols is None else min(ncols, inp.n_reads)
+    flopC = np.zeros(n, dtype=np.uint32)
+    nnzC = np.zeros(n, dtype=np.uint32)
+    colptrC = np.zeros(n + 1, dtype=np.uint32)
+    import time
+    t0 = time.perf_counter()
+    L.oracle_estimate_flop(ctypes.c_uint32(n), _p(inp.A_colptr), _p(inp.A_rowids), _p(inp.B_colptr), _p(inp.B_rowids), _p(flopC))
+    t1 = time.perf_counter()
+    L.oracle_estimate_nnz(ctypes.c_uint32(n), _p(inp.A_colptr), _p(inp.A_rowids), _p(inp.B_colptr), _p(inp.B_rowids), _p(flopC), _p(nnzC))
+    L.oracle_prefixsum(_p(nnzC), ctypes.c_uint32(n), _p(colptrC))
+    t2 = time.perf_counter()
+    Z = int(colptrC[n])
+    rows = np.zeros(max(Z, 1), dtype=np.uint32)
+    cnt = np.zeros(max(Z, 1), dtype=np.uint16)
+    pH = np.zeros(max(Z, 1), dtype=np.uint16)
+    pV = np.zeros(max(Z, 1), dtype=np.uint16)
+    aux = np.zeros((max(Z, 1), 3), dtype=np.uint16) if want_aux else None
+    rc = L.oracle_local_spgemm(ctypes.c_uint32(0), ctypes.c_uint32(n),
+                               _p(inp.A_colptr), _p(inp.A_rowids), _p(inp.A_values), _p(inp.A_strand),
+                               _p(inp.B_colptr), _p(inp.B_rowids), _p(inp.B_values), _p(inp.B_strand),
+                               _p(inp.read_len), ctypes.c_uint16(inp.kmer_size), ctypes.c_uint16(inp.bin_size),
+                               _p(colptrC), _p(rows), _p(cnt), _p(pH), _p(pV), _p(aux) if want_aux else None)
+    t3 = time.perf_counter()
+    if rc < 0:
+        raise RuntimeError("oracle_local_spgemm failed")
+    return Result(flopC, colptrC, rows[:Z], cnt[:Z], pH[:Z], pV[:Z], aux[:Z] if want_aux else None,
+                  times=(t1 - t0, t2 - t1, t3 - t2), unpinned=int(rc))
+
+
+def ref_spgemm(inp, ncols=None, nthreads=0, want_aux=True):
+    """The UNMODIFIED reference (oracle/_ref) on the same arrays; needs inp.seqs."""
+    L = ref()
+    assert inp.seqs is not None, "the reference multiply compares read substrings: sequences required"
+    h = L.bella_ref_create(ctypes.c_uint32(inp.n_reads), ctypes.c_uint32(inp.n_kmers),
+                           ctypes.c_uint32(inp.nnz), _p(inp.A_colptr), _p(inp.A_rowids), _p(inp.A_values),
+                           ctypes.c_uint32(inp.nnz), _p(inp.B_colptr), _p(inp.B_rowids), _p(inp.B_values),
+                           _p(inp.seqs), _p(inp.seq_off), ctypes.c_uint16(inp.kmer_size), ctypes.c_uint16(inp.bin_size),
+                           ctypes.c_uint32(0 if ncols is None else ncols), ctypes.c_int(nthreads))
+    if not h:
+        raise RuntimeError("bella_ref_create: empty matrix")
+    h = ctypes.c_void_p(h)
+    try:
+        n = L.bella_ref_cols(h)
+        flopC = np.ctypeslib.as_array(ctypes.cast(L.bella_ref_flopC(h), ctypes.POINTER(ctypes.c_uint32)), (n,)).copy()
+        colptrC = np.ctypeslib.as_array(ctypes.cast(L.bella_ref_colptrC(h), ctypes.POINTER(ctypes.c_uint32)), (n + 1,)).copy()
+        Z = int(colptrC[n])
+        rows = np.zeros(max(Z, 1), dtype=np.uint32)
+        cnt = np.zeros(max(Z, 1), dtype=np.uint16)
+        pH = np.zeros(max(Z, 1), dtype=np.uint16)
+        pV = np.zeros(max(Z, 1), dtype=np.uint16)
+        aux = np.zeros((max(Z, 1), 3), dtype=np.uint16) if want_aux else None
+        rc = L.bella_ref_numeric(h, ctypes.c_uint32(0), ctypes.c_uint32(n), _p(rows), _p(cnt), _p(pH), _p(pV),
+                                 _p(aux) if want_aux else None)
+        if rc != 0:
+            raise RuntimeError(f"bella_ref_numeric failed: {rc}")
+        t = (ctypes.c_double * 3)()
+        L.bella_ref_times(h, t)
+        return Result(flopC, colptrC, rows[:Z], cnt[:Z], pH[:Z], pV[:Z], aux[:Z] if want_aux else None, times=tuple(t))
+    finally:
+        L.bella_ref_destroy(h)
+
+
+def assert_same(a, b, aux=True):
+    np.testing.assert_array_equal(a.flopC, b.flopC)
+    np.testing.assert_array_equal(a.colptrC, b.colptrC)
+    np.testing.assert_array_equal(a.rowids, b.rowids)
+    np.testing.assert_array_equal(a.count, b.count)
+    np.testing.assert_array_equal(a.posH, b.posH)
+    np.testing.assert_array_equal(a.posV, b.posV)
+    if aux and a.aux is not None and b.aux is not None:
+        np.testing.assert_array_equal(a.aux, b.aux)
