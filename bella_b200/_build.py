@@ -55,12 +55,6 @@ def build_frontend(force=False):
     return LIB_FE
 
 
-def build_oracle():
-    """Test infrastructure: oracle/_build/libbella_oracle.so and, when /root/reference exists, oracle/_ref."""
-    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"], check=True)
-
-
 if __name__ == "__main__":
     build_frontend()
     build_cuda(verbose=True)
-    build_oracle()

@@ -1,0 +1,184 @@
+"""Host-side Python binding of the C-ABI (include/bella_b200.h) over libbella_b200.so.
+
+`OverlapSpGEMM` mirrors the reference's HashSpGEMM structure (include/overlap.hpp:650-789):
+set_inputs(A, B, reads-as-lengths+strand-bits, k, binSize) -> symbolic() == estimateFLOP +
+estimateNNZ_Hash + prefix sums -> numeric(col_begin, col_end) == LocalSpGEMM + choose().
+There is no CPU fallback: importing works anywhere, but creating a handle without a B200 raises."""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _build
+
+_lib = None
+
+ERRORS = {-1: "bad argument", -2: "CUDA error / no usable sm_100 device (there is no CPU fallback)",
+          -3: "device out of memory", -4: "count exceeds the reference's index types", -5: "internal device error"}
+
+
+class CscView(ctypes.Structure):
+    _fields_ = [("rows", ctypes.c_uint32), ("cols", ctypes.c_uint32), ("nnz", ctypes.c_uint32),
+                ("colptr", ctypes.c_void_p), ("rowids", ctypes.c_void_p), ("values", ctypes.c_void_p)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.LIB_CUDA
+        if not os.path.exists(path):
+            path = _build.build_cuda()
+        L = ctypes.CDLL(path)
+        vp, H = ctypes.c_void_p, ctypes.c_void_p
+        L.bella_b200_create.argtypes = [ctypes.POINTER(H), ctypes.c_int]
+        L.bella_b200_destroy.argtypes = [H]
+        L.bella_b200_last_error.argtypes = [H]
+        L.bella_b200_last_error.restype = ctypes.c_char_p
+        for f in ("bella_b200_set_inputs", "bella_b200_set_inputs_device"):
+            getattr(L, f).argtypes = [H, ctypes.POINTER(CscView), ctypes.POINTER(CscView), vp, vp, vp, ctypes.c_uint16, ctypes.c_uint16]
+        L.bella_b200_set_column_range.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32]
+        L.bella_b200_symbolic.argtypes = [H, ctypes.POINTER(ctypes.c_uint64), vp, vp]
+        L.bella_b200_numeric.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp, vp]
+        L.bella_b200_numeric_aux.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp]
+        L.bella_b200_numeric_device.argtypes = [H]
+        L.bella_b200_result_device.argtypes = [H] + [ctypes.POINTER(vp)] * 5 + [ctypes.POINTER(ctypes.c_uint64)]
+        L.bella_b200_run_resident.argtypes = [H, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+        L.bella_b200_get_timings.argtypes = [H, ctypes.POINTER(ctypes.c_float)]
+        L.bella_b200_stream.argtypes = [H]
+        L.bella_b200_stream.restype = vp
+        _lib = L
+    return _lib
+
+
+EXPORTS = ["bella_b200_create", "bella_b200_destroy", "bella_b200_last_error", "bella_b200_set_inputs",
+           "bella_b200_set_inputs_device", "bella_b200_set_column_range", "bella_b200_symbolic",
+           "bella_b200_numeric", "bella_b200_numeric_aux", "bella_b200_numeric_device",
+           "bella_b200_result_device", "bella_b200_run_resident", "bella_b200_get_timings", "bella_b200_stream"]
+
+
+class BellaB200Error(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return ctypes.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):          # torch tensor (device-resident inputs)
+        return ctypes.c_void_p(a.data_ptr())
+    return ctypes.c_void_p(int(a))
+
+
+class OverlapSpGEMM:
+    """One handle = one GPU (one process per GPU in the multi-GPU layout)."""
+
+    def __init__(self, device=0):
+        self._L = lib()
+        self._h = ctypes.c_void_p()
+        rc = self._L.bella_b200_create(ctypes.byref(self._h), device)
+        if rc != 0:
+            self._h = None
+            raise BellaB200Error(f"bella_b200_create(device={device}) failed: {ERRORS.get(rc, rc)}")
+        self.n = self.m = 0
+        self.lo = self.hi = 0
+        self.flops = 0
+        self.colptrC = None
+        self._keep = None
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._L.bella_b200_last_error(self._h)
+            raise BellaB200Error(f"{what}: {ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self._h:
+            self._L.bella_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _views(self, n, m, nnz, A, B):
+        vB = CscView(m, n, nnz, _ptr(B[0]), _ptr(B[1]), _ptr(B[2]))
+        vA = CscView(n, m, nnz, _ptr(A[0]), _ptr(A[1]), _ptr(A[2])) if A is not None else None
+        return vA, vB
+
+    def set_inputs(self, inp, with_A=True):
+        """inp: frontend.OverlapInputs (host numpy arrays)."""
+        A = (inp.A_colptr, inp.A_rowids, inp.A_values) if with_A else None
+        vA, vB = self._views(inp.n_reads, inp.n_kmers, inp.nnz, A, (inp.B_colptr, inp.B_rowids, inp.B_values))
+        self._keep = inp
+        rc = self._L.bella_b200_set_inputs(self._h, ctypes.byref(vA) if vA is not None else None, ctypes.byref(vB),
+                                           _ptr(inp.read_len), _ptr(inp.A_strand) if with_A else None, _ptr(inp.B_strand),
+                                           inp.kmer_size, inp.bin_size)
+        self._check(rc, "bella_b200_set_inputs")
+        self.n, self.m, self.lo, self.hi = inp.n_reads, inp.n_kmers, 0, inp.n_reads
+
+    def set_inputs_device(self, n, m, nnz, B, read_len, strand_B, kmer_size, bin_size, A=None, strand_A=None):
+        """Device-resident inputs (torch CUDA tensors or raw device pointers); nothing is copied."""
+        vA, vB = self._views(n, m, nnz, A, B)
+        self._keep = (B, read_len, strand_B, A, strand_A)
+        rc = self._L.bella_b200_set_inputs_device(self._h, ctypes.byref(vA) if vA is not None else None, ctypes.byref(vB),
+                                                  _ptr(read_len), _ptr(strand_A), _ptr(strand_B), kmer_size, bin_size)
+        self._check(rc, "bella_b200_set_inputs_device")
+        self.n, self.m, self.lo, self.hi = n, m, 0, n
+
+    def set_column_range(self, lo, hi):
+        self._check(self._L.bella_b200_set_column_range(self._h, lo, hi), "bella_b200_set_column_range")
+        self.lo, self.hi = lo, hi
+
+    def symbolic(self):
+        """-> (flops, flopC[ncols], colptrC[ncols+1])"""
+        nc = self.hi - self.lo
+        flops = ctypes.c_uint64(0)
+        flopC = np.zeros(nc, dtype=np.uint32)
+        colptrC = np.zeros(nc + 1, dtype=np.uint32)
+        self._check(self._L.bella_b200_symbolic(self._h, ctypes.byref(flops), _ptr(flopC), _ptr(colptrC)), "bella_b200_symbolic")
+        self.flops, self.colptrC = flops.value, colptrC
+        return flops.value, flopC, colptrC
+
+    def numeric(self, col_begin=None, col_end=None, aux=False):
+        """-> (rowids, count, posH, posV[, aux(nnz,3)]) for global columns [col_begin, col_end)."""
+        c0 = self.lo if col_begin is None else col_begin
+        c1 = self.hi if col_end is None else col_end
+        z = int(self.colptrC[c1 - self.lo]) - int(self.colptrC[c0 - self.lo])
+        rows = np.zeros(max(z, 1), dtype=np.uint32)
+        cnt = np.zeros(max(z, 1), dtype=np.uint16)
+        pH = np.zeros(max(z, 1), dtype=np.uint16)
+        pV = np.zeros(max(z, 1), dtype=np.uint16)
+        self._check(self._L.bella_b200_numeric(self._h, c0, c1, _ptr(rows), _ptr(cnt), _ptr(pH), _ptr(pV)), "bella_b200_numeric")
+        out = (rows[:z], cnt[:z], pH[:z], pV[:z])
+        if aux:
+            a = np.zeros((3, max(z, 1)), dtype=np.uint16)
+            self._check(self._L.bella_b200_numeric_aux(self._h, c0, c1, _ptr(a[0]), _ptr(a[1]), _ptr(a[2])), "bella_b200_numeric_aux")
+            out = out + (np.ascontiguousarray(a[:, :z].T),)
+        return out
+
+    def run_resident(self):
+        """layout + symbolic + numeric on device-resident inputs, no result copy. -> (nnzC, flops)"""
+        z, f = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        self._check(self._L.bella_b200_run_resident(self._h, ctypes.byref(z), ctypes.byref(f)), "bella_b200_run_resident")
+        return z.value, f.value
+
+    def timings(self):
+        t = (ctypes.c_float * 8)()
+        self._L.bella_b200_get_timings(self._h, t)
+        return {"layout_ms": t[0], "symbolic_ms": t[1], "numeric_ms": t[2], "h2d_ms": t[3], "d2h_ms": t[4],
+                "launches": int(t[5]), "expand_ms": t[6]}
+
+
+def overlap_spgemm(inp, device=0, with_A=True, aux=False):
+    """Convenience: whole pass through the C-ABI with host buffers. -> dict of numpy arrays"""
+    g = OverlapSpGEMM(device)
+    try:
+        g.set_inputs(inp, with_A=with_A)
+        flops, flopC, colptrC = g.symbolic()
+        res = g.numeric(aux=aux)
+        return {"flops": flops, "flopC": flopC, "colptrC": colptrC, "rowids": res[0], "count": res[1],
+                "posH": res[2], "posV": res[3], "aux": res[4] if aux else None, "timings": g.timings()}
+    finally:
+        g.close()

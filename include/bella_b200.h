@@ -1,0 +1,130 @@
+/* bella_b200.h -- C-ABI of the B200-native overlap-detection SpGEMM  C = A * A^T  for BELLA.
+ *
+ * Drop-in boundary for the reference's  estimateFLOP / estimateNNZ_Hash / LocalSpGEMM  trio inside
+ * HashSpGEMM (reference include/overlap.hpp:157-363, called from include/overlap.hpp:667-719, whose
+ * only call site is src/main.cpp:499-525).  The reference has no FFI of its own: the
+ * binding a maintainer adds is the header-only shim bella_b200/csrc/overlap_b200.hpp, which has
+ * HashSpGEMM's template signature, packs the CSC<uint32_t, unsigned short> members into
+ * bella_csc_view, and calls the functions below.
+ *
+ * Conventions: plain C, POD only, `int` status return (0 = ok, negative = error, never exit()),
+ * the caller owns every buffer it passes, one caller thread per handle, one handle per GPU.
+ * There is no CPU fallback: every entry point fails with BELLA_B200_ERR_CUDA when no sm_100 device
+ * is usable.
+ *
+ * Semantics (must match the reference bit-for-bit on the same arrays):
+ *   - A = reads x k-mers (the reference's `spmat`,  src/main.cpp:489), CSC, rows unsorted in a column
+ *   - B = k-mers x reads (the reference's `transpmat`, src/main.cpp:476), CSC; the ORDER of the
+ *     nonzeros inside a column of B is the fold order of the semiring and is significant
+ *   - values are k-mer start positions in the read (unsigned short)
+ *   - only the strictly lower triangle is produced (row > col; include/overlap.hpp:315)
+ *   - multiply = multiop / overlapop (include/chain.hpp:47-86), add = chainop
+ *     (include/chain.hpp:100-150), final pick = spmatType_::choose() (include/common/common.h:162-170)
+ *   - the substring comparison of checkstrand (include/chain.hpp:35-44) is replaced by per-nonzero
+ *     strand bits: bit = 1 iff the k-mer window in the read equals the k-mer's canonical
+ *     representative; oriented(product) = (strand_A[k] == strand_B[j]).
+ *   - inside one output column the rows are returned in ascending order (the reference's order is
+ *     hash-slot order and already schedule dependent).
+ */
+#ifndef BELLA_B200_H_
+#define BELLA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BELLA_B200_OK            0
+#define BELLA_B200_ERR_ARG      -1   /* bad argument / call order                                  */
+#define BELLA_B200_ERR_CUDA     -2   /* CUDA runtime error or no usable device (no CPU fallback)     */
+#define BELLA_B200_ERR_OOM      -3   /* device allocation failed                                     */
+#define BELLA_B200_ERR_RANGE    -4   /* a count does not fit the reference's index types (u32 / u15) */
+#define BELLA_B200_ERR_INTERNAL -5   /* inconsistency detected on the device                         */
+
+typedef struct bella_b200_handle bella_b200_handle;
+
+/* Mirror of the public members of CSC<uint32_t, unsigned short> (reference include/common/CSC.h:88-95). */
+typedef struct bella_csc_view {
+	uint32_t rows, cols, nnz;
+	const uint32_t* colptr;   /* [cols+1] */
+	const uint32_t* rowids;   /* [nnz]    */
+	const uint16_t* values;   /* [nnz]    */
+} bella_csc_view;
+
+/* One handle per GPU.  device = CUDA ordinal. */
+int bella_b200_create(bella_b200_handle** out, int device);
+int bella_b200_destroy(bella_b200_handle* h);
+const char* bella_b200_last_error(const bella_b200_handle* h);
+
+/* Inputs from HOST memory (copied to the device here).  Replaces the `A, B, reads, bpars` arguments
+ * of HashSpGEMM (include/overlap.hpp:650-652): read_len[n] and the strand bits stand in for `reads`,
+ * kmer_size/bin_size for BELLApars.{kmerSize,binSize}.  strand bits are bit-packed, LSB first, one
+ * bit per nonzero in that matrix's array order.
+ * A may be NULL: then A is derived on the device as the transpose of B (A == B^T is what BELLA
+ * always passes).  B.cols == number of reads n, B.rows == number of k-mers m. */
+int bella_b200_set_inputs(bella_b200_handle* h, const bella_csc_view* A, const bella_csc_view* B,
+		const uint32_t* read_len, const uint8_t* strand_A, const uint8_t* strand_B,
+		uint16_t kmer_size, uint16_t bin_size);
+
+/* Same, but every pointer (including those inside the views) is a DEVICE pointer on the handle's
+ * GPU; nothing is copied and the caller keeps the buffers alive until the next set_inputs/destroy.
+ * This is the entry the multi-GPU path uses after the NCCL all-gather of the B panel. */
+int bella_b200_set_inputs_device(bella_b200_handle* h, const bella_csc_view* A, const bella_csc_view* B,
+		const uint32_t* read_len, const uint8_t* strand_A, const uint8_t* strand_B,
+		uint16_t kmer_size, uint16_t bin_size);
+
+/* Restrict this handle to output columns [col_lo, col_hi) (row sharding across GPUs).
+ * Default after set_inputs: [0, n). */
+int bella_b200_set_column_range(bella_b200_handle* h, uint32_t col_lo, uint32_t col_hi);
+
+/* Symbolic phase == estimateFLOP + prefixsum + estimateNNZ_Hash + prefixsum
+ * (include/overlap.hpp:667-679) for the handle's column range.
+ *   flops    (nullable) total number of kept products (64-bit; the reference's is uint32_t)
+ *   flopC    (nullable) HOST [col_hi-col_lo] per-column product count   == estimateFLOP()
+ *   colptrC  (nullable) HOST [col_hi-col_lo+1] exclusive scan of per-column nnz(C), colptrC[0]=0
+ *                       == prefixsum(estimateNNZ_Hash()) restricted to the range */
+int bella_b200_symbolic(bella_b200_handle* h, uint64_t* flops, uint32_t* flopC, uint32_t* colptrC);
+
+/* Numeric phase == LocalSpGEMM(col_begin, col_end, ...) + choose() (include/overlap.hpp:281-363,
+ * include/common/common.h:162-170).  [col_begin, col_end) are GLOBAL column ids inside the handle's
+ * range.  Outputs are HOST arrays of colptrC[col_end]-colptrC[col_begin] entries; column i's
+ * entries start at colptrC[i]-colptrC[col_begin], rows ascending.
+ *   rowidsC : row read id (the "H" read, larger id)
+ *   count   : spmatType_::count (u16 recurrence of chain.hpp:105,140)
+ *   posH/posV : first k-mer of the most supported bin (position on the row / column read)
+ * Any output pointer may be NULL. */
+int bella_b200_numeric(bella_b200_handle* h, uint32_t col_begin, uint32_t col_end,
+		uint32_t* rowidsC, uint16_t* count, uint16_t* posH, uint16_t* posV);
+
+/* Optional per-nonzero extras for the same range (HOST, nullable each):
+ *   nbins    number of bins of the pair's final value
+ *   support  support of the chosen bin            (spmatType_::chain(), common.h:142-149)
+ *   overlap  overlap estimate of the chosen bin   (spmatType_::overlaplength(), common.h:152-159) */
+int bella_b200_numeric_aux(bella_b200_handle* h, uint32_t col_begin, uint32_t col_end,
+		uint16_t* nbins, uint16_t* support, uint16_t* overlap);
+
+/* Device-resident results of the whole column range after bella_b200_numeric_device():
+ * runs the numeric phase without any device->host copy. */
+int bella_b200_numeric_device(bella_b200_handle* h);
+int bella_b200_result_device(bella_b200_handle* h, const uint32_t** colptrC, const uint32_t** rowidsC,
+		const uint16_t** count, const uint16_t** posH, const uint16_t** posV, uint64_t* nnzC);
+
+/* One full pass (layout + symbolic + numeric) over device-resident inputs with no host
+ * synchronisation except the final one; used by bench.py for the device-resident figure.
+ * nnzC_out / flops_out nullable. */
+int bella_b200_run_resident(bella_b200_handle* h, uint64_t* nnzC_out, uint64_t* flops_out);
+
+/* Timings of the last pass in milliseconds (CUDA events on the handle's stream):
+ *   [0] layout (pack/transposes)  [1] symbolic kernels  [2] numeric (fold) kernels
+ *   [3] host->device copies       [4] device->host copies  [5] kernels launched (count)
+ *   [6] expand kernels only       [7] reserved */
+int bella_b200_get_timings(bella_b200_handle* h, float* ms8);
+
+/* cudaStream_t of the handle as an opaque pointer (so a caller can order its own work after it). */
+void* bella_b200_stream(bella_b200_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BELLA_B200_H_ */
