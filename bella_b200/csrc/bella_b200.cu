@@ -456,6 +456,7 @@ struct DevBuf {
 struct bella_b200_handle {
 	int device = 0;
 	cudaStream_t stream = nullptr;
+	bool own_stream = true;
 	std::string err;
 	// problem
 	uint32_t n = 0, m = 0, lo = 0, hi = 0;
@@ -716,7 +717,7 @@ int bella_b200_destroy(bella_b200_handle* h)
 		&h->posV, &h->aux};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& e : h->ev) if (e) cudaEventDestroy(e);
-	cudaStreamDestroy(h->stream);
+	if (h->own_stream) cudaStreamDestroy(h->stream);
 	delete h;
 	return BELLA_B200_OK;
 }
@@ -897,5 +898,16 @@ int bella_b200_get_timings(bella_b200_handle* h, float* ms8)
 }
 
 void* bella_b200_stream(bella_b200_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int bella_b200_set_stream(bella_b200_handle* h, void* stream)
+{
+	if (!h) return BELLA_B200_ERR_ARG;
+	cudaSetDevice(h->device);
+	cudaStreamSynchronize(h->stream);
+	if (h->own_stream) cudaStreamDestroy(h->stream);
+	h->stream = (cudaStream_t)stream;
+	h->own_stream = false;
+	return BELLA_B200_OK;
+}
 
 } // extern "C"

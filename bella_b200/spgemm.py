@@ -46,6 +46,7 @@ def lib():
         L.bella_b200_get_timings.argtypes = [H, ctypes.POINTER(ctypes.c_float)]
         L.bella_b200_stream.argtypes = [H]
         L.bella_b200_stream.restype = vp
+        L.bella_b200_set_stream.argtypes = [H, vp]
         _lib = L
     return _lib
 
@@ -53,7 +54,8 @@ def lib():
 EXPORTS = ["bella_b200_create", "bella_b200_destroy", "bella_b200_last_error", "bella_b200_set_inputs",
            "bella_b200_set_inputs_device", "bella_b200_set_column_range", "bella_b200_symbolic",
            "bella_b200_numeric", "bella_b200_numeric_aux", "bella_b200_numeric_device",
-           "bella_b200_result_device", "bella_b200_run_resident", "bella_b200_get_timings", "bella_b200_stream"]
+           "bella_b200_result_device", "bella_b200_run_resident", "bella_b200_get_timings", "bella_b200_stream",
+           "bella_b200_set_stream"]
 
 
 class BellaB200Error(RuntimeError):
@@ -126,6 +128,10 @@ class OverlapSpGEMM:
                                                   _ptr(read_len), _ptr(strand_A), _ptr(strand_B), kmer_size, bin_size)
         self._check(rc, "bella_b200_set_inputs_device")
         self.n, self.m, self.lo, self.hi = n, m, 0, n
+
+    def set_stream(self, cuda_stream_ptr):
+        """Run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._check(self._L.bella_b200_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)), "bella_b200_set_stream")
 
     def set_column_range(self, lo, hi):
         self._check(self._L.bella_b200_set_column_range(self._h, lo, hi), "bella_b200_set_column_range")

@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- A·Aᵀ overlap SpGEMM throughput (output-nnz/s) on B200, BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one whole pass of the hot path (device layout + symbolic + numeric) over the workload
+BASELINE.json quotes the metric on: configs[1], "synthetic 50k PacBio reads x 10 kb, e=0.15, k=17"
+(genome 16.67 Mb, 30x, [l,u]=[2,8], seed 2), matrices built once by the host front end
+(bella_b200/csrc/frontend.cpp) outside the timed region.
+
+  value         output nnz / s with A, B (raw CSC arrays), strand bits and read lengths resident in HBM
+  e2e           the same through the host-buffer C-ABI calls (set_inputs -> symbolic -> numeric):
+                H2D of every input and D2H of colptrC/rowids/count/posH/posV inside the timed region
+  roofline      dominant kernel: algorithmic bytes / its CUDA-event duration vs the measured HBM peak
+  cpu_baseline  the reference's own OpenMP estimateFLOP+estimateNNZ_Hash+LocalSpGEMM (oracle/_ref, kind
+                "reference") or the C port (oracle/, kind "port") on a bounded column-prefix sample
+--impl reference times that CPU path alone (all host threads) and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(n_reads=50000, read_len=10000, coverage=30.0, err=0.15, seed=2, k=17, lo=2, hi=8, bin_size=500)
+METRIC = "A·Aᵀ output-nnz/s"
+UNIT = "output-nnz/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def workload_name(w):
+    return (f"synthetic {w['n_reads']} PacBio reads x {w['read_len']} bp, e={w['err']}, k={w['k']}, "
+            f"[l,u]=[{w['lo']},{w['hi']}], {w['coverage']:.0f}x, seed {w['seed']}")
+
+
+def load_workload(w, need_seqs):
+    """Build (or load from the /dev/shm cache shared by both arms and all ranks) the matrices."""
+    from bella_b200 import frontend as fe
+    key = "_".join(f"{k}{v}" for k, v in sorted(w.items()))
+    cache = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", f"bella_b200_{key}.npz")
+    if os.path.exists(cache):
+        try:
+            inp = fe.OverlapInputs.load(cache)
+            if inp.seqs is not None or not need_seqs:
+                return inp
+        except Exception:
+            pass
+    t0 = time.time()
+    inp = fe.synthetic(w["n_reads"], w["read_len"], coverage=w["coverage"], err=w["err"], seed=w["seed"], k=w["k"],
+                       lo=w["lo"], hi=w["hi"], bin_size=w["bin_size"])
+    log(f"[bench] front end built A ({inp.n_reads} x {inp.n_kmers}, nnz {inp.nnz}) in {time.time() - t0:.1f}s")
+    try:
+        tmp = cache + f".{os.getpid()}.tmp.npz"
+        d = {k: v for k, v in inp.__dict__.items() if isinstance(v, np.ndarray)}
+        d["meta"] = np.array([inp.n_reads, inp.n_kmers, inp.nnz, inp.kmer_size, inp.bin_size], dtype=np.int64)
+        np.savez(tmp, **d)
+        os.replace(tmp, cache)
+    except Exception as e:  # cache is best effort
+        log(f"[bench] cache write failed: {e}")
+    return inp
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(inp, Z, flops):
+    """SURVEY.md 8d / DESIGN.md: bytes the path must move once, whatever the implementation:
+    stream B (u32 id + u16 pos) and its colptr, two A-colptr words per B nonzero, the gathered A
+    entries that survive the row>col filter (u32 id + u16 pos each), read lengths and strand bits,
+    and the output (u32 row + 3 x u16) with its colptr."""
+    nz, n = inp.nnz, inp.n_reads
+    return 6 * nz + 4 * (n + 1) + 8 * nz + 6 * flops + 4 * n + nz // 4 + 10 * Z + 4 * (n + 1)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(inp, ncols, nthreads=0):
+    """One run of the CPU reference arm on output columns [0, ncols). -> (Z_sample, seconds, kind, cores)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    if ol.have_ref() and inp.seqs is not None:
+        r = ol.ref_spgemm(inp, ncols=ncols, nthreads=nthreads, want_aux=False)
+        return r.nnz, float(sum(r.times)), "reference", ol.ref().bella_ref_max_threads()
+    r = ol.oracle_spgemm(inp, ncols=ncols, nthreads=nthreads, want_aux=False)
+    return r.nnz, float(sum(r.times)), "port", ol.oracle().oracle_max_threads()
+
+
+def pick_sample_cols(inp, budget_s):
+    """Column-prefix sample sized to ~budget_s seconds of CPU work (calibrated on a small prefix)."""
+    c0 = min(inp.n_reads, 1500)
+    z, t, _, _ = cpu_reference_run(inp, c0)
+    if c0 == inp.n_reads:
+        return c0
+    c = int(c0 * budget_s / max(t, 1e-3))
+    return max(c0, min(inp.n_reads, c))
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    inp = load_workload(w, need_seqs=True)
+    total = args.steps + args.warmup
+    budget = min(8.0, 150.0 / max(total, 1))
+    ncols = pick_sample_cols(inp, budget)
+    for _ in range(args.warmup):
+        cpu_reference_run(inp, ncols)
+    times, z, kind, cores = [], 0, "port", 1
+    for _ in range(args.steps):
+        z, t, kind, cores = cpu_reference_run(inp, ncols)
+        times.append(t)
+    tot = float(sum(times))
+    value = z * len(times) / tot
+    sample = f"output columns [0,{ncols}) of {inp.n_reads} ({z} of the workload's output nnz); estimateFLOP+estimateNNZ_Hash+LocalSpGEMM"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u16/u32", "data": "synthetic",
+            "config": {"workload": workload_name(w)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200_arm(args, w):
+    import torch
+    import torch.distributed as dist
+    from bella_b200 import spgemm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    inp = None
+    if world > 1 and rank != 0:
+        dist.barrier()          # rank 0 builds and caches the matrices first
+    inp = load_workload(w, need_seqs=(rank == 0 and world == 1))
+    if world > 1 and rank == 0:
+        dist.barrier()
+
+    if world > 1:
+        from bella_b200 import distributed as bd
+        return bd.bench_multi(args, w, inp, rank, world, local, METRIC, UNIT, workload_name(w), ClockSampler, algorithmic_bytes,
+                              measured_peak)
+
+    g = spgemm.OverlapSpGEMM(local)
+    stream = torch.cuda.current_stream()
+    g.set_stream(stream.cuda_stream)
+
+    # ---- device-resident arm: raw CSC arrays of A and B in HBM before the timed region ----
+    def dev_t(a):
+        return torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a.view(np.int16) if a.dtype == np.uint16 else a).to(dev)
+    d = {k: dev_t(getattr(inp, k)) for k in ("A_colptr", "A_rowids", "A_values", "A_strand", "B_colptr", "B_rowids", "B_values",
+                                             "B_strand", "read_len")}
+    in_bytes = sum(int(t.numel() * t.element_size()) for t in d.values())
+
+    def resident_step():
+        g.set_inputs_device(inp.n_reads, inp.n_kmers, inp.nnz, (d["B_colptr"], d["B_rowids"], d["B_values"]), d["read_len"],
+                            d["B_strand"], inp.kmer_size, inp.bin_size, A=(d["A_colptr"], d["A_rowids"], d["A_values"]),
+                            strand_A=d["A_strand"])
+        return g.run_resident()
+
+    for _ in range(max(args.warmup, 3)):
+        Z, flops = resident_step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    launches = 0
+    phase = np.zeros(4)
+    for _ in range(args.steps):
+        Z, flops = resident_step()
+        t = g.timings()
+        launches += t["launches"]
+        phase += [t["layout_ms"], t["symbolic_ms"], t["numeric_ms"], t["expand_ms"]]
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    clocks = sampler.stop()
+    phase /= args.steps
+    value = Z / (ms * 1e-3)
+
+    # ---- e2e arm: host buffers (pinned) through the public C-ABI calls ----
+    import copy
+    hin = copy.copy(inp)
+    pinned = {}
+    for k in ("A_colptr", "A_rowids", "A_values", "A_strand", "B_colptr", "B_rowids", "B_values", "B_strand", "read_len"):
+        a = getattr(inp, k)
+        t_ = torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a.view(np.int16) if a.dtype == np.uint16 else a).pin_memory()
+        pinned[k] = t_
+        setattr(hin, k, t_.numpy().view(a.dtype))
+
+    def e2e_step():
+        g.set_inputs(hin)
+        _, _, colptrC = g.symbolic()
+        return colptrC, g.numeric()
+
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        colptrC, res = e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        colptrC, res = e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    d2h = int(colptrC.nbytes + sum(r.nbytes for r in res))
+    e2e = {"value": Z / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h,
+           "ms_per_step": e2e_ms}
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = measured_peak()
+    alg = algorithmic_bytes(inp, Z, flops)
+    kern = {"layout(pack/sort)": phase[0], "expand(k_expand)": phase[3], "fold(k_fold)": phase[2]}
+    dom = max(kern, key=kern.get)
+    # per-kernel algorithmic bytes: expand streams B and gathers the kept A entries; fold
+    # reads the grouped products once and writes the output
+    kbytes = {"layout(pack/sort)": 14 * inp.nnz + 8 * inp.nnz, "expand(k_expand)": 6 * inp.nnz + 6 * flops + 4 * inp.n_reads,
+              "fold(k_fold)": 10 * Z + 4 * inp.n_reads}
+    roof = {"bound": "hbm", "kernel": dom, "achieved": kbytes[dom] / (kern[dom] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "peak_source": peak_src, "traffic": None,
+            "whole_step": {"algorithmic_bytes": alg, "achieved": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak},
+            "phase_ms": {k: float(v) for k, v in kern.items()}}
+    roof["frac"] = roof["achieved"] / peak
+
+    # ---- CPU baseline beside it (bounded sample) ----
+    cpu = None
+    if not args.no_cpu:
+        ncols = pick_sample_cols(inp, 15.0)
+        zc, tc, kind, cores = cpu_reference_run(inp, ncols)
+        cpu = {"value": zc / tc, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"output columns [0,{ncols}) of {inp.n_reads}: {zc} output nnz in {tc:.2f}s (estimateFLOP+estimateNNZ_Hash+LocalSpGEMM)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u16/u32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(w), "n_kmers": inp.n_kmers, "nnz_A": inp.nnz, "products": int(flops),
+                       "output_nnz": int(Z), "l2": "inputs (%.0f MB) larger than L2, no flush" % (in_bytes / 1e6)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    g.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=None, help="override the workload size (testing only)")
+    ap.add_argument("--read-len", type=int, default=None)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    w = dict(WORKLOAD)
+    if args.reads:
+        w["n_reads"] = args.reads
+    if args.read_len:
+        w["read_len"] = args.read_len
+    if args.impl == "reference":
+        return run_reference_arm(args, w)
+    return run_b200_arm(args, w)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

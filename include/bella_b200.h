@@ -123,6 +123,9 @@ int bella_b200_get_timings(bella_b200_handle* h, float* ms8);
 
 /* cudaStream_t of the handle as an opaque pointer (so a caller can order its own work after it). */
 void* bella_b200_stream(bella_b200_handle* h);
+/* Run all further work of the handle on the caller's stream (a cudaStream_t; NULL = the legacy default
+ * stream).  The handle does not take ownership. */
+int bella_b200_set_stream(bella_b200_handle* h, void* stream);
 
 #ifdef __cplusplus
 }
