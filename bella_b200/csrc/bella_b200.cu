@@ -27,7 +27,6 @@ constexpr uint32_t EMPTY = 0xFFFFFFFFu;
 constexpr int N_CLASSES = 4;                    // expand size classes, by products per column
 constexpr uint32_t CLASS_LIMIT[3] = {2048, 4096, 8192};
 constexpr int EXPAND_THREADS = 128;
-constexpr int FOLD_THREADS = 128;
 
 // ---------------------------------------------------------------------------------------------
 // Device data layout (DESIGN.md "Data layout in HBM")
@@ -407,30 +406,288 @@ __device__ void fold_pair(uint64_t* rec, uint32_t np, int lenH, int lenV, uint32
 	out_nbins = nbins; out_sup = best_sup & 0xFFFFu; out_ov = (uint32_t)(r >> 32) & 0xFFFFu;
 }
 
-__global__ void __launch_bounds__(FOLD_THREADS) k_fold(Params P, uint32_t c0, uint32_t c1)
+// ---- fold, restated without mutable per-k-mer state ---------------------------------------------
+// chainop only ever merges whole bins: whether bin b is absorbed at step t depends on the overlap
+// values alone (|ov_b - ov_t| < binSize, chain.hpp:114), never on the k-mers.  So the bins form a
+// forest: parent[b] = the first later product whose overlap is within binSize of bin b's overlap
+// (bin b's overlap is the overlap of the product that created it).  A k-mer s then meets exactly
+// its ancestors, in order, and is dropped at the first ancestor a with |dh| <= K or |dv| <= K
+// (chain.hpp:121).  With c_s = number of ancestors s passes:
+//     count   = (P + sum_s c_s) mod 2^16            (chain.hpp:105,140)
+//     bins    = roots of the forest; support(root) = number of k-mers that reach it (the creator included)
+//     choose  = root with the largest support, ties -> the most recent one (bin order = newest first)
+// When every consecutive pair of overlaps is within binSize (the common case) the forest is the
+// chain t -> t+1 and the whole fold is an all-pairs test with no sequential dependency.
+
+constexpr int NBUCKETS = 7;            // P==1 | 2..4 | 5..8 | 9..16 | 17..32 | 33..256 (warp) | >256 (in-place)
+constexpr uint32_t NONE16 = 0xFFFFu;
+
+struct FDesc { uint32_t row, col; unsigned long long off_len; };   // off(48) | len(16)<<48
+
+struct FoldMeta { unsigned int count[8]; };
+
+__device__ __forceinline__ int bucket_of(uint32_t len)
 {
-	const uint32_t i = c0 + blockIdx.x;
-	if (i >= c1) return;
-	const uint32_t li = i - P.lo;
-	const uint32_t Z = P.nnzC[li];
-	const uint64_t base = P.flopptr[li];
-	const uint32_t out0 = P.colptrC[li];
-	const int lenV = (int)P.read_len[i];
-	for (uint32_t p = threadIdx.x; p < Z; p += blockDim.x) {
-		uint32_t row = P.prow[base + p];
-		uint2 d = P.pdesc[base + p];
-		uint32_t cnt, h, v, nb, sup, ov;
-		fold_pair(P.prod + base + d.x, d.y, (int)P.read_len[row], lenV, P.K, (int)P.BIN, cnt, h, v, nb, sup, ov);
-		P.rowsC[out0 + p] = row;
-		P.countC[out0 + p] = (uint16_t)cnt;
-		P.posH[out0 + p] = (uint16_t)h;
-		P.posV[out0 + p] = (uint16_t)v;
-		P.aux[3 * (size_t)(out0 + p) + 0] = (uint16_t)nb;
-		P.aux[3 * (size_t)(out0 + p) + 1] = (uint16_t)sup;
-		P.aux[3 * (size_t)(out0 + p) + 2] = (uint16_t)ov;
+	return len == 1 ? 0 : len <= 4 ? 1 : len <= 8 ? 2 : len <= 16 ? 3 : len <= 32 ? 4 : len <= 256 ? 5 : 6;
+}
+
+// one warp per column: flat pair descriptors at their final output index + per-bucket work lists
+__global__ void k_flatten(Params P, FDesc* __restrict__ fdesc, uint32_t* __restrict__ lists, uint64_t list_cap, FoldMeta* meta)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	const uint32_t ncols = P.hi - P.lo;
+	for (uint32_t li = warp; li < ncols; li += nwarps) {
+		const uint32_t Z = P.nnzC[li];
+		if (!Z) continue;
+		const uint64_t base = P.flopptr[li];
+		const uint32_t out0 = P.colptrC[li];
+		for (uint32_t p0 = 0; p0 < Z; p0 += 32) {
+			uint32_t p = p0 + lane;
+			int b = -1;
+			uint32_t g = out0 + p;
+			if (p < Z) {
+				uint2 d = P.pdesc[base + p];
+				FDesc f;
+				f.row = P.prow[base + p]; f.col = P.lo + li;
+				f.off_len = (base + d.x) | ((unsigned long long)d.y << 48);
+				fdesc[g] = f;
+				b = bucket_of(d.y);
+			}
+			for (int k = 0; k < NBUCKETS; ++k) {
+				uint32_t m = __ballot_sync(0xFFFFFFFFu, b == k);
+				if (!m) continue;
+				uint32_t start = 0;
+				if (lane == (uint32_t)(__ffs(m) - 1)) start = atomicAdd(&meta->count[k], (unsigned)__popc(m));
+				start = __shfl_sync(0xFFFFFFFFu, start, __ffs(m) - 1);
+				if (b == k) lists[(uint64_t)k * list_cap + start + __popc(m & ((1u << lane) - 1))] = g;
+			}
+		}
 	}
 }
 
+__device__ __forceinline__ void store_result(const Params& P, uint32_t g, uint32_t row, uint32_t cnt, uint32_t hv,
+		uint32_t nb, uint32_t sup, uint32_t ov)
+{
+	P.rowsC[g] = row;
+	P.countC[g] = (uint16_t)cnt;
+	P.posH[g] = (uint16_t)(hv & 0xFFFFu);
+	P.posV[g] = (uint16_t)(hv >> 16);
+	P.aux[3 * (size_t)g + 0] = (uint16_t)nb;
+	P.aux[3 * (size_t)g + 1] = (uint16_t)sup;
+	P.aux[3 * (size_t)g + 2] = (uint16_t)ov;
+}
+
+__device__ __forceinline__ bool is_far(uint32_t x, uint32_t A, uint32_t B, uint32_t K2)
+{
+	// |h_t - h_s| > K  <=>  (unsigned)(h_t - h_s + K) > 2K ; A = K - h_s, B = K - v_s
+	return ((x & 0xFFFFu) + A) > K2 && ((x >> 16) + B) > K2;
+}
+
+// thread per pair, P <= CAP
+template <int CAP>
+__global__ void __launch_bounds__(128) k_fold_short(Params P, const FDesc* __restrict__ fdesc, const uint32_t* __restrict__ list,
+		const unsigned int* __restrict__ count_ptr)
+{
+	const uint32_t count = *count_ptr;
+	const uint32_t K = P.K, K2 = 2 * P.K;
+	const int BIN = (int)P.BIN;
+	for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < count; it += gridDim.x * blockDim.x) {
+		const uint32_t g = list[it];
+		const FDesc f = fdesc[g];
+		const uint32_t np = (uint32_t)(f.off_len >> 48);
+		const uint64_t* rec = P.prod + (f.off_len & 0xFFFFFFFFFFFFull);
+		const int lenH = (int)P.read_len[f.row], lenV = (int)P.read_len[f.col];
+		if (CAP == 1) {
+			uint64_t r = rec[0];
+			uint32_t hv = (uint32_t)r;
+			store_result(P, g, f.row, 1, hv, 1, 1, overlap_estimate(lenH, lenV, hv & 0xFFFFu, hv >> 16, (uint32_t)(r >> 48) & 1u, K));
+			continue;
+		}
+		uint32_t hv[CAP];
+		uint16_t ov[CAP], jr[CAP];
+		for (uint32_t a = 0; a < np; ++a) {          // insertion sort into B-column order
+			uint64_t r = rec[a];
+			uint32_t x = (uint32_t)r;
+			uint16_t key = (uint16_t)(r >> 32);
+			uint16_t o = (uint16_t)overlap_estimate(lenH, lenV, x & 0xFFFFu, x >> 16, (uint32_t)(r >> 48) & 1u, K);
+			uint32_t b = a;
+			while (b > 0 && jr[b - 1] > key) { jr[b] = jr[b - 1]; hv[b] = hv[b - 1]; ov[b] = ov[b - 1]; --b; }
+			jr[b] = key; hv[b] = x; ov[b] = o;
+		}
+		bool linear = true;
+		for (uint32_t t = 1; t < np; ++t) linear &= abs((int)ov[t] - (int)ov[t - 1]) < BIN;
+		uint32_t csum = 0;
+		if (linear) {
+			uint32_t surv = 0;
+			for (uint32_t s = 0; s < np; ++s) {
+				uint32_t x = hv[s], A = K - (x & 0xFFFFu), B = K - (x >> 16), t = s + 1;
+				while (t < np && is_far(hv[t], A, B, K2)) ++t;
+				csum += t - s - 1;
+				surv += (t == np);
+			}
+			store_result(P, g, f.row, (np + csum) & 0xFFFFu, hv[np - 1], 1, surv, ov[np - 1]);
+		} else {
+			uint16_t par[CAP], sup[CAP];
+			uint32_t nlive = 0;                       // jr[] is free now: reuse it as the live-bin list
+			for (uint32_t t = 0; t < np; ++t) {
+				for (uint32_t q = 0; q < nlive;) {
+					uint32_t b = jr[q];
+					if (abs((int)ov[b] - (int)ov[t]) < BIN) { par[b] = (uint16_t)t; jr[q] = jr[--nlive]; } else ++q;
+				}
+				jr[nlive++] = (uint16_t)t;
+				sup[t] = 0;
+			}
+			for (uint32_t q = 0; q < nlive; ++q) par[jr[q]] = NONE16;
+			for (uint32_t s = 0; s < np; ++s) {
+				uint32_t x = hv[s], A = K - (x & 0xFFFFu), B = K - (x >> 16);
+				uint32_t a = par[s], last = s;
+				while (a != NONE16 && is_far(hv[a], A, B, K2)) { ++csum; last = a; a = par[a]; }
+				if (a == NONE16) ++sup[last];
+			}
+			uint32_t best = 0, bt = 0;
+			for (uint32_t t = 0; t < np; ++t) if (par[t] == NONE16 && sup[t] >= best) { best = sup[t]; bt = t; }
+			store_result(P, g, f.row, (np + csum) & 0xFFFFu, hv[bt], nlive, best, ov[bt]);
+		}
+	}
+}
+
+// warp per pair, 33 <= P <= 256
+constexpr int WARP_FOLD_MAX = 256;
+constexpr int WARP_FOLD_WARPS = 8;
+
+__global__ void __launch_bounds__(WARP_FOLD_WARPS * 32) k_fold_long(Params P, const FDesc* __restrict__ fdesc,
+		const uint32_t* __restrict__ list, const unsigned int* __restrict__ count_ptr)
+{
+	__shared__ uint32_t s_hv[WARP_FOLD_WARPS][WARP_FOLD_MAX];
+	__shared__ uint32_t s_sup[WARP_FOLD_WARPS][WARP_FOLD_MAX];
+	__shared__ uint16_t s_ov[WARP_FOLD_WARPS][WARP_FOLD_MAX];
+	__shared__ uint16_t s_jr[WARP_FOLD_WARPS][WARP_FOLD_MAX];
+	__shared__ uint16_t s_par[WARP_FOLD_WARPS][WARP_FOLD_MAX];
+	const uint32_t FULL = 0xFFFFFFFFu;
+	const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint32_t* shv = s_hv[w]; uint32_t* ssup = s_sup[w];
+	uint16_t* sov = s_ov[w]; uint16_t* sjr = s_jr[w]; uint16_t* spar = s_par[w];
+	const uint32_t count = *count_ptr;
+	const uint32_t K = P.K, K2 = 2 * P.K;
+	const int BIN = (int)P.BIN;
+	for (uint32_t it = blockIdx.x * WARP_FOLD_WARPS + w; it < count; it += gridDim.x * WARP_FOLD_WARPS) {
+		const uint32_t g = list[it];
+		const FDesc f = fdesc[g];
+		const uint32_t np = (uint32_t)(f.off_len >> 48);
+		uint64_t* rec = P.prod + (f.off_len & 0xFFFFFFFFFFFFull);
+		const int lenH = (int)P.read_len[f.row], lenV = (int)P.read_len[f.col];
+		const uint32_t R = (np + 31) >> 5;
+		__syncwarp();
+		// load, rank by jrank (counting), scatter into B-column order
+		uint32_t myhv[WARP_FOLD_MAX / 32], myjr[WARP_FOLD_MAX / 32], myov[WARP_FOLD_MAX / 32], rank[WARP_FOLD_MAX / 32];
+#pragma unroll
+		for (int r = 0; r < WARP_FOLD_MAX / 32; ++r) {
+			uint32_t idx = lane + 32 * r;
+			rank[r] = 0; myjr[r] = 0xFFFFFFFFu; myhv[r] = 0; myov[r] = 0;
+			if (r < (int)R && idx < np) {
+				uint64_t x = rec[idx];
+				myhv[r] = (uint32_t)x; myjr[r] = (uint32_t)(x >> 32) & 0xFFFFu;
+				myov[r] = overlap_estimate(lenH, lenV, myhv[r] & 0xFFFFu, myhv[r] >> 16, (uint32_t)(x >> 48) & 1u, K);
+				sjr[idx] = (uint16_t)myjr[r];
+			}
+		}
+		__syncwarp();
+		for (uint32_t b = 0; b < np; ++b) {
+			uint32_t x = sjr[b];
+#pragma unroll
+			for (int r = 0; r < WARP_FOLD_MAX / 32; ++r) rank[r] += (x < myjr[r]);
+		}
+#pragma unroll
+		for (int r = 0; r < WARP_FOLD_MAX / 32; ++r)
+			if (r < (int)R && lane + 32 * r < np) { shv[rank[r]] = myhv[r]; sov[rank[r]] = (uint16_t)myov[r]; }
+		__syncwarp();
+		// is the bin forest the chain t -> t+1 ?
+		bool lin = true;
+		for (uint32_t idx = lane + 1; idx < np; idx += 32) lin &= abs((int)sov[idx] - (int)sov[idx - 1]) < BIN;
+		const bool linear = __all_sync(FULL, lin);
+		bool fallback = false;
+		if (!linear) {
+			// phase A: parents of the bin forest; each lane keeps one live bin
+			uint32_t lb = NONE16;
+			for (uint32_t idx = lane; idx < np; idx += 32) ssup[idx] = 0;
+			for (uint32_t t = 0; t < np; ++t) {
+				int ot = (int)sov[t];
+				if (lb != NONE16 && abs((int)sov[lb] - ot) < BIN) { spar[lb] = (uint16_t)t; lb = NONE16; }
+				uint32_t freem = __ballot_sync(FULL, lb == NONE16);
+				if (!freem) { fallback = true; break; }
+				if (lane == (uint32_t)(__ffs(freem) - 1)) lb = t;
+			}
+			if (lb != NONE16) spar[lb] = NONE16;
+			__syncwarp();
+		}
+		if (fallback) {     // more than 32 simultaneous bins: sequential in-place fold by one lane
+			if (lane == 0) {
+				uint32_t cnt, h, v, nb, sup, ov;
+				fold_pair(rec, np, lenH, lenV, K, BIN, cnt, h, v, nb, sup, ov);
+				store_result(P, g, f.row, cnt, h | (v << 16), nb, sup, ov);
+			}
+			continue;
+		}
+		// phase B: every k-mer walks its ancestors; lanes take s from alternating ends for balance
+		uint32_t csum = 0, surv = 0, r = 0, s = 0, t = 0, A = 0, B = 0, last = 0;
+		bool active = false;
+		auto advance = [&]() {
+			active = false;
+			while (r < R) {
+				s = (r & 1) ? 32 * r + 31 - lane : 32 * r + lane;
+				++r;
+				if (s < np) {
+					uint32_t x = shv[s];
+					A = K - (x & 0xFFFFu); B = K - (x >> 16);
+					t = linear ? s + 1 : spar[s];
+					last = s; active = true;
+					return;
+				}
+			}
+		};
+		advance();
+		while (__any_sync(FULL, active)) {
+			if (active) {
+				if (t >= np) {                       // reached a root alive
+					if (linear) ++surv; else atomicAdd(&ssup[last], 1u);
+					advance();
+				} else if (is_far(shv[t], A, B, K2)) {
+					++csum; last = t;
+					t = linear ? t + 1 : spar[t];
+				} else {
+					advance();
+				}
+			}
+		}
+		for (int o = 16; o; o >>= 1) { csum += __shfl_xor_sync(FULL, csum, o); surv += __shfl_xor_sync(FULL, surv, o); }
+		uint32_t root = np - 1, nb = 1, sup = surv;
+		if (!linear) {
+			__syncwarp();
+			uint32_t best = 0, nroots = 0;
+			for (uint32_t idx = lane; idx < np; idx += 32)
+				if (spar[idx] == NONE16) { ++nroots; uint32_t c = (ssup[idx] << 16) | idx; best = max(best, c); }
+			for (int o = 16; o; o >>= 1) { best = max(best, __shfl_xor_sync(FULL, best, o)); nroots += __shfl_xor_sync(FULL, nroots, o); }
+			root = best & 0xFFFFu; sup = best >> 16; nb = nroots;
+		}
+		if (lane == 0) store_result(P, g, f.row, (np + csum) & 0xFFFFu, shv[root], nb, sup, sov[root]);
+	}
+}
+
+// P > 256: sequential in-place fold, thread per pair (rare)
+__global__ void k_fold_huge(Params P, const FDesc* __restrict__ fdesc, const uint32_t* __restrict__ list,
+		const unsigned int* __restrict__ count_ptr)
+{
+	const uint32_t count = *count_ptr;
+	for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < count; it += gridDim.x * blockDim.x) {
+		const uint32_t g = list[it];
+		const FDesc f = fdesc[g];
+		uint32_t cnt, h, v, nb, sup, ov;
+		fold_pair(P.prod + (f.off_len & 0xFFFFFFFFFFFFull), (uint32_t)(f.off_len >> 48), (int)P.read_len[f.row], (int)P.read_len[f.col],
+			P.K, (int)P.BIN, cnt, h, v, nb, sup, ov);
+		store_result(P, g, f.row, cnt, h | (v << 16), nb, sup, ov);
+	}
+}
 
 // ---- host side ------------------------------------------------------------------------------
 
@@ -470,7 +727,7 @@ struct bella_b200_handle {
 	DevBuf oA_colptr, oA_rowids, oA_values, oA_strand, oB_colptr, oB_rowids, oB_values, oB_strand, o_len;
 	// layout + work
 	DevBuf Aent, Bent, tA_colptr, tcursor, flopC, flop64, flopptr, nnzC, colptrC, lists, meta, errflag, cubtmp, slab;
-	DevBuf prod, prow, pdesc, rowsC, countC, posH, posV, aux;
+	DevBuf prod, prow, pdesc, rowsC, countC, posH, posV, aux, fdesc, flists, fmeta;
 	Meta hmeta{};
 	uint64_t flops = 0, Z = 0;
 	cudaEvent_t ev[8]{};
@@ -644,11 +901,26 @@ int run_numeric(bella_b200_handle* h)
 	ENSURE(h->posH, sizeof(uint16_t) * (Z + 1));
 	ENSURE(h->posV, sizeof(uint16_t) * (Z + 1));
 	ENSURE(h->aux, sizeof(uint16_t) * 3 * (Z + 1));
+	ENSURE(h->fdesc, sizeof(FDesc) * (Z + 1));
+	ENSURE(h->flists, sizeof(uint32_t) * NBUCKETS * (Z + 1));
+	ENSURE(h->fmeta, sizeof(FoldMeta));
 	Params P = make_params(h);
-	if (ncols) {
-		k_fold<<<ncols, FOLD_THREADS, 0, h->stream>>>(P, h->lo, h->hi);
-		LAUNCHED();
-	}
+	if (!ncols || !Z) { h->numeric_done = true; return 0; }
+	CK(cudaMemsetAsync(h->fmeta.p, 0, sizeof(FoldMeta), h->stream));
+	FDesc* fd = h->fdesc.as<FDesc>();
+	uint32_t* lists = h->flists.as<uint32_t>();
+	FoldMeta* fm = h->fmeta.as<FoldMeta>();
+	const uint64_t cap = Z + 1;
+	k_flatten<<<grid_for((uint64_t)ncols * 32, 256), 256, 0, h->stream>>>(P, fd, lists, cap, fm);
+	LAUNCHED();
+	const int g = 148 * 8;
+	k_fold_short<1><<<g, 128, 0, h->stream>>>(P, fd, lists + 0 * cap, &fm->count[0]); LAUNCHED();
+	k_fold_short<4><<<g, 128, 0, h->stream>>>(P, fd, lists + 1 * cap, &fm->count[1]); LAUNCHED();
+	k_fold_short<8><<<g, 128, 0, h->stream>>>(P, fd, lists + 2 * cap, &fm->count[2]); LAUNCHED();
+	k_fold_short<16><<<g, 128, 0, h->stream>>>(P, fd, lists + 3 * cap, &fm->count[3]); LAUNCHED();
+	k_fold_short<32><<<g, 128, 0, h->stream>>>(P, fd, lists + 4 * cap, &fm->count[4]); LAUNCHED();
+	k_fold_long<<<148 * 4, WARP_FOLD_WARPS * 32, 0, h->stream>>>(P, fd, lists + 5 * cap, &fm->count[5]); LAUNCHED();
+	k_fold_huge<<<148, 128, 0, h->stream>>>(P, fd, lists + 6 * cap, &fm->count[6]); LAUNCHED();
 	h->numeric_done = true;
 	return 0;
 }
@@ -714,7 +986,7 @@ int bella_b200_destroy(bella_b200_handle* h)
 	DevBuf* bufs[] = {&h->oA_colptr, &h->oA_rowids, &h->oA_values, &h->oA_strand, &h->oB_colptr, &h->oB_rowids, &h->oB_values,
 		&h->oB_strand, &h->o_len, &h->Aent, &h->Bent, &h->tA_colptr, &h->tcursor, &h->flopC, &h->flop64, &h->flopptr, &h->nnzC, &h->colptrC,
 		&h->lists, &h->meta, &h->errflag, &h->cubtmp, &h->slab, &h->prod, &h->prow, &h->pdesc, &h->rowsC, &h->countC, &h->posH,
-		&h->posV, &h->aux};
+		&h->posV, &h->aux, &h->fdesc, &h->flists, &h->fmeta};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& e : h->ev) if (e) cudaEventDestroy(e);
 	if (h->own_stream) cudaStreamDestroy(h->stream);
