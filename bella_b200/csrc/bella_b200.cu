@@ -142,12 +142,21 @@ __global__ void k_pack_B(uint32_t lo, uint32_t hi, const uint32_t* __restrict__ 
 		for (uint32_t j = j0 + lane; j < j1; j += 32) {
 			uint32_t c = Brow[j];
 			uint32_t s = Acolptr[c], e = Acolptr[c + 1];
-			// upper_bound(row <= i) in the sorted column
-			uint32_t a = s, b = e;
-			if (e - s <= 16) {
-				while (a < e && (uint32_t)Aent[a] <= i) ++a;
-			} else {
-				while (a < b) { uint32_t mid = (a + b) >> 1; if ((uint32_t)Aent[mid] <= i) a = mid + 1; else b = mid; }
+			// upper_bound(row <= i) in the sorted column; the first 8 rows are fetched with independent
+			// loads (one round trip covers every column when u <= 8)
+			uint32_t a;
+			{
+				uint32_t le = 0;
+#pragma unroll
+				for (int q = 0; q < 8; ++q) {
+					uint32_t r = (s + q < e) ? (uint32_t)Aent[s + q] : 0xFFFFFFFFu;
+					le += (r <= i);
+				}
+				a = s + le;
+				if (le == 8 && e - s > 8) {
+					uint32_t b = e;
+					while (a < b) { uint32_t mid = (a + b) >> 1; if ((uint32_t)Aent[mid] <= i) a = mid + 1; else b = mid; }
+				}
 			}
 			uint32_t cnt = e - a;
 			if (cnt > 32767u) { set_err(err, BELLA_B200_ERR_RANGE); cnt = 32767u; }
