@@ -158,7 +158,7 @@ Params make_params(bella_b200_handle* h)
 	P.B_colptr = h->dB_colptr; P.B_rowids = h->dB_rowids; P.A_colptr = h->dA_colptr; P.read_len = h->d_len;
 	P.Aent = h->Aent.as<uint64_t>(); P.Bent = h->Bent.as<uint64_t>();
 	P.flop64 = h->flop64.as<unsigned long long>(); P.flopptr = h->flopptr.as<uint64_t>();
-	P.cursor = h->cursor.as<uint32_t>(); P.raw = h->raw.as<uint32_t>(); P.bcount = h->bcount.as<uint32_t>();
+	P.cursor = h->cursor.as<uint32_t>(); P.raw = h->raw.as<uint4>(); P.bcount = h->bcount.as<uint32_t>();
 	P.nnzC = h->nnzC.as<uint32_t>(); P.colptrC = h->colptrC.as<uint32_t>();
 	P.prod = h->prod.as<uint64_t>(); P.prod_half = h->flops; P.prow = h->prow.as<uint32_t>(); P.pdesc = h->pdesc.as<uint2>();
 	P.rowsC = h->rowsC.as<uint32_t>(); P.countC = h->countC.as<uint16_t>(); P.posH = h->posH.as<uint16_t>();
@@ -196,7 +196,7 @@ int run_symbolic(bella_b200_handle* h)
 	const uint64_t F = h->flops;
 	const uint32_t* cc = h->hmeta.class_count;
 	const bool need_gather = cc[2] + cc[3] > 0;
-	ENSURE(h->raw, sizeof(uint32_t) * 3 * (F + 1));
+	ENSURE(h->raw, sizeof(uint4) * (F + 1));
 	ENSURE(h->prod, sizeof(uint64_t) * ((need_gather ? 2 : 1) * F + 1));
 	ENSURE(h->prow, sizeof(uint32_t) * (F + 1));
 	ENSURE(h->pdesc, sizeof(uint2) * (F + 1));

@@ -30,7 +30,7 @@ constexpr uint32_t GATHER_SMEM_LIMIT = 8192;
 // Packed formats (64-bit unless noted)
 //   Aent  : row(32) | pos(16)<<32 | strand(1)<<48            A's columns, rows ascending
 //   Bent  : aoff(32) | pos(16)<<32 | cnt(15)<<48 | strand<<63 only for gather-fallback columns
-//   raw   : 3 x u32 per product  { row | oriented<<31,  h | v<<16,  k-mer id }
+//   raw   : uint4 per product    { row | oriented<<31,  h | v<<16,  k-mer id, 0 }  (one 16-byte store)
 //   prod  : h(16) | v(16)<<16 | overlap(16)<<32 [| fold state label(16)<<48]   grouped by pair, in fold order
 
 struct Params {
@@ -44,7 +44,7 @@ struct Params {
 	unsigned long long* flop64;   // [ncols+1] products per column
 	uint64_t* flopptr;            // [ncols+1] exclusive scan
 	uint32_t* cursor;             // [ncols]   scatter cursors
-	uint32_t* raw;                // [3F]
+	uint4* raw;                   // [F]
 	uint32_t* nnzC;               // [ncols+1]
 	uint32_t* colptrC;            // [ncols+1]
 	uint32_t* bcount;             // [NBUCKETS*ncols+1] pairs per fold bucket per column, then scanned in place -> boffs
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) k_build_A(uint32_t m, uint32_t lo, uint32
 // products (col r_a, row r_b), b > a; the run is written contiguously into column r_a's region.
 __global__ void __launch_bounds__(256) k_scatter(uint32_t m, uint32_t lo, uint32_t hi, const uint32_t* __restrict__ Acolptr,
 		const uint64_t* __restrict__ Aent, const uint64_t* __restrict__ flopptr, uint32_t* __restrict__ cursor,
-		uint32_t* __restrict__ raw)
+		uint4* __restrict__ raw)
 {
 	for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < m; c += gridDim.x * blockDim.x) {
 		const uint32_t s = Acolptr[c], e = Acolptr[c + 1];
@@ -173,9 +173,7 @@ __global__ void __launch_bounds__(256) k_scatter(uint32_t m, uint32_t lo, uint32
 			for (uint32_t b = a + 1; b < e; ++b, ++q) {
 				const uint64_t eb = Aent[b];
 				const uint32_t h = (uint32_t)(eb >> 32) & 0xFFFFu, sb = (uint32_t)(eb >> 48) & 1u;
-				raw[3 * q + 0] = (uint32_t)eb | ((sa == sb) << 31);
-				raw[3 * q + 1] = h | (v << 16);
-				raw[3 * q + 2] = c;
+				raw[q] = make_uint4((uint32_t)eb | ((sa == sb) << 31), h | (v << 16), c, 0u);
 			}
 		}
 	}
@@ -322,17 +320,26 @@ __device__ __forceinline__ uint32_t overlap_estimate(int lenH, int lenV, uint32_
 
 // ================================ group =====================================================
 // One CTA per output column i.  Shared memory (FCAP products, KHT k-mer slots):
-//   prodS  u64[FCAP]   h | v<<16 | jrank<<32 | oriented<<47 | pair<<48
-//   pkeys  u32[FCAP], pval u32[FCAP]              row-id hash (slot -> count, then -> pair index)
-//   X      phase 1: kkeys u32[KHT] + kjr u16[KHT]  k-mer id -> position in B's column
-//          phase 2: skeys/poff/cursor/rlen u32[FCAP+1] + grp u16[FCAP]
+//   prodS  u64[FCAP]     h | v<<16 | jrank<<32 | oriented<<47 | slot-then-pair<<48
+//   pkeys  u32[FCAP+2]   row-id hash keys; after the pairs are numbered the region holds poff[] (u32)
+//   pcnt   u16[FCAP]     per slot: product count, then pair index (16-bit halves, packed atomics)
+//   X      phase 1: kkeys u32[KHT] + kjr u16[KHT]    k-mer id -> position in B's column
+//          phase 2: skeys u32[FCAP] + cursor u16[FCAP] + grp u16[FCAP] + jrs u16[FCAP]
 template <int FCAP, int KHT>
 struct GroupSmem {
 	static constexpr size_t X1 = (size_t)KHT * 6;
-	static constexpr size_t X2 = (size_t)(FCAP + 1) * 16 + (size_t)FCAP * 2 + 16;
+	static constexpr size_t X2 = (size_t)FCAP * 10;
 	static constexpr size_t X = X1 > X2 ? X1 : X2;
-	static constexpr size_t BYTES = (size_t)FCAP * 8 + (size_t)FCAP * 8 + X;
+	static constexpr size_t BYTES = (size_t)FCAP * 8 + (size_t)(FCAP + 2) * 4 + (size_t)FCAP * 2 + X;
 };
+
+// atomicAdd on a 16-bit counter packed two per 32-bit word (no carry: counts stay < 65536)
+__device__ __forceinline__ uint32_t atomic_add16(uint16_t* base, uint32_t idx, uint32_t v)
+{
+	uint32_t sh = (idx & 1u) * 16u;
+	uint32_t old = atomicAdd((uint32_t*)base + (idx >> 1), v << sh);
+	return (old >> sh) & 0xFFFFu;
+}
 
 template <int FCAP, int KHT>
 __global__ void __launch_bounds__(256) k_group(Params P, const uint32_t* __restrict__ list, uint32_t count)
@@ -343,15 +350,15 @@ __global__ void __launch_bounds__(256) k_group(Params P, const uint32_t* __restr
 	__shared__ uint32_t s_bc[NBUCKETS];
 	uint64_t* prodS = (uint64_t*)smem_raw;
 	uint32_t* pkeys = (uint32_t*)(prodS + FCAP);
-	uint32_t* pval = pkeys + FCAP;
-	unsigned char* X = (unsigned char*)(pval + FCAP);
+	uint32_t* poff = pkeys;                                  // alias, valid after the pairs are numbered
+	uint16_t* pcnt = (uint16_t*)(pkeys + FCAP + 2);
+	unsigned char* X = (unsigned char*)(pcnt + FCAP);
 	uint32_t* kkeys = (uint32_t*)X;
 	uint16_t* kjr = (uint16_t*)(kkeys + KHT);
 	uint32_t* skeys = (uint32_t*)X;
-	uint32_t* poff = skeys + (FCAP + 1);
-	uint32_t* cursor = poff + (FCAP + 1);
-	uint32_t* rlen = cursor + (FCAP + 1);
-	uint16_t* grp = (uint16_t*)(rlen + (FCAP + 1));
+	uint16_t* cursor = (uint16_t*)(skeys + FCAP);
+	uint16_t* grp = cursor + FCAP;
+	uint16_t* jrs = grp + FCAP;
 	const uint32_t tid = threadIdx.x, nt = blockDim.x;
 	const uint32_t ncols = P.hi - P.lo;
 
@@ -366,7 +373,8 @@ __global__ void __launch_bounds__(256) k_group(Params P, const uint32_t* __restr
 		uint32_t kht = 32; int kshift = 27;
 		while (kht * 3 < L * 4) { kht <<= 1; --kshift; }
 		const uint32_t mask = ht - 1, kmask = kht - 1;
-		for (uint32_t s = tid; s < ht; s += nt) { pkeys[s] = EMPTY; pval[s] = 0; }
+		for (uint32_t s = tid; s < ht; s += nt) pkeys[s] = EMPTY;
+		for (uint32_t s = tid; s < (ht >> 1); s += nt) ((uint32_t*)pcnt)[s] = 0;
 		for (uint32_t s = tid; s < kht; s += nt) kkeys[s] = EMPTY;
 		if (tid < NBUCKETS) s_bc[tid] = 0;
 		if (tid == 0) s_z = 0;
@@ -379,14 +387,13 @@ __global__ void __launch_bounds__(256) k_group(Params P, const uint32_t* __restr
 		__syncthreads();
 		// products: k-mer -> jrank, row -> pair slot, count
 		for (uint32_t x = tid; x < Fi; x += nt) {
-			const uint32_t* r = P.raw + 3 * (base + x);
-			uint32_t w0 = r[0], hv = r[1], c = r[2];
-			uint32_t ks = ht_find_checked(kkeys, kmask, kshift, c);
+			const uint4 r = P.raw[base + x];
+			uint32_t ks = ht_find_checked(kkeys, kmask, kshift, r.z);
 			uint32_t jr = 0;
 			if (ks == EMPTY) set_err(P.err, -5); else jr = kjr[ks];
-			uint32_t slot = ht_insert(pkeys, mask, shift, w0 & 0x7FFFFFFFu);
-			atomicAdd(&pval[slot], 1u);
-			prodS[x] = (uint64_t)hv | ((uint64_t)jr << 32) | ((uint64_t)(w0 >> 31) << 47) | ((uint64_t)slot << 48);
+			uint32_t slot = ht_insert(pkeys, mask, shift, r.x & 0x7FFFFFFFu);
+			atomic_add16(pcnt, slot, 1u);
+			prodS[x] = (uint64_t)r.y | ((uint64_t)jr << 32) | ((uint64_t)(r.x >> 31) << 47) | ((uint64_t)slot << 48);
 		}
 		__syncthreads();
 		// --- phase 2: the k-mer hash is dead, X is reused ---
@@ -401,40 +408,60 @@ __global__ void __launch_bounds__(256) k_group(Params P, const uint32_t* __restr
 		for (uint32_t s = Z + tid; s < Zp; s += nt) skeys[s] = EMPTY;
 		__syncthreads();
 		block_bitonic_sort(skeys, Zp);
-		for (uint32_t p = tid; p < Z; p += nt) {
-			uint32_t row = skeys[p];
-			uint32_t slot = ht_find(pkeys, mask, shift, row);
-			uint32_t len = pval[slot];
-			poff[p] = len;
-			pval[slot] = p;
-			cursor[p] = 0;
-			rlen[p] = P.read_len[row];
-			P.prow[base + p] = row;
-			atomicAdd(&s_bc[bucket_of(len)], 1u);
+		// number the pairs by ascending row; per-pair product counts (kept in registers across the
+		// barrier, because poff[] overwrites the hash keys they were found through)
+		uint32_t mylen[FCAP / 256];
+#pragma unroll
+		for (int q = 0; q < FCAP / 256; ++q) {
+			uint32_t p = tid + q * 256;
+			mylen[q] = 0;
+			if (p < Z) {
+				uint32_t row = skeys[p];
+				uint32_t slot = ht_find(pkeys, mask, shift, row);
+				mylen[q] = pcnt[slot];
+				pcnt[slot] = (uint16_t)p;
+				P.prow[base + p] = row;
+				atomicAdd(&s_bc[bucket_of(mylen[q])], 1u);
+			}
 		}
 		__syncthreads();
+#pragma unroll
+		for (int q = 0; q < FCAP / 256; ++q) {
+			uint32_t p = tid + q * 256;
+			if (p < Z) poff[p] = mylen[q];
+		}
+		for (uint32_t s = tid; s < ((Z + 1) >> 1); s += nt) ((uint32_t*)cursor)[s] = 0;
+		__syncthreads();
 		block_excl_scan(poff, Z, s_tmp);            // poff[Z] = Fi
-		for (uint32_t p = tid; p < Z; p += nt) P.pdesc[base + p] = make_uint2(poff[p], poff[p + 1] - poff[p]);
+#pragma unroll
+		for (int q = 0; q < FCAP / 256; ++q) {
+			uint32_t p = tid + q * 256;
+			if (p < Z) P.pdesc[base + p] = make_uint2(poff[p], mylen[q]);
+		}
 		if (tid == 0) P.nnzC[li] = Z;
 		if (tid < NBUCKETS) P.bcount[(size_t)tid * ncols + li] = s_bc[tid];
-		// unordered membership lists
+		// unordered membership lists + compact jrank array in pair order
 		for (uint32_t x = tid; x < Fi; x += nt) {
 			uint64_t r = prodS[x];
-			uint32_t p = pval[(uint32_t)(r >> 48)];
-			grp[poff[p] + atomicAdd(&cursor[p], 1u)] = (uint16_t)x;
+			uint32_t p = pcnt[(uint32_t)(r >> 48)];
+			uint32_t y = poff[p] + atomic_add16(cursor, p, 1u);
+			grp[y] = (uint16_t)x;
+			jrs[y] = (uint16_t)((uint32_t)(r >> 32) & 0x7FFFu);
 			prodS[x] = (r & 0x0000FFFFFFFFFFFFull) | ((uint64_t)p << 48);
 		}
 		__syncthreads();
 		// rank inside the pair by position in B's column, overlap estimate, ordered write
 		const int lenV = (int)P.read_len[i];
 		for (uint32_t y = tid; y < Fi; y += nt) {
-			uint32_t x = grp[y];
-			uint64_t r = prodS[x];
-			uint32_t p = (uint32_t)(r >> 48), jr = (uint32_t)(r >> 32) & 0x7FFFu;
+			uint64_t r = prodS[grp[y]];
+			uint32_t p = (uint32_t)(r >> 48), jr = jrs[y];
 			uint32_t s0 = poff[p], s1 = poff[p + 1], rank = 0;
-			for (uint32_t z = s0; z < s1; ++z) rank += (((uint32_t)(prodS[grp[z]] >> 32) & 0x7FFFu) < jr);
+			if (s1 - s0 > 1) {
+#pragma unroll 4
+				for (uint32_t z = s0; z < s1; ++z) rank += (jrs[z] < jr);
+			}
 			uint32_t hv = (uint32_t)r;
-			uint32_t ov = overlap_estimate((int)rlen[p], lenV, hv & 0xFFFFu, hv >> 16, (uint32_t)(r >> 47) & 1u, P.K);
+			uint32_t ov = overlap_estimate((int)P.read_len[skeys[p]], lenV, hv & 0xFFFFu, hv >> 16, (uint32_t)(r >> 47) & 1u, P.K);
 			P.prod[base + s0 + rank] = (uint64_t)hv | ((uint64_t)ov << 32);
 		}
 		__syncthreads();
