@@ -3,17 +3,18 @@
 // kernel-by-kernel roofline.  There is no CPU fallback in this file.
 //
 // Reference behaviour reproduced (bit-exact), by reference file:line:
-//   estimateFLOP        include/overlap.hpp:157-202   -> k_pack_B (per-column kept-product count)
-//   estimateNNZ_Hash    include/overlap.hpp:205-276   -> k_expand (distinct rows > col)
-//   LocalSpGEMM         include/overlap.hpp:281-363   -> k_expand (group products by pair, in B-column
-//                                                        order) + k_fold
+//   estimateFLOP        include/overlap.hpp:157-202   -> k_bucket (per-column kept-product count)
+//   estimateNNZ_Hash    include/overlap.hpp:205-276   -> k_group_fold (distinct rows > col, two-level bitmap)
+//   LocalSpGEMM         include/overlap.hpp:281-363   -> k_scatter + k_group_fold (products grouped by pair
+//                                                        in B-column order, then folded)
 //   multiop/overlapop   include/chain.hpp:47-86       -> overlap_estimate()
-//   chainop             include/chain.hpp:100-150     -> fold_pair()
-//   choose()            include/common/common.h:162-170 -> end of fold_pair()
+//   chainop             include/chain.hpp:100-150     -> fold_short() / fold_coop()
+//   choose()            include/common/common.h:162-170 -> end of fold_short() / fold_coop()
 #include "bella_b200.h"
 
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -52,20 +53,26 @@ struct bella_b200_handle {
 	std::string err;
 	// problem
 	uint32_t n = 0, m = 0, lo = 0, hi = 0;
-	uint64_t nnzA = 0, nnzB = 0;
+	uint64_t nnzB = 0;
 	uint16_t K = 17, BIN = 500;
-	bool have_inputs = false, have_A = false, layout_done = false, symbolic_done = false, numeric_done = false;
+	bool have_inputs = false, symbolic_done = false, numeric_done = false;
 	// input device pointers (borrowed or pointing into the owned buffers below)
-	const uint32_t *dA_colptr = nullptr, *dA_rowids = nullptr, *dB_colptr = nullptr, *dB_rowids = nullptr, *d_len = nullptr;
-	const uint16_t *dA_values = nullptr, *dB_values = nullptr;
-	const uint8_t *dA_strand = nullptr, *dB_strand = nullptr;
-	DevBuf oA_colptr, oA_rowids, oA_values, oA_strand, oB_colptr, oB_rowids, oB_values, oB_strand, o_len;
-	// layout + work
-	DevBuf Aent, Bent, tA_colptr, tcursor, flop64, flopptr, cursor, raw, bcount, nnzC, colptrC, lists, meta, errflag, cubtmp, slab;
-	DevBuf prod, prow, pdesc, rowsC, countC, posH, posV, aux, fdesc, flists;
+	const uint32_t *dB_colptr = nullptr, *dB_rowids = nullptr, *d_len = nullptr;
+	const uint16_t* dB_values = nullptr;
+	const uint8_t* dB_strand = nullptr;
+	DevBuf oB_colptr, oB_rowids, oB_values, oB_strand, o_len;
+	// transpose
+	uint32_t W = 0, NB = 0;                    // k-mers per bucket, buckets
+	DevBuf bhist, boff, bcur, partK, partE, Aent, Acolptr, flop32;
+	// plan
+	uint32_t ucap = 0, U = 0, round = 0;
+	DevBuf nunits, ubase, shv, refine, colinfo, ucol, ucount, uptr, ucur, lists, unnz, uoff;
+	// products and results
+	DevBuf raw, out, colptrC, rowsC, countC, posH, posV, aux;
+	DevBuf meta, errflag, cubtmp;
 	Meta hmeta{};
 	uint64_t flops = 0, Z = 0;
-	cudaEvent_t ev[8]{};
+	cudaEvent_t ev[12]{};
 	float t_ms[8]{};
 	int launches = 0;
 };
@@ -85,6 +92,9 @@ int fail(bella_b200_handle* h, int code, const char* fmt, ...)
 #define ENSURE(buf, bytes) do { if ((buf).ensure(bytes)) return fail(h, BELLA_B200_ERR_OOM, "device allocation of %zu bytes failed (%s)", (size_t)(bytes), #buf); } while (0)
 #define LAUNCHED() do { ++h->launches; CK(cudaGetLastError()); } while (0)
 
+constexpr int ERR_BUCKET = -6;     // internal: a transpose bucket overflowed -> retry with narrower buckets
+constexpr int ERR_UCAP = -7;       // internal: more units than the arrays hold -> retry with larger arrays
+
 inline int grid_for(uint64_t work, int threads, int cap = 148 * 16)
 {
 	uint64_t g = (work + threads - 1) / threads;
@@ -92,6 +102,8 @@ inline int grid_for(uint64_t work, int threads, int cap = 148 * 16)
 	if (g > (uint64_t)cap) g = cap;
 	return (int)g;
 }
+
+struct PadEven { __host__ __device__ unsigned long long operator()(uint32_t x) const { return ((unsigned long long)x + 1ull) & ~1ull; } };
 
 template <class In, class Out>
 int exclusive_scan(bella_b200_handle* h, In in, Out out, uint32_t count)
@@ -104,50 +116,104 @@ int exclusive_scan(bella_b200_handle* h, In in, Out out, uint32_t count)
 	return 0;
 }
 
-int check_device_error(bella_b200_handle* h)
+int read_flags(bella_b200_handle* h, int* e)
 {
-	int e = 0;
-	CK(cudaMemcpyAsync(&e, h->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	CK(cudaMemcpyAsync(&h->hmeta, h->meta.p, sizeof(Meta), cudaMemcpyDeviceToHost, h->stream));
+	CK(cudaMemcpyAsync(e, h->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
 	CK(cudaStreamSynchronize(h->stream));
-	if (e == BELLA_B200_ERR_RANGE)
-		return fail(h, e, "a column of B has more than 65535 nonzeros, a k-mer occurs in more than 32767 reads, or a column needs more than 2^32-1 products");
-	if (e) return fail(h, e, "device-side error %d", e);
 	return 0;
 }
 
-// layout: Aent (columns sorted by read id) + per-column product counts for the handle's column range
-int run_layout(bella_b200_handle* h)
+int report_device_error(bella_b200_handle* h, int e)
+{
+	if (e == BELLA_B200_ERR_RANGE)
+		return fail(h, e, "a read has more than 65536 k-mers, or one read pair shares more than 65535 k-mers");
+	return fail(h, BELLA_B200_ERR_INTERNAL, "device-side error %d", e);
+}
+
+// transpose: B (read-major) -> Aent (k-mer-major, columns sorted by read id) + per-column product counts
+int run_transpose(bella_b200_handle* h)
 {
 	const uint32_t n = h->n, m = h->m;
 	const uint64_t nnz = h->nnzB;
 	const uint32_t ncols = h->hi - h->lo;
-	ENSURE(h->Aent, sizeof(uint64_t) * (nnz + 1));
-	ENSURE(h->flop64, sizeof(uint64_t) * ((size_t)ncols + 1));
-	ENSURE(h->errflag, sizeof(int));
-	CK(cudaMemsetAsync(h->errflag.p, 0, sizeof(int), h->stream));
-	CK(cudaMemsetAsync(h->flop64.p, 0, sizeof(uint64_t) * ((size_t)ncols + 1), h->stream));
-	if (!nnz || !m) { h->layout_done = true; return 0; }
-	if (h->have_A) {
-		k_build_A<false><<<grid_for(m, 256), 256, 0, h->stream>>>(m, h->lo, h->hi, h->dA_colptr, h->dA_rowids, h->dA_values,
-			h->dA_strand, h->Aent.as<uint64_t>(), h->flop64.as<unsigned long long>(), h->errflag.as<int>());
-		LAUNCHED();
-	} else {
-		ENSURE(h->tA_colptr, sizeof(uint32_t) * ((size_t)m + 2));
-		ENSURE(h->tcursor, sizeof(uint32_t) * ((size_t)m + 2));
-		CK(cudaMemsetAsync(h->tcursor.p, 0, sizeof(uint32_t) * ((size_t)m + 2), h->stream));
-		k_count_deg<<<grid_for(nnz, 256), 256, 0, h->stream>>>(h->dB_rowids, nnz, h->tcursor.as<uint32_t>());
-		LAUNCHED();
-		if (int rc = exclusive_scan(h, h->tcursor.as<uint32_t>(), h->tA_colptr.as<uint32_t>(), m + 1)) return rc;
-		CK(cudaMemsetAsync(h->tcursor.p, 0, sizeof(uint32_t) * ((size_t)m + 2), h->stream));
-		k_transpose_fill<<<grid_for((uint64_t)n * 32, 256), 256, 0, h->stream>>>(n, h->dB_colptr, h->dB_rowids, h->dB_values,
-			h->dB_strand, h->tA_colptr.as<uint32_t>(), h->tcursor.as<uint32_t>(), h->Aent.as<uint64_t>());
-		LAUNCHED();
-		h->dA_colptr = h->tA_colptr.as<uint32_t>();
-		k_build_A<true><<<grid_for(m, 256), 256, 0, h->stream>>>(m, h->lo, h->hi, h->dA_colptr, nullptr, nullptr, nullptr,
-			h->Aent.as<uint64_t>(), h->flop64.as<unsigned long long>(), h->errflag.as<int>());
-		LAUNCHED();
+	ENSURE(h->flop32, sizeof(uint32_t) * ((size_t)ncols + 1));
+	ENSURE(h->Acolptr, sizeof(uint32_t) * ((size_t)m + 2));
+	ENSURE(h->Aent, sizeof(uint64_t) * (nnz + 2));
+	CK(cudaMemsetAsync(h->flop32.p, 0, sizeof(uint32_t) * ((size_t)ncols + 1), h->stream));
+	if (!nnz || !m || !ncols) {
+		CK(cudaMemsetAsync(h->Acolptr.p, 0, sizeof(uint32_t) * ((size_t)m + 2), h->stream));
+		return 0;
 	}
-	h->layout_done = true;
+	if (!h->W) {
+		double avg = (double)nnz / (double)m;
+		double w = 0.6 * BUCKET_CAP / (avg > 0.25 ? avg : 0.25);
+		h->W = (uint32_t)(w < 1 ? 1 : w > BUCKET_WMAX ? BUCKET_WMAX : w);
+	}
+	const uint32_t W = h->W;
+	const uint32_t NB = (uint32_t)(((uint64_t)m + W - 1) / W);
+	h->NB = NB;
+	ENSURE(h->bhist, sizeof(uint32_t) * ((size_t)NB + 2));
+	ENSURE(h->boff, sizeof(uint32_t) * ((size_t)NB + 2));
+	ENSURE(h->bcur, sizeof(uint32_t) * ((size_t)NB + 2));
+	ENSURE(h->partK, sizeof(uint32_t) * (nnz + 2));
+	ENSURE(h->partE, sizeof(uint64_t) * (nnz + 2));
+	CK(cudaMemsetAsync(h->bhist.p, 0, sizeof(uint32_t) * ((size_t)NB + 2), h->stream));
+	k_bucket_hist<<<grid_for(nnz / 4 + 1, 256), 256, 0, h->stream>>>(h->dB_colptr, h->lo, nnz, h->dB_rowids, W, h->bhist.as<uint32_t>());
+	LAUNCHED();
+	if (int rc = exclusive_scan(h, h->bhist.as<uint32_t>(), h->boff.as<uint32_t>(), NB + 1)) return rc;
+	CK(cudaMemcpyAsync(h->bcur.p, h->boff.p, sizeof(uint32_t) * (size_t)NB, cudaMemcpyDeviceToDevice, h->stream));
+	k_partition<<<grid_for((uint64_t)(n - h->lo) * 32, 256), 256, 0, h->stream>>>(n, h->lo, h->dB_colptr, h->dB_rowids, h->dB_values,
+		h->dB_strand, W, h->bcur.as<uint32_t>(), h->partK.as<uint32_t>(), h->partE.as<uint64_t>(), h->errflag.as<int>());
+	LAUNCHED();
+	CK(cudaFuncSetAttribute(k_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BUCKET_SMEM));
+	k_bucket<<<NB < 148u * 12 ? NB : 148u * 12, 256, BUCKET_SMEM, h->stream>>>(m, h->lo, h->hi, W, NB, h->boff.as<uint32_t>(), h->partK.as<uint32_t>(),
+		h->partE.as<uint64_t>(), h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), h->flop32.as<uint32_t>(), h->errflag.as<int>());
+	LAUNCHED();
+	return 0;
+}
+
+// plan: columns -> units, unit sizes, region offsets, classes.  Everything is enqueued without a host
+// synchronisation; the caller reads meta + error flag afterwards and retries when asked to.
+int run_plan(bella_b200_handle* h)
+{
+	const uint32_t ncols = h->hi - h->lo;
+	if (h->ucap < ncols + 1) h->ucap = ncols + 1;
+	const uint32_t ucap = h->ucap;
+	ENSURE(h->nunits, sizeof(uint32_t) * ((size_t)ncols + 1));
+	ENSURE(h->ubase, sizeof(uint32_t) * ((size_t)ncols + 1));
+	ENSURE(h->shv, (size_t)ncols + 1);
+	ENSURE(h->colinfo, sizeof(ColInfo) * ((size_t)ncols + 1));
+	ENSURE(h->ucol, sizeof(uint32_t) * ((size_t)ucap + 1));
+	ENSURE(h->ucount, sizeof(uint32_t) * ((size_t)ucap + 2));
+	ENSURE(h->uptr, sizeof(uint64_t) * ((size_t)ucap + 2));
+	ENSURE(h->ucur, sizeof(uint64_t) * ((size_t)ucap + 2));
+	ENSURE(h->unnz, sizeof(uint32_t) * ((size_t)ucap + 2));
+	ENSURE(h->uoff, sizeof(uint32_t) * ((size_t)ucap + 2));
+	ENSURE(h->lists, sizeof(uint32_t) * (size_t)(NCLASS + 1) * ((size_t)ucap + 1));
+	CK(cudaMemsetAsync(h->meta.p, 0, sizeof(Meta), h->stream));
+	CK(cudaMemsetAsync(h->nunits.p, 0, sizeof(uint32_t) * ((size_t)ncols + 1), h->stream));
+	CK(cudaMemsetAsync(h->ucount.p, 0, sizeof(uint32_t) * ((size_t)ucap + 2), h->stream));
+	CK(cudaMemsetAsync(h->unnz.p, 0, sizeof(uint32_t) * ((size_t)ucap + 2), h->stream));
+	if (!ncols) return 0;
+	k_plan<<<grid_for(ncols, 256), 256, 0, h->stream>>>(h->n, h->lo, ncols, h->flop32.as<uint32_t>(), h->refine.as<uint8_t>(),
+		h->nunits.as<uint32_t>(), h->shv.as<uint8_t>(), h->meta.as<Meta>());
+	LAUNCHED();
+	if (int rc = exclusive_scan(h, h->nunits.as<uint32_t>(), h->ubase.as<uint32_t>(), ncols + 1)) return rc;
+	k_units_init<<<grid_for(ncols, 256), 256, 0, h->stream>>>(ncols, ucap, h->flop32.as<uint32_t>(), h->ubase.as<uint32_t>(), h->shv.as<uint8_t>(),
+		h->colinfo.as<ColInfo>(), h->ucol.as<uint32_t>(), h->ucount.as<uint32_t>(), h->meta.as<Meta>(), h->errflag.as<int>());
+	LAUNCHED();
+	k_count_units<<<grid_for(h->m, 256), 256, 0, h->stream>>>(h->m, h->lo, h->hi, h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(),
+		h->colinfo.as<ColInfo>(), h->ucount.as<uint32_t>(), h->meta.as<Meta>(), h->errflag.as<int>());
+	LAUNCHED();
+	{
+		auto padded = thrust::make_transform_iterator((const uint32_t*)h->ucount.as<uint32_t>(), PadEven());
+		if (int rc = exclusive_scan(h, padded, h->uptr.as<unsigned long long>(), ucap + 1)) return rc;
+	}
+	k_classify_units<<<grid_for(ucap, 256), 256, 0, h->stream>>>(ucap, h->ucol.as<uint32_t>(), h->ucount.as<uint32_t>(), h->colinfo.as<ColInfo>(),
+		h->uptr.as<uint64_t>(), h->ucur.as<unsigned long long>(), h->lists.as<uint32_t>(), h->refine.as<uint8_t>(), h->round,
+		h->meta.as<Meta>(), h->errflag.as<int>());
+	LAUNCHED();
 	return 0;
 }
 
@@ -155,129 +221,124 @@ Params make_params(bella_b200_handle* h)
 {
 	Params P{};
 	P.n = h->n; P.m = h->m; P.lo = h->lo; P.hi = h->hi; P.K = h->K; P.BIN = h->BIN;
-	P.B_colptr = h->dB_colptr; P.B_rowids = h->dB_rowids; P.A_colptr = h->dA_colptr; P.read_len = h->d_len;
-	P.Aent = h->Aent.as<uint64_t>(); P.Bent = h->Bent.as<uint64_t>();
-	P.flop64 = h->flop64.as<unsigned long long>(); P.flopptr = h->flopptr.as<uint64_t>();
-	P.cursor = h->cursor.as<uint32_t>(); P.raw = h->raw.as<uint4>(); P.bcount = h->bcount.as<uint32_t>();
-	P.nnzC = h->nnzC.as<uint32_t>(); P.colptrC = h->colptrC.as<uint32_t>();
-	P.prod = h->prod.as<uint64_t>(); P.prod_half = h->flops; P.prow = h->prow.as<uint32_t>(); P.pdesc = h->pdesc.as<uint2>();
-	P.rowsC = h->rowsC.as<uint32_t>(); P.countC = h->countC.as<uint16_t>(); P.posH = h->posH.as<uint16_t>();
-	P.posV = h->posV.as<uint16_t>(); P.aux = h->aux.as<uint16_t>(); P.err = h->errflag.as<int>();
+	P.B_colptr = h->dB_colptr; P.B_values = h->dB_values; P.B_strand = h->dB_strand; P.read_len = h->d_len;
+	P.A_colptr = h->Acolptr.as<uint32_t>(); P.Aent = h->Aent.as<uint64_t>();
+	P.colinfo = h->colinfo.as<ColInfo>(); P.ucol = h->ucol.as<uint32_t>(); P.ucount = h->ucount.as<uint32_t>();
+	P.uptr = h->uptr.as<uint64_t>(); P.ucur = h->ucur.as<unsigned long long>();
+	P.raw = h->raw.as<uint64_t>(); P.out = h->out.as<uint4>(); P.unnz = h->unnz.as<uint32_t>();
+	P.err = h->errflag.as<int>();
 	return P;
 }
 
-// symbolic: product-count scan, outer-product scatter, per-column grouping (distinct rows = nnz(C)), scans
+template <int CAP>
+int launch_group(bella_b200_handle* h, const Params& P, const uint32_t* list, uint32_t count, uint32_t l1cap, int ctas_per_sm)
+{
+	if (!count) return 0;
+	const size_t smem = GF<CAP>::bytes(l1cap);
+	CK(cudaFuncSetAttribute(k_group_fold<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	uint32_t grid = count < 148u * ctas_per_sm ? count : 148u * ctas_per_sm;
+	k_group_fold<CAP><<<grid, GF_THREADS, smem, h->stream>>>(P, list, count, l1cap);
+	LAUNCHED();
+	return 0;
+}
+
+// the whole symbolic phase; on return C's colptr and the per-unit results are on the device
 int run_symbolic(bella_b200_handle* h)
 {
 	const uint32_t ncols = h->hi - h->lo;
-	const uint32_t m = h->m;
-	ENSURE(h->flopptr, sizeof(uint64_t) * ((size_t)ncols + 1));
-	ENSURE(h->cursor, sizeof(uint32_t) * ((size_t)ncols + 1));
-	ENSURE(h->bcount, sizeof(uint32_t) * ((size_t)NBUCKETS * ncols + 1));
-	ENSURE(h->nnzC, sizeof(uint32_t) * ((size_t)ncols + 1));
-	ENSURE(h->colptrC, sizeof(uint32_t) * ((size_t)ncols + 1));
-	ENSURE(h->lists, sizeof(uint32_t) * (size_t)N_CLASSES * (ncols + 1));
 	ENSURE(h->meta, sizeof(Meta));
-	if (int rc = exclusive_scan(h, h->flop64.as<unsigned long long>(), h->flopptr.as<unsigned long long>(), ncols + 1)) return rc;
-	CK(cudaMemsetAsync(h->meta.p, 0, sizeof(Meta), h->stream));
-	CK(cudaMemsetAsync(h->nnzC.p, 0, sizeof(uint32_t) * ((size_t)ncols + 1), h->stream));
-	CK(cudaMemsetAsync(h->cursor.p, 0, sizeof(uint32_t) * ((size_t)ncols + 1), h->stream));
-	CK(cudaMemsetAsync(h->bcount.p, 0, sizeof(uint32_t) * ((size_t)NBUCKETS * ncols + 1), h->stream));
-	if (ncols) {
-		k_classify<<<grid_for(ncols, 256), 256, 0, h->stream>>>(h->lo, ncols, h->flop64.as<unsigned long long>(), h->dB_colptr,
-			h->lists.as<uint32_t>(), h->meta.as<Meta>(), h->errflag.as<int>());
-		LAUNCHED();
-	}
-	k_set_total<<<1, 1, 0, h->stream>>>(h->meta.as<Meta>(), h->flopptr.as<uint64_t>(), ncols);
-	LAUNCHED();
-	CK(cudaMemcpyAsync(&h->hmeta, h->meta.p, sizeof(Meta), cudaMemcpyDeviceToHost, h->stream));
-	if (int rc = check_device_error(h)) return rc;     // synchronises
-	h->flops = h->hmeta.flops;
-	const uint64_t F = h->flops;
-	const uint32_t* cc = h->hmeta.class_count;
-	const bool need_gather = cc[2] + cc[3] > 0;
-	ENSURE(h->raw, sizeof(uint4) * (F + 1));
-	ENSURE(h->prod, sizeof(uint64_t) * ((need_gather ? 2 : 1) * F + 1));
-	ENSURE(h->prow, sizeof(uint32_t) * (F + 1));
-	ENSURE(h->pdesc, sizeof(uint2) * (F + 1));
-	if (need_gather) ENSURE(h->Bent, sizeof(uint64_t) * (h->nnzB + 1));
-	Params P = make_params(h);
-	CK(cudaEventRecord(h->ev[6], h->stream));
-	if (F) {
-		k_scatter<<<grid_for(m, 256), 256, 0, h->stream>>>(m, h->lo, h->hi, h->dA_colptr, P.Aent, P.flopptr, P.cursor, P.raw);
-		LAUNCHED();
-	}
-	const uint32_t* lists = h->lists.as<uint32_t>();
-	if (cc[0]) {
-		using G = GroupSmem<2048, 4096>;
-		CK(cudaFuncSetAttribute(k_group<2048, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::BYTES));
-		k_group<2048, 4096><<<cc[0], 256, G::BYTES, h->stream>>>(P, lists, cc[0]);
-		LAUNCHED();
-	}
-	if (cc[1]) {
-		using G = GroupSmem<4096, 8192>;
-		CK(cudaFuncSetAttribute(k_group<4096, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::BYTES));
-		k_group<4096, 8192><<<cc[1], 256, G::BYTES, h->stream>>>(P, lists + (size_t)ncols, cc[1]);
-		LAUNCHED();
-	}
-	for (int c = 2; c < 4; ++c) {
-		if (!cc[c]) continue;
-		const uint32_t* l = lists + (size_t)c * ncols;
-		k_pack_B_list<<<grid_for((uint64_t)cc[c] * 32, 256), 256, 0, h->stream>>>(h->lo, l, cc[c], h->dB_colptr, h->dB_rowids,
-			h->dB_values, h->dB_strand, h->dA_colptr, P.Aent, h->Bent.as<uint64_t>(), h->errflag.as<int>());
-		LAUNCHED();
-		if (c == 2) {
-			size_t smem = (size_t)5 * (GATHER_SMEM_LIMIT + 1) * sizeof(uint32_t);
-			CK(cudaFuncSetAttribute(k_expand_gather<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-			k_expand_gather<false><<<cc[c], 256, smem, h->stream>>>(P, l, cc[c], GATHER_SMEM_LIMIT, nullptr);
-			LAUNCHED();
-		} else {
-			uint32_t htmax = 32;
-			while (htmax < h->hmeta.max_flop) htmax <<= 1;
-			uint32_t ctas = cc[c] < 148 ? cc[c] : 148;
-			while (ctas > 1 && (size_t)ctas * 5 * ((size_t)htmax + 1) * sizeof(uint32_t) > ((size_t)8 << 30)) ctas >>= 1;
-			ENSURE(h->slab, (size_t)ctas * 5 * ((size_t)htmax + 1) * sizeof(uint32_t));
-			k_expand_gather<true><<<ctas, 256, 0, h->stream>>>(P, l, cc[c], htmax, h->slab.as<uint32_t>());
-			LAUNCHED();
+	ENSURE(h->errflag, sizeof(int));
+	ENSURE(h->refine, (size_t)ncols + 1);
+	ENSURE(h->colptrC, sizeof(uint32_t) * ((size_t)ncols + 1));
+	CK(cudaMemsetAsync(h->errflag.p, 0, sizeof(int), h->stream));
+	CK(cudaMemsetAsync(h->refine.p, 0, (size_t)ncols + 1, h->stream));
+	h->round = 0;
+	CK(cudaEventRecord(h->ev[0], h->stream));
+	bool need_transpose = true;
+	for (int attempt = 0;; ++attempt) {
+		if (attempt > 40) return fail(h, BELLA_B200_ERR_INTERNAL, "planning did not converge");
+		if (need_transpose) { if (int rc = run_transpose(h)) return rc; CK(cudaEventRecord(h->ev[1], h->stream)); }
+		if (int rc = run_plan(h)) return rc;
+		int e = 0;
+		if (int rc = read_flags(h, &e)) return rc;
+		if (e == ERR_BUCKET) {
+			if (h->W <= 1) return fail(h, BELLA_B200_ERR_RANGE, "a k-mer occurs in more than %u reads", BUCKET_CAP);
+			h->W = h->W / 2;
+			need_transpose = true;
+			CK(cudaMemsetAsync(h->errflag.p, 0, sizeof(int), h->stream));
+			continue;
 		}
+		need_transpose = false;
+		if (e == ERR_UCAP) {
+			h->ucap = h->hmeta.n_units + 1;
+			CK(cudaMemsetAsync(h->errflag.p, 0, sizeof(int), h->stream));
+			continue;
+		}
+		if (e) return report_device_error(h, e);
+		if (h->hmeta.n_refine) { ++h->round; continue; }
+		break;
 	}
-	CK(cudaEventRecord(h->ev[7], h->stream));
-	if (int rc = exclusive_scan(h, h->nnzC.as<uint32_t>(), h->colptrC.as<uint32_t>(), ncols + 1)) return rc;
-	if (int rc = exclusive_scan(h, h->bcount.as<uint32_t>(), h->bcount.as<uint32_t>(), NBUCKETS * ncols + 1)) return rc;
+	h->flops = h->hmeta.flops;
+	h->U = h->hmeta.n_units;
+	const uint64_t F = h->flops;
+	const uint32_t U = h->U, ucap = h->ucap;
+	const uint32_t* cc = h->hmeta.class_count;
+	ENSURE(h->raw, sizeof(uint64_t) * (F + U + 2));
+	ENSURE(h->out, sizeof(uint4) * (F + U + 2));
+	Params P = make_params(h);
+	CK(cudaEventRecord(h->ev[2], h->stream));
+	if (F) {
+		k_scatter<<<grid_for(h->m, 256), 256, 0, h->stream>>>(h->m, h->lo, h->hi, P.A_colptr, P.Aent, P.colinfo, P.ucur, P.raw);
+		LAUNCHED();
+	}
+	CK(cudaEventRecord(h->ev[3], h->stream));
+	// level-1 bitmap words a unit can need: light columns span at most n rows, heavy units at most 2^MAX_SPAN_SHIFT
+	uint32_t span = h->n < (1u << MAX_SPAN_SHIFT) ? h->n : (1u << MAX_SPAN_SHIFT);
+	const uint32_t l1cap = (span + 1023 + 32) / 1024 + 1;
+	const uint32_t* lists = h->lists.as<uint32_t>();
+	if (int rc = launch_group<2048>(h, P, lists, cc[0], l1cap, 4)) return rc;
+	if (int rc = launch_group<4096>(h, P, lists + (size_t)ucap, cc[1], l1cap, 2)) return rc;
+	if (int rc = launch_group<8192>(h, P, lists + (size_t)2 * ucap, cc[2], l1cap, 1)) return rc;
+	if (cc[3]) {
+		k_huge_pair<<<cc[3] < 148u ? cc[3] : 148u, 1024, 0, h->stream>>>(P, lists + (size_t)3 * ucap, cc[3]);
+		LAUNCHED();
+	}
+	CK(cudaEventRecord(h->ev[4], h->stream));
+	if (int rc = exclusive_scan(h, h->unnz.as<uint32_t>(), h->uoff.as<uint32_t>(), U + 1)) return rc;
+	k_colptr<<<grid_for(ncols + 1, 256), 256, 0, h->stream>>>(ncols, h->ubase.as<uint32_t>(), h->uoff.as<uint32_t>(), h->colptrC.as<uint32_t>());
+	LAUNCHED();
 	uint32_t z32 = 0;
-	CK(cudaMemcpyAsync(&z32, h->colptrC.as<uint32_t>() + ncols, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-	if (int rc = check_device_error(h)) return rc;
+	int e = 0;
+	CK(cudaMemcpyAsync(&z32, h->uoff.as<uint32_t>() + U, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+	CK(cudaMemcpyAsync(&e, h->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	CK(cudaEventRecord(h->ev[5], h->stream));
+	CK(cudaStreamSynchronize(h->stream));
+	if (e) return report_device_error(h, e);
 	h->Z = z32;
+	CK(cudaEventElapsedTime(&h->t_ms[0], h->ev[0], h->ev[2]));    // transpose + plan
+	CK(cudaEventElapsedTime(&h->t_ms[7], h->ev[2], h->ev[3]));    // scatter
+	CK(cudaEventElapsedTime(&h->t_ms[1], h->ev[3], h->ev[4]));    // group + fold
+	CK(cudaEventElapsedTime(&h->t_ms[6], h->ev[4], h->ev[5]));    // scans + colptr
 	h->symbolic_done = true;
 	h->numeric_done = false;
 	return 0;
 }
 
+// numeric: the values were produced together with the structure; what is left is the compaction
+// of the per-unit records into C's arrays
 int run_numeric(bella_b200_handle* h)
 {
-	const uint32_t ncols = h->hi - h->lo;
 	const uint64_t Z = h->Z;
 	ENSURE(h->rowsC, sizeof(uint32_t) * (Z + 1));
 	ENSURE(h->countC, sizeof(uint16_t) * (Z + 1));
 	ENSURE(h->posH, sizeof(uint16_t) * (Z + 1));
 	ENSURE(h->posV, sizeof(uint16_t) * (Z + 1));
 	ENSURE(h->aux, sizeof(uint16_t) * 3 * (Z + 1));
-	ENSURE(h->fdesc, sizeof(FDesc) * (Z + 1));
-	ENSURE(h->flists, sizeof(uint32_t) * (Z + 1));
-	Params P = make_params(h);
-	if (!ncols || !Z) { h->numeric_done = true; return 0; }
-	FDesc* fd = h->fdesc.as<FDesc>();
-	uint32_t* fl = h->flists.as<uint32_t>();
-	k_flatten<<<grid_for((uint64_t)ncols * 32, 256), 256, 0, h->stream>>>(P, fd, fl);
-	LAUNCHED();
-	const int g = 148 * 8;
-	k_fold_short<1><<<g, 128, 0, h->stream>>>(P, fd, fl, 0); LAUNCHED();
-	k_fold_short<4><<<g, 128, 0, h->stream>>>(P, fd, fl, 1); LAUNCHED();
-	k_fold_short<8><<<g, 128, 0, h->stream>>>(P, fd, fl, 2); LAUNCHED();
-	k_fold_short<16><<<g, 128, 0, h->stream>>>(P, fd, fl, 3); LAUNCHED();
-	k_fold_short<32><<<g, 128, 0, h->stream>>>(P, fd, fl, 4); LAUNCHED();
-	k_fold_long<<<148 * 4, WARP_FOLD_WARPS * 32, 0, h->stream>>>(P, fd, fl, 5); LAUNCHED();
-	k_fold_huge<<<148, 128, 0, h->stream>>>(P, fd, fl, 6); LAUNCHED();
+	if (Z && h->U) {
+		k_compact<<<grid_for((uint64_t)h->U * 32, 256), 256, 0, h->stream>>>(h->U, h->uptr.as<uint64_t>(), h->uoff.as<uint32_t>(), h->out.as<uint4>(),
+			h->rowsC.as<uint32_t>(), h->countC.as<uint16_t>(), h->posH.as<uint16_t>(), h->posV.as<uint16_t>(), h->aux.as<uint16_t>());
+		LAUNCHED();
+	}
 	h->numeric_done = true;
 	return 0;
 }
@@ -291,25 +352,24 @@ int copy_in(bella_b200_handle* h, DevBuf& buf, const void* src, size_t bytes, co
 }
 
 int validate_views(bella_b200_handle* h, const bella_csc_view* A, const bella_csc_view* B, const uint32_t* read_len,
-		const uint8_t* sA, const uint8_t* sB)
+		const uint8_t* sB)
 {
 	if (!h) return BELLA_B200_ERR_ARG;
 	if (!B || !B->colptr || !read_len || !sB) return fail(h, BELLA_B200_ERR_ARG, "B, read_len and strand_B are required");
 	if (B->nnz && (!B->rowids || !B->values)) return fail(h, BELLA_B200_ERR_ARG, "B.rowids/B.values missing");
 	if (B->cols > 0x7FFFFFFFu) return fail(h, BELLA_B200_ERR_RANGE, "more than 2^31-1 reads");
-	if (A) {
-		if (!A->colptr || !sA || (A->nnz && (!A->rowids || !A->values))) return fail(h, BELLA_B200_ERR_ARG, "A view incomplete (or strand_A missing)");
-		if (A->rows != B->cols || A->cols != B->rows) return fail(h, BELLA_B200_ERR_ARG, "A is %ux%u but B is %ux%u", A->rows, A->cols, B->rows, B->cols);
-	}
+	if (A && (A->rows != B->cols || A->cols != B->rows || A->nnz != B->nnz))
+		return fail(h, BELLA_B200_ERR_ARG, "A is %ux%u (nnz %u) but B is %ux%u (nnz %u): A must be the transpose of B", A->rows, A->cols,
+			A->nnz, B->rows, B->cols, B->nnz);
 	return 0;
 }
 
-void reset_problem(bella_b200_handle* h, const bella_csc_view* A, const bella_csc_view* B, uint16_t K, uint16_t BIN)
+void reset_problem(bella_b200_handle* h, const bella_csc_view* B, uint16_t K, uint16_t BIN)
 {
-	h->n = B->cols; h->m = B->rows; h->nnzB = B->nnz; h->nnzA = A ? A->nnz : B->nnz;
+	h->n = B->cols; h->m = B->rows; h->nnzB = B->nnz;
 	h->lo = 0; h->hi = h->n; h->K = K; h->BIN = BIN;
-	h->have_A = A != nullptr;
-	h->have_inputs = true; h->layout_done = h->symbolic_done = h->numeric_done = false;
+	h->W = 0;
+	h->have_inputs = true; h->symbolic_done = h->numeric_done = false;
 	h->flops = h->Z = 0;
 }
 
@@ -341,10 +401,10 @@ int bella_b200_destroy(bella_b200_handle* h)
 	if (!h) return BELLA_B200_ERR_ARG;
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->stream);
-	DevBuf* bufs[] = {&h->oA_colptr, &h->oA_rowids, &h->oA_values, &h->oA_strand, &h->oB_colptr, &h->oB_rowids, &h->oB_values,
-		&h->oB_strand, &h->o_len, &h->Aent, &h->Bent, &h->tA_colptr, &h->tcursor, &h->flop64, &h->flopptr, &h->cursor, &h->raw, &h->bcount, &h->nnzC, &h->colptrC,
-		&h->lists, &h->meta, &h->errflag, &h->cubtmp, &h->slab, &h->prod, &h->prow, &h->pdesc, &h->rowsC, &h->countC, &h->posH,
-		&h->posV, &h->aux, &h->fdesc, &h->flists};
+	DevBuf* bufs[] = {&h->oB_colptr, &h->oB_rowids, &h->oB_values, &h->oB_strand, &h->o_len, &h->bhist, &h->boff, &h->bcur, &h->partK,
+		&h->partE, &h->Aent, &h->Acolptr, &h->flop32, &h->nunits, &h->ubase, &h->shv, &h->refine, &h->colinfo, &h->ucol, &h->ucount,
+		&h->uptr, &h->ucur, &h->lists, &h->unnz, &h->uoff, &h->raw, &h->out, &h->colptrC, &h->rowsC, &h->countC, &h->posH, &h->posV,
+		&h->aux, &h->meta, &h->errflag, &h->cubtmp};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& e : h->ev) if (e) cudaEventDestroy(e);
 	if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -357,36 +417,31 @@ const char* bella_b200_last_error(const bella_b200_handle* h) { return h ? h->er
 int bella_b200_set_inputs(bella_b200_handle* h, const bella_csc_view* A, const bella_csc_view* B,
 		const uint32_t* read_len, const uint8_t* strand_A, const uint8_t* strand_B, uint16_t kmer_size, uint16_t bin_size)
 {
-	if (int rc = validate_views(h, A, B, read_len, strand_A, strand_B)) return rc;
+	(void)strand_A;
+	if (int rc = validate_views(h, A, B, read_len, strand_B)) return rc;
 	CK(cudaSetDevice(h->device));
-	reset_problem(h, A, B, kmer_size, bin_size);
-	CK(cudaEventRecord(h->ev[0], h->stream));
+	reset_problem(h, B, kmer_size, bin_size);
+	CK(cudaEventRecord(h->ev[10], h->stream));
 	const void* p;
 	if (int rc = copy_in(h, h->oB_colptr, B->colptr, sizeof(uint32_t) * ((size_t)B->cols + 1), &p)) return rc; h->dB_colptr = (const uint32_t*)p;
 	if (int rc = copy_in(h, h->oB_rowids, B->rowids, sizeof(uint32_t) * (size_t)B->nnz, &p)) return rc; h->dB_rowids = (const uint32_t*)p;
 	if (int rc = copy_in(h, h->oB_values, B->values, sizeof(uint16_t) * (size_t)B->nnz, &p)) return rc; h->dB_values = (const uint16_t*)p;
 	if (int rc = copy_in(h, h->oB_strand, strand_B, ((size_t)B->nnz + 7) / 8, &p)) return rc; h->dB_strand = (const uint8_t*)p;
 	if (int rc = copy_in(h, h->o_len, read_len, sizeof(uint32_t) * (size_t)B->cols, &p)) return rc; h->d_len = (const uint32_t*)p;
-	if (A) {
-		if (int rc = copy_in(h, h->oA_colptr, A->colptr, sizeof(uint32_t) * ((size_t)A->cols + 1), &p)) return rc; h->dA_colptr = (const uint32_t*)p;
-		if (int rc = copy_in(h, h->oA_rowids, A->rowids, sizeof(uint32_t) * (size_t)A->nnz, &p)) return rc; h->dA_rowids = (const uint32_t*)p;
-		if (int rc = copy_in(h, h->oA_values, A->values, sizeof(uint16_t) * (size_t)A->nnz, &p)) return rc; h->dA_values = (const uint16_t*)p;
-		if (int rc = copy_in(h, h->oA_strand, strand_A, ((size_t)A->nnz + 7) / 8, &p)) return rc; h->dA_strand = (const uint8_t*)p;
-	}
-	CK(cudaEventRecord(h->ev[1], h->stream));
+	CK(cudaEventRecord(h->ev[11], h->stream));
 	CK(cudaStreamSynchronize(h->stream));
-	CK(cudaEventElapsedTime(&h->t_ms[3], h->ev[0], h->ev[1]));
+	CK(cudaEventElapsedTime(&h->t_ms[3], h->ev[10], h->ev[11]));
 	return BELLA_B200_OK;
 }
 
 int bella_b200_set_inputs_device(bella_b200_handle* h, const bella_csc_view* A, const bella_csc_view* B,
 		const uint32_t* read_len, const uint8_t* strand_A, const uint8_t* strand_B, uint16_t kmer_size, uint16_t bin_size)
 {
-	if (int rc = validate_views(h, A, B, read_len, strand_A, strand_B)) return rc;
+	(void)strand_A;
+	if (int rc = validate_views(h, A, B, read_len, strand_B)) return rc;
 	CK(cudaSetDevice(h->device));
-	reset_problem(h, A, B, kmer_size, bin_size);
+	reset_problem(h, B, kmer_size, bin_size);
 	h->dB_colptr = B->colptr; h->dB_rowids = B->rowids; h->dB_values = B->values; h->dB_strand = strand_B; h->d_len = read_len;
-	if (A) { h->dA_colptr = A->colptr; h->dA_rowids = A->rowids; h->dA_values = A->values; h->dA_strand = strand_A; }
 	h->t_ms[3] = 0;
 	return BELLA_B200_OK;
 }
@@ -396,7 +451,7 @@ int bella_b200_set_column_range(bella_b200_handle* h, uint32_t col_lo, uint32_t 
 	if (!h || !h->have_inputs) return fail(h, BELLA_B200_ERR_ARG, "set_inputs first");
 	if (col_lo > col_hi || col_hi > h->n) return fail(h, BELLA_B200_ERR_ARG, "column range [%u,%u) outside [0,%u)", col_lo, col_hi, h->n);
 	h->lo = col_lo; h->hi = col_hi;
-	h->layout_done = h->symbolic_done = h->numeric_done = false;
+	h->symbolic_done = h->numeric_done = false;
 	return BELLA_B200_OK;
 }
 
@@ -404,16 +459,7 @@ static int do_symbolic(bella_b200_handle* h)
 {
 	CK(cudaSetDevice(h->device));
 	h->launches = 0;
-	CK(cudaEventRecord(h->ev[0], h->stream));
-	if (int rc = run_layout(h)) return rc;
-	CK(cudaEventRecord(h->ev[1], h->stream));
-	if (int rc = run_symbolic(h)) return rc;
-	CK(cudaEventRecord(h->ev[2], h->stream));
-	CK(cudaStreamSynchronize(h->stream));
-	CK(cudaEventElapsedTime(&h->t_ms[0], h->ev[0], h->ev[1]));
-	CK(cudaEventElapsedTime(&h->t_ms[1], h->ev[1], h->ev[2]));
-	CK(cudaEventElapsedTime(&h->t_ms[6], h->ev[6], h->ev[7]));
-	return 0;
+	return run_symbolic(h);
 }
 
 int bella_b200_symbolic(bella_b200_handle* h, uint64_t* flops, uint32_t* flopC, uint32_t* colptrC)
@@ -421,17 +467,12 @@ int bella_b200_symbolic(bella_b200_handle* h, uint64_t* flops, uint32_t* flopC, 
 	if (!h || !h->have_inputs) return fail(h, BELLA_B200_ERR_ARG, "set_inputs first");
 	if (int rc = do_symbolic(h)) return rc;
 	const uint32_t ncols = h->hi - h->lo;
-	CK(cudaEventRecord(h->ev[3], h->stream));
-	std::vector<unsigned long long> f64;
-	if (flopC && ncols) {
-		f64.resize(ncols);
-		CK(cudaMemcpyAsync(f64.data(), h->flop64.p, sizeof(uint64_t) * ncols, cudaMemcpyDeviceToHost, h->stream));
-	}
+	CK(cudaEventRecord(h->ev[10], h->stream));
+	if (flopC && ncols) CK(cudaMemcpyAsync(flopC, h->flop32.p, sizeof(uint32_t) * ncols, cudaMemcpyDeviceToHost, h->stream));
 	if (colptrC) CK(cudaMemcpyAsync(colptrC, h->colptrC.p, sizeof(uint32_t) * ((size_t)ncols + 1), cudaMemcpyDeviceToHost, h->stream));
-	CK(cudaEventRecord(h->ev[4], h->stream));
+	CK(cudaEventRecord(h->ev[11], h->stream));
 	CK(cudaStreamSynchronize(h->stream));
-	CK(cudaEventElapsedTime(&h->t_ms[4], h->ev[3], h->ev[4]));
-	for (size_t i = 0; i < f64.size(); ++i) flopC[i] = (uint32_t)f64[i];   // < 2^32, checked on the device
+	CK(cudaEventElapsedTime(&h->t_ms[4], h->ev[10], h->ev[11]));
 	if (flops) *flops = h->flops;
 	return BELLA_B200_OK;
 }
@@ -441,11 +482,11 @@ int bella_b200_numeric_device(bella_b200_handle* h)
 	if (!h || !h->symbolic_done) return fail(h, BELLA_B200_ERR_ARG, "bella_b200_symbolic first");
 	if (h->numeric_done) return BELLA_B200_OK;
 	CK(cudaSetDevice(h->device));
-	CK(cudaEventRecord(h->ev[2], h->stream));
+	CK(cudaEventRecord(h->ev[6], h->stream));
 	if (int rc = run_numeric(h)) return rc;
-	CK(cudaEventRecord(h->ev[3], h->stream));
-	if (int rc = check_device_error(h)) return rc;
-	CK(cudaEventElapsedTime(&h->t_ms[2], h->ev[2], h->ev[3]));
+	CK(cudaEventRecord(h->ev[7], h->stream));
+	CK(cudaStreamSynchronize(h->stream));
+	CK(cudaEventElapsedTime(&h->t_ms[2], h->ev[6], h->ev[7]));
 	return BELLA_B200_OK;
 }
 
@@ -466,16 +507,16 @@ int bella_b200_numeric(bella_b200_handle* h, uint32_t col_begin, uint32_t col_en
 	if (int rc = bella_b200_numeric_device(h)) return rc;
 	uint64_t off, cnt;
 	if (int rc = copy_range(h, col_begin, col_end, &off, &cnt)) return rc;
-	CK(cudaEventRecord(h->ev[4], h->stream));
+	CK(cudaEventRecord(h->ev[10], h->stream));
 	if (cnt) {
 		if (rowidsC) CK(cudaMemcpyAsync(rowidsC, h->rowsC.as<uint32_t>() + off, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, h->stream));
 		if (count) CK(cudaMemcpyAsync(count, h->countC.as<uint16_t>() + off, sizeof(uint16_t) * cnt, cudaMemcpyDeviceToHost, h->stream));
 		if (posH) CK(cudaMemcpyAsync(posH, h->posH.as<uint16_t>() + off, sizeof(uint16_t) * cnt, cudaMemcpyDeviceToHost, h->stream));
 		if (posV) CK(cudaMemcpyAsync(posV, h->posV.as<uint16_t>() + off, sizeof(uint16_t) * cnt, cudaMemcpyDeviceToHost, h->stream));
 	}
-	CK(cudaEventRecord(h->ev[5], h->stream));
+	CK(cudaEventRecord(h->ev[11], h->stream));
 	CK(cudaStreamSynchronize(h->stream));
-	float t; CK(cudaEventElapsedTime(&t, h->ev[4], h->ev[5]));
+	float t; CK(cudaEventElapsedTime(&t, h->ev[10], h->ev[11]));
 	h->t_ms[4] += t;
 	return BELLA_B200_OK;
 }
@@ -514,11 +555,9 @@ int bella_b200_result_device(bella_b200_handle* h, const uint32_t** colptrC, con
 int bella_b200_run_resident(bella_b200_handle* h, uint64_t* nnzC_out, uint64_t* flops_out)
 {
 	if (!h || !h->have_inputs) return fail(h, BELLA_B200_ERR_ARG, "set_inputs first");
-	h->layout_done = h->symbolic_done = h->numeric_done = false;
+	h->symbolic_done = h->numeric_done = false;
 	if (int rc = do_symbolic(h)) return rc;
-	int launches = h->launches;
 	if (int rc = bella_b200_numeric_device(h)) return rc;
-	(void)launches;
 	if (nnzC_out) *nnzC_out = h->Z;
 	if (flops_out) *flops_out = h->flops;
 	return BELLA_B200_OK;

@@ -1,312 +1,434 @@
 // kernels.cuh -- device code of the B200 overlap SpGEMM (included once, by bella_b200.cu).
 //
-// Pipeline (DESIGN.md has the traffic model of every stage):
-//   layout   k_build_A      A's columns (k-mers) as packed entries sorted by read id, plus the per
-//                           output-column product count == estimateFLOP (overlap.hpp:157-202)
-//            k_count_deg / k_transpose_fill   A = B^T on the device when the caller passes only B
-//   scatter  k_scatter      outer-product expansion on the A side: k-mer column (r0<r1<..) emits the
-//                           kept products (col r_a, row r_b), a<b, into column r_a's private region.
-//                           Streams A once; the write frontier (one cursor per output column) lives
-//                           in L2, so no random DRAM gathers.
-//   group    k_group        one CTA per output column: shared-memory hash of the column's k-mers
-//                           (k-mer id -> position in B's column = fold order) and of the row ids
-//                           (== estimateNNZ_Hash, overlap.hpp:205-276); groups the products by pair
-//                           in B-column order (== LocalSpGEMM's visiting order, overlap.hpp:306-341)
-//            k_expand_gather  fallback for columns that do not fit shared memory (gather formulation)
-//   fold     k_flatten, k_fold_short<>, k_fold_long, k_fold_huge   the semiring (chain.hpp:74-150)
-//                           + choose() (common.h:162-170), bucketed by products per pair
+// The whole path is a chain of "partition into contiguous regions, then finish each region in
+// shared memory" stages, so that every HBM access is either a coalesced stream or a small store
+// to one of a few thousand write frontiers that live in L2 (DESIGN.md has the traffic model):
+//
+//   transpose  k_bucket_hist / k_partition   B's nonzeros (read-major) -> buckets of consecutive k-mer ids
+//              k_bucket                      one CTA per bucket: counting sort by k-mer, columns sorted by
+//                                            read id, written as packed entries `Aent` + A's colptr, and the
+//                                            per-output-column product count == estimateFLOP
+//                                            (overlap.hpp:157-202)
+//   plan       k_plan / k_units_init / k_count_units / k_classify_units
+//                                            output columns -> units (a column, or a row range of a heavy
+//                                            column) of at most UNIT_CAP products
+//   scatter    k_scatter                     outer-product expansion on the A side: k-mer column
+//                                            (r0<r1<..) emits the kept products (col r_a, row r_b), a<b,
+//                                            into the unit's region (one 8-byte record per product)
+//   group+fold k_group_fold<CAP>             one CTA per unit: region staged into shared memory with one
+//                                            bulk async copy (TMA 1-D), distinct rows through a two-level
+//                                            bitmap (== estimateNNZ_Hash, overlap.hpp:205-276), products
+//                                            grouped by pair in B-column order (== LocalSpGEMM's visiting
+//                                            order, overlap.hpp:306-341), then the semiring fold
+//                                            (chain.hpp:74-150) and choose() (common.h:162-170) without
+//                                            leaving shared memory
+//              k_huge_pair                   a single pair with more products than fit in shared memory
+//   output     k_colptr / k_compact          per-unit results -> C in CSC order, rows ascending
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace bk {
 
-constexpr uint32_t EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t NONE16 = 0xFFFFu;
-constexpr int N_CLASSES = 4;          // group classes: S, M (shared memory), gather-smem, gather-global
-constexpr int NBUCKETS = 7;           // fold buckets: P==1 | 2..4 | 5..8 | 9..16 | 17..32 | 33..256 | >256
-constexpr uint32_t GATHER_SMEM_LIMIT = 8192;
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+constexpr int NCLASS = 3;
+constexpr uint32_t CLASS_CAP[NCLASS] = {2048, 4096, 8192};
+constexpr uint32_t UNIT_CAP = 8192;        // products per unit (largest shared-memory class)
+constexpr uint32_t BUCKET_CAP = 4096;      // entries per transpose bucket
+constexpr uint32_t BUCKET_WMAX = 4096;     // k-mers per transpose bucket
+constexpr uint32_t MAX_SPAN_SHIFT = 22;    // a unit covers at most 2^22 rows (two-level bitmap: 4097 words)
+constexpr uint32_t SHORT_FOLD = 8;         // pairs up to this many products are folded by one thread
+constexpr int GF_THREADS = 256;
+constexpr size_t BUCKET_SMEM = (size_t)BUCKET_CAP * 12 + ((size_t)BUCKET_WMAX + 2) * 4;
 
-// Packed formats (64-bit unless noted)
-//   Aent  : row(32) | pos(16)<<32 | strand(1)<<48            A's columns, rows ascending
-//   Bent  : aoff(32) | pos(16)<<32 | cnt(15)<<48 | strand<<63 only for gather-fallback columns
-//   raw   : uint4 per product    { row | oriented<<31,  h | v<<16,  k-mer id, 0 }  (one 16-byte store)
-//   prod  : h(16) | v(16)<<16 | overlap(16)<<32 [| fold state label(16)<<48]   grouped by pair, in fold order
+// Packed formats (64-bit)
+//   Aent : row(31) | strand<<31 | pos(16)<<32 | jrank(16)<<48     A's columns, rows ascending;
+//          jrank = position of the k-mer inside B's column of that read (the fold order)
+//   raw  : row(31) | strandH<<31 | h(16)<<32 | jrank(16)<<48      one per kept product, in the unit's region;
+//          row/strandH/h come from the row read's entry, jrank from the column read's entry
+//   fin  : h(16) | v(16)<<16 | overlap(16)<<32                     grouped by pair, in fold order (shared memory)
+//   out  : uint4 { row, count | nbins<<16, h | v<<16, support | overlap<<16 }  per pair, per unit
+
+struct ColInfo { uint32_t ubase; uint32_t sh; };
 
 struct Params {
 	uint32_t n, m, lo, hi, K, BIN;
 	const uint32_t* B_colptr;
-	const uint32_t* B_rowids;
-	const uint32_t* A_colptr;
+	const uint16_t* B_values;
+	const uint8_t* B_strand;
 	const uint32_t* read_len;
-	const uint64_t* Aent;
-	const uint64_t* Bent;
-	unsigned long long* flop64;   // [ncols+1] products per column
-	uint64_t* flopptr;            // [ncols+1] exclusive scan
-	uint32_t* cursor;             // [ncols]   scatter cursors
-	uint4* raw;                   // [F]
-	uint32_t* nnzC;               // [ncols+1]
-	uint32_t* colptrC;            // [ncols+1]
-	uint32_t* bcount;             // [NBUCKETS*ncols+1] pairs per fold bucket per column, then scanned in place -> boffs
-	uint64_t* prod;               // [2F]  (second half: ordered output of the gather fallback)
-	uint64_t prod_half;           // F
-	uint32_t* prow;               // [F]   pair row id at flopptr[col]+p
-	uint2* pdesc;                 // [F]   {absolute start in prod (low 32 bits of offset from region base), length}
-	uint32_t* rowsC;
-	uint16_t* countC;
-	uint16_t* posH;
-	uint16_t* posV;
-	uint16_t* aux;
+	const uint32_t* A_colptr;     // [m+1]
+	const uint64_t* Aent;         // [nnz]
+	const ColInfo* colinfo;       // [ncols]
+	const uint32_t* ucol;         // [U]  local column of the unit
+	const uint32_t* ucount;       // [U]  products of the unit
+	const uint64_t* uptr;         // [U+1] region start (even-padded sizes)
+	unsigned long long* ucur;     // [U]  scatter cursors (start at uptr)
+	uint64_t* raw;                // [F + U]
+	uint4* out;                   // [F + U] per-unit pair records at uptr[u] + p
+	uint32_t* unnz;               // [U+1] pairs per unit
 	int* err;
 };
 
 struct Meta {
 	unsigned long long flops;
-	unsigned int class_count[N_CLASSES];
-	unsigned int max_flop;
-	unsigned int pad;
+	unsigned int class_count[NCLASS + 1];   // + overflow
+	unsigned int n_heavy_cols;
+	unsigned int n_units;
+	unsigned int max_bucket;
+	unsigned int n_refine;
 };
 
 __device__ __forceinline__ void set_err(int* err, int code) { atomicCAS(err, 0, code); }
 __device__ __forceinline__ uint32_t getbit(const uint8_t* __restrict__ bits, uint64_t i) { return (bits[i >> 3] >> (i & 7)) & 1u; }
+__device__ __forceinline__ uint32_t ent_row(uint64_t e) { return (uint32_t)e & 0x7FFFFFFFu; }
 
-// ================================ layout ====================================================
+// ================================ block helpers =============================================
 
-__global__ void k_count_deg(const uint32_t* __restrict__ Brow, uint64_t nnz, uint32_t* __restrict__ deg)
-{
-	for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < nnz; j += (uint64_t)gridDim.x * blockDim.x)
-		atomicAdd(&deg[Brow[j]], 1u);
-}
-
-// A = B^T: one warp per column (read) of B scatters its nonzeros into A's columns (unsorted).
-__global__ void k_transpose_fill(uint32_t n, const uint32_t* __restrict__ Bcolptr, const uint32_t* __restrict__ Brow,
-		const uint16_t* __restrict__ Bval, const uint8_t* __restrict__ Bstrand,
-		const uint32_t* __restrict__ Acolptr, uint32_t* __restrict__ cursor, uint64_t* __restrict__ Aent)
-{
-	uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-	for (uint32_t i = warp; i < n; i += nwarps) {
-		uint32_t j1 = Bcolptr[i + 1];
-		for (uint32_t j = Bcolptr[i] + lane; j < j1; j += 32) {
-			uint32_t c = Brow[j];
-			uint32_t slot = atomicAdd(&cursor[c], 1u);
-			Aent[Acolptr[c] + slot] = (uint64_t)i | ((uint64_t)Bval[j] << 32) | ((uint64_t)getbit(Bstrand, j) << 48);
-		}
-	}
-}
-
-// Thread per k-mer column: pack (FROM_ENT = false: from the caller's CSC arrays) or re-read
-// (FROM_ENT = true: after k_transpose_fill) the column, sort it by read id, write it back, and add
-// each entry's kept-product count (the entries after it) to its read's column counter.
-template <bool FROM_ENT>
-__global__ void __launch_bounds__(256) k_build_A(uint32_t m, uint32_t lo, uint32_t hi, const uint32_t* __restrict__ Acolptr,
-		const uint32_t* __restrict__ Arow, const uint16_t* __restrict__ Aval, const uint8_t* __restrict__ Astrand,
-		uint64_t* __restrict__ Aent, unsigned long long* __restrict__ flop64, int* err)
-{
-	constexpr int LOCAL = 16;
-	for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < m; c += gridDim.x * blockDim.x) {
-		const uint32_t s = Acolptr[c], e = Acolptr[c + 1], d = e - s;
-		if (d == 0) continue;
-		if (d > 32768u) { set_err(err, -4); continue; }
-		if (d <= LOCAL) {
-			uint64_t ent[LOCAL];
-#pragma unroll
-			for (int q = 0; q < LOCAL; ++q) {
-				if (q < (int)d) {
-					uint64_t x;
-					if (FROM_ENT) x = Aent[s + q];
-					else x = (uint64_t)Arow[s + q] | ((uint64_t)Aval[s + q] << 32) | ((uint64_t)getbit(Astrand, (uint64_t)s + q) << 48);
-					// insertion into the sorted prefix (static indices keep ent[] in registers)
-					ent[q] = x;
-#pragma unroll
-					for (int b = q; b > 0; --b) {
-						if ((uint32_t)ent[b - 1] > (uint32_t)ent[b]) { uint64_t t = ent[b - 1]; ent[b - 1] = ent[b]; ent[b] = t; }
-					}
-				}
-			}
-#pragma unroll
-			for (int q = 0; q < LOCAL; ++q) {
-				if (q < (int)d) {
-					Aent[s + q] = ent[q];
-					uint32_t r = (uint32_t)ent[q];
-					if (q + 1 < (int)d && r >= lo && r < hi) atomicAdd(&flop64[r - lo], (unsigned long long)(d - 1 - q));
-				}
-			}
-		} else {
-			if (!FROM_ENT)
-				for (uint32_t q = s; q < e; ++q)
-					Aent[q] = (uint64_t)Arow[q] | ((uint64_t)Aval[q] << 32) | ((uint64_t)getbit(Astrand, q) << 48);
-			for (uint32_t a = s + 1; a < e; ++a) {
-				uint64_t x = Aent[a];
-				uint32_t b = a;
-				while (b > s) {
-					uint64_t y = Aent[b - 1];
-					if ((uint32_t)y <= (uint32_t)x) break;
-					Aent[b] = y;
-					--b;
-				}
-				if (b != a) Aent[b] = x;
-			}
-			for (uint32_t q = s; q + 1 < e; ++q) {
-				uint32_t r = (uint32_t)Aent[q];
-				if (r >= lo && r < hi) atomicAdd(&flop64[r - lo], (unsigned long long)(e - 1 - q));
-			}
-		}
-	}
-}
-
-// Outer-product expansion.  Thread per k-mer column (r_0 < r_1 < ...): entry a owns the run of
-// products (col r_a, row r_b), b > a; the run is written contiguously into column r_a's region.
-__global__ void __launch_bounds__(256) k_scatter(uint32_t m, uint32_t lo, uint32_t hi, const uint32_t* __restrict__ Acolptr,
-		const uint64_t* __restrict__ Aent, const uint64_t* __restrict__ flopptr, uint32_t* __restrict__ cursor,
-		uint4* __restrict__ raw)
-{
-	for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < m; c += gridDim.x * blockDim.x) {
-		const uint32_t s = Acolptr[c], e = Acolptr[c + 1];
-		for (uint32_t a = s; a + 1 < e; ++a) {
-			const uint64_t ea = Aent[a];
-			const uint32_t ra = (uint32_t)ea;
-			if (ra < lo || ra >= hi) continue;
-			const uint32_t run = e - 1 - a;
-			const uint32_t v = (uint32_t)(ea >> 32) & 0xFFFFu, sa = (uint32_t)(ea >> 48) & 1u;
-			uint64_t q = flopptr[ra - lo] + atomicAdd(&cursor[ra - lo], run);
-			for (uint32_t b = a + 1; b < e; ++b, ++q) {
-				const uint64_t eb = Aent[b];
-				const uint32_t h = (uint32_t)(eb >> 32) & 0xFFFFu, sb = (uint32_t)(eb >> 48) & 1u;
-				raw[q] = make_uint4((uint32_t)eb | ((sa == sb) << 31), h | (v << 16), c, 0u);
-			}
-		}
-	}
-}
-
-// Bent for the gather-fallback columns only (list of local column ids)
-__global__ void k_pack_B_list(uint32_t lo, const uint32_t* __restrict__ list, uint32_t count, const uint32_t* __restrict__ Bcolptr,
-		const uint32_t* __restrict__ Brow, const uint16_t* __restrict__ Bval, const uint8_t* __restrict__ Bstrand,
-		const uint32_t* __restrict__ Acolptr, const uint64_t* __restrict__ Aent, uint64_t* __restrict__ Bent, int* err)
-{
-	uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-	for (uint32_t it = warp; it < count; it += nwarps) {
-		const uint32_t i = lo + list[it];
-		uint32_t j0 = Bcolptr[i], j1 = Bcolptr[i + 1];
-		for (uint32_t j = j0 + lane; j < j1; j += 32) {
-			uint32_t c = Brow[j];
-			uint32_t s = Acolptr[c], e = Acolptr[c + 1];
-			uint32_t a = s, b = e;      // upper_bound(row <= i) in the sorted column
-			while (a < b) { uint32_t mid = (a + b) >> 1; if ((uint32_t)Aent[mid] <= i) a = mid + 1; else b = mid; }
-			uint32_t cnt = e - a;
-			if (cnt > 32767u) { set_err(err, -4); cnt = 32767u; }
-			Bent[j] = (uint64_t)a | ((uint64_t)Bval[j] << 32) | ((uint64_t)cnt << 48) | ((uint64_t)getbit(Bstrand, j) << 63);
-		}
-	}
-}
-
-constexpr uint32_t CLASS_F[2] = {2048, 4096};       // product capacity of the shared-memory group classes
-constexpr uint32_t CLASS_L[2] = {3072, 6144};       // B-column length capacity (k-mer hash = 4/3 of it, pow2)
-
-__global__ void k_classify(uint32_t lo, uint32_t ncols, const unsigned long long* __restrict__ flop64,
-		const uint32_t* __restrict__ Bcolptr, uint32_t* __restrict__ lists, Meta* meta, int* err)
-{
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ncols; i += gridDim.x * blockDim.x) {
-		unsigned long long f = flop64[i];
-		if (f == 0) continue;
-		uint32_t L = Bcolptr[lo + i + 1] - Bcolptr[lo + i];
-		if (f > 0xFFFFFFFFull || L > 65535u) { set_err(err, -4); continue; }
-		int c = (f <= CLASS_F[0] && L <= CLASS_L[0]) ? 0 : (f <= CLASS_F[1] && L <= CLASS_L[1]) ? 1 : f <= GATHER_SMEM_LIMIT ? 2 : 3;
-		uint32_t idx = atomicAdd(&meta->class_count[c], 1u);
-		lists[(size_t)c * ncols + idx] = i;
-		if (c == 3) atomicMax(&meta->max_flop, (unsigned int)f);
-	}
-}
-
-__global__ void k_set_total(Meta* meta, const uint64_t* flopptr, uint32_t ncols) { meta->flops = flopptr[ncols]; }
-
-// ================================ hashing helpers ===========================================
-
-__device__ __forceinline__ uint32_t ht_insert(uint32_t* keys, uint32_t mask, int shift, uint32_t key)
-{
-	uint32_t h = (key * 0x9E3779B1u) >> shift;
-	for (;;) {
-		uint32_t k = *(volatile uint32_t*)(keys + h);
-		if (k == EMPTY) {
-			k = atomicCAS(keys + h, EMPTY, key);
-			if (k == EMPTY) return h;
-		}
-		if (k == key) return h;
-		h = (h + 1) & mask;
-	}
-}
-
-__device__ __forceinline__ uint32_t ht_find(const uint32_t* keys, uint32_t mask, int shift, uint32_t key)
-{
-	uint32_t h = (key * 0x9E3779B1u) >> shift;
-	while (keys[h] != key) h = (h + 1) & mask;
-	return h;
-}
-
-// bounded probe: returns EMPTY when the key is absent (internal consistency check)
-__device__ __forceinline__ uint32_t ht_find_checked(const uint32_t* keys, uint32_t mask, int shift, uint32_t key)
-{
-	uint32_t h = (key * 0x9E3779B1u) >> shift;
-	for (uint32_t probes = 0; probes <= mask; ++probes) {
-		uint32_t k = keys[h];
-		if (k == key) return h;
-		if (k == EMPTY) return EMPTY;
-		h = (h + 1) & mask;
-	}
-	return EMPTY;
-}
-
-// exclusive scan of a[0..n) in place, block-wide; s_tmp needs 34 words; also leaves the total in a[n]
-__device__ void block_excl_scan(uint32_t* a, uint32_t n, uint32_t* s_tmp)
+// exclusive scan of a[0..n) in place (T = uint16_t or uint32_t), block-wide; total left in a[n].
+// s_tmp needs 34 words.  Ends with a barrier.
+template <class T>
+__device__ void block_excl_scan(T* a, uint32_t n, uint32_t* s_tmp)
 {
 	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
 	if (tid == 0) s_tmp[32] = 0;
 	__syncthreads();
 	for (uint32_t base = 0; base < n; base += blockDim.x) {
 		uint32_t idx = base + tid;
-		uint32_t x = idx < n ? a[idx] : 0, v = x;
-		for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= o) v += y; }
+		uint32_t x = idx < n ? (uint32_t)a[idx] : 0, v = x;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, v, o); if (lane >= (uint32_t)o) v += y; }
 		if (lane == 31) s_tmp[wid] = v;
 		__syncthreads();
 		if (wid == 0) {
 			uint32_t w = lane < nw ? s_tmp[lane] : 0, ws = w;
-			for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, ws, o); if (lane >= o) ws += y; }
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, ws, o); if (lane >= (uint32_t)o) ws += y; }
 			s_tmp[lane] = ws - w;
 			if (lane == 31) s_tmp[33] = ws;
 		}
 		__syncthreads();
 		uint32_t carry = s_tmp[32];
-		if (idx < n) a[idx] = v - x + s_tmp[wid] + carry;
+		if (idx < n) a[idx] = (T)(v - x + s_tmp[wid] + carry);
 		__syncthreads();
 		if (tid == 0) s_tmp[32] = carry + s_tmp[33];
 		__syncthreads();
 	}
-	if (tid == 0) a[n] = s_tmp[32];
+	if (tid == 0) a[n] = (T)s_tmp[32];
 	__syncthreads();
 }
 
-__device__ __forceinline__ void block_bitonic_sort(uint32_t* a, uint32_t np2)
+// pre[i] = sum_{j<i} popc(bits[j]), pre[n] = total.  Ends with a barrier.
+template <class T>
+__device__ void block_popc_scan(const uint32_t* bits, T* pre, uint32_t n, uint32_t* s_tmp)
 {
-	const uint32_t tid = threadIdx.x, nt = blockDim.x;
-	for (uint32_t k = 2; k <= np2; k <<= 1)
-		for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-			for (uint32_t x = tid; x < np2; x += nt) {
-				uint32_t y = x ^ j;
-				if (y > x) {
-					uint32_t u = a[x], w = a[y];
-					bool up = (x & k) == 0;
-					if ((u > w) == up) { a[x] = w; a[y] = u; }
-				}
-			}
-			__syncthreads();
-		}
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) pre[i] = (T)__popc(bits[i]);
+	__syncthreads();
+	block_excl_scan<T>(pre, n, s_tmp);
 }
 
-__device__ __forceinline__ int bucket_of(uint32_t len)
+// atomicAdd on a 16-bit counter packed two per 32-bit word (no carry: counts stay < 65536)
+__device__ __forceinline__ uint32_t atomic_add16(uint16_t* base, uint32_t idx, uint32_t v)
 {
-	return len == 1 ? 0 : len <= 4 ? 1 : len <= 8 ? 2 : len <= 16 ? 3 : len <= 32 ? 4 : len <= 256 ? 5 : 6;
+	uint32_t sh = (idx & 1u) * 16u;
+	uint32_t old = atomicAdd((uint32_t*)base + (idx >> 1), v << sh);
+	return (old >> sh) & 0xFFFFu;
 }
+
+// ---- 1-D bulk async copy global -> shared (TMA), completion on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n .reg .pred p;\n"
+		"WAIT_%=:\n"
+		" mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		" @p bra DONE_%=;\n"
+		" bra WAIT_%=;\n"
+		"DONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ================================ transpose =================================================
+
+// entries per bucket of W consecutive k-mer ids (B nonzeros j >= jlo = B_colptr[lo]: rows below lo never matter)
+__global__ void __launch_bounds__(256) k_bucket_hist(const uint32_t* __restrict__ Bcolptr, uint32_t lo, uint64_t nnz,
+		const uint32_t* __restrict__ Brow, uint32_t W, uint32_t* __restrict__ bhist)
+{
+	const uint64_t jlo = Bcolptr[lo];
+	for (uint64_t j = jlo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < nnz; j += (uint64_t)gridDim.x * blockDim.x)
+		atomicAdd(&bhist[Brow[j] / W], 1u);
+}
+
+__global__ void k_bucket_max(const uint32_t* __restrict__ bhist, uint32_t nb, Meta* meta)
+{
+	uint32_t mx = 0;
+	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) mx = max(mx, bhist[b]);
+	for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+	if ((threadIdx.x & 31) == 0 && mx) atomicMax(&meta->max_bucket, mx);
+}
+
+// One warp per read (column of B): its nonzeros go to their k-mer bucket's region as (k-mer id, entry).
+// The write frontier is one open sector per bucket, so the small stores merge in L2.
+__global__ void __launch_bounds__(256) k_partition(uint32_t n, uint32_t lo, const uint32_t* __restrict__ Bcolptr,
+		const uint32_t* __restrict__ Brow, const uint16_t* __restrict__ Bval, const uint8_t* __restrict__ Bstrand,
+		uint32_t W, uint32_t* __restrict__ bcur, uint32_t* __restrict__ partK, uint64_t* __restrict__ partE, int* err)
+{
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t i = lo + warp; i < n; i += nwarps) {
+		const uint32_t j0 = Bcolptr[i], j1 = Bcolptr[i + 1];
+		if (j1 - j0 > 65536u) { if (lane == 0) set_err(err, -4); continue; }
+		for (uint32_t jb = j0; jb < j1; jb += 128) {
+			uint32_t c[4], q[4];
+#pragma unroll
+			for (int u = 0; u < 4; ++u) {
+				uint32_t j = jb + u * 32 + lane;
+				if (j < j1) { c[u] = Brow[j]; q[u] = atomicAdd(&bcur[c[u] / W], 1u); }
+			}
+#pragma unroll
+			for (int u = 0; u < 4; ++u) {
+				uint32_t j = jb + u * 32 + lane;
+				if (j < j1) {
+					partK[q[u]] = c[u];
+					partE[q[u]] = (uint64_t)i | ((uint64_t)getbit(Bstrand, j) << 31) | ((uint64_t)Bval[j] << 32) | ((uint64_t)(j - j0) << 48);
+				}
+			}
+		}
+	}
+}
+
+// One CTA per bucket: counting sort by k-mer in shared memory, each column sorted by read id,
+// coalesced write of Aent and A's colptr, product counts per output column.
+__global__ void __launch_bounds__(256) k_bucket(uint32_t m, uint32_t lo, uint32_t hi, uint32_t W, uint32_t nb,
+		const uint32_t* __restrict__ boff, const uint32_t* __restrict__ partK, const uint64_t* __restrict__ partE,
+		uint32_t* __restrict__ Acolptr, uint64_t* __restrict__ Aent, uint32_t* __restrict__ flop32, int* err)
+{
+	extern __shared__ __align__(16) unsigned char bsm[];
+	uint64_t* E = (uint64_t*)bsm;                              // [BUCKET_CAP]
+	uint32_t* tmp = (uint32_t*)(E + BUCKET_CAP);               // [BUCKET_CAP]
+	uint32_t* off = tmp + BUCKET_CAP;                          // [BUCKET_WMAX + 2]
+	__shared__ uint32_t s_tmp[34];
+	const uint32_t tid = threadIdx.x, nt = blockDim.x;
+	for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
+		const uint32_t o0 = boff[b], size = boff[b + 1] - o0;
+		const uint32_t kbase = b * W, kw = min(W, m - kbase);
+		if (size > BUCKET_CAP) { if (tid == 0) set_err(err, -6); continue; }
+		for (uint32_t k = tid; k <= kw; k += nt) off[k] = 0;
+		__syncthreads();
+		for (uint32_t x = tid; x < size; x += nt) {
+			uint32_t k = partK[o0 + x] - kbase;
+			uint32_t arr = atomicAdd(&off[k], 1u);
+			tmp[x] = k | (arr << 12);
+		}
+		__syncthreads();
+		block_excl_scan<uint32_t>(off, kw, s_tmp);
+		for (uint32_t x = tid; x < size; x += nt) {
+			uint32_t t = tmp[x];
+			E[off[t & 0xFFFu] + (t >> 12)] = partE[o0 + x];
+		}
+		__syncthreads();
+		for (uint32_t k = tid; k < kw; k += nt) {
+			const uint32_t s = off[k], e = off[k + 1];
+			Acolptr[kbase + k] = o0 + s;
+			for (uint32_t a = s + 1; a < e; ++a) {          // insertion sort by read id (columns are 2..8 long)
+				uint64_t x = E[a];
+				uint32_t p = a;
+				while (p > s && ent_row(E[p - 1]) > ent_row(x)) { E[p] = E[p - 1]; --p; }
+				E[p] = x;
+			}
+			for (uint32_t a = s; a + 1 < e; ++a) {
+				uint32_t r = ent_row(E[a]);
+				if (r >= lo && r < hi) atomicAdd(&flop32[r - lo], e - 1 - a);
+			}
+		}
+		if (b == nb - 1 && tid == 0) Acolptr[m] = o0 + size;
+		__syncthreads();
+		for (uint32_t x = tid; x < size; x += nt) Aent[o0 + x] = E[x];
+		__syncthreads();
+	}
+}
+
+// ================================ plan ======================================================
+
+// Units of a column: row buckets of width 2^sh over (i, n).  Light columns: one unit (sh = 31).
+__global__ void k_plan(uint32_t n, uint32_t lo, uint32_t ncols, const uint32_t* __restrict__ flop32,
+		const uint8_t* __restrict__ refine, uint32_t* __restrict__ nunits, uint8_t* __restrict__ shv, Meta* meta)
+{
+	unsigned long long fsum = 0;
+	uint32_t heavy = 0;
+	for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < ncols; li += gridDim.x * blockDim.x) {
+		const uint32_t f = flop32[li], i = lo + li;
+		fsum += f;
+		uint32_t sh = 31, nb = f ? 1u : 0u;
+		const uint32_t span = n - 1 - i;                     // rows i+1 .. n-1
+		if (f && (f > UNIT_CAP || span > (1u << MAX_SPAN_SHIFT))) {
+			uint32_t parts = (uint32_t)min((unsigned long long)span, ((unsigned long long)f * 8 + UNIT_CAP - 1) / UNIT_CAP);
+			uint32_t width = max(1u, span / max(parts, 1u));
+			sh = 31 - __clz(width);
+			sh = min(sh, MAX_SPAN_SHIFT);
+			uint32_t fine = refine[li];                        // each refinement round: 8x narrower row buckets
+			sh = sh > 3 * fine ? sh - 3 * fine : 0;
+			nb = ((n - 1) >> sh) - ((i + 1) >> sh) + 1;
+			++heavy;
+		}
+		nunits[li] = nb;
+		shv[li] = (uint8_t)sh;
+	}
+	for (int o = 16; o; o >>= 1) { fsum += __shfl_xor_sync(FULL, fsum, o); heavy += __shfl_xor_sync(FULL, heavy, o); }
+	if ((threadIdx.x & 31) == 0) {
+		if (fsum) atomicAdd(&meta->flops, fsum);
+		if (heavy) atomicAdd(&meta->n_heavy_cols, heavy);
+	}
+}
+
+__global__ void k_units_init(uint32_t ncols, uint32_t ucap, const uint32_t* __restrict__ flop32, const uint32_t* __restrict__ ubase,
+		const uint8_t* __restrict__ shv, ColInfo* __restrict__ colinfo, uint32_t* __restrict__ ucol, uint32_t* __restrict__ ucount,
+		Meta* meta, int* err)
+{
+	const uint32_t U = ubase[ncols];
+	if (blockIdx.x == 0 && threadIdx.x == 0) meta->n_units = U;
+	if (U > ucap) { if (blockIdx.x == 0 && threadIdx.x == 0) set_err(err, -7); return; }
+	for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < ncols; li += gridDim.x * blockDim.x) {
+		const uint32_t u0 = ubase[li], u1 = ubase[li + 1];
+		colinfo[li] = ColInfo{u0, shv[li]};
+		if (shv[li] == 31) { if (u1 > u0) { ucol[u0] = li; ucount[u0] = flop32[li]; } }
+		else for (uint32_t u = u0; u < u1; ++u) { ucol[u] = li; ucount[u] = 0; }
+	}
+}
+
+__device__ __forceinline__ uint32_t unit_of(const ColInfo ci, uint32_t i, uint32_t row)
+{
+	return ci.sh == 31 ? ci.ubase : ci.ubase + (row >> ci.sh) - ((i + 1) >> ci.sh);
+}
+
+// products per unit of the heavy columns (light columns were filled by k_units_init)
+__global__ void __launch_bounds__(256) k_count_units(uint32_t m, uint32_t lo, uint32_t hi, const uint32_t* __restrict__ Acolptr,
+		const uint64_t* __restrict__ Aent, const ColInfo* __restrict__ colinfo, uint32_t* __restrict__ ucount, const Meta* meta,
+		const int* err)
+{
+	if (meta->n_heavy_cols == 0 || *err != 0) return;
+	for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < m; c += gridDim.x * blockDim.x) {
+		const uint32_t s = Acolptr[c], e = Acolptr[c + 1];
+		for (uint32_t a = s; a + 1 < e; ++a) {
+			const uint32_t ra = ent_row(Aent[a]);
+			if (ra < lo || ra >= hi) continue;
+			const ColInfo ci = colinfo[ra - lo];
+			if (ci.sh == 31) continue;
+			for (uint32_t b = a + 1; b < e; ++b) atomicAdd(&ucount[unit_of(ci, ra, ent_row(Aent[b]))], 1u);
+		}
+	}
+}
+
+// classes by unit size; units that do not fit ask for a finer split of their column (refine) unless
+// they already are a single row (sh == 0): those go to the huge-pair list (class NCLASS).
+__global__ void k_classify_units(uint32_t ucap, const uint32_t* __restrict__ ucol, const uint32_t* __restrict__ ucount,
+		const ColInfo* __restrict__ colinfo, const uint64_t* __restrict__ uptr, unsigned long long* __restrict__ ucur,
+		uint32_t* __restrict__ lists, uint8_t* __restrict__ refine, uint32_t round, Meta* meta, const int* err)
+{
+	if (*err != 0) return;
+	const uint32_t U = meta->n_units;
+	for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += gridDim.x * blockDim.x) {
+		const uint32_t f = ucount[u];
+		ucur[u] = uptr[u];
+		if (!f) continue;
+		int c = f <= CLASS_CAP[0] ? 0 : f <= CLASS_CAP[1] ? 1 : f <= CLASS_CAP[2] ? 2 : 3;
+		if (c == 3) {
+			const uint32_t li = ucol[u];
+			if (colinfo[li].sh != 0) { refine[li] = (uint8_t)(round + 1); atomicAdd(&meta->n_refine, 1u); continue; }
+		}
+		uint32_t idx = atomicAdd(&meta->class_count[c], 1u);
+		lists[(size_t)c * ucap + idx] = u;
+	}
+}
+
+// ================================ scatter ===================================================
+// Thread per k-mer column (r_0 < r_1 < ...): entry a owns the run of products (col r_a, row r_b), b > a.
+// A light column's run is written contiguously into the column's region after one cursor atomic.
+__global__ void __launch_bounds__(256) k_scatter(uint32_t m, uint32_t lo, uint32_t hi, const uint32_t* __restrict__ Acolptr,
+		const uint64_t* __restrict__ Aent, const ColInfo* __restrict__ colinfo, unsigned long long* __restrict__ ucur,
+		uint64_t* __restrict__ raw)
+{
+	constexpr int D = 8;
+	constexpr uint64_t LOW48 = 0x0000FFFFFFFFFFFFull;
+	for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < m; c += gridDim.x * blockDim.x) {
+		const uint32_t s = Acolptr[c], e = Acolptr[c + 1], d = e - s;
+		if (d < 2) continue;
+		if (d <= D) {
+			uint64_t ent[D];
+			unsigned long long q[D];
+			uint32_t heavy = 0;
+#pragma unroll
+			for (int a = 0; a < D; ++a) ent[a] = a < (int)d ? Aent[s + a] : 0;
+#pragma unroll
+			for (int a = 0; a < D - 1; ++a) {
+				q[a] = ~0ull;
+				if (a + 1 < (int)d) {
+					const uint32_t ra = ent_row(ent[a]);
+					if (ra >= lo && ra < hi) {
+						const ColInfo ci = colinfo[ra - lo];
+						if (ci.sh == 31) q[a] = atomicAdd(&ucur[ci.ubase], (unsigned long long)(d - 1 - a));
+						else heavy |= 1u << a;
+					}
+				}
+			}
+#pragma unroll
+			for (int a = 0; a < D - 1; ++a) {
+				if (q[a] != ~0ull) {
+					const uint64_t top = ent[a] & ~LOW48;
+					unsigned long long p = q[a];
+#pragma unroll
+					for (int b = a + 1; b < D; ++b)
+						if (b < (int)d) raw[p++] = (ent[b] & LOW48) | top;
+				}
+			}
+			if (heavy) {
+#pragma unroll
+				for (int a = 0; a < D - 1; ++a) {
+					if (heavy >> a & 1u) {
+						const uint32_t ra = ent_row(ent[a]);
+						const ColInfo ci = colinfo[ra - lo];
+						const uint64_t top = ent[a] & ~LOW48;
+#pragma unroll
+						for (int b = a + 1; b < D; ++b)
+							if (b < (int)d) raw[atomicAdd(&ucur[unit_of(ci, ra, ent_row(ent[b]))], 1ull)] = (ent[b] & LOW48) | top;
+					}
+				}
+			}
+		} else {
+			for (uint32_t a = s; a + 1 < e; ++a) {
+				const uint64_t ea = Aent[a];
+				const uint32_t ra = ent_row(ea);
+				if (ra < lo || ra >= hi) continue;
+				const ColInfo ci = colinfo[ra - lo];
+				const uint64_t top = ea & ~LOW48;
+				if (ci.sh == 31) {
+					unsigned long long p = atomicAdd(&ucur[ci.ubase], (unsigned long long)(e - 1 - a));
+					for (uint32_t b = a + 1; b < e; ++b) raw[p++] = (Aent[b] & LOW48) | top;
+				} else {
+					for (uint32_t b = a + 1; b < e; ++b) {
+						const uint64_t eb = Aent[b];
+						raw[atomicAdd(&ucur[unit_of(ci, ra, ent_row(eb))], 1ull)] = (eb & LOW48) | top;
+					}
+				}
+			}
+		}
+	}
+}
+
+// ================================ the semiring ==============================================
 
 // multiop -> overlapop (chain.hpp:47-71), checkstrand replaced by the strand-bit comparison.
 __device__ __forceinline__ uint32_t overlap_estimate(int lenH, int lenV, uint32_t h, uint32_t v, uint32_t oriented, uint32_t K)
@@ -318,255 +440,6 @@ __device__ __forceinline__ uint32_t overlap_estimate(int lenH, int lenV, uint32_
 	return (uint32_t)(m1 + m2 + (int)K) & 0xFFFFu;                      // stored into vector<unsigned short>
 }
 
-// ================================ group =====================================================
-// One CTA per output column i.  Shared memory (FCAP products, KHT k-mer slots):
-//   prodS  u64[FCAP]     h | v<<16 | jrank<<32 | oriented<<47 | slot-then-pair<<48
-//   pkeys  u32[FCAP+2]   row-id hash keys; after the pairs are numbered the region holds poff[] (u32)
-//   pcnt   u16[FCAP]     per slot: product count, then pair index (16-bit halves, packed atomics)
-//   X      phase 1: kkeys u32[KHT] + kjr u16[KHT]    k-mer id -> position in B's column
-//          phase 2: skeys u32[FCAP] + cursor u16[FCAP] + grp u16[FCAP] + jrs u16[FCAP]
-template <int FCAP, int KHT>
-struct GroupSmem {
-	static constexpr size_t X1 = (size_t)KHT * 6;
-	static constexpr size_t X2 = (size_t)FCAP * 10;
-	static constexpr size_t X = X1 > X2 ? X1 : X2;
-	static constexpr size_t BYTES = (size_t)FCAP * 8 + (size_t)(FCAP + 2) * 4 + (size_t)FCAP * 2 + X;
-};
-
-// atomicAdd on a 16-bit counter packed two per 32-bit word (no carry: counts stay < 65536)
-__device__ __forceinline__ uint32_t atomic_add16(uint16_t* base, uint32_t idx, uint32_t v)
-{
-	uint32_t sh = (idx & 1u) * 16u;
-	uint32_t old = atomicAdd((uint32_t*)base + (idx >> 1), v << sh);
-	return (old >> sh) & 0xFFFFu;
-}
-
-template <int FCAP, int KHT>
-__global__ void __launch_bounds__(256) k_group(Params P, const uint32_t* __restrict__ list, uint32_t count)
-{
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	__shared__ uint32_t s_z;
-	__shared__ uint32_t s_tmp[34];
-	__shared__ uint32_t s_bc[NBUCKETS];
-	uint64_t* prodS = (uint64_t*)smem_raw;
-	uint32_t* pkeys = (uint32_t*)(prodS + FCAP);
-	uint32_t* poff = pkeys;                                  // alias, valid after the pairs are numbered
-	uint16_t* pcnt = (uint16_t*)(pkeys + FCAP + 2);
-	unsigned char* X = (unsigned char*)(pcnt + FCAP);
-	uint32_t* kkeys = (uint32_t*)X;
-	uint16_t* kjr = (uint16_t*)(kkeys + KHT);
-	uint32_t* skeys = (uint32_t*)X;
-	uint16_t* cursor = (uint16_t*)(skeys + FCAP);
-	uint16_t* grp = cursor + FCAP;
-	uint16_t* jrs = grp + FCAP;
-	const uint32_t tid = threadIdx.x, nt = blockDim.x;
-	const uint32_t ncols = P.hi - P.lo;
-
-	for (uint32_t it = blockIdx.x; it < count; it += gridDim.x) {
-		const uint32_t li = list[it];
-		const uint32_t i = P.lo + li;
-		const uint32_t j0 = P.B_colptr[i], L = P.B_colptr[i + 1] - j0;
-		const uint64_t base = P.flopptr[li];
-		const uint32_t Fi = (uint32_t)(P.flopptr[li + 1] - base);
-		uint32_t ht = 32; int shift = 27;
-		while (ht < Fi) { ht <<= 1; --shift; }
-		uint32_t kht = 32; int kshift = 27;
-		while (kht * 3 < L * 4) { kht <<= 1; --kshift; }
-		const uint32_t mask = ht - 1, kmask = kht - 1;
-		for (uint32_t s = tid; s < ht; s += nt) pkeys[s] = EMPTY;
-		for (uint32_t s = tid; s < (ht >> 1); s += nt) ((uint32_t*)pcnt)[s] = 0;
-		for (uint32_t s = tid; s < kht; s += nt) kkeys[s] = EMPTY;
-		if (tid < NBUCKETS) s_bc[tid] = 0;
-		if (tid == 0) s_z = 0;
-		__syncthreads();
-		// the column's k-mers: id -> position in B's column (the fold order)
-		for (uint32_t j = tid; j < L; j += nt) {
-			uint32_t slot = ht_insert(kkeys, kmask, kshift, P.B_rowids[j0 + j]);
-			kjr[slot] = (uint16_t)j;
-		}
-		__syncthreads();
-		// products: k-mer -> jrank, row -> pair slot, count
-		for (uint32_t x = tid; x < Fi; x += nt) {
-			const uint4 r = P.raw[base + x];
-			uint32_t ks = ht_find_checked(kkeys, kmask, kshift, r.z);
-			uint32_t jr = 0;
-			if (ks == EMPTY) set_err(P.err, -5); else jr = kjr[ks];
-			uint32_t slot = ht_insert(pkeys, mask, shift, r.x & 0x7FFFFFFFu);
-			atomic_add16(pcnt, slot, 1u);
-			prodS[x] = (uint64_t)r.y | ((uint64_t)jr << 32) | ((uint64_t)(r.x >> 31) << 47) | ((uint64_t)slot << 48);
-		}
-		__syncthreads();
-		// --- phase 2: the k-mer hash is dead, X is reused ---
-		for (uint32_t s = tid; s < ht; s += nt) {
-			uint32_t k = pkeys[s];
-			if (k != EMPTY) skeys[atomicAdd(&s_z, 1u)] = k;
-		}
-		__syncthreads();
-		const uint32_t Z = s_z;
-		uint32_t Zp = 1;
-		while (Zp < Z) Zp <<= 1;
-		for (uint32_t s = Z + tid; s < Zp; s += nt) skeys[s] = EMPTY;
-		__syncthreads();
-		block_bitonic_sort(skeys, Zp);
-		// number the pairs by ascending row; per-pair product counts (kept in registers across the
-		// barrier, because poff[] overwrites the hash keys they were found through)
-		uint32_t mylen[FCAP / 256];
-#pragma unroll
-		for (int q = 0; q < FCAP / 256; ++q) {
-			uint32_t p = tid + q * 256;
-			mylen[q] = 0;
-			if (p < Z) {
-				uint32_t row = skeys[p];
-				uint32_t slot = ht_find(pkeys, mask, shift, row);
-				mylen[q] = pcnt[slot];
-				pcnt[slot] = (uint16_t)p;
-				P.prow[base + p] = row;
-				atomicAdd(&s_bc[bucket_of(mylen[q])], 1u);
-			}
-		}
-		__syncthreads();
-#pragma unroll
-		for (int q = 0; q < FCAP / 256; ++q) {
-			uint32_t p = tid + q * 256;
-			if (p < Z) poff[p] = mylen[q];
-		}
-		for (uint32_t s = tid; s < ((Z + 1) >> 1); s += nt) ((uint32_t*)cursor)[s] = 0;
-		__syncthreads();
-		block_excl_scan(poff, Z, s_tmp);            // poff[Z] = Fi
-#pragma unroll
-		for (int q = 0; q < FCAP / 256; ++q) {
-			uint32_t p = tid + q * 256;
-			if (p < Z) P.pdesc[base + p] = make_uint2(poff[p], mylen[q]);
-		}
-		if (tid == 0) P.nnzC[li] = Z;
-		if (tid < NBUCKETS) P.bcount[(size_t)tid * ncols + li] = s_bc[tid];
-		// unordered membership lists + compact jrank array in pair order
-		for (uint32_t x = tid; x < Fi; x += nt) {
-			uint64_t r = prodS[x];
-			uint32_t p = pcnt[(uint32_t)(r >> 48)];
-			uint32_t y = poff[p] + atomic_add16(cursor, p, 1u);
-			grp[y] = (uint16_t)x;
-			jrs[y] = (uint16_t)((uint32_t)(r >> 32) & 0x7FFFu);
-			prodS[x] = (r & 0x0000FFFFFFFFFFFFull) | ((uint64_t)p << 48);
-		}
-		__syncthreads();
-		// rank inside the pair by position in B's column, overlap estimate, ordered write
-		const int lenV = (int)P.read_len[i];
-		for (uint32_t y = tid; y < Fi; y += nt) {
-			uint64_t r = prodS[grp[y]];
-			uint32_t p = (uint32_t)(r >> 48), jr = jrs[y];
-			uint32_t s0 = poff[p], s1 = poff[p + 1], rank = 0;
-			if (s1 - s0 > 1) {
-#pragma unroll 4
-				for (uint32_t z = s0; z < s1; ++z) rank += (jrs[z] < jr);
-			}
-			uint32_t hv = (uint32_t)r;
-			uint32_t ov = overlap_estimate((int)P.read_len[skeys[p]], lenV, hv & 0xFFFFu, hv >> 16, (uint32_t)(r >> 47) & 1u, P.K);
-			P.prod[base + s0 + rank] = (uint64_t)hv | ((uint64_t)ov << 32);
-		}
-		__syncthreads();
-	}
-}
-
-// Gather formulation for columns that exceed the shared-memory classes: products are fetched from
-// A through Bent (aoff,cnt) twice; GLOBAL = tables in a global slab.  Ordered output goes to the
-// second half of prod.
-template <bool GLOBAL>
-__global__ void __launch_bounds__(256) k_expand_gather(Params P, const uint32_t* __restrict__ list, uint32_t count,
-		uint32_t htmax, uint32_t* __restrict__ slab)
-{
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	__shared__ uint32_t s_z;
-	__shared__ uint32_t s_tmp[34];
-	__shared__ uint32_t s_bc[NBUCKETS];
-	const uint32_t tid = threadIdx.x, nt = blockDim.x;
-	const uint32_t ncols = P.hi - P.lo;
-	uint32_t* tbl = GLOBAL ? slab + (size_t)blockIdx.x * 5 * ((size_t)htmax + 1) : (uint32_t*)smem_raw;
-	uint32_t* keys = tbl;
-	uint32_t* val = keys + (htmax + 1);
-	uint32_t* skeys = val + (htmax + 1);
-	uint32_t* poff = skeys + (htmax + 1);
-	uint32_t* cursor = poff + (htmax + 1);
-
-	for (uint32_t it = blockIdx.x; it < count; it += gridDim.x) {
-		const uint32_t li = list[it];
-		const uint32_t i = P.lo + li;
-		const uint32_t j0 = P.B_colptr[i], j1 = P.B_colptr[i + 1];
-		const uint64_t base = P.flopptr[li];
-		const uint32_t Fi = (uint32_t)(P.flopptr[li + 1] - base);
-		uint32_t ht = 32; int shift = 27;
-		while (ht < Fi) { ht <<= 1; --shift; }
-		const uint32_t mask = ht - 1;
-		for (uint32_t s = tid; s < ht; s += nt) { keys[s] = EMPTY; val[s] = 0; }
-		if (tid == 0) s_z = 0;
-		if (tid < NBUCKETS) s_bc[tid] = 0;
-		__syncthreads();
-		for (uint32_t j = j0 + tid; j < j1; j += nt) {
-			uint64_t be = P.Bent[j];
-			uint32_t aoff = (uint32_t)be, cnt = (uint32_t)(be >> 48) & 0x7FFFu;
-			for (uint32_t e = 0; e < cnt; ++e) {
-				uint32_t slot = ht_insert(keys, mask, shift, (uint32_t)P.Aent[aoff + e]);
-				atomicAdd(&val[slot], 1u);
-			}
-		}
-		__syncthreads();
-		for (uint32_t s = tid; s < ht; s += nt) {
-			uint32_t k = keys[s];
-			if (k != EMPTY) skeys[atomicAdd(&s_z, 1u)] = k;
-		}
-		__syncthreads();
-		const uint32_t Z = s_z;
-		uint32_t Zp = 1;
-		while (Zp < Z) Zp <<= 1;
-		for (uint32_t s = Z + tid; s < Zp; s += nt) skeys[s] = EMPTY;
-		__syncthreads();
-		block_bitonic_sort(skeys, Zp);
-		for (uint32_t p = tid; p < Z; p += nt) {
-			uint32_t slot = ht_find(keys, mask, shift, skeys[p]);
-			uint32_t len = val[slot];
-			poff[p] = len;
-			val[slot] = p;
-			cursor[p] = 0;
-			P.prow[base + p] = skeys[p];
-			atomicAdd(&s_bc[bucket_of(len)], 1u);
-		}
-		__syncthreads();
-		block_excl_scan(poff, Z, s_tmp);
-		// descriptors point at the ordered copy in the second half of prod
-		for (uint32_t p = tid; p < Z; p += nt) P.pdesc[base + p] = make_uint2(poff[p], (poff[p + 1] - poff[p]) | 0x80000000u);
-		if (tid == 0) P.nnzC[li] = Z;
-		if (tid < NBUCKETS) P.bcount[(size_t)tid * ncols + li] = s_bc[tid];
-		// unordered placement, tagged with the position in B's column
-		for (uint32_t j = j0 + tid; j < j1; j += nt) {
-			uint64_t be = P.Bent[j];
-			uint32_t aoff = (uint32_t)be, cnt = (uint32_t)(be >> 48) & 0x7FFFu;
-			uint32_t v = (uint32_t)(be >> 32) & 0xFFFFu, sB = (uint32_t)(be >> 63);
-			for (uint32_t e = 0; e < cnt; ++e) {
-				uint64_t ae = P.Aent[aoff + e];
-				uint32_t p = val[ht_find(keys, mask, shift, (uint32_t)ae)];
-				uint32_t pos = poff[p] + atomicAdd(&cursor[p], 1u);
-				uint32_t h = (uint32_t)(ae >> 32) & 0xFFFFu, sA = (uint32_t)(ae >> 48) & 1u;
-				P.prod[base + pos] = (uint64_t)h | ((uint64_t)v << 16) | ((uint64_t)(j - j0) << 32) | ((uint64_t)(sA == sB) << 48) | ((uint64_t)p << 49);
-			}
-		}
-		__threadfence_block();
-		__syncthreads();
-		// order inside each pair -> second half
-		const int lenV = (int)P.read_len[i];
-		for (uint32_t y = tid; y < Fi; y += nt) {
-			uint64_t r = P.prod[base + y];
-			uint32_t p = (uint32_t)(r >> 49), jr = (uint32_t)(r >> 32) & 0xFFFFu;
-			uint32_t s0 = poff[p], s1 = poff[p + 1], rank = 0;
-			for (uint32_t z = s0; z < s1; ++z) rank += (((uint32_t)(P.prod[base + z] >> 32) & 0xFFFFu) < jr);
-			uint32_t hv = (uint32_t)r;
-			uint32_t ov = overlap_estimate((int)P.read_len[skeys[p]], lenV, hv & 0xFFFFu, hv >> 16, (uint32_t)(r >> 48) & 1u, P.K);
-			P.prod[P.prod_half + base + s0 + rank] = (uint64_t)hv | ((uint64_t)ov << 32);
-		}
-		__syncthreads();
-	}
-}
-
-// ================================ fold ======================================================
 // chainop only ever merges whole bins: whether bin b is absorbed at step t depends on the overlap
 // values alone (|ov_b - ov_t| < binSize, chain.hpp:114), never on the k-mers.  So the bins form a
 // forest: parent[b] = the first later product whose overlap is within binSize of bin b's overlap
@@ -579,283 +452,385 @@ __global__ void __launch_bounds__(256) k_expand_gather(Params P, const uint32_t*
 // When every consecutive pair of overlaps is within binSize (the common case) the forest is the
 // chain t -> t+1 and the whole fold is an all-pairs test with no sequential dependency.
 
-struct FDesc { uint32_t row, col; unsigned long long off_len; };   // off(48) | len(16)<<48
-
-// one warp per column: flat pair descriptors at their final output index + per-bucket work lists
-// (list positions come from the scanned per-column bucket counts: no atomics, deterministic)
-__global__ void k_flatten(Params P, FDesc* __restrict__ fdesc, uint32_t* __restrict__ flist)
-{
-	const uint32_t lane = threadIdx.x & 31;
-	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-	const uint32_t ncols = P.hi - P.lo;
-	for (uint32_t li = warp; li < ncols; li += nwarps) {
-		const uint32_t Z = P.nnzC[li];
-		if (!Z) continue;
-		const uint64_t base = P.flopptr[li];
-		const uint32_t out0 = P.colptrC[li];
-		uint32_t run = (lane < NBUCKETS) ? P.bcount[(size_t)lane * ncols + li] : 0;   // scanned: list offset of bucket `lane`
-		for (uint32_t p0 = 0; p0 < Z; p0 += 32) {
-			uint32_t p = p0 + lane;
-			int b = -1;
-			uint32_t g = out0 + p;
-			if (p < Z) {
-				uint2 d = P.pdesc[base + p];
-				uint32_t len = d.y & 0x7FFFFFFFu;
-				FDesc f;
-				f.row = P.prow[base + p]; f.col = P.lo + li;
-				f.off_len = (base + d.x + ((d.y >> 31) ? P.prod_half : 0ull)) | ((unsigned long long)len << 48);
-				fdesc[g] = f;
-				b = bucket_of(len);
-			}
-#pragma unroll
-			for (int k = 0; k < NBUCKETS; ++k) {
-				uint32_t m = __ballot_sync(0xFFFFFFFFu, b == k);
-				uint32_t start = __shfl_sync(0xFFFFFFFFu, run, k);
-				if (b == k) flist[start + __popc(m & ((1u << lane) - 1))] = g;
-				if (lane == (uint32_t)k) run += __popc(m);
-			}
-		}
-	}
-}
-
-__device__ __forceinline__ void store_result(const Params& P, uint32_t g, uint32_t row, uint32_t cnt, uint32_t hv,
-		uint32_t nb, uint32_t sup, uint32_t ov)
-{
-	P.rowsC[g] = row;
-	P.countC[g] = (uint16_t)cnt;
-	P.posH[g] = (uint16_t)(hv & 0xFFFFu);
-	P.posV[g] = (uint16_t)(hv >> 16);
-	P.aux[3 * (size_t)g + 0] = (uint16_t)nb;
-	P.aux[3 * (size_t)g + 1] = (uint16_t)sup;
-	P.aux[3 * (size_t)g + 2] = (uint16_t)ov;
-}
-
 __device__ __forceinline__ bool is_far(uint32_t x, uint32_t A, uint32_t B, uint32_t K2)
 {
 	// |h_t - h_s| > K  <=>  (unsigned)(h_t - h_s + K) > 2K ; A = K - h_s, B = K - v_s
 	return ((x & 0xFFFFu) + A) > K2 && ((x >> 16) + B) > K2;
 }
 
-// thread per pair, P <= CAP, records already in fold order
-template <int CAP>
-__global__ void __launch_bounds__(128) k_fold_short(Params P, const FDesc* __restrict__ fdesc, const uint32_t* __restrict__ flist,
-		int bucket)
+struct PairResult { uint32_t count, hv, nbins, sup, ov; };
+
+__device__ __forceinline__ uint4 pack_result(uint32_t row, const PairResult& r)
 {
-	const uint32_t ncols = P.hi - P.lo;
-	const uint32_t start = P.bcount[(size_t)bucket * ncols], count = P.bcount[(size_t)(bucket + 1) * ncols] - start;
-	const uint32_t* list = flist + start;
-	const uint32_t K = P.K, K2 = 2 * P.K;
-	const int BIN = (int)P.BIN;
-	for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < count; it += gridDim.x * blockDim.x) {
-		const uint32_t g = list[it];
-		const FDesc f = fdesc[g];
-		const uint32_t np = (uint32_t)(f.off_len >> 48);
-		const uint64_t* rec = P.prod + (f.off_len & 0xFFFFFFFFFFFFull);
-		if (CAP == 1) {
-			uint64_t r = rec[0];
-			store_result(P, g, f.row, 1, (uint32_t)r, 1, 1, (uint32_t)(r >> 32) & 0xFFFFu);
-			continue;
-		}
-		uint32_t hv[CAP];
-		uint16_t ov[CAP];
-		bool linear = true;
-		for (uint32_t a = 0; a < np; ++a) {
-			uint64_t r = rec[a];
+	return make_uint4(row, (r.count & 0xFFFFu) | (r.nbins << 16), r.hv, (r.sup & 0xFFFFu) | (r.ov << 16));
+}
+
+// one thread, P <= SHORT_FOLD, records in fold order
+__device__ __forceinline__ PairResult fold_short(const uint64_t* fin, uint32_t np, uint32_t K, int BIN)
+{
+	constexpr int CAP = SHORT_FOLD;
+	const uint32_t K2 = 2 * K;
+	uint32_t hv[CAP];
+	uint16_t ov[CAP];
+	bool linear = true;
+#pragma unroll
+	for (int a = 0; a < CAP; ++a) {
+		if (a < (int)np) {
+			uint64_t r = fin[a];
 			hv[a] = (uint32_t)r; ov[a] = (uint16_t)(r >> 32);
 			if (a) linear &= abs((int)ov[a] - (int)ov[a - 1]) < BIN;
-		}
-		uint32_t csum = 0;
-		if (linear) {
-			uint32_t surv = 0;
-			for (uint32_t s = 0; s < np; ++s) {
-				uint32_t x = hv[s], A = K - (x & 0xFFFFu), B = K - (x >> 16), t = s + 1;
-				while (t < np && is_far(hv[t], A, B, K2)) ++t;
-				csum += t - s - 1;
-				surv += (t == np);
-			}
-			store_result(P, g, f.row, (np + csum) & 0xFFFFu, hv[np - 1], 1, surv, ov[np - 1]);
-		} else {
-			uint16_t par[CAP], sup[CAP], live[CAP];
-			uint32_t nlive = 0;
-			for (uint32_t t = 0; t < np; ++t) {
-				for (uint32_t q = 0; q < nlive;) {
-					uint32_t b = live[q];
-					if (abs((int)ov[b] - (int)ov[t]) < BIN) { par[b] = (uint16_t)t; live[q] = live[--nlive]; } else ++q;
-				}
-				live[nlive++] = (uint16_t)t;
-				sup[t] = 0;
-			}
-			for (uint32_t q = 0; q < nlive; ++q) par[live[q]] = NONE16;
-			for (uint32_t s = 0; s < np; ++s) {
+		} else { hv[a] = 0; ov[a] = 0; }
+	}
+	PairResult R;
+	uint32_t csum = 0;
+	if (np == 1) { R.count = 1; R.hv = hv[0]; R.nbins = 1; R.sup = 1; R.ov = ov[0]; return R; }
+	if (linear) {
+		uint32_t surv = 0, last_hv = 0, last_ov = 0;
+#pragma unroll
+		for (int s = 0; s < CAP; ++s) {
+			if (s < (int)np) {
 				uint32_t x = hv[s], A = K - (x & 0xFFFFu), B = K - (x >> 16);
-				uint32_t a = par[s], last = s;
-				while (a != NONE16 && is_far(hv[a], A, B, K2)) { ++csum; last = a; a = par[a]; }
-				if (a == NONE16) ++sup[last];
+				bool alive = true;
+#pragma unroll
+				for (int t = s + 1; t < CAP; ++t) {
+					if (t < (int)np) { alive = alive && is_far(hv[t], A, B, K2); csum += alive; }
+				}
+				surv += alive;
+				last_hv = x; last_ov = ov[s];
 			}
-			uint32_t best = 0, bt = 0;
-			for (uint32_t t = 0; t < np; ++t) if (par[t] == NONE16 && sup[t] >= best) { best = sup[t]; bt = t; }
-			store_result(P, g, f.row, (np + csum) & 0xFFFFu, hv[bt], nlive, best, ov[bt]);
+		}
+		R.count = (np + csum) & 0xFFFFu; R.hv = last_hv; R.nbins = 1; R.sup = surv; R.ov = last_ov;
+		return R;
+	}
+	uint8_t par[CAP], sup[CAP];
+#pragma unroll
+	for (int b = 0; b < CAP; ++b) {
+		par[b] = 0xFF; sup[b] = 0;
+		if (b < (int)np) {
+#pragma unroll
+			for (int t = CAP - 1; t > b; --t)
+				if (t < (int)np && abs((int)ov[t] - (int)ov[b]) < BIN) par[b] = (uint8_t)t;
 		}
 	}
+	for (uint32_t s = 0; s < np; ++s) {
+		uint32_t x = hv[s], A = K - (x & 0xFFFFu), B = K - (x >> 16);
+		uint32_t a = par[s], last = s;
+		while (a != 0xFF && is_far(hv[a], A, B, K2)) { ++csum; last = a; a = par[a]; }
+		if (a == 0xFF) ++sup[last];
+	}
+	uint32_t best = 0, bt = 0, nb = 0;
+	for (uint32_t t = 0; t < np; ++t)
+		if (par[t] == 0xFF) { ++nb; if (sup[t] >= best) { best = sup[t]; bt = t; } }
+	R.count = (np + csum) & 0xFFFFu; R.hv = hv[bt]; R.nbins = nb; R.sup = best; R.ov = ov[bt];
+	return R;
 }
 
-// Sequential in-place fold (any P): state per processed product s is bin overlap (bits 32..47) and
-// label = creator index of its bin (bits 48..63, 0xFFFF = dropped).  Literal chainop.
-__device__ void fold_pair_inplace(uint64_t* rec, uint32_t np, uint32_t K, int BIN,
-		uint32_t& out_count, uint32_t& out_hv, uint32_t& out_nbins, uint32_t& out_sup, uint32_t& out_ov)
+// Cooperative fold of one pair by `nw` warps (this is warp `w` of them); fin/par/sup may be shared
+// or global memory.  part[0..1] (shared) accumulates csum/surv when nw > 1 (zeroed by the caller).
+// Every participating thread returns the same result.  Caller synchronises the group around it.
+template <bool GROUP>
+__device__ PairResult fold_coop(const uint64_t* fin, uint16_t* par, uint32_t* sup, uint32_t P, uint32_t K, int BIN,
+		uint32_t w, uint32_t nw, uint32_t* part)
 {
-	uint32_t count = 0;
-	for (uint32_t t = 0; t < np; ++t) {
-		const uint64_t rt = rec[t];
-		const uint32_t h = (uint32_t)rt & 0xFFFFu, v = (uint32_t)(rt >> 16) & 0xFFFFu, ov = (uint32_t)(rt >> 32) & 0xFFFFu;
-		uint32_t nrel = 0;
-		for (uint32_t s = 0; s < t; ++s) {
-			uint64_t r = rec[s];
-			uint32_t lab = (uint32_t)(r >> 48);
-			if (lab == 0xFFFFu) continue;
-			int bo = (int)((uint32_t)(r >> 32) & 0xFFFFu);
-			if (abs(bo - (int)ov) < BIN) {                                   // chain.hpp:114
-				int hs = (int)((uint32_t)r & 0xFFFFu), vs = (int)((uint32_t)(r >> 16) & 0xFFFFu);
-				if (abs((int)h - hs) > (int)K && abs((int)v - vs) > (int)K) { // chain.hpp:121
-					rec[s] = (r & 0xFFFFFFFFull) | ((uint64_t)ov << 32) | ((uint64_t)t << 48);
-					++nrel;
-				} else {
-					rec[s] = r | (0xFFFFull << 48);
-				}
+	const uint32_t lane = threadIdx.x & 31, K2 = 2 * K;
+	auto sync_group = [&]() { if (GROUP) __syncthreads(); else __syncwarp(); };
+	bool lin = true;
+	for (uint32_t t = 1 + lane + 32 * w; t < P; t += 32 * nw)
+		lin &= abs((int)((uint32_t)(fin[t] >> 32) & 0xFFFFu) - (int)((uint32_t)(fin[t - 1] >> 32) & 0xFFFFu)) < BIN;
+	bool linear = GROUP ? (bool)__syncthreads_and(lin) : (bool)__all_sync(FULL, lin);
+	uint32_t csum = 0, surv = 0;
+	PairResult R;
+	if (linear) {
+		for (uint32_t r0 = 32 * w; r0 < P; r0 += 32 * nw) {
+			const uint32_t s = r0 + lane;
+			bool alive = s < P;
+			const uint32_t x = alive ? (uint32_t)fin[s] : 0u, A = K - (x & 0xFFFFu), B = K - (x >> 16);
+			for (uint32_t t = r0 + 1; t < P; ++t) {
+				const uint32_t xt = (uint32_t)fin[t];
+				if (t > s) { alive = alive && is_far(xt, A, B, K2); csum += alive; }
 			}
-		}
-		count = t == 0 ? 1u : (((1u + count) & 0xFFFFu) + nrel) & 0xFFFFu;   // chain.hpp:105,140
-		rec[t] = (rt & 0xFFFFFFFFFFFFull) | ((uint64_t)t << 48);
-	}
-	uint32_t best_sup = 0, best_c = 0, nbins = 0;
-	for (uint32_t c = np; c-- > 0;) {
-		uint64_t r = rec[c];
-		if ((uint32_t)(r >> 48) != c) continue;
-		++nbins;
-		uint32_t sup = 0;
-		for (uint32_t s = 0; s <= c; ++s) sup += ((uint32_t)(rec[s] >> 48) == c);
-		if (sup > best_sup) { best_sup = sup; best_c = c; }
-	}
-	uint64_t r = rec[best_c];
-	out_count = count; out_hv = (uint32_t)r; out_nbins = nbins; out_sup = best_sup & 0xFFFFu; out_ov = (uint32_t)(r >> 32) & 0xFFFFu;
-}
-
-// warp per pair, 33 <= P <= 256
-constexpr int WARP_FOLD_MAX = 256;
-constexpr int WARP_FOLD_WARPS = 8;
-
-__global__ void __launch_bounds__(WARP_FOLD_WARPS * 32) k_fold_long(Params P, const FDesc* __restrict__ fdesc,
-		const uint32_t* __restrict__ flist, int bucket)
-{
-	__shared__ uint32_t s_hv[WARP_FOLD_WARPS][WARP_FOLD_MAX];
-	__shared__ uint32_t s_sup[WARP_FOLD_WARPS][WARP_FOLD_MAX];
-	__shared__ uint16_t s_ov[WARP_FOLD_WARPS][WARP_FOLD_MAX];
-	__shared__ uint16_t s_par[WARP_FOLD_WARPS][WARP_FOLD_MAX];
-	const uint32_t FULL = 0xFFFFFFFFu;
-	const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	uint32_t* shv = s_hv[w]; uint32_t* ssup = s_sup[w];
-	uint16_t* sov = s_ov[w]; uint16_t* spar = s_par[w];
-	const uint32_t ncols = P.hi - P.lo;
-	const uint32_t start = P.bcount[(size_t)bucket * ncols], count = P.bcount[(size_t)(bucket + 1) * ncols] - start;
-	const uint32_t* list = flist + start;
-	const uint32_t K = P.K, K2 = 2 * P.K;
-	const int BIN = (int)P.BIN;
-	for (uint32_t it = blockIdx.x * WARP_FOLD_WARPS + w; it < count; it += gridDim.x * WARP_FOLD_WARPS) {
-		const uint32_t g = list[it];
-		const FDesc f = fdesc[g];
-		const uint32_t np = (uint32_t)(f.off_len >> 48);
-		uint64_t* rec = P.prod + (f.off_len & 0xFFFFFFFFFFFFull);
-		const uint32_t R = (np + 31) >> 5;
-		__syncwarp();
-		for (uint32_t idx = lane; idx < np; idx += 32) {
-			uint64_t x = rec[idx];
-			shv[idx] = (uint32_t)x; sov[idx] = (uint16_t)(x >> 32);
-		}
-		__syncwarp();
-		// is the bin forest the chain t -> t+1 ?
-		bool lin = true;
-		for (uint32_t idx = lane + 1; idx < np; idx += 32) lin &= abs((int)sov[idx] - (int)sov[idx - 1]) < BIN;
-		const bool linear = __all_sync(FULL, lin);
-		bool fallback = false;
-		if (!linear) {
-			// phase A: parents of the bin forest; each lane keeps one live bin
-			uint32_t lb = NONE16;
-			for (uint32_t idx = lane; idx < np; idx += 32) ssup[idx] = 0;
-			for (uint32_t t = 0; t < np; ++t) {
-				int ot = (int)sov[t];
-				if (lb != NONE16 && abs((int)sov[lb] - ot) < BIN) { spar[lb] = (uint16_t)t; lb = NONE16; }
-				uint32_t freem = __ballot_sync(FULL, lb == NONE16);
-				if (!freem) { fallback = true; break; }
-				if (lane == (uint32_t)(__ffs(freem) - 1)) lb = t;
-			}
-			if (lb != NONE16) spar[lb] = NONE16;
-			__syncwarp();
-		}
-		if (fallback) {     // more than 32 simultaneous bins: sequential in-place fold by one lane
-			if (lane == 0) {
-				uint32_t cnt, hv, nb, sup, ov;
-				fold_pair_inplace(rec, np, K, BIN, cnt, hv, nb, sup, ov);
-				store_result(P, g, f.row, cnt, hv, nb, sup, ov);
-			}
-			continue;
-		}
-		// phase B: every k-mer walks its ancestors; lanes take s from alternating ends for balance
-		uint32_t csum = 0, surv = 0, r = 0, s = 0, t = 0, A = 0, B = 0, last = 0;
-		bool active = false;
-		auto advance = [&]() {
-			active = false;
-			while (r < R) {
-				s = (r & 1) ? 32 * r + 31 - lane : 32 * r + lane;
-				++r;
-				if (s < np) {
-					uint32_t x = shv[s];
-					A = K - (x & 0xFFFFu); B = K - (x >> 16);
-					t = linear ? s + 1 : spar[s];
-					last = s; active = true;
-					return;
-				}
-			}
-		};
-		advance();
-		while (__any_sync(FULL, active)) {
-			if (active) {
-				if (t >= np) {                       // reached a root alive
-					if (linear) ++surv; else atomicAdd(&ssup[last], 1u);
-					advance();
-				} else if (is_far(shv[t], A, B, K2)) {
-					++csum; last = t;
-					t = linear ? t + 1 : spar[t];
-				} else {
-					advance();
-				}
-			}
+			surv += alive && s < P;
 		}
 		for (int o = 16; o; o >>= 1) { csum += __shfl_xor_sync(FULL, csum, o); surv += __shfl_xor_sync(FULL, surv, o); }
-		uint32_t root = np - 1, nb = 1, sup = surv;
-		if (!linear) {
-			__syncwarp();
-			uint32_t best = 0, nroots = 0;
-			for (uint32_t idx = lane; idx < np; idx += 32)
-				if (spar[idx] == NONE16) { ++nroots; uint32_t c = (ssup[idx] << 16) | idx; best = max(best, c); }
-			for (int o = 16; o; o >>= 1) { best = max(best, __shfl_xor_sync(FULL, best, o)); nroots += __shfl_xor_sync(FULL, nroots, o); }
-			root = best & 0xFFFFu; sup = best >> 16; nb = nroots;
+		if (GROUP) {
+			if (lane == 0) { atomicAdd(&part[0], csum); atomicAdd(&part[1], surv); }
+			__syncthreads();
+			csum = part[0]; surv = part[1];
 		}
-		if (lane == 0) store_result(P, g, f.row, (np + csum) & 0xFFFFu, shv[root], nb, sup, sov[root]);
+		const uint64_t last = fin[P - 1];
+		R.count = (P + csum) & 0xFFFFu; R.hv = (uint32_t)last; R.nbins = 1; R.sup = surv; R.ov = (uint32_t)(last >> 32) & 0xFFFFu;
+		return R;
+	}
+	for (uint32_t b = lane + 32 * w; b < P; b += 32 * nw) {
+		const int ob = (int)((uint32_t)(fin[b] >> 32) & 0xFFFFu);
+		uint32_t t = b + 1;
+		while (t < P && abs((int)((uint32_t)(fin[t] >> 32) & 0xFFFFu) - ob) >= BIN) ++t;
+		par[b] = t < P ? (uint16_t)t : (uint16_t)NONE16;
+		sup[b] = 0;
+	}
+	sync_group();
+	for (uint32_t s = lane + 32 * w; s < P; s += 32 * nw) {
+		const uint32_t x = (uint32_t)fin[s], A = K - (x & 0xFFFFu), B = K - (x >> 16);
+		uint32_t a = par[s], last = s;
+		while (a != NONE16 && is_far((uint32_t)fin[a], A, B, K2)) { ++csum; last = a; a = par[a]; }
+		if (a == NONE16) atomicAdd(&sup[last], 1u);
+	}
+	sync_group();
+	uint32_t best = 0, nroots = 0;
+	for (uint32_t idx = lane + 32 * w; idx < P; idx += 32 * nw)
+		if (par[idx] == NONE16) { ++nroots; best = max(best, (sup[idx] << 16) | idx); }
+	for (int o = 16; o; o >>= 1) {
+		csum += __shfl_xor_sync(FULL, csum, o); nroots += __shfl_xor_sync(FULL, nroots, o);
+		best = max(best, __shfl_xor_sync(FULL, best, o));
+	}
+	if (GROUP) {
+		if (lane == 0) { atomicAdd(&part[0], csum); atomicAdd(&part[1], nroots); atomicMax(&part[2], best); }
+		__syncthreads();
+		csum = part[0]; nroots = part[1]; best = part[2];
+	}
+	const uint64_t rr = fin[best & 0xFFFFu];
+	R.count = (P + csum) & 0xFFFFu; R.hv = (uint32_t)rr; R.nbins = nroots; R.sup = best >> 16; R.ov = (uint32_t)(rr >> 32) & 0xFFFFu;
+	return R;
+}
+
+// ================================ group + fold ==============================================
+
+template <int CAP>
+struct GF {
+	static constexpr size_t PROD = 0;                                  // u64[CAP]  raw -> packed -> fin
+	static constexpr size_t REC = PROD + 8 * (size_t)CAP;              // u64[CAP]  bits u32[CAP] + pre2 u16[CAP+2] | recA | par u16[CAP] + sup u32[CAP]
+	static constexpr size_t PID = REC + 8 * (size_t)CAP + 16;          // u16[CAP]  pair of the arrival slot | long-pair list
+	static constexpr size_t CNT = PID + 2 * (size_t)CAP;               // u16[CAP+2] per pair count -> poff
+	static constexpr size_t ROW = CNT + 2 * (size_t)CAP + 16;          // u32[CAP]  row id of the pair
+	static constexpr size_t L1 = ROW + 4 * (size_t)CAP;                // u32[l1cap+1] bitmap words + u32[l1cap+2] prefix
+	static size_t bytes(uint32_t l1cap) { return L1 + 8 * ((size_t)l1cap + 2); }
+};
+
+template <int CAP>
+__global__ void __launch_bounds__(GF_THREADS) k_group_fold(Params P, const uint32_t* __restrict__ list, uint32_t count, uint32_t l1cap)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	__shared__ __align__(8) uint64_t s_bar;
+	__shared__ uint32_t s_tmp[34];
+	__shared__ uint32_t s_nlong, s_nhuge;
+	__shared__ uint32_t s_part[3];
+	uint64_t* prodS = (uint64_t*)(smem + GF<CAP>::PROD);
+	uint64_t* recA = (uint64_t*)(smem + GF<CAP>::REC);
+	uint32_t* bits = (uint32_t*)(smem + GF<CAP>::REC);
+	uint16_t* pre2 = (uint16_t*)(smem + GF<CAP>::REC + 4 * (size_t)CAP);
+	uint16_t* parS = (uint16_t*)(smem + GF<CAP>::REC);
+	uint32_t* supS = (uint32_t*)(smem + GF<CAP>::REC + 2 * (size_t)CAP);
+	uint16_t* pid = (uint16_t*)(smem + GF<CAP>::PID);
+	uint16_t* cnt = (uint16_t*)(smem + GF<CAP>::CNT);
+	uint32_t* rowS = (uint32_t*)(smem + GF<CAP>::ROW);
+	uint32_t* l1 = (uint32_t*)(smem + GF<CAP>::L1);
+	uint32_t* l1pre = l1 + l1cap + 1;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	constexpr uint32_t NT = GF_THREADS, NW = GF_THREADS / 32;
+	const uint32_t K = P.K;
+	const int BIN = (int)P.BIN;
+
+	if (tid == 0) mbar_init(&s_bar, 1);
+	__syncthreads();
+	uint32_t phase = 0;
+
+	for (uint32_t it = blockIdx.x; it < count; it += gridDim.x) {
+		const uint32_t u = list[it];
+		const uint32_t li = P.ucol[u], i = P.lo + li;
+		const uint64_t base = P.uptr[u];
+		const uint32_t Fi = P.ucount[u];
+		const ColInfo ci = P.colinfo[li];
+		// rows covered by this unit: (i, n) for a light column, else one 2^sh-aligned bucket of it
+		uint32_t r0 = i + 1, r1 = P.n;
+		if (ci.sh != 31) {
+			const uint32_t bk = ((i + 1) >> ci.sh) + (u - ci.ubase);
+			r0 = max(r0, bk << ci.sh);
+			r1 = min(r1, (bk + 1) << ci.sh);
+		}
+		const uint32_t rbase = r0 & ~31u;
+		const uint32_t l1w = ((r1 - rbase + 1023) >> 10);       // level-1 words (each covers 1024 rows)
+		if (Fi > (uint32_t)CAP || l1w > l1cap) { if (tid == 0) { set_err(P.err, -5); P.unnz[u] = 0; } continue; }
+
+		// --- stage the unit's products: one bulk async copy, overlapped with clearing the tables ---
+		if (tid == 0) {
+			fence_proxy_async();
+			bulk_load(prodS, P.raw + base, ((Fi + 1) & ~1u) * 8u, &s_bar);
+		}
+		for (uint32_t s = tid; s <= l1w; s += NT) l1[s] = 0;
+		for (uint32_t s = tid; s < ((Fi + 3) >> 1); s += NT) ((uint32_t*)cnt)[s] = 0;
+		if (tid == 0) { s_nlong = 0; s_nhuge = 0; }
+		mbar_wait(&s_bar, phase);
+		phase ^= 1;
+		__syncthreads();                                           // tables cleared by all threads before anyone sets a bit
+
+		// level 1: which 32-row words are occupied
+		for (uint32_t x = tid; x < Fi; x += NT) {
+			const uint32_t rel = ent_row(prodS[x]) - rbase;
+			atomicOr(&l1[rel >> 10], 1u << ((rel >> 5) & 31));
+		}
+		__syncthreads();
+		block_popc_scan<uint32_t>(l1, l1pre, l1w, s_tmp);
+		const uint32_t Q = l1pre[l1w];
+		for (uint32_t s = tid; s < Q; s += NT) bits[s] = 0;
+		__syncthreads();
+		// level 2: the occupied words themselves
+		for (uint32_t x = tid; x < Fi; x += NT) {
+			const uint32_t rel = ent_row(prodS[x]) - rbase, w = rel >> 5;
+			const uint32_t q = l1pre[w >> 5] + __popc(l1[w >> 5] & ((1u << (w & 31)) - 1u));
+			atomicOr(&bits[q], 1u << (rel & 31));
+		}
+		__syncthreads();
+		block_popc_scan<uint16_t>(bits, pre2, Q, s_tmp);
+		const uint32_t Z = pre2[Q];                                // distinct rows == nnz of this unit
+		// pair index (rows ascending), arrival slot inside the pair
+		for (uint32_t x = tid; x < Fi; x += NT) {
+			const uint64_t r = prodS[x];
+			const uint32_t row = ent_row(r), rel = row - rbase, w = rel >> 5;
+			const uint32_t q = l1pre[w >> 5] + __popc(l1[w >> 5] & ((1u << (w & 31)) - 1u));
+			const uint32_t p = pre2[q] + __popc(bits[q] & ((1u << (rel & 31)) - 1u));
+			const uint32_t a = atomic_add16(cnt, p, 1u);
+			rowS[p] = row;
+			prodS[x] = ((r >> 32) & 0xFFFFFFFFull) | ((uint64_t)p << 32) | ((uint64_t)a << 46) | ((uint64_t)((uint32_t)r >> 31) << 60);
+		}
+		__syncthreads();
+		block_excl_scan<uint16_t>(cnt, Z, s_tmp);                   // cnt -> poff, poff[Z] = Fi
+		const uint16_t* poff = cnt;
+		// multiply (overlap estimate) and placement in arrival order
+		const uint32_t j0 = P.B_colptr[i];
+		const int lenV = (int)P.read_len[i];
+		for (uint32_t x = tid; x < Fi; x += NT) {
+			const uint64_t t = prodS[x];
+			const uint32_t h = (uint32_t)t & 0xFFFFu, jr = ((uint32_t)t >> 16), p = (uint32_t)(t >> 32) & 0x3FFFu;
+			const uint32_t a = (uint32_t)(t >> 46) & 0x3FFFu, sH = (uint32_t)(t >> 60) & 1u;
+			const uint32_t jg = j0 + jr;
+			const uint32_t v = P.B_values[jg], sV = getbit(P.B_strand, jg);
+			const uint32_t ov = overlap_estimate((int)P.read_len[rowS[p]], lenV, h, v, sH == sV, K);
+			const uint32_t y0 = poff[p] + a;
+			recA[y0] = (uint64_t)(h | (v << 16)) | ((uint64_t)ov << 32) | ((uint64_t)jr << 48);
+			pid[y0] = (uint16_t)p;
+		}
+		__syncthreads();
+		// fold order inside the pair = position in B's column
+		uint64_t* fin = prodS;
+		for (uint32_t y = tid; y < Fi; y += NT) {
+			const uint64_t r = recA[y];
+			const uint32_t p = pid[y], s0 = poff[p], s1 = poff[p + 1], jr = (uint32_t)(r >> 48);
+			uint32_t rank = 0;
+			if (s1 - s0 > 1)
+				for (uint32_t z = s0; z < s1; ++z) rank += ((uint32_t)(recA[z] >> 48) < jr);
+			fin[s0 + rank] = r & 0x0000FFFFFFFFFFFFull;
+		}
+		__syncthreads();
+		// --- fold ---
+		uint16_t* longlist = pid;
+		uint4* out = P.out + base;
+		for (uint32_t p = tid; p < Z; p += NT) {
+			const uint32_t s0 = poff[p], len = poff[p + 1] - s0;
+			if (len <= SHORT_FOLD) out[p] = pack_result(rowS[p], fold_short(fin + s0, len, K, BIN));
+			else longlist[atomicAdd(&s_nlong, 1u)] = (uint16_t)p;
+		}
+		__syncthreads();
+		const uint32_t nlong = s_nlong;
+		for (uint32_t q = wid; q < nlong; q += NW) {
+			const uint32_t p = longlist[q], s0 = poff[p], len = poff[p + 1] - s0;
+			if (len > 1024) { if (lane == 0) longlist[CAP - 1 - atomicAdd(&s_nhuge, 1u)] = (uint16_t)p; continue; }
+			PairResult R = fold_coop<false>(fin + s0, parS + s0, supS + s0, len, K, BIN, 0, 1, nullptr);
+			if (lane == 0) out[p] = pack_result(rowS[p], R);
+		}
+		__syncthreads();
+		const uint32_t nhuge = s_nhuge;                             // at most CAP/1024 pairs: the whole CTA takes each
+		for (uint32_t q = 0; q < nhuge; ++q) {
+			const uint32_t p = longlist[CAP - 1 - q], s0 = poff[p], len = poff[p + 1] - s0;
+			if (tid < 3) s_part[tid] = 0;
+			__syncthreads();
+			PairResult R = fold_coop<true>(fin + s0, parS + s0, supS + s0, len, K, BIN, wid, NW, s_part);
+			if (tid == 0) out[p] = pack_result(rowS[p], R);
+			__syncthreads();
+		}
+		if (tid == 0) P.unnz[u] = Z;
+		__syncthreads();
 	}
 }
 
-// P > 256: sequential in-place fold, thread per pair (rare)
-__global__ void k_fold_huge(Params P, const FDesc* __restrict__ fdesc, const uint32_t* __restrict__ flist, int bucket)
+// A single pair with more than UNIT_CAP products (a unit of one row): its products have distinct
+// positions in B's column, so a bitmap over those positions ranks them.  One CTA per unit, the
+// ordered list and the fold's scratch live in global memory (the `out` region of the unit is big enough:
+// 16 bytes per product).
+__global__ void __launch_bounds__(1024) k_huge_pair(Params P, const uint32_t* __restrict__ list, uint32_t count)
 {
-	const uint32_t ncols = P.hi - P.lo;
-	const uint32_t start = P.bcount[(size_t)bucket * ncols], count = P.bcount[(size_t)(bucket + 1) * ncols] - start;
-	const uint32_t* list = flist + start;
-	for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < count; it += gridDim.x * blockDim.x) {
-		const uint32_t g = list[it];
-		const FDesc f = fdesc[g];
-		uint32_t cnt, hv, nb, sup, ov;
-		fold_pair_inplace(P.prod + (f.off_len & 0xFFFFFFFFFFFFull), (uint32_t)(f.off_len >> 48), P.K, (int)P.BIN, cnt, hv, nb, sup, ov);
-		store_result(P, g, f.row, cnt, hv, nb, sup, ov);
+	__shared__ uint32_t jbits[2048];       // 65536 positions
+	__shared__ uint32_t jpre[2050];
+	__shared__ uint32_t s_tmp[34];
+	__shared__ uint32_t s_part[3];
+	const uint32_t tid = threadIdx.x, NT = blockDim.x;
+	for (uint32_t it = blockIdx.x; it < count; it += gridDim.x) {
+		const uint32_t u = list[it];
+		const uint32_t li = P.ucol[u], i = P.lo + li;
+		const uint64_t base = P.uptr[u];
+		const uint32_t Fi = P.ucount[u];
+		const uint64_t* raw = P.raw + base;
+		uint64_t* fin = (uint64_t*)(P.out + base) + 2;             // out[0] is the result; 16 B/product region: fin 8 B, par 2 B, sup 4 B
+		uint16_t* par = (uint16_t*)(fin + Fi);
+		uint32_t* sup = (uint32_t*)(par + ((Fi + 1) & ~1u));
+		const uint32_t row = ent_row(raw[0]);
+		if (Fi > 65535u) { if (tid == 0) { set_err(P.err, -4); P.unnz[u] = 0; } continue; }
+		for (uint32_t s = tid; s < 2048; s += NT) jbits[s] = 0;
+		__syncthreads();
+		for (uint32_t x = tid; x < Fi; x += NT) {
+			const uint32_t jr = (uint32_t)(raw[x] >> 48);
+			atomicOr(&jbits[jr >> 5], 1u << (jr & 31));
+		}
+		__syncthreads();
+		block_popc_scan<uint32_t>(jbits, jpre, 2048, s_tmp);
+		if (jpre[2048] != Fi) { if (tid == 0) { set_err(P.err, -5); P.unnz[u] = 0; } continue; }
+		const uint32_t j0 = P.B_colptr[i];
+		const int lenV = (int)P.read_len[i], lenH = (int)P.read_len[row];
+		for (uint32_t x = tid; x < Fi; x += NT) {
+			const uint64_t r = raw[x];
+			const uint32_t jr = (uint32_t)(r >> 48), h = (uint32_t)(r >> 32) & 0xFFFFu, sH = ((uint32_t)r >> 31);
+			const uint32_t rank = jpre[jr >> 5] + __popc(jbits[jr >> 5] & ((1u << (jr & 31)) - 1u));
+			const uint32_t v = P.B_values[j0 + jr], sV = getbit(P.B_strand, j0 + jr);
+			const uint32_t ov = overlap_estimate(lenH, lenV, h, v, sH == sV, P.K);
+			fin[rank] = (uint64_t)(h | (v << 16)) | ((uint64_t)ov << 32);
+		}
+		if (tid < 3) s_part[tid] = 0;
+		__threadfence_block();
+		__syncthreads();
+		PairResult R = fold_coop<true>(fin, par, sup, Fi, P.K, (int)P.BIN, tid >> 5, NT >> 5, s_part);
+		__syncthreads();
+		if (tid == 0) { P.out[base] = pack_result(row, R); P.unnz[u] = 1; }
+		__syncthreads();
+	}
+}
+
+// ================================ output ====================================================
+
+__global__ void k_colptr(uint32_t ncols, const uint32_t* __restrict__ ubase, const uint32_t* __restrict__ uoff, uint32_t* __restrict__ colptrC)
+{
+	for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li <= ncols; li += gridDim.x * blockDim.x) colptrC[li] = uoff[ubase[li]];
+}
+
+// one warp per unit: per-unit pair records -> C (SoA), at the unit's final offset
+__global__ void __launch_bounds__(256) k_compact(uint32_t U, const uint64_t* __restrict__ uptr, const uint32_t* __restrict__ uoff,
+		const uint4* __restrict__ out, uint32_t* __restrict__ rowsC, uint16_t* __restrict__ countC, uint16_t* __restrict__ posH,
+		uint16_t* __restrict__ posV, uint16_t* __restrict__ aux)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t u = warp; u < U; u += nwarps) {
+		const uint32_t g0 = uoff[u], Z = uoff[u + 1] - g0;
+		const uint4* src = out + uptr[u];
+		for (uint32_t p = lane; p < Z; p += 32) {
+			const uint4 r = src[p];
+			const size_t g = (size_t)g0 + p;
+			rowsC[g] = r.x;
+			countC[g] = (uint16_t)(r.y & 0xFFFFu);
+			posH[g] = (uint16_t)(r.z & 0xFFFFu);
+			posV[g] = (uint16_t)(r.z >> 16);
+			aux[3 * g + 0] = (uint16_t)(r.y >> 16);
+			aux[3 * g + 1] = (uint16_t)(r.w & 0xFFFFu);
+			aux[3 * g + 2] = (uint16_t)(r.w >> 16);
+		}
 	}
 }
 

@@ -109,8 +109,9 @@ class OverlapSpGEMM:
         vA = CscView(n, m, nnz, _ptr(A[0]), _ptr(A[1]), _ptr(A[2])) if A is not None else None
         return vA, vB
 
-    def set_inputs(self, inp, with_A=True):
-        """inp: frontend.OverlapInputs (host numpy arrays)."""
+    def set_inputs(self, inp, with_A=False):
+        """inp: frontend.OverlapInputs (host numpy arrays).  A (== Bᵀ, what BELLA always passes) is only
+        checked for shape: the device derives it from B, so its arrays are never copied."""
         A = (inp.A_colptr, inp.A_rowids, inp.A_values) if with_A else None
         vA, vB = self._views(inp.n_reads, inp.n_kmers, inp.nnz, A, (inp.B_colptr, inp.B_rowids, inp.B_values))
         self._keep = inp
@@ -173,11 +174,11 @@ class OverlapSpGEMM:
     def timings(self):
         t = (ctypes.c_float * 8)()
         self._L.bella_b200_get_timings(self._h, t)
-        return {"layout_ms": t[0], "symbolic_ms": t[1], "numeric_ms": t[2], "h2d_ms": t[3], "d2h_ms": t[4],
-                "launches": int(t[5]), "expand_ms": t[6]}
+        return {"transpose_ms": t[0], "group_fold_ms": t[1], "output_ms": t[2] + t[6], "h2d_ms": t[3], "d2h_ms": t[4],
+                "launches": int(t[5]), "scatter_ms": t[7]}
 
 
-def overlap_spgemm(inp, device=0, with_A=True, aux=False):
+def overlap_spgemm(inp, device=0, with_A=False, aux=False):
     """Convenience: whole pass through the C-ABI with host buffers. -> dict of numpy arrays"""
     g = OverlapSpGEMM(device)
     try:

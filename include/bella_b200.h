@@ -61,8 +61,10 @@ const char* bella_b200_last_error(const bella_b200_handle* h);
  * of HashSpGEMM (include/overlap.hpp:650-652): read_len[n] and the strand bits stand in for `reads`,
  * kmer_size/bin_size for BELLApars.{kmerSize,binSize}.  strand bits are bit-packed, LSB first, one
  * bit per nonzero in that matrix's array order.
- * A may be NULL: then A is derived on the device as the transpose of B (A == B^T is what BELLA
- * always passes).  B.cols == number of reads n, B.rows == number of k-mers m. */
+ * A == B^T is what BELLA always passes (src/main.cpp:489), so the device derives A from B itself
+ * (it needs each nonzero's position inside B's column, which A's arrays do not carry): A may be
+ * NULL; when given, only its shape is checked against B and its arrays and strand_A are never
+ * read or copied.  B.cols == number of reads n, B.rows == number of k-mers m. */
 int bella_b200_set_inputs(bella_b200_handle* h, const bella_csc_view* A, const bella_csc_view* B,
 		const uint32_t* read_len, const uint8_t* strand_A, const uint8_t* strand_B,
 		uint16_t kmer_size, uint16_t bin_size);
@@ -87,7 +89,8 @@ int bella_b200_set_column_range(bella_b200_handle* h, uint32_t col_lo, uint32_t 
 int bella_b200_symbolic(bella_b200_handle* h, uint64_t* flops, uint32_t* flopC, uint32_t* colptrC);
 
 /* Numeric phase == LocalSpGEMM(col_begin, col_end, ...) + choose() (include/overlap.hpp:281-363,
- * include/common/common.h:162-170).  [col_begin, col_end) are GLOBAL column ids inside the handle's
+ * include/common/common.h:162-170).  (The device computes the values together with the structure
+ * during bella_b200_symbolic; this call compacts them into C's arrays and copies the range out.)  [col_begin, col_end) are GLOBAL column ids inside the handle's
  * range.  Outputs are HOST arrays of colptrC[col_end]-colptrC[col_begin] entries; column i's
  * entries start at colptrC[i]-colptrC[col_begin], rows ascending.
  *   rowidsC : row read id (the "H" read, larger id)
@@ -116,9 +119,9 @@ int bella_b200_result_device(bella_b200_handle* h, const uint32_t** colptrC, con
 int bella_b200_run_resident(bella_b200_handle* h, uint64_t* nnzC_out, uint64_t* flops_out);
 
 /* Timings of the last pass in milliseconds (CUDA events on the handle's stream):
- *   [0] layout (pack/transposes)  [1] symbolic kernels  [2] numeric (fold) kernels
- *   [3] host->device copies       [4] device->host copies  [5] kernels launched (count)
- *   [6] expand kernels only       [7] reserved */
+ *   [0] transpose + plan (B -> A, product counts, units)   [1] group + fold kernels
+ *   [2] output compaction         [3] host->device copies   [4] device->host copies
+ *   [5] kernels launched (count)  [6] output scans          [7] scatter kernel */
 int bella_b200_get_timings(bella_b200_handle* h, float* ms8);
 
 /* cudaStream_t of the handle as an opaque pointer (so a caller can order its own work after it). */
