@@ -63,7 +63,7 @@ struct bella_b200_handle {
 	DevBuf oB_colptr, oB_rowids, oB_values, oB_strand, o_len;
 	// transpose
 	uint32_t W = 0, NB = 0;                    // k-mers per bucket, buckets
-	DevBuf bhist, boff, bcur, partK, partE, Aent, Acolptr, flop32;
+	DevBuf boff, bcur, part, Aent, Acolptr, flop32;
 	// plan
 	uint32_t ucap = 0, U = 0, round = 0;
 	DevBuf nunits, ubase, shv, refine, colinfo, ucol, ucount, uptr, ucur, lists, unnz, uoff;
@@ -153,22 +153,17 @@ int run_transpose(bella_b200_handle* h)
 	const uint32_t W = h->W;
 	const uint32_t NB = (uint32_t)(((uint64_t)m + W - 1) / W);
 	h->NB = NB;
-	ENSURE(h->bhist, sizeof(uint32_t) * ((size_t)NB + 2));
-	ENSURE(h->boff, sizeof(uint32_t) * ((size_t)NB + 2));
 	ENSURE(h->bcur, sizeof(uint32_t) * ((size_t)NB + 2));
-	ENSURE(h->partK, sizeof(uint32_t) * (nnz + 2));
-	ENSURE(h->partE, sizeof(uint64_t) * (nnz + 2));
-	CK(cudaMemsetAsync(h->bhist.p, 0, sizeof(uint32_t) * ((size_t)NB + 2), h->stream));
-	k_bucket_hist<<<grid_for(nnz / 4 + 1, 256), 256, 0, h->stream>>>(h->dB_colptr, h->lo, nnz, h->dB_rowids, W, h->bhist.as<uint32_t>());
-	LAUNCHED();
-	if (int rc = exclusive_scan(h, h->bhist.as<uint32_t>(), h->boff.as<uint32_t>(), NB + 1)) return rc;
-	CK(cudaMemcpyAsync(h->bcur.p, h->boff.p, sizeof(uint32_t) * (size_t)NB, cudaMemcpyDeviceToDevice, h->stream));
+	ENSURE(h->boff, sizeof(uint32_t) * ((size_t)NB + 2));
+	ENSURE(h->part, sizeof(uint4) * (size_t)NB * BUCKET_CAP);
+	CK(cudaMemsetAsync(h->bcur.p, 0, sizeof(uint32_t) * ((size_t)NB + 2), h->stream));
 	k_partition<<<grid_for((uint64_t)(n - h->lo) * 32, 256), 256, 0, h->stream>>>(n, h->lo, h->dB_colptr, h->dB_rowids, h->dB_values,
-		h->dB_strand, W, h->bcur.as<uint32_t>(), h->partK.as<uint32_t>(), h->partE.as<uint64_t>(), h->errflag.as<int>());
+		h->dB_strand, W, h->bcur.as<uint32_t>(), h->part.as<uint4>(), h->errflag.as<int>());
 	LAUNCHED();
+	if (int rc = exclusive_scan(h, h->bcur.as<uint32_t>(), h->boff.as<uint32_t>(), NB + 1)) return rc;
 	CK(cudaFuncSetAttribute(k_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BUCKET_SMEM));
-	k_bucket<<<NB < 148u * 12 ? NB : 148u * 12, 256, BUCKET_SMEM, h->stream>>>(m, h->lo, h->hi, W, NB, h->boff.as<uint32_t>(), h->partK.as<uint32_t>(),
-		h->partE.as<uint64_t>(), h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), h->flop32.as<uint32_t>(), h->errflag.as<int>());
+	k_bucket<<<NB < 148u * 12 ? NB : 148u * 12, 256, BUCKET_SMEM, h->stream>>>(m, h->lo, h->hi, W, NB, h->boff.as<uint32_t>(),
+		h->part.as<uint4>(), h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), h->flop32.as<uint32_t>(), h->errflag.as<int>());
 	LAUNCHED();
 	return 0;
 }
@@ -401,8 +396,8 @@ int bella_b200_destroy(bella_b200_handle* h)
 	if (!h) return BELLA_B200_ERR_ARG;
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->stream);
-	DevBuf* bufs[] = {&h->oB_colptr, &h->oB_rowids, &h->oB_values, &h->oB_strand, &h->o_len, &h->bhist, &h->boff, &h->bcur, &h->partK,
-		&h->partE, &h->Aent, &h->Acolptr, &h->flop32, &h->nunits, &h->ubase, &h->shv, &h->refine, &h->colinfo, &h->ucol, &h->ucount,
+	DevBuf* bufs[] = {&h->oB_colptr, &h->oB_rowids, &h->oB_values, &h->oB_strand, &h->o_len, &h->boff, &h->bcur, &h->part,
+		&h->Aent, &h->Acolptr, &h->flop32, &h->nunits, &h->ubase, &h->shv, &h->refine, &h->colinfo, &h->ucol, &h->ucount,
 		&h->uptr, &h->ucur, &h->lists, &h->unnz, &h->uoff, &h->raw, &h->out, &h->colptrC, &h->rowsC, &h->countC, &h->posH, &h->posV,
 		&h->aux, &h->meta, &h->errflag, &h->cubtmp};
 	for (DevBuf* b : bufs) b->release();

@@ -163,28 +163,12 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 // ================================ transpose =================================================
 
-// entries per bucket of W consecutive k-mer ids (B nonzeros j >= jlo = B_colptr[lo]: rows below lo never matter)
-__global__ void __launch_bounds__(256) k_bucket_hist(const uint32_t* __restrict__ Bcolptr, uint32_t lo, uint64_t nnz,
-		const uint32_t* __restrict__ Brow, uint32_t W, uint32_t* __restrict__ bhist)
-{
-	const uint64_t jlo = Bcolptr[lo];
-	for (uint64_t j = jlo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < nnz; j += (uint64_t)gridDim.x * blockDim.x)
-		atomicAdd(&bhist[Brow[j] / W], 1u);
-}
-
-__global__ void k_bucket_max(const uint32_t* __restrict__ bhist, uint32_t nb, Meta* meta)
-{
-	uint32_t mx = 0;
-	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) mx = max(mx, bhist[b]);
-	for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
-	if ((threadIdx.x & 31) == 0 && mx) atomicMax(&meta->max_bucket, mx);
-}
-
-// One warp per read (column of B): its nonzeros go to their k-mer bucket's region as (k-mer id, entry).
-// The write frontier is one open sector per bucket, so the small stores merge in L2.
+// One warp per read (column of B): its nonzeros go to their k-mer bucket (W consecutive k-mer ids,
+// a fixed-capacity region of BUCKET_CAP 16-byte records {k-mer id, -, entry}).  The write frontier is
+// one open sector per bucket, so the small stores merge in L2.  Rows below lo never matter.
 __global__ void __launch_bounds__(256) k_partition(uint32_t n, uint32_t lo, const uint32_t* __restrict__ Bcolptr,
 		const uint32_t* __restrict__ Brow, const uint16_t* __restrict__ Bval, const uint8_t* __restrict__ Bstrand,
-		uint32_t W, uint32_t* __restrict__ bcur, uint32_t* __restrict__ partK, uint64_t* __restrict__ partE, int* err)
+		uint32_t W, uint32_t* __restrict__ bcnt, uint4* __restrict__ part, int* err)
 {
 	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -192,18 +176,19 @@ __global__ void __launch_bounds__(256) k_partition(uint32_t n, uint32_t lo, cons
 		const uint32_t j0 = Bcolptr[i], j1 = Bcolptr[i + 1];
 		if (j1 - j0 > 65536u) { if (lane == 0) set_err(err, -4); continue; }
 		for (uint32_t jb = j0; jb < j1; jb += 128) {
-			uint32_t c[4], q[4];
+			uint32_t c[4], b[4], q[4];
 #pragma unroll
 			for (int u = 0; u < 4; ++u) {
 				uint32_t j = jb + u * 32 + lane;
-				if (j < j1) { c[u] = Brow[j]; q[u] = atomicAdd(&bcur[c[u] / W], 1u); }
+				if (j < j1) { c[u] = Brow[j]; b[u] = c[u] / W; q[u] = atomicAdd(&bcnt[b[u]], 1u); }
 			}
 #pragma unroll
 			for (int u = 0; u < 4; ++u) {
 				uint32_t j = jb + u * 32 + lane;
 				if (j < j1) {
-					partK[q[u]] = c[u];
-					partE[q[u]] = (uint64_t)i | ((uint64_t)getbit(Bstrand, j) << 31) | ((uint64_t)Bval[j] << 32) | ((uint64_t)(j - j0) << 48);
+					if (q[u] >= BUCKET_CAP) { set_err(err, -6); continue; }
+					const uint64_t e = (uint64_t)i | ((uint64_t)getbit(Bstrand, j) << 31) | ((uint64_t)Bval[j] << 32) | ((uint64_t)(j - j0) << 48);
+					part[(size_t)b[u] * BUCKET_CAP + q[u]] = make_uint4(c[u], 0u, (uint32_t)e, (uint32_t)(e >> 32));
 				}
 			}
 		}
@@ -213,8 +198,8 @@ __global__ void __launch_bounds__(256) k_partition(uint32_t n, uint32_t lo, cons
 // One CTA per bucket: counting sort by k-mer in shared memory, each column sorted by read id,
 // coalesced write of Aent and A's colptr, product counts per output column.
 __global__ void __launch_bounds__(256) k_bucket(uint32_t m, uint32_t lo, uint32_t hi, uint32_t W, uint32_t nb,
-		const uint32_t* __restrict__ boff, const uint32_t* __restrict__ partK, const uint64_t* __restrict__ partE,
-		uint32_t* __restrict__ Acolptr, uint64_t* __restrict__ Aent, uint32_t* __restrict__ flop32, int* err)
+		const uint32_t* __restrict__ boff, const uint4* __restrict__ part,
+		uint32_t* __restrict__ Acolptr, uint64_t* __restrict__ Aent, uint32_t* __restrict__ flop32, const int* err)
 {
 	extern __shared__ __align__(16) unsigned char bsm[];
 	uint64_t* E = (uint64_t*)bsm;                              // [BUCKET_CAP]
@@ -222,22 +207,31 @@ __global__ void __launch_bounds__(256) k_bucket(uint32_t m, uint32_t lo, uint32_
 	uint32_t* off = tmp + BUCKET_CAP;                          // [BUCKET_WMAX + 2]
 	__shared__ uint32_t s_tmp[34];
 	const uint32_t tid = threadIdx.x, nt = blockDim.x;
+	if (*err != 0) return;                                     // a bucket overflowed: the host retries with narrower buckets
 	for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
 		const uint32_t o0 = boff[b], size = boff[b + 1] - o0;
 		const uint32_t kbase = b * W, kw = min(W, m - kbase);
-		if (size > BUCKET_CAP) { if (tid == 0) set_err(err, -6); continue; }
+		const uint4* src = part + (size_t)b * BUCKET_CAP;
 		for (uint32_t k = tid; k <= kw; k += nt) off[k] = 0;
 		__syncthreads();
 		for (uint32_t x = tid; x < size; x += nt) {
-			uint32_t k = partK[o0 + x] - kbase;
-			uint32_t arr = atomicAdd(&off[k], 1u);
+			const uint4 r = src[x];
+			const uint32_t k = r.x - kbase;
+			const uint32_t arr = atomicAdd(&off[k], 1u);
 			tmp[x] = k | (arr << 12);
+			E[x] = (uint64_t)r.z | ((uint64_t)r.w << 32);
 		}
 		__syncthreads();
 		block_excl_scan<uint32_t>(off, kw, s_tmp);
-		for (uint32_t x = tid; x < size; x += nt) {
-			uint32_t t = tmp[x];
-			E[off[t & 0xFFFu] + (t >> 12)] = partE[o0 + x];
+		// permute in place through registers: every thread first reads its elements, then all write
+		uint64_t ev[BUCKET_CAP / 256];
+#pragma unroll
+		for (int q = 0; q < (int)(BUCKET_CAP / 256); ++q) { uint32_t x = tid + q * 256; ev[q] = x < size ? E[x] : 0; }
+		__syncthreads();
+#pragma unroll
+		for (int q = 0; q < (int)(BUCKET_CAP / 256); ++q) {
+			uint32_t x = tid + q * 256;
+			if (x < size) { uint32_t t = tmp[x]; E[off[t & 0xFFFu] + (t >> 12)] = ev[q]; }
 		}
 		__syncthreads();
 		for (uint32_t k = tid; k < kw; k += nt) {
@@ -593,6 +587,139 @@ __device__ PairResult fold_coop(const uint64_t* fin, uint16_t* par, uint32_t* su
 	return R;
 }
 
+constexpr uint32_t WSCR_WORDS = 192;       // per-warp scratch: position bitmap [128] + its prefix u16[128] | 4 cell bitmaps [32]
+constexpr uint32_t JR_BITMAP_MAX = 4096;   // columns of B up to this length rank through the bitmap
+
+// One warp orders the products of a pair (rec, arrival order) by their position in B's column into
+// fin.  The positions of one pair are distinct, so a bitmap over them ranks in O(len + L/32).
+__device__ __forceinline__ void warp_rank_pair(const uint64_t* rec, uint64_t* fin, uint32_t len, uint32_t L, uint32_t* scr, uint32_t lane)
+{
+	constexpr uint64_t LOW48 = 0x0000FFFFFFFFFFFFull;
+	if (L <= JR_BITMAP_MAX) {
+		const uint32_t Lw = (L + 31) >> 5;
+		uint16_t* jpre = (uint16_t*)(scr + 128);
+		for (uint32_t w = lane; w < Lw; w += 32) scr[w] = 0;
+		__syncwarp();
+		for (uint32_t y = lane; y < len; y += 32) {
+			const uint32_t jr = (uint32_t)(rec[y] >> 48);
+			atomicOr(&scr[jr >> 5], 1u << (jr & 31));
+		}
+		__syncwarp();
+		uint32_t carry = 0;
+		for (uint32_t w0 = 0; w0 < Lw; w0 += 32) {
+			const uint32_t w = w0 + lane;
+			const uint32_t c = w < Lw ? __popc(scr[w]) : 0;
+			uint32_t v = c;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, v, o); if (lane >= (uint32_t)o) v += y; }
+			if (w < Lw) jpre[w] = (uint16_t)(carry + v - c);
+			carry += __shfl_sync(FULL, v, 31);
+		}
+		__syncwarp();
+		for (uint32_t y = lane; y < len; y += 32) {
+			const uint64_t r = rec[y];
+			const uint32_t jr = (uint32_t)(r >> 48);
+			fin[jpre[jr >> 5] + __popc(scr[jr >> 5] & ((1u << (jr & 31)) - 1u))] = r & LOW48;
+		}
+	} else {
+		for (uint32_t y = lane; y < len; y += 32) {
+			const uint64_t r = rec[y];
+			const uint32_t jr = (uint32_t)(r >> 48);
+			uint32_t rank = 0;
+			for (uint32_t z = 0; z < len; ++z) rank += ((uint32_t)(rec[z] >> 48) < jr);
+			fin[rank] = r & LOW48;
+		}
+	}
+	__syncwarp();
+}
+
+// One warp folds a pair of P > SHORT_FOLD products (fin, fold order).  `own` is the pair's own
+// 8*P-byte scratch (its consumed arrival-order records); scr the warp's scratch words.
+// Linear case: product s is dropped by the first later t with |dh| <= K or |dv| <= K.  For noisy
+// reads such neighbours are rare, so 64-wide cells of h and of v are marked first and only the
+// products with an occupied neighbouring cell scan forward; the others pass every later product.
+__device__ __forceinline__ PairResult warp_fold_pair(const uint64_t* fin, uint64_t* own, uint32_t P, uint32_t K, int BIN, uint32_t* scr,
+		uint32_t lane)
+{
+	const uint32_t K2 = 2 * K;
+	bool lin = true;
+	for (uint32_t t = 1 + lane; t < P; t += 32)
+		lin &= abs((int)((uint32_t)(fin[t] >> 32) & 0xFFFFu) - (int)((uint32_t)(fin[t - 1] >> 32) & 0xFFFFu)) < BIN;
+	const bool linear = __all_sync(FULL, lin);
+	uint32_t csum = 0, surv = 0;
+	PairResult R;
+	if (linear) {
+		if (K <= 64) {
+			uint32_t *occH = scr, *dupH = scr + 32, *occV = scr + 64, *dupV = scr + 96;
+			for (uint32_t w = lane; w < 128; w += 32) scr[w] = 0;
+			__syncwarp();
+			for (uint32_t s = lane; s < P; s += 32) {
+				const uint32_t x = (uint32_t)fin[s], ch = (x & 0xFFFFu) >> 6, cv = x >> 22;
+				uint32_t b = 1u << (ch & 31);
+				if (atomicOr(&occH[ch >> 5], b) & b) atomicOr(&dupH[ch >> 5], b);
+				b = 1u << (cv & 31);
+				if (atomicOr(&occV[cv >> 5], b) & b) atomicOr(&dupV[cv >> 5], b);
+			}
+			__syncwarp();
+			auto occ = [](const uint32_t* bm, uint32_t c) { return c < 1024u ? (bm[c >> 5] >> (c & 31)) & 1u : 0u; };
+			for (uint32_t s = lane; s < P; s += 32) {
+				const uint32_t x = (uint32_t)fin[s], ch = (x & 0xFFFFu) >> 6, cv = x >> 22;
+				const uint32_t cand = occ(dupH, ch) | occ(occH, ch - 1) | occ(occH, ch + 1) | occ(dupV, cv) | occ(occV, cv - 1) | occ(occV, cv + 1);
+				if (!cand) { csum += P - 1 - s; ++surv; }
+				else {
+					const uint32_t A = K - (x & 0xFFFFu), B = K - (x >> 16);
+					uint32_t t = s + 1;
+					while (t < P && is_far((uint32_t)fin[t], A, B, K2)) ++t;
+					csum += t - s - 1; surv += (t == P);
+				}
+			}
+		} else {
+			for (uint32_t r0 = 0; r0 < P; r0 += 32) {
+				const uint32_t s = r0 + lane;
+				bool alive = s < P;
+				const uint32_t x = alive ? (uint32_t)fin[s] : 0u, A = K - (x & 0xFFFFu), B = K - (x >> 16);
+				for (uint32_t t = r0 + 1; t < P; ++t) {
+					const uint32_t xt = (uint32_t)fin[t];
+					if (t > s) { alive = alive && is_far(xt, A, B, K2); csum += alive; }
+				}
+				surv += alive && s < P;
+			}
+		}
+		for (int o = 16; o; o >>= 1) { csum += __shfl_xor_sync(FULL, csum, o); surv += __shfl_xor_sync(FULL, surv, o); }
+		const uint64_t last = fin[P - 1];
+		R.count = (P + csum) & 0xFFFFu; R.hv = (uint32_t)last; R.nbins = 1; R.sup = surv; R.ov = (uint32_t)(last >> 32) & 0xFFFFu;
+		return R;
+	}
+	__syncwarp();
+	uint16_t* par = (uint16_t*)own;
+	uint32_t* sup = (uint32_t*)own + ((P + 1) >> 1);
+	for (uint32_t b = lane; b < P; b += 32) {
+		const int ob = (int)((uint32_t)(fin[b] >> 32) & 0xFFFFu);
+		uint32_t t = b + 1;
+		while (t < P && abs((int)((uint32_t)(fin[t] >> 32) & 0xFFFFu) - ob) >= BIN) ++t;
+		par[b] = t < P ? (uint16_t)t : (uint16_t)NONE16;
+		sup[b] = 0;
+	}
+	__syncwarp();
+	for (uint32_t s = lane; s < P; s += 32) {
+		const uint32_t x = (uint32_t)fin[s], A = K - (x & 0xFFFFu), B = K - (x >> 16);
+		uint32_t a = par[s], last = s;
+		while (a != NONE16 && is_far((uint32_t)fin[a], A, B, K2)) { ++csum; last = a; a = par[a]; }
+		if (a == NONE16) atomicAdd(&sup[last], 1u);
+	}
+	__syncwarp();
+	uint32_t best = 0, nroots = 0;
+	for (uint32_t idx = lane; idx < P; idx += 32)
+		if (par[idx] == NONE16) { ++nroots; best = max(best, (sup[idx] << 16) | idx); }
+	for (int o = 16; o; o >>= 1) {
+		csum += __shfl_xor_sync(FULL, csum, o); nroots += __shfl_xor_sync(FULL, nroots, o);
+		best = max(best, __shfl_xor_sync(FULL, best, o));
+	}
+	const uint64_t rr = fin[best & 0xFFFFu];
+	R.count = (P + csum) & 0xFFFFu; R.hv = (uint32_t)rr; R.nbins = nroots; R.sup = best >> 16; R.ov = (uint32_t)(rr >> 32) & 0xFFFFu;
+	return R;
+}
+
 // ================================ group + fold ==============================================
 
 template <int CAP>
@@ -612,14 +739,14 @@ __global__ void __launch_bounds__(GF_THREADS) k_group_fold(Params P, const uint3
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) uint64_t s_bar;
 	__shared__ uint32_t s_tmp[34];
-	__shared__ uint32_t s_nlong, s_nhuge;
+	__shared__ uint32_t s_nlong, s_nhuge, s_next;
 	__shared__ uint32_t s_part[3];
+	__shared__ uint16_t hugelist[8];
+	__shared__ uint32_t wscr[(GF_THREADS / 32) * WSCR_WORDS];
 	uint64_t* prodS = (uint64_t*)(smem + GF<CAP>::PROD);
 	uint64_t* recA = (uint64_t*)(smem + GF<CAP>::REC);
 	uint32_t* bits = (uint32_t*)(smem + GF<CAP>::REC);
 	uint16_t* pre2 = (uint16_t*)(smem + GF<CAP>::REC + 4 * (size_t)CAP);
-	uint16_t* parS = (uint16_t*)(smem + GF<CAP>::REC);
-	uint32_t* supS = (uint32_t*)(smem + GF<CAP>::REC + 2 * (size_t)CAP);
 	uint16_t* pid = (uint16_t*)(smem + GF<CAP>::PID);
 	uint16_t* cnt = (uint16_t*)(smem + GF<CAP>::CNT);
 	uint32_t* rowS = (uint32_t*)(smem + GF<CAP>::ROW);
@@ -658,7 +785,7 @@ __global__ void __launch_bounds__(GF_THREADS) k_group_fold(Params P, const uint3
 		}
 		for (uint32_t s = tid; s <= l1w; s += NT) l1[s] = 0;
 		for (uint32_t s = tid; s < ((Fi + 3) >> 1); s += NT) ((uint32_t*)cnt)[s] = 0;
-		if (tid == 0) { s_nlong = 0; s_nhuge = 0; }
+		if (tid == 0) { s_nlong = 0; s_nhuge = 0; s_next = 0; }
 		mbar_wait(&s_bar, phase);
 		phase ^= 1;
 		__syncthreads();                                           // tables cleared by all threads before anyone sets a bit
@@ -710,18 +837,19 @@ __global__ void __launch_bounds__(GF_THREADS) k_group_fold(Params P, const uint3
 			pid[y0] = (uint16_t)p;
 		}
 		__syncthreads();
-		// fold order inside the pair = position in B's column
+		// fold order inside the pair = position in B's column.  Short pairs: one thread per product.
 		uint64_t* fin = prodS;
 		for (uint32_t y = tid; y < Fi; y += NT) {
+			const uint32_t p = pid[y], s0 = poff[p], len = poff[p + 1] - s0;
+			if (len > SHORT_FOLD) continue;
 			const uint64_t r = recA[y];
-			const uint32_t p = pid[y], s0 = poff[p], s1 = poff[p + 1], jr = (uint32_t)(r >> 48);
+			const uint32_t jr = (uint32_t)(r >> 48);
 			uint32_t rank = 0;
-			if (s1 - s0 > 1)
-				for (uint32_t z = s0; z < s1; ++z) rank += ((uint32_t)(recA[z] >> 48) < jr);
+			for (uint32_t z = s0; z < s0 + len; ++z) rank += ((uint32_t)(recA[z] >> 48) < jr);
 			fin[s0 + rank] = r & 0x0000FFFFFFFFFFFFull;
 		}
 		__syncthreads();
-		// --- fold ---
+		// --- fold: short pairs by one thread each, the others are queued for the warps ---
 		uint16_t* longlist = pid;
 		uint4* out = P.out + base;
 		for (uint32_t p = tid; p < Z; p += NT) {
@@ -731,19 +859,35 @@ __global__ void __launch_bounds__(GF_THREADS) k_group_fold(Params P, const uint3
 		}
 		__syncthreads();
 		const uint32_t nlong = s_nlong;
-		for (uint32_t q = wid; q < nlong; q += NW) {
+		const uint32_t Lcol = P.B_colptr[i + 1] - j0;
+		uint32_t* scr = wscr + wid * WSCR_WORDS;
+		for (;;) {
+			uint32_t q = 0;
+			if (lane == 0) q = atomicAdd(&s_next, 1u);
+			q = __shfl_sync(FULL, q, 0);
+			if (q >= nlong) break;
 			const uint32_t p = longlist[q], s0 = poff[p], len = poff[p + 1] - s0;
-			if (len > 1024) { if (lane == 0) longlist[CAP - 1 - atomicAdd(&s_nhuge, 1u)] = (uint16_t)p; continue; }
-			PairResult R = fold_coop<false>(fin + s0, parS + s0, supS + s0, len, K, BIN, 0, 1, nullptr);
+			if (len > 1024) { if (lane == 0) hugelist[atomicAdd(&s_nhuge, 1u)] = (uint16_t)p; continue; }
+			warp_rank_pair(recA + s0, fin + s0, len, Lcol, scr, lane);
+			PairResult R = warp_fold_pair(fin + s0, recA + s0, len, K, BIN, scr, lane);
 			if (lane == 0) out[p] = pack_result(rowS[p], R);
 		}
 		__syncthreads();
 		const uint32_t nhuge = s_nhuge;                             // at most CAP/1024 pairs: the whole CTA takes each
 		for (uint32_t q = 0; q < nhuge; ++q) {
-			const uint32_t p = longlist[CAP - 1 - q], s0 = poff[p], len = poff[p + 1] - s0;
+			const uint32_t p = hugelist[q], s0 = poff[p], len = poff[p + 1] - s0;
+			for (uint32_t y = tid; y < len; y += NT) {
+				const uint64_t r = recA[s0 + y];
+				const uint32_t jr = (uint32_t)(r >> 48);
+				uint32_t rank = 0;
+				for (uint32_t z = s0; z < s0 + len; ++z) rank += ((uint32_t)(recA[z] >> 48) < jr);
+				fin[s0 + rank] = r & 0x0000FFFFFFFFFFFFull;
+			}
 			if (tid < 3) s_part[tid] = 0;
 			__syncthreads();
-			PairResult R = fold_coop<true>(fin + s0, parS + s0, supS + s0, len, K, BIN, wid, NW, s_part);
+			uint16_t* par = (uint16_t*)(recA + s0);
+			uint32_t* sup = (uint32_t*)(recA + s0) + ((len + 1) >> 1);
+			PairResult R = fold_coop<true>(fin + s0, par, sup, len, K, BIN, wid, NW, s_part);
 			if (tid == 0) out[p] = pack_result(rowS[p], R);
 			__syncthreads();
 		}
