@@ -446,10 +446,24 @@ __device__ __forceinline__ uint32_t overlap_estimate(int lenH, int lenV, uint32_
 // When every consecutive pair of overlaps is within binSize (the common case) the forest is the
 // chain t -> t+1 and the whole fold is an all-pairs test with no sequential dependency.
 
-__device__ __forceinline__ bool is_far(uint32_t x, uint32_t A, uint32_t B, uint32_t K2)
+// Far test (chain.hpp:121 through operator>, chain.hpp:93-97): |h_t - h_s| > K && |v_t - v_s| > K.
+// Packed form: with the key (K - h_s | K - v_s) per 16-bit half, x + key per half is d + K mod 2^16, and
+// far <=> both halves > 2K <=> min(x + key, 2K+1) == 2K+1 per half: one VIADDMNMX.U16x2 and one compare.
+// It is exact whenever every position is <= 65535 - K (k-mer start positions of reads shorter than
+// 64 Ki always are); EXACT = true is the 32-bit form, which holds for any u16 values.
+struct FarKey { uint32_t a, b; };
+template <bool EXACT> __device__ __forceinline__ FarKey far_key(uint32_t x, uint32_t K)
 {
-	// |h_t - h_s| > K  <=>  (unsigned)(h_t - h_s + K) > 2K ; A = K - h_s, B = K - v_s
-	return ((x & 0xFFFFu) + A) > K2 && ((x >> 16) + B) > K2;
+	FarKey k;
+	if (EXACT) { k.a = K - (x & 0xFFFFu); k.b = K - (x >> 16); }
+	else { k.a = ((K - (x & 0xFFFFu)) & 0xFFFFu) | ((K - (x >> 16)) << 16); k.b = 0; }
+	return k;
+}
+template <bool EXACT> __device__ __forceinline__ uint32_t far_limit(uint32_t K) { return EXACT ? 2 * K : (2 * K + 1) * 0x10001u; }
+template <bool EXACT> __device__ __forceinline__ bool is_far(uint32_t x, const FarKey k, uint32_t lim)
+{
+	if (EXACT) return ((x & 0xFFFFu) + k.a) > lim && ((x >> 16) + k.b) > lim;
+	return __vminu2(__vadd2(x, k.a), lim) == lim;
 }
 
 struct PairResult { uint32_t count, hv, nbins, sup, ov; };
@@ -459,19 +473,19 @@ __device__ __forceinline__ uint4 pack_result(uint32_t row, const PairResult& r)
 	return make_uint4(row, (r.count & 0xFFFFu) | (r.nbins << 16), r.hv, (r.sup & 0xFFFFu) | (r.ov << 16));
 }
 
-// one thread, P <= SHORT_FOLD, records in fold order
-__device__ __forceinline__ PairResult fold_short(const uint64_t* fin, uint32_t np, uint32_t K, int BIN)
+// one thread, P <= SHORT_FOLD, products in fold order (hv = h | v<<16, ov = overlap estimate)
+template <bool EXACT>
+__device__ __forceinline__ PairResult fold_short(const uint32_t* hvp, const uint16_t* ovp, uint32_t np, uint32_t K, int BIN)
 {
 	constexpr int CAP = SHORT_FOLD;
-	const uint32_t K2 = 2 * K;
+	const uint32_t lim = far_limit<EXACT>(K);
 	uint32_t hv[CAP];
 	uint16_t ov[CAP];
 	bool linear = true;
 #pragma unroll
 	for (int a = 0; a < CAP; ++a) {
 		if (a < (int)np) {
-			uint64_t r = fin[a];
-			hv[a] = (uint32_t)r; ov[a] = (uint16_t)(r >> 32);
+			hv[a] = hvp[a]; ov[a] = ovp[a];
 			if (a) linear &= abs((int)ov[a] - (int)ov[a - 1]) < BIN;
 		} else { hv[a] = 0; ov[a] = 0; }
 	}
@@ -483,14 +497,14 @@ __device__ __forceinline__ PairResult fold_short(const uint64_t* fin, uint32_t n
 #pragma unroll
 		for (int s = 0; s < CAP; ++s) {
 			if (s < (int)np) {
-				uint32_t x = hv[s], A = K - (x & 0xFFFFu), B = K - (x >> 16);
+				const FarKey key = far_key<EXACT>(hv[s], K);
 				bool alive = true;
 #pragma unroll
 				for (int t = s + 1; t < CAP; ++t) {
-					if (t < (int)np) { alive = alive && is_far(hv[t], A, B, K2); csum += alive; }
+					if (t < (int)np) { alive = alive && is_far<EXACT>(hv[t], key, lim); csum += alive; }
 				}
 				surv += alive;
-				last_hv = x; last_ov = ov[s];
+				last_hv = hv[s]; last_ov = ov[s];
 			}
 		}
 		R.count = (np + csum) & 0xFFFFu; R.hv = last_hv; R.nbins = 1; R.sup = surv; R.ov = last_ov;
@@ -507,9 +521,9 @@ __device__ __forceinline__ PairResult fold_short(const uint64_t* fin, uint32_t n
 		}
 	}
 	for (uint32_t s = 0; s < np; ++s) {
-		uint32_t x = hv[s], A = K - (x & 0xFFFFu), B = K - (x >> 16);
+		const FarKey key = far_key<EXACT>(hv[s], K);
 		uint32_t a = par[s], last = s;
-		while (a != 0xFF && is_far(hv[a], A, B, K2)) { ++csum; last = a; a = par[a]; }
+		while (a != 0xFF && is_far<EXACT>(hv[a], key, lim)) { ++csum; last = a; a = par[a]; }
 		if (a == 0xFF) ++sup[last];
 	}
 	uint32_t best = 0, bt = 0, nb = 0;
@@ -519,82 +533,104 @@ __device__ __forceinline__ PairResult fold_short(const uint64_t* fin, uint32_t n
 	return R;
 }
 
-// Cooperative fold of one pair by `nw` warps (this is warp `w` of them); fin/par/sup may be shared
-// or global memory.  part[0..1] (shared) accumulates csum/surv when nw > 1 (zeroed by the caller).
-// Every participating thread returns the same result.  Caller synchronises the group around it.
-template <bool GROUP>
-__device__ PairResult fold_coop(const uint64_t* fin, uint16_t* par, uint32_t* sup, uint32_t P, uint32_t K, int BIN,
-		uint32_t w, uint32_t nw, uint32_t* part)
+// The forest part shared by the cooperative folds: parents, ancestor walks, best root.
+// Threads tid0, tid0+stride, ... of the group take the products; sync() separates the phases.
+template <class Sync>
+__device__ __forceinline__ void fold_forest(const uint32_t* hv, const uint16_t* ov, uint16_t* par, uint32_t* sup, uint32_t P, uint32_t K,
+		int BIN, uint32_t tid0, uint32_t stride, Sync sync, uint32_t& csum, uint32_t& nroots, uint32_t& best)
 {
-	const uint32_t lane = threadIdx.x & 31, K2 = 2 * K;
-	auto sync_group = [&]() { if (GROUP) __syncthreads(); else __syncwarp(); };
-	bool lin = true;
-	for (uint32_t t = 1 + lane + 32 * w; t < P; t += 32 * nw)
-		lin &= abs((int)((uint32_t)(fin[t] >> 32) & 0xFFFFu) - (int)((uint32_t)(fin[t - 1] >> 32) & 0xFFFFu)) < BIN;
-	bool linear = GROUP ? (bool)__syncthreads_and(lin) : (bool)__all_sync(FULL, lin);
-	uint32_t csum = 0, surv = 0;
-	PairResult R;
-	if (linear) {
-		for (uint32_t r0 = 32 * w; r0 < P; r0 += 32 * nw) {
-			const uint32_t s = r0 + lane;
-			bool alive = s < P;
-			const uint32_t x = alive ? (uint32_t)fin[s] : 0u, A = K - (x & 0xFFFFu), B = K - (x >> 16);
-			for (uint32_t t = r0 + 1; t < P; ++t) {
-				const uint32_t xt = (uint32_t)fin[t];
-				if (t > s) { alive = alive && is_far(xt, A, B, K2); csum += alive; }
-			}
-			surv += alive && s < P;
-		}
-		for (int o = 16; o; o >>= 1) { csum += __shfl_xor_sync(FULL, csum, o); surv += __shfl_xor_sync(FULL, surv, o); }
-		if (GROUP) {
-			if (lane == 0) { atomicAdd(&part[0], csum); atomicAdd(&part[1], surv); }
-			__syncthreads();
-			csum = part[0]; surv = part[1];
-		}
-		const uint64_t last = fin[P - 1];
-		R.count = (P + csum) & 0xFFFFu; R.hv = (uint32_t)last; R.nbins = 1; R.sup = surv; R.ov = (uint32_t)(last >> 32) & 0xFFFFu;
-		return R;
-	}
-	for (uint32_t b = lane + 32 * w; b < P; b += 32 * nw) {
-		const int ob = (int)((uint32_t)(fin[b] >> 32) & 0xFFFFu);
+	const uint32_t lim = far_limit<true>(K);
+	for (uint32_t b = tid0; b < P; b += stride) {
+		const int ob = (int)ov[b];
 		uint32_t t = b + 1;
-		while (t < P && abs((int)((uint32_t)(fin[t] >> 32) & 0xFFFFu) - ob) >= BIN) ++t;
+		while (t < P && abs((int)ov[t] - ob) >= BIN) ++t;
 		par[b] = t < P ? (uint16_t)t : (uint16_t)NONE16;
 		sup[b] = 0;
 	}
-	sync_group();
-	for (uint32_t s = lane + 32 * w; s < P; s += 32 * nw) {
-		const uint32_t x = (uint32_t)fin[s], A = K - (x & 0xFFFFu), B = K - (x >> 16);
+	sync();
+	for (uint32_t s = tid0; s < P; s += stride) {
+		const FarKey key = far_key<true>(hv[s], K);
 		uint32_t a = par[s], last = s;
-		while (a != NONE16 && is_far((uint32_t)fin[a], A, B, K2)) { ++csum; last = a; a = par[a]; }
+		while (a != NONE16 && is_far<true>(hv[a], key, lim)) { ++csum; last = a; a = par[a]; }
 		if (a == NONE16) atomicAdd(&sup[last], 1u);
 	}
-	sync_group();
-	uint32_t best = 0, nroots = 0;
-	for (uint32_t idx = lane + 32 * w; idx < P; idx += 32 * nw)
+	sync();
+	for (uint32_t idx = tid0; idx < P; idx += stride)
 		if (par[idx] == NONE16) { ++nroots; best = max(best, (sup[idx] << 16) | idx); }
 	for (int o = 16; o; o >>= 1) {
 		csum += __shfl_xor_sync(FULL, csum, o); nroots += __shfl_xor_sync(FULL, nroots, o);
 		best = max(best, __shfl_xor_sync(FULL, best, o));
 	}
-	if (GROUP) {
-		if (lane == 0) { atomicAdd(&part[0], csum); atomicAdd(&part[1], nroots); atomicMax(&part[2], best); }
-		__syncthreads();
-		csum = part[0]; nroots = part[1]; best = part[2];
+}
+
+// linear case, one warp's share: rounds r0 = first, first + step, ... of 32 products s; every later
+// product t is tested against the 32 lanes at once (t broadcast from memory, four per 16-byte load).
+template <bool EXACT>
+__device__ __forceinline__ void fold_linear_rounds(const uint32_t* hv, uint32_t P, uint32_t K, uint32_t first, uint32_t step,
+		uint32_t& csum, uint32_t& surv)
+{
+	const uint32_t lane = threadIdx.x & 31, lim = far_limit<EXACT>(K);
+	for (uint32_t r0 = first; r0 < P; r0 += step) {
+		const uint32_t s = r0 + lane;
+		bool alive = s < P;
+		const FarKey key = far_key<EXACT>(alive ? hv[s] : 0u, K);
+		const uint32_t tend = min(r0 + 32, P);
+		for (uint32_t t = r0 + 1; t < tend; ++t) {
+			const bool f = is_far<EXACT>(hv[t], key, lim);
+			if (t > s) { alive = alive && f; csum += alive; }
+		}
+		uint32_t t = tend;
+		if (!__any_sync(FULL, alive)) continue;
+		for (; t < P && ((uintptr_t)(hv + t) & 15u); ++t) { alive = alive && is_far<EXACT>(hv[t], key, lim); csum += alive; }
+		for (; t + 4 <= P; t += 4) {
+			const uint4 q = *reinterpret_cast<const uint4*>(hv + t);
+			alive = alive && is_far<EXACT>(q.x, key, lim); csum += alive;
+			alive = alive && is_far<EXACT>(q.y, key, lim); csum += alive;
+			alive = alive && is_far<EXACT>(q.z, key, lim); csum += alive;
+			alive = alive && is_far<EXACT>(q.w, key, lim); csum += alive;
+		}
+		for (; t < P; ++t) { alive = alive && is_far<EXACT>(hv[t], key, lim); csum += alive; }
+		surv += alive;
 	}
-	const uint64_t rr = fin[best & 0xFFFFu];
-	R.count = (P + csum) & 0xFFFFu; R.hv = (uint32_t)rr; R.nbins = nroots; R.sup = best >> 16; R.ov = (uint32_t)(rr >> 32) & 0xFFFFu;
+	for (int o = 16; o; o >>= 1) { csum += __shfl_xor_sync(FULL, csum, o); surv += __shfl_xor_sync(FULL, surv, o); }
+}
+
+// Whole-CTA fold of one pair (hv/ov/par/sup in shared or global memory, hv 16-byte aligned at
+// index 0).  part[0..2] (shared, zeroed by the caller) combines the warps.  All threads return the result.
+__device__ PairResult fold_cta(const uint32_t* hv, const uint16_t* ov, uint16_t* par, uint32_t* sup, uint32_t P, uint32_t K, int BIN,
+		uint32_t* part)
+{
+	const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+	bool lin = true;
+	for (uint32_t t = 1 + tid; t < P; t += blockDim.x) lin &= abs((int)ov[t] - (int)ov[t - 1]) < BIN;
+	const bool linear = (bool)__syncthreads_and(lin);
+	uint32_t csum = 0;
+	PairResult R;
+	if (linear) {
+		uint32_t surv = 0;
+		fold_linear_rounds<true>(hv, P, K, 32 * w, 32 * nw, csum, surv);
+		if (lane == 0) { atomicAdd(&part[0], csum); atomicAdd(&part[1], surv); }
+		__syncthreads();
+		R.count = (P + part[0]) & 0xFFFFu; R.hv = hv[P - 1]; R.nbins = 1; R.sup = part[1]; R.ov = ov[P - 1];
+		return R;
+	}
+	uint32_t nroots = 0, best = 0;
+	fold_forest(hv, ov, par, sup, P, K, BIN, tid, blockDim.x, [] { __syncthreads(); }, csum, nroots, best);
+	if (lane == 0) { atomicAdd(&part[0], csum); atomicAdd(&part[1], nroots); atomicMax(&part[2], best); }
+	__syncthreads();
+	best = part[2];
+	R.count = (P + part[0]) & 0xFFFFu; R.hv = hv[best & 0xFFFFu]; R.nbins = part[1]; R.sup = best >> 16; R.ov = ov[best & 0xFFFFu];
 	return R;
 }
 
-constexpr uint32_t WSCR_WORDS = 192;       // per-warp scratch: position bitmap [128] + its prefix u16[128] | 4 cell bitmaps [32]
+constexpr uint32_t WSCR_WORDS = 192;       // per-warp scratch: position bitmap [128] + its prefix u16[128]
 constexpr uint32_t JR_BITMAP_MAX = 4096;   // columns of B up to this length rank through the bitmap
 
 // One warp orders the products of a pair (rec, arrival order) by their position in B's column into
-// fin.  The positions of one pair are distinct, so a bitmap over them ranks in O(len + L/32).
-__device__ __forceinline__ void warp_rank_pair(const uint64_t* rec, uint64_t* fin, uint32_t len, uint32_t L, uint32_t* scr, uint32_t lane)
+// hv/ov.  The positions of one pair are distinct, so a bitmap over them ranks in O(len + L/32).
+__device__ __forceinline__ void warp_rank_pair(const uint64_t* rec, uint32_t* hv, uint16_t* ov, uint32_t len, uint32_t L, uint32_t* scr,
+		uint32_t lane)
 {
-	constexpr uint64_t LOW48 = 0x0000FFFFFFFFFFFFull;
 	if (L <= JR_BITMAP_MAX) {
 		const uint32_t Lw = (L + 31) >> 5;
 		uint16_t* jpre = (uint16_t*)(scr + 128);
@@ -619,7 +655,8 @@ __device__ __forceinline__ void warp_rank_pair(const uint64_t* rec, uint64_t* fi
 		for (uint32_t y = lane; y < len; y += 32) {
 			const uint64_t r = rec[y];
 			const uint32_t jr = (uint32_t)(r >> 48);
-			fin[jpre[jr >> 5] + __popc(scr[jr >> 5] & ((1u << (jr & 31)) - 1u))] = r & LOW48;
+			const uint32_t rank = jpre[jr >> 5] + __popc(scr[jr >> 5] & ((1u << (jr & 31)) - 1u));
+			hv[rank] = (uint32_t)r; ov[rank] = (uint16_t)(r >> 32);
 		}
 	} else {
 		for (uint32_t y = lane; y < len; y += 32) {
@@ -627,96 +664,34 @@ __device__ __forceinline__ void warp_rank_pair(const uint64_t* rec, uint64_t* fi
 			const uint32_t jr = (uint32_t)(r >> 48);
 			uint32_t rank = 0;
 			for (uint32_t z = 0; z < len; ++z) rank += ((uint32_t)(rec[z] >> 48) < jr);
-			fin[rank] = r & LOW48;
+			hv[rank] = (uint32_t)r; ov[rank] = (uint16_t)(r >> 32);
 		}
 	}
 	__syncwarp();
 }
 
-// One warp folds a pair of P > SHORT_FOLD products (fin, fold order).  `own` is the pair's own
-// 8*P-byte scratch (its consumed arrival-order records); scr the warp's scratch words.
-// Linear case: product s is dropped by the first later t with |dh| <= K or |dv| <= K.  For noisy
-// reads such neighbours are rare, so 64-wide cells of h and of v are marked first and only the
-// products with an occupied neighbouring cell scan forward; the others pass every later product.
-__device__ __forceinline__ PairResult warp_fold_pair(const uint64_t* fin, uint64_t* own, uint32_t P, uint32_t K, int BIN, uint32_t* scr,
+// One warp folds a pair of P > SHORT_FOLD products (hv/ov in fold order; hv + P0 is the pair's slice of a
+// 16-byte aligned array, see fold_linear_rounds).  `own` is the pair's own 8*P-byte scratch.
+template <bool EXACT>
+__device__ __forceinline__ PairResult warp_fold_pair(const uint32_t* hv, const uint16_t* ov, uint64_t* own, uint32_t P, uint32_t K, int BIN,
 		uint32_t lane)
 {
-	const uint32_t K2 = 2 * K;
 	bool lin = true;
-	for (uint32_t t = 1 + lane; t < P; t += 32)
-		lin &= abs((int)((uint32_t)(fin[t] >> 32) & 0xFFFFu) - (int)((uint32_t)(fin[t - 1] >> 32) & 0xFFFFu)) < BIN;
+	for (uint32_t t = 1 + lane; t < P; t += 32) lin &= abs((int)ov[t] - (int)ov[t - 1]) < BIN;
 	const bool linear = __all_sync(FULL, lin);
-	uint32_t csum = 0, surv = 0;
+	uint32_t csum = 0;
 	PairResult R;
 	if (linear) {
-		if (K <= 64) {
-			uint32_t *occH = scr, *dupH = scr + 32, *occV = scr + 64, *dupV = scr + 96;
-			for (uint32_t w = lane; w < 128; w += 32) scr[w] = 0;
-			__syncwarp();
-			for (uint32_t s = lane; s < P; s += 32) {
-				const uint32_t x = (uint32_t)fin[s], ch = (x & 0xFFFFu) >> 6, cv = x >> 22;
-				uint32_t b = 1u << (ch & 31);
-				if (atomicOr(&occH[ch >> 5], b) & b) atomicOr(&dupH[ch >> 5], b);
-				b = 1u << (cv & 31);
-				if (atomicOr(&occV[cv >> 5], b) & b) atomicOr(&dupV[cv >> 5], b);
-			}
-			__syncwarp();
-			auto occ = [](const uint32_t* bm, uint32_t c) { return c < 1024u ? (bm[c >> 5] >> (c & 31)) & 1u : 0u; };
-			for (uint32_t s = lane; s < P; s += 32) {
-				const uint32_t x = (uint32_t)fin[s], ch = (x & 0xFFFFu) >> 6, cv = x >> 22;
-				const uint32_t cand = occ(dupH, ch) | occ(occH, ch - 1) | occ(occH, ch + 1) | occ(dupV, cv) | occ(occV, cv - 1) | occ(occV, cv + 1);
-				if (!cand) { csum += P - 1 - s; ++surv; }
-				else {
-					const uint32_t A = K - (x & 0xFFFFu), B = K - (x >> 16);
-					uint32_t t = s + 1;
-					while (t < P && is_far((uint32_t)fin[t], A, B, K2)) ++t;
-					csum += t - s - 1; surv += (t == P);
-				}
-			}
-		} else {
-			for (uint32_t r0 = 0; r0 < P; r0 += 32) {
-				const uint32_t s = r0 + lane;
-				bool alive = s < P;
-				const uint32_t x = alive ? (uint32_t)fin[s] : 0u, A = K - (x & 0xFFFFu), B = K - (x >> 16);
-				for (uint32_t t = r0 + 1; t < P; ++t) {
-					const uint32_t xt = (uint32_t)fin[t];
-					if (t > s) { alive = alive && is_far(xt, A, B, K2); csum += alive; }
-				}
-				surv += alive && s < P;
-			}
-		}
-		for (int o = 16; o; o >>= 1) { csum += __shfl_xor_sync(FULL, csum, o); surv += __shfl_xor_sync(FULL, surv, o); }
-		const uint64_t last = fin[P - 1];
-		R.count = (P + csum) & 0xFFFFu; R.hv = (uint32_t)last; R.nbins = 1; R.sup = surv; R.ov = (uint32_t)(last >> 32) & 0xFFFFu;
+		uint32_t surv = 0;
+		fold_linear_rounds<EXACT>(hv, P, K, 0, 32, csum, surv);
+		R.count = (P + csum) & 0xFFFFu; R.hv = hv[P - 1]; R.nbins = 1; R.sup = surv; R.ov = ov[P - 1];
 		return R;
 	}
-	__syncwarp();
 	uint16_t* par = (uint16_t*)own;
 	uint32_t* sup = (uint32_t*)own + ((P + 1) >> 1);
-	for (uint32_t b = lane; b < P; b += 32) {
-		const int ob = (int)((uint32_t)(fin[b] >> 32) & 0xFFFFu);
-		uint32_t t = b + 1;
-		while (t < P && abs((int)((uint32_t)(fin[t] >> 32) & 0xFFFFu) - ob) >= BIN) ++t;
-		par[b] = t < P ? (uint16_t)t : (uint16_t)NONE16;
-		sup[b] = 0;
-	}
-	__syncwarp();
-	for (uint32_t s = lane; s < P; s += 32) {
-		const uint32_t x = (uint32_t)fin[s], A = K - (x & 0xFFFFu), B = K - (x >> 16);
-		uint32_t a = par[s], last = s;
-		while (a != NONE16 && is_far((uint32_t)fin[a], A, B, K2)) { ++csum; last = a; a = par[a]; }
-		if (a == NONE16) atomicAdd(&sup[last], 1u);
-	}
-	__syncwarp();
-	uint32_t best = 0, nroots = 0;
-	for (uint32_t idx = lane; idx < P; idx += 32)
-		if (par[idx] == NONE16) { ++nroots; best = max(best, (sup[idx] << 16) | idx); }
-	for (int o = 16; o; o >>= 1) {
-		csum += __shfl_xor_sync(FULL, csum, o); nroots += __shfl_xor_sync(FULL, nroots, o);
-		best = max(best, __shfl_xor_sync(FULL, best, o));
-	}
-	const uint64_t rr = fin[best & 0xFFFFu];
-	R.count = (P + csum) & 0xFFFFu; R.hv = (uint32_t)rr; R.nbins = nroots; R.sup = best >> 16; R.ov = (uint32_t)(rr >> 32) & 0xFFFFu;
+	uint32_t nroots = 0, best = 0;
+	fold_forest(hv, ov, par, sup, P, K, BIN, lane, 32, [] { __syncwarp(); }, csum, nroots, best);
+	R.count = (P + csum) & 0xFFFFu; R.hv = hv[best & 0xFFFFu]; R.nbins = nroots; R.sup = best >> 16; R.ov = ov[best & 0xFFFFu];
 	return R;
 }
 
@@ -739,7 +714,7 @@ __global__ void __launch_bounds__(GF_THREADS) k_group_fold(Params P, const uint3
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) uint64_t s_bar;
 	__shared__ uint32_t s_tmp[34];
-	__shared__ uint32_t s_nlong, s_nhuge, s_next;
+	__shared__ uint32_t s_nlong, s_nhuge, s_next, s_wide;
 	__shared__ uint32_t s_part[3];
 	__shared__ uint16_t hugelist[8];
 	__shared__ uint32_t wscr[(GF_THREADS / 32) * WSCR_WORDS];
@@ -785,7 +760,7 @@ __global__ void __launch_bounds__(GF_THREADS) k_group_fold(Params P, const uint3
 		}
 		for (uint32_t s = tid; s <= l1w; s += NT) l1[s] = 0;
 		for (uint32_t s = tid; s < ((Fi + 3) >> 1); s += NT) ((uint32_t*)cnt)[s] = 0;
-		if (tid == 0) { s_nlong = 0; s_nhuge = 0; s_next = 0; }
+		if (tid == 0) { s_nlong = 0; s_nhuge = 0; s_next = 0; s_wide = (K > 16383u); }
 		mbar_wait(&s_bar, phase);
 		phase ^= 1;
 		__syncthreads();                                           // tables cleared by all threads before anyone sets a bit
@@ -833,12 +808,14 @@ __global__ void __launch_bounds__(GF_THREADS) k_group_fold(Params P, const uint3
 			const uint32_t v = P.B_values[jg], sV = getbit(P.B_strand, jg);
 			const uint32_t ov = overlap_estimate((int)P.read_len[rowS[p]], lenV, h, v, sH == sV, K);
 			const uint32_t y0 = poff[p] + a;
+			if (max(h, v) > 65535u - K) s_wide = 1;                   // positions this large need the 32-bit far test
 			recA[y0] = (uint64_t)(h | (v << 16)) | ((uint64_t)ov << 32) | ((uint64_t)jr << 48);
 			pid[y0] = (uint16_t)p;
 		}
 		__syncthreads();
 		// fold order inside the pair = position in B's column.  Short pairs: one thread per product.
-		uint64_t* fin = prodS;
+		uint32_t* hvF = (uint32_t*)prodS;
+		uint16_t* ovF = (uint16_t*)(smem + GF<CAP>::PROD + 4 * (size_t)CAP);
 		for (uint32_t y = tid; y < Fi; y += NT) {
 			const uint32_t p = pid[y], s0 = poff[p], len = poff[p + 1] - s0;
 			if (len > SHORT_FOLD) continue;
@@ -846,15 +823,17 @@ __global__ void __launch_bounds__(GF_THREADS) k_group_fold(Params P, const uint3
 			const uint32_t jr = (uint32_t)(r >> 48);
 			uint32_t rank = 0;
 			for (uint32_t z = s0; z < s0 + len; ++z) rank += ((uint32_t)(recA[z] >> 48) < jr);
-			fin[s0 + rank] = r & 0x0000FFFFFFFFFFFFull;
+			hvF[s0 + rank] = (uint32_t)r; ovF[s0 + rank] = (uint16_t)(r >> 32);
 		}
 		__syncthreads();
 		// --- fold: short pairs by one thread each, the others are queued for the warps ---
+		const bool wide = s_wide != 0;
 		uint16_t* longlist = pid;
 		uint4* out = P.out + base;
 		for (uint32_t p = tid; p < Z; p += NT) {
 			const uint32_t s0 = poff[p], len = poff[p + 1] - s0;
-			if (len <= SHORT_FOLD) out[p] = pack_result(rowS[p], fold_short(fin + s0, len, K, BIN));
+			if (len <= SHORT_FOLD)
+				out[p] = pack_result(rowS[p], wide ? fold_short<true>(hvF + s0, ovF + s0, len, K, BIN) : fold_short<false>(hvF + s0, ovF + s0, len, K, BIN));
 			else longlist[atomicAdd(&s_nlong, 1u)] = (uint16_t)p;
 		}
 		__syncthreads();
@@ -868,8 +847,9 @@ __global__ void __launch_bounds__(GF_THREADS) k_group_fold(Params P, const uint3
 			if (q >= nlong) break;
 			const uint32_t p = longlist[q], s0 = poff[p], len = poff[p + 1] - s0;
 			if (len > 1024) { if (lane == 0) hugelist[atomicAdd(&s_nhuge, 1u)] = (uint16_t)p; continue; }
-			warp_rank_pair(recA + s0, fin + s0, len, Lcol, scr, lane);
-			PairResult R = warp_fold_pair(fin + s0, recA + s0, len, K, BIN, scr, lane);
+			warp_rank_pair(recA + s0, hvF + s0, ovF + s0, len, Lcol, scr, lane);
+			PairResult R = wide ? warp_fold_pair<true>(hvF + s0, ovF + s0, recA + s0, len, K, BIN, lane)
+			                    : warp_fold_pair<false>(hvF + s0, ovF + s0, recA + s0, len, K, BIN, lane);
 			if (lane == 0) out[p] = pack_result(rowS[p], R);
 		}
 		__syncthreads();
@@ -881,13 +861,13 @@ __global__ void __launch_bounds__(GF_THREADS) k_group_fold(Params P, const uint3
 				const uint32_t jr = (uint32_t)(r >> 48);
 				uint32_t rank = 0;
 				for (uint32_t z = s0; z < s0 + len; ++z) rank += ((uint32_t)(recA[z] >> 48) < jr);
-				fin[s0 + rank] = r & 0x0000FFFFFFFFFFFFull;
+				hvF[s0 + rank] = (uint32_t)r; ovF[s0 + rank] = (uint16_t)(r >> 32);
 			}
 			if (tid < 3) s_part[tid] = 0;
 			__syncthreads();
 			uint16_t* par = (uint16_t*)(recA + s0);
 			uint32_t* sup = (uint32_t*)(recA + s0) + ((len + 1) >> 1);
-			PairResult R = fold_coop<true>(fin + s0, par, sup, len, K, BIN, wid, NW, s_part);
+			PairResult R = fold_cta(hvF + s0, ovF + s0, par, sup, len, K, BIN, s_part);
 			if (tid == 0) out[p] = pack_result(rowS[p], R);
 			__syncthreads();
 		}
@@ -913,8 +893,9 @@ __global__ void __launch_bounds__(1024) k_huge_pair(Params P, const uint32_t* __
 		const uint64_t base = P.uptr[u];
 		const uint32_t Fi = P.ucount[u];
 		const uint64_t* raw = P.raw + base;
-		uint64_t* fin = (uint64_t*)(P.out + base) + 2;             // out[0] is the result; 16 B/product region: fin 8 B, par 2 B, sup 4 B
-		uint16_t* par = (uint16_t*)(fin + Fi);
+		uint32_t* hv = (uint32_t*)(P.out + base + 1);              // out[0] is the result; 16 B/product region: hv 4, ov 2, par 2, sup 4
+		uint16_t* ov = (uint16_t*)(hv + ((Fi + 3) & ~3u));
+		uint16_t* par = ov + ((Fi + 1) & ~1u);
 		uint32_t* sup = (uint32_t*)(par + ((Fi + 1) & ~1u));
 		const uint32_t row = ent_row(raw[0]);
 		if (Fi > 65535u) { if (tid == 0) { set_err(P.err, -4); P.unnz[u] = 0; } continue; }
@@ -934,13 +915,13 @@ __global__ void __launch_bounds__(1024) k_huge_pair(Params P, const uint32_t* __
 			const uint32_t jr = (uint32_t)(r >> 48), h = (uint32_t)(r >> 32) & 0xFFFFu, sH = ((uint32_t)r >> 31);
 			const uint32_t rank = jpre[jr >> 5] + __popc(jbits[jr >> 5] & ((1u << (jr & 31)) - 1u));
 			const uint32_t v = P.B_values[j0 + jr], sV = getbit(P.B_strand, j0 + jr);
-			const uint32_t ov = overlap_estimate(lenH, lenV, h, v, sH == sV, P.K);
-			fin[rank] = (uint64_t)(h | (v << 16)) | ((uint64_t)ov << 32);
+			hv[rank] = h | (v << 16);
+			ov[rank] = (uint16_t)overlap_estimate(lenH, lenV, h, v, sH == sV, P.K);
 		}
 		if (tid < 3) s_part[tid] = 0;
 		__threadfence_block();
 		__syncthreads();
-		PairResult R = fold_coop<true>(fin, par, sup, Fi, P.K, (int)P.BIN, tid >> 5, NT >> 5, s_part);
+		PairResult R = fold_cta(hv, ov, par, sup, Fi, P.K, (int)P.BIN, s_part);
 		__syncthreads();
 		if (tid == 0) { P.out[base] = pack_result(row, R); P.unnz[u] = 1; }
 		__syncthreads();
