@@ -216,7 +216,7 @@ Params make_params(bella_b200_handle* h)
 {
 	Params P{};
 	P.n = h->n; P.m = h->m; P.lo = h->lo; P.hi = h->hi; P.K = h->K; P.BIN = h->BIN;
-	P.B_colptr = h->dB_colptr; P.B_values = h->dB_values; P.B_strand = h->dB_strand; P.read_len = h->d_len;
+	P.B_colptr = h->dB_colptr; P.B_rowids = h->dB_rowids; P.B_values = h->dB_values; P.B_strand = h->dB_strand; P.read_len = h->d_len;
 	P.A_colptr = h->Acolptr.as<uint32_t>(); P.Aent = h->Aent.as<uint64_t>();
 	P.colinfo = h->colinfo.as<ColInfo>(); P.ucol = h->ucol.as<uint32_t>(); P.ucount = h->ucount.as<uint32_t>();
 	P.uptr = h->uptr.as<uint64_t>(); P.ucur = h->ucur.as<unsigned long long>();
@@ -350,7 +350,8 @@ int validate_views(bella_b200_handle* h, const bella_csc_view* A, const bella_cs
 		const uint8_t* sB)
 {
 	if (!h) return BELLA_B200_ERR_ARG;
-	if (!B || !B->colptr || !read_len || !sB) return fail(h, BELLA_B200_ERR_ARG, "B, read_len and strand_B are required");
+	if (!B || !B->colptr || !read_len) return fail(h, BELLA_B200_ERR_ARG, "B and read_len are required");
+	if (!sB && B->rows > 0x80000000u) return fail(h, BELLA_B200_ERR_RANGE, "strand bits inside B.rowids need fewer than 2^31 k-mers");
 	if (B->nnz && (!B->rowids || !B->values)) return fail(h, BELLA_B200_ERR_ARG, "B.rowids/B.values missing");
 	if (B->cols > 0x7FFFFFFFu) return fail(h, BELLA_B200_ERR_RANGE, "more than 2^31-1 reads");
 	if (A && (A->rows != B->cols || A->cols != B->rows || A->nnz != B->nnz))
@@ -421,7 +422,8 @@ int bella_b200_set_inputs(bella_b200_handle* h, const bella_csc_view* A, const b
 	if (int rc = copy_in(h, h->oB_colptr, B->colptr, sizeof(uint32_t) * ((size_t)B->cols + 1), &p)) return rc; h->dB_colptr = (const uint32_t*)p;
 	if (int rc = copy_in(h, h->oB_rowids, B->rowids, sizeof(uint32_t) * (size_t)B->nnz, &p)) return rc; h->dB_rowids = (const uint32_t*)p;
 	if (int rc = copy_in(h, h->oB_values, B->values, sizeof(uint16_t) * (size_t)B->nnz, &p)) return rc; h->dB_values = (const uint16_t*)p;
-	if (int rc = copy_in(h, h->oB_strand, strand_B, ((size_t)B->nnz + 7) / 8, &p)) return rc; h->dB_strand = (const uint8_t*)p;
+	h->dB_strand = nullptr;
+	if (strand_B) { if (int rc = copy_in(h, h->oB_strand, strand_B, ((size_t)B->nnz + 7) / 8, &p)) return rc; h->dB_strand = (const uint8_t*)p; }
 	if (int rc = copy_in(h, h->o_len, read_len, sizeof(uint32_t) * (size_t)B->cols, &p)) return rc; h->d_len = (const uint32_t*)p;
 	CK(cudaEventRecord(h->ev[11], h->stream));
 	CK(cudaStreamSynchronize(h->stream));

@@ -55,8 +55,9 @@ struct ColInfo { uint32_t ubase; uint32_t sh; };
 struct Params {
 	uint32_t n, m, lo, hi, K, BIN;
 	const uint32_t* B_colptr;
+	const uint32_t* B_rowids;
 	const uint16_t* B_values;
-	const uint8_t* B_strand;
+	const uint8_t* B_strand;      // bit-packed, or NULL: then the strand bit is bit 31 of B_rowids (panel format)
 	const uint32_t* read_len;
 	const uint32_t* A_colptr;     // [m+1]
 	const uint64_t* Aent;         // [nnz]
@@ -83,6 +84,10 @@ struct Meta {
 __device__ __forceinline__ void set_err(int* err, int code) { atomicCAS(err, 0, code); }
 __device__ __forceinline__ uint32_t getbit(const uint8_t* __restrict__ bits, uint64_t i) { return (bits[i >> 3] >> (i & 7)) & 1u; }
 __device__ __forceinline__ uint32_t ent_row(uint64_t e) { return (uint32_t)e & 0x7FFFFFFFu; }
+__device__ __forceinline__ uint32_t strand_of(const uint8_t* __restrict__ bits, const uint32_t* __restrict__ rowids, uint64_t j)
+{
+	return bits ? getbit(bits, j) : rowids[j] >> 31;
+}
 
 // ================================ block helpers =============================================
 
@@ -180,15 +185,16 @@ __global__ void __launch_bounds__(256) k_partition(uint32_t n, uint32_t lo, cons
 #pragma unroll
 			for (int u = 0; u < 4; ++u) {
 				uint32_t j = jb + u * 32 + lane;
-				if (j < j1) { c[u] = Brow[j]; b[u] = c[u] / W; q[u] = atomicAdd(&bcnt[b[u]], 1u); }
+				if (j < j1) { c[u] = Brow[j]; b[u] = (Bstrand ? c[u] : c[u] & 0x7FFFFFFFu) / W; q[u] = atomicAdd(&bcnt[b[u]], 1u); }
 			}
 #pragma unroll
 			for (int u = 0; u < 4; ++u) {
 				uint32_t j = jb + u * 32 + lane;
 				if (j < j1) {
 					if (q[u] >= BUCKET_CAP) { set_err(err, -6); continue; }
-					const uint64_t e = (uint64_t)i | ((uint64_t)getbit(Bstrand, j) << 31) | ((uint64_t)Bval[j] << 32) | ((uint64_t)(j - j0) << 48);
-					part[(size_t)b[u] * BUCKET_CAP + q[u]] = make_uint4(c[u], 0u, (uint32_t)e, (uint32_t)(e >> 32));
+					const uint32_t st = Bstrand ? getbit(Bstrand, j) : c[u] >> 31;
+					const uint64_t e = (uint64_t)i | ((uint64_t)st << 31) | ((uint64_t)Bval[j] << 32) | ((uint64_t)(j - j0) << 48);
+					part[(size_t)b[u] * BUCKET_CAP + q[u]] = make_uint4(Bstrand ? c[u] : c[u] & 0x7FFFFFFFu, 0u, (uint32_t)e, (uint32_t)(e >> 32));
 				}
 			}
 		}
@@ -805,7 +811,7 @@ __global__ void __launch_bounds__(GF_THREADS) k_group_fold(Params P, const uint3
 			const uint32_t h = (uint32_t)t & 0xFFFFu, jr = ((uint32_t)t >> 16), p = (uint32_t)(t >> 32) & 0x3FFFu;
 			const uint32_t a = (uint32_t)(t >> 46) & 0x3FFFu, sH = (uint32_t)(t >> 60) & 1u;
 			const uint32_t jg = j0 + jr;
-			const uint32_t v = P.B_values[jg], sV = getbit(P.B_strand, jg);
+			const uint32_t v = P.B_values[jg], sV = strand_of(P.B_strand, P.B_rowids, jg);
 			const uint32_t ov = overlap_estimate((int)P.read_len[rowS[p]], lenV, h, v, sH == sV, K);
 			const uint32_t y0 = poff[p] + a;
 			if (max(h, v) > 65535u - K) s_wide = 1;                   // positions this large need the 32-bit far test
@@ -914,7 +920,7 @@ __global__ void __launch_bounds__(1024) k_huge_pair(Params P, const uint32_t* __
 			const uint64_t r = raw[x];
 			const uint32_t jr = (uint32_t)(r >> 48), h = (uint32_t)(r >> 32) & 0xFFFFu, sH = ((uint32_t)r >> 31);
 			const uint32_t rank = jpre[jr >> 5] + __popc(jbits[jr >> 5] & ((1u << (jr & 31)) - 1u));
-			const uint32_t v = P.B_values[j0 + jr], sV = getbit(P.B_strand, j0 + jr);
+			const uint32_t v = P.B_values[j0 + jr], sV = strand_of(P.B_strand, P.B_rowids, j0 + jr);
 			hv[rank] = h | (v << 16);
 			ov[rank] = (uint16_t)overlap_estimate(lenH, lenV, h, v, sH == sV, P.K);
 		}

@@ -1,0 +1,295 @@
+"""Row-sharded multi-GPU overlap SpGEMM: one process per GPU, `torch.distributed` for the plumbing.
+
+Layout (the reference has no distributed code, so there is no call site to mirror):
+  * A is row-sharded: rank r owns the reads [read_lo_r, read_hi_r) -- equivalently the columns of
+    B = A^T of those reads -- as a *compressed column panel*: per nonzero the k-mer id with the strand
+    bit in bit 31 (u32) and the position (u16), plus per read its k-mer count and length.
+  * per batch ONE all-gather of the panels (NCCL over NVLink) gives every rank the whole B;
+  * output columns are independent (overlap.hpp:286-287), so every rank then runs the single-GPU
+    path (bella_b200_set_inputs_device + set_column_range + symbolic/numeric) on its own contiguous
+    column range.  Ranges are balanced on the product estimate  len_i * (n-1-i)  (the strictly lower
+    triangle makes low column ids heavier; the reference balances its stages on the nnz prefix,
+    overlap.hpp:703-710).  Outputs are disjoint column ranges: no reduction, the caller concatenates.
+
+Everything in this file is host-side plumbing on torch tensors (CPU tensors with gloo in the unit
+tests, CUDA tensors with NCCL on the box); the arithmetic is in libbella_b200.so.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HEADER_WORDS = 4          # int64: n_reads, nnz, read_lo, reserved
+ALIGN = 16
+
+
+def _up(x, a=ALIGN):
+    return (x + a - 1) // a * a
+
+
+def panel_layout(n_r, nnz_r):
+    """Byte offsets of the sections of one packed panel. -> dict, total bytes"""
+    off = {}
+    o = HEADER_WORDS * 8
+    off["rowids"] = o; o = _up(o + 4 * nnz_r)
+    off["values"] = o; o = _up(o + 2 * nnz_r)
+    off["counts"] = o; o = _up(o + 4 * n_r)
+    off["read_len"] = o; o = _up(o + 4 * n_r)
+    return off, o
+
+
+def shard_bounds(B_colptr, world):
+    """Read ranges owned by the ranks before the exchange: contiguous, about equal nnz."""
+    n = len(B_colptr) - 1
+    nnz = int(B_colptr[-1])
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(B_colptr, nnz * r // world, side="left")))
+    cuts.append(n)
+    return [min(max(c, 0), n) for c in cuts]
+
+
+def pack_panel(inp, r0, r1):
+    """Compressed column panel of reads [r0, r1) of `inp` (frontend.OverlapInputs) as one uint8 array."""
+    if inp.n_kmers > 0x80000000:
+        raise ValueError("panel format keeps the strand bit in bit 31 of the k-mer id: needs < 2^31 k-mers")
+    j0, j1 = int(inp.B_colptr[r0]), int(inp.B_colptr[r1])
+    n_r, nnz_r = r1 - r0, j1 - j0
+    off, total = panel_layout(n_r, nnz_r)
+    buf = np.zeros(total, dtype=np.uint8)
+    buf[:HEADER_WORDS * 8].view(np.int64)[:] = [n_r, nnz_r, r0, 0]
+    strand = np.unpackbits(inp.B_strand, bitorder="little")[j0:j1].astype(np.uint32)
+    buf[off["rowids"]:off["rowids"] + 4 * nnz_r].view(np.uint32)[:] = inp.B_rowids[j0:j1] | (strand << 31)
+    buf[off["values"]:off["values"] + 2 * nnz_r].view(np.uint16)[:] = inp.B_values[j0:j1]
+    buf[off["counts"]:off["counts"] + 4 * n_r].view(np.uint32)[:] = np.diff(inp.B_colptr[r0:r1 + 1])
+    buf[off["read_len"]:off["read_len"] + 4 * n_r].view(np.uint32)[:] = inp.read_len[r0:r1]
+    return buf
+
+
+def exchange_sizes(n_r, nnz_r, device):
+    """Tiny all-gather of the panel shapes (once per sharding, not per batch). -> [(n_r, nnz_r)] per rank"""
+    world = dist.get_world_size()
+    mine = torch.tensor([n_r, nnz_r], dtype=torch.int64, device=device)
+    allm = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allm, mine)
+    return [(int(t[0]), int(t[1])) for t in allm]
+
+
+def all_gather_panels(panel, max_bytes):
+    """THE collective of the batch: every rank contributes its panel (padded to max_bytes). -> (world, max_bytes) uint8"""
+    world = dist.get_world_size()
+    assert panel.dtype == torch.uint8 and panel.numel() == max_bytes
+    out = torch.empty((world, max_bytes), dtype=torch.uint8, device=panel.device)
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(out.view(-1), panel)
+    else:
+        dist.all_gather(list(out.unbind(0)), panel)
+    return out
+
+
+def unpack_panels(gathered, shapes):
+    """(world, max_bytes) uint8 + per-rank (n_r, nnz_r) -> B of all reads as tensors on the same device:
+    colptr int32 [n+1] (uint32 bit pattern), rowids int32 [nnz] (strand in bit 31), values int16 [nnz], read_len int32 [n]"""
+    rows, vals, cnts, lens = [], [], [], []
+    for r, (n_r, nnz_r) in enumerate(shapes):
+        off, _ = panel_layout(n_r, nnz_r)
+        b = gathered[r]
+        rows.append(b[off["rowids"]:off["rowids"] + 4 * nnz_r].view(torch.int32))
+        vals.append(b[off["values"]:off["values"] + 2 * nnz_r].view(torch.int16))
+        cnts.append(b[off["counts"]:off["counts"] + 4 * n_r].view(torch.int32))
+        lens.append(b[off["read_len"]:off["read_len"] + 4 * n_r].view(torch.int32))
+    counts = torch.cat(cnts).to(torch.int64)
+    colptr64 = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=gathered.device)
+    torch.cumsum(counts, 0, out=colptr64[1:])
+    return {"colptr64": colptr64, "colptr": colptr64.to(torch.int32), "rowids": torch.cat(rows), "values": torch.cat(vals),
+            "read_len": torch.cat(lens)}
+
+
+RHO = 0.28      # cost of transposing one nonzero relative to one estimated product (measured on B200)
+
+
+def column_ranges(colptr64, world, rho=RHO):
+    """Contiguous output-column ranges [b_r, b_{r+1}) that equalise the modelled per-rank time
+         rho * nnz(rows >= b_r)  +  sum_{i in range} len_i * (n-1-i)/(n-1)
+    -- a rank transposes every read at or above its first column (rows below never pair with its
+    columns) and expands the kept products of its own columns, whose number is estimated by the read
+    length times the share of reads with a larger id (the strictly lower triangle makes low column ids
+    heavier; the reference balances its stages on the nnz prefix, overlap.hpp:703-710).
+    Deterministic in its inputs, so every rank computes the same bounds. -> list of world+1 ints"""
+    cp = colptr64.detach().cpu().numpy().astype(np.float64)
+    n = cp.size - 1
+    if n == 0:
+        return [0] * (world + 1)
+    nnz = cp[-1]
+    if nnz <= 0 or world == 1:
+        return [n * r // world for r in range(world + 1)]
+    lens = np.diff(cp)
+    w = lens * (np.arange(n - 1, -1, -1, dtype=np.float64) / max(n - 1, 1))
+    W = np.concatenate([[0.0], np.cumsum(w)])
+    tail = nnz - cp                          # nnz of rows >= i, i = 0..n
+    g = rho * tail - W                       # decreasing in i
+
+    def assign(T):
+        bounds = [n]
+        hi = n
+        for _ in range(world - 1):
+            # smallest lo with rho*tail[lo] + W[hi] - W[lo] <= T
+            lo = int(np.searchsorted(-g[:hi + 1], -(T - W[hi]), side="left"))
+            lo = min(lo, hi)
+            bounds.append(lo)
+            hi = lo
+        return bounds[::-1], rho * nnz + W[hi]      # bounds[1:], cost of rank 0 = columns [0, hi)
+
+    lo_T, hi_T = 0.0, rho * nnz + W[-1]
+    for _ in range(60):
+        T = 0.5 * (lo_T + hi_T)
+        _, c0 = assign(T)
+        if c0 <= T:
+            hi_T = T
+        else:
+            lo_T = T
+    inner, _ = assign(hi_T)
+    bounds = [0] + [int(x) for x in inner]
+    for k in range(1, len(bounds)):
+        bounds[k] = min(max(bounds[k], bounds[k - 1]), n)
+    bounds[-1] = n
+    return bounds
+
+
+class ShardedOverlapSpGEMM:
+    """One instance per rank.  load_shard() once; step() per batch: all-gather + local SpGEMM of this rank's columns."""
+
+    def __init__(self, device_index):
+        from . import spgemm
+        self.dev = torch.device("cuda", device_index)
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.g = spgemm.OverlapSpGEMM(device_index)
+        self.g.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+        self.panel = None
+        self.keep = None
+
+    def load_shard(self, inp, pinned=False):
+        """Take this rank's reads of `inp`, pack the panel and make it device resident."""
+        cuts = shard_bounds(inp.B_colptr, self.world)
+        r0, r1 = cuts[self.rank], cuts[self.rank + 1]
+        host = pack_panel(inp, r0, r1)
+        n_r, nnz_r = r1 - r0, int(inp.B_colptr[r1]) - int(inp.B_colptr[r0])
+        self.shapes = exchange_sizes(n_r, nnz_r, self.dev)
+        self.max_bytes = max(panel_layout(a, b)[1] for a, b in self.shapes)
+        self.n_kmers, self.kmer_size, self.bin_size = inp.n_kmers, inp.kmer_size, inp.bin_size
+        self.host_panel = torch.zeros(self.max_bytes, dtype=torch.uint8)
+        self.host_panel[:host.size] = torch.from_numpy(host)
+        if pinned:
+            self.host_panel = self.host_panel.pin_memory()
+        self.panel = self.host_panel.to(self.dev)
+        return r0, r1
+
+    def upload(self):
+        """e2e leg: host panel -> device inside the timed region."""
+        self.panel.copy_(self.host_panel, non_blocking=True)
+
+    def step(self, fetch=False):
+        """-> (Z of this rank's columns, products, (col_lo, col_hi)[, host results when fetch=True])"""
+        gathered = all_gather_panels(self.panel, self.max_bytes)
+        B = unpack_panels(gathered, self.shapes)
+        bounds = column_ranges(B["colptr64"], self.world)
+        lo, hi = bounds[self.rank], bounds[self.rank + 1]
+        n = B["read_len"].numel()
+        nnz = B["rowids"].numel()
+        self.keep = (gathered, B)
+        self.g.set_inputs_device(n, self.n_kmers, nnz, (B["colptr"], B["rowids"], B["values"]), B["read_len"], None,
+                                 self.kmer_size, self.bin_size)
+        self.g.set_column_range(lo, hi)
+        if fetch:       # the public host-facing calls: colptrC and the tuples of this rank's columns come back to the host
+            flops, _, colptrC = self.g.symbolic(want_flopC=False, pinned=True)
+            res = self.g.numeric(pinned=True)
+            return int(colptrC[hi - lo]), flops, (lo, hi), (colptrC[:hi - lo + 1],) + res
+        Z, flops = self.g.run_resident()
+        return Z, flops, (lo, hi)
+
+    def close(self):
+        self.g.close()
+
+
+def bench_multi(args, w, inp, rank, world, local, METRIC, UNIT, workload, ClockSampler, algorithmic_bytes, measured_peak):
+    """bench.py body for N > 1 (launched under torchrun): strong scaling of the N=1 workload."""
+    import json
+    import time
+    dev = torch.device("cuda", local)
+    sh = ShardedOverlapSpGEMM(local)
+    sh.load_shard(inp, pinned=True)
+    stream = torch.cuda.current_stream(dev)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        out = None
+        for _ in range(steps):
+            out = fn()
+        ev1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([ev0.elapsed_time(ev1) / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), out
+
+    for _ in range(max(args.warmup, 3)):
+        sh.step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches = [0]
+    phases = np.zeros(4)
+
+    def resident():
+        r = sh.step()
+        t = sh.g.timings()
+        launches[0] += t["launches"]
+        phases[:] += [t["transpose_ms"], t["scatter_ms"], t["group_fold_ms"], t["output_ms"]]
+        return r
+
+    ms, (Z, flops, rng) = timed(resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    tot = torch.tensor([Z, flops, launches[0]], dtype=torch.int64, device=dev)
+    dist.all_reduce(tot)
+    Zt, Ft, Lt = int(tot[0]), int(tot[1]), int(tot[2])
+
+    # e2e: host panel -> device, exchange, SpGEMM, results of this rank's columns back to the host
+    def e2e():
+        sh.upload()
+        return sh.step(fetch=True)[3]
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e()
+    e2e_ms, res = timed(e2e, e2e_steps)
+    d2h = torch.tensor([int(sum(a.nbytes for a in res))], dtype=torch.int64, device=dev)
+    h2d = torch.tensor([int(sh.max_bytes)], dtype=torch.int64, device=dev)
+    dist.all_reduce(d2h)
+    dist.all_reduce(h2d)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg = algorithmic_bytes(inp, Zt, Ft)
+        ph = phases / args.steps
+        line = {"metric": METRIC, "value": Zt / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u16/u32", "data": "synthetic",
+                "config": {"workload": workload, "n_kmers": inp.n_kmers, "nnz_A": inp.nnz, "products": Ft, "output_nnz": Zt,
+                           "parallelism": f"row-sharded x{world}, one all-gather of the B panel per step",
+                           "l2": "inputs larger than L2, no flush"},
+                "clocks": clocks,
+                "e2e": {"value": Zt / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(d2h[0]),
+                        "ms_per_step": e2e_ms},
+                "gpu_launches": Lt,
+                "roofline": {"bound": "hbm", "kernel": "whole step (rank 0 phases below)", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak * world,
+                             "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src,
+                             "rank0_phase_ms": {"transpose": float(ph[0]), "k_scatter": float(ph[1]), "k_group_fold": float(ph[2]),
+                                                "output": float(ph[3])}},
+                "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    sh.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

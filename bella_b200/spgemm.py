@@ -87,6 +87,21 @@ class OverlapSpGEMM:
         self.flops = 0
         self.colptrC = None
         self._keep = None
+        self._pinned = {}
+
+    def _host(self, name, dtype, count, pinned):
+        """Output buffer: a fresh numpy array, or (pinned=True) a reused page-locked one -- device->host
+        copies into pageable memory run at a fraction of the PCIe rate."""
+        count = max(int(count), 1)
+        if not pinned:
+            return np.zeros(count, dtype=dtype)
+        import torch
+        tdt = {np.uint32: torch.int32, np.uint16: torch.int16}[dtype]
+        t = self._pinned.get(name)
+        if t is None or t.numel() < count or t.dtype != tdt:
+            t = torch.empty(int(count * 1.25) + 16, dtype=tdt).pin_memory()
+            self._pinned[name] = t
+        return t.numpy()[:count].view(dtype)
 
     def _check(self, rc, what):
         if rc != 0:
@@ -138,25 +153,26 @@ class OverlapSpGEMM:
         self._check(self._L.bella_b200_set_column_range(self._h, lo, hi), "bella_b200_set_column_range")
         self.lo, self.hi = lo, hi
 
-    def symbolic(self):
-        """-> (flops, flopC[ncols], colptrC[ncols+1])"""
+    def symbolic(self, want_flopC=True, pinned=False):
+        """-> (flops, flopC[ncols] or None, colptrC[ncols+1])"""
         nc = self.hi - self.lo
         flops = ctypes.c_uint64(0)
-        flopC = np.zeros(nc, dtype=np.uint32)
-        colptrC = np.zeros(nc + 1, dtype=np.uint32)
+        flopC = self._host("flopC", np.uint32, nc, pinned)[:nc] if want_flopC else None
+        colptrC = self._host("colptrC", np.uint32, nc + 1, pinned)
         self._check(self._L.bella_b200_symbolic(self._h, ctypes.byref(flops), _ptr(flopC), _ptr(colptrC)), "bella_b200_symbolic")
         self.flops, self.colptrC = flops.value, colptrC
         return flops.value, flopC, colptrC
 
-    def numeric(self, col_begin=None, col_end=None, aux=False):
-        """-> (rowids, count, posH, posV[, aux(nnz,3)]) for global columns [col_begin, col_end)."""
+    def numeric(self, col_begin=None, col_end=None, aux=False, pinned=False):
+        """-> (rowids, count, posH, posV[, aux(nnz,3)]) for global columns [col_begin, col_end).
+        pinned=True returns views of page-locked buffers that the next call overwrites."""
         c0 = self.lo if col_begin is None else col_begin
         c1 = self.hi if col_end is None else col_end
         z = int(self.colptrC[c1 - self.lo]) - int(self.colptrC[c0 - self.lo])
-        rows = np.zeros(max(z, 1), dtype=np.uint32)
-        cnt = np.zeros(max(z, 1), dtype=np.uint16)
-        pH = np.zeros(max(z, 1), dtype=np.uint16)
-        pV = np.zeros(max(z, 1), dtype=np.uint16)
+        rows = self._host("rows", np.uint32, z, pinned)
+        cnt = self._host("cnt", np.uint16, z, pinned)
+        pH = self._host("pH", np.uint16, z, pinned)
+        pV = self._host("pV", np.uint16, z, pinned)
         self._check(self._L.bella_b200_numeric(self._h, c0, c1, _ptr(rows), _ptr(cnt), _ptr(pH), _ptr(pV)), "bella_b200_numeric")
         out = (rows[:z], cnt[:z], pH[:z], pV[:z])
         if aux:

@@ -60,7 +60,9 @@ const char* bella_b200_last_error(const bella_b200_handle* h);
 /* Inputs from HOST memory (copied to the device here).  Replaces the `A, B, reads, bpars` arguments
  * of HashSpGEMM (include/overlap.hpp:650-652): read_len[n] and the strand bits stand in for `reads`,
  * kmer_size/bin_size for BELLApars.{kmerSize,binSize}.  strand bits are bit-packed, LSB first, one
- * bit per nonzero in that matrix's array order.
+ * bit per nonzero in that matrix's array order.  strand_B may be NULL: then bit 31 of every
+ * B.rowids entry is that nonzero's strand bit and the k-mer id is the low 31 bits (the compressed
+ * panel format the multi-GPU all-gather exchanges; needs fewer than 2^31 k-mers).
  * A == B^T is what BELLA always passes (src/main.cpp:489), so the device derives A from B itself
  * (it needs each nonzero's position inside B's column, which A's arrays do not carry): A may be
  * NULL; when given, only its shape is checked against B and its arrays and strand_A are never

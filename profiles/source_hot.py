@@ -26,5 +26,5 @@ for r in rows:
         pass
 ti = sum(v[0] for v in agg.values()); ts = sum(v[1] for v in agg.values())
 print(f"total warp-instructions {ti}  samples {ts}")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][int(__import__("os").environ.get("BYINST","0")) ^ 1])[:top]:
     print(f"{k[0]:5d} inst {100*v[0]/max(ti,1):5.1f}%  samples {100*v[1]/max(ts,1):5.1f}%  {k[1]}")

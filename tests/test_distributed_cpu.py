@@ -1,0 +1,82 @@
+"""CPU, world_size 2 and 3, gloo: the host-side logic of the row-sharded multi-GPU path
+(bella_b200/distributed.py) -- panel packing, the all-gather, reconstruction of B, the balanced
+column ranges -- and that the union of the per-rank column ranges reproduces the whole result
+(each rank's range is evaluated with the CPU oracle here; on the box the same ranges go to the GPUs)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, tmpdir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from bella_b200 import distributed as bd, frontend as fe
+    import oracle_lib as ol
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    inp = fe.synthetic(900, 3000, seed=21)
+    cuts = bd.shard_bounds(inp.B_colptr, world)
+    r0, r1 = cuts[rank], cuts[rank + 1]
+    host = bd.pack_panel(inp, r0, r1)
+    shapes = bd.exchange_sizes(r1 - r0, int(inp.B_colptr[r1]) - int(inp.B_colptr[r0]), torch.device("cpu"))
+    assert sum(a for a, _ in shapes) == inp.n_reads and sum(b for _, b in shapes) == inp.nnz
+    max_bytes = max(bd.panel_layout(a, b)[1] for a, b in shapes)
+    panel = torch.zeros(max_bytes, dtype=torch.uint8)
+    panel[:host.size] = torch.from_numpy(host)
+    B = bd.unpack_panels(bd.all_gather_panels(panel, max_bytes), shapes)
+    # every rank reconstructs the whole B
+    strand = np.unpackbits(inp.B_strand, bitorder="little")[:inp.nnz].astype(np.uint32)
+    np.testing.assert_array_equal(B["colptr"].numpy().view(np.uint32), inp.B_colptr)
+    np.testing.assert_array_equal(B["rowids"].numpy().view(np.uint32), inp.B_rowids | (strand << 31))
+    np.testing.assert_array_equal(B["values"].numpy().view(np.uint16), inp.B_values)
+    np.testing.assert_array_equal(B["read_len"].numpy().view(np.uint32), inp.read_len)
+    bounds = bd.column_ranges(B["colptr64"], world)
+    assert bounds[0] == 0 and bounds[-1] == inp.n_reads and all(a <= b for a, b in zip(bounds[:-1], bounds[1:]))
+    # this rank's columns (oracle stands in for the GPU here), checked against the whole result on rank 0
+    want = ol.oracle_spgemm(inp)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    z0, z1 = int(want.colptrC[lo]), int(want.colptrC[hi])
+    mine = torch.tensor([z1 - z0, int(want.flopC[lo:hi].astype(np.int64).sum())], dtype=torch.int64)
+    allm = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allm, mine)
+    assert sum(int(t[0]) for t in allm) == want.nnz
+    # modelled per-rank time (transposition of every read at or above the range + this range's products) is even
+    flops = [int(t[1]) for t in allm]
+    scale = sum(flops) / max(1.0, float(sum(np.diff(inp.B_colptr.astype(np.int64)) * np.arange(inp.n_reads - 1, -1, -1)) / (inp.n_reads - 1)))
+    cost = [bd.RHO * scale * (inp.nnz - int(inp.B_colptr[bounds[r]])) + flops[r] for r in range(world)]
+    assert max(cost) <= 1.3 * (sum(cost) / world), f"unbalanced ranges: {cost}"
+    np.save(os.path.join(tmpdir, f"rows_{rank}.npy"), want.rowids[z0:z1])
+    dist.barrier()
+    if rank == 0:
+        rows = np.concatenate([np.load(os.path.join(tmpdir, f"rows_{r}.npy")) for r in range(world)])
+        np.testing.assert_array_equal(rows, want.rowids)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_exchange_and_ranges(world, tmp_path):
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+
+
+def test_column_ranges_degenerate():
+    from bella_b200 import distributed as bd
+    assert bd.column_ranges(torch.zeros(1, dtype=torch.int64), 4) == [0, 0, 0, 0, 0]
+    b = bd.column_ranges(torch.arange(0, 11, dtype=torch.int64) * 0, 2)      # all-empty reads
+    assert b[0] == 0 and b[-1] == 10
