@@ -91,3 +91,63 @@ def test_gpu_errors_are_reported(small_inputs):
     with pytest.raises(spgemm.BellaB200Error):
         g.set_column_range(5, small_inputs.n_reads + 1)
     g.close()
+
+
+def test_gpu_heavy_columns_row_range_units():
+    # low-error reads with a permissive multiplicity filter: thousands of products per column and hundreds per
+    # pair -> columns are split into row-range units, long pairs fold on warps / the whole CTA
+    from bella_b200 import frontend as fe
+    inp = fe.synthetic(700, 5000, coverage=40.0, err=0.01, seed=13, hi=80)
+    want = ol.oracle_spgemm(inp)
+    assert int(want.flopC.max()) > 3 * 8192
+    ol.assert_same(gpu_result(inp), want)
+
+
+def test_gpu_single_pair_larger_than_shared_memory():
+    # a pair sharing more than 8192 k-mers: the unit is one row and is folded from global memory
+    from bella_b200 import frontend as fe
+    inp = fe.synthetic(24, 14000, coverage=8.0, err=0.002, seed=17, hi=40)
+    want = ol.oracle_spgemm(inp)
+    per_pair = want.flopC.astype(np.int64).sum() / max(want.nnz, 1)
+    assert per_pair > 2000
+    ol.assert_same(gpu_result(inp), want)
+
+
+def test_gpu_positions_near_the_u16_limit(small_inputs):
+    # positions above 65535-k cannot use the packed 16-bit far test: the kernel must switch to the exact one.
+    # (Such positions are not valid k-mer starts; the oracle applies the same arithmetic to them.)
+    import copy
+    inp = copy.copy(small_inputs)
+    rng = np.random.default_rng(1)
+    Bv = inp.B_values.copy()
+    idx = rng.choice(inp.nnz, inp.nnz // 50, replace=False)
+    Bv[idx] = rng.integers(65400, 65536, idx.size).astype(np.uint16)
+    inp.B_values = Bv
+    # the device derives A from B, but the oracle reads A's values: keep A == B^T by matching (k-mer, read) keys
+    reads_of = np.repeat(np.arange(inp.n_reads, dtype=np.int64), np.diff(inp.B_colptr.astype(np.int64)))
+    kmers_of = np.repeat(np.arange(inp.n_kmers, dtype=np.int64), np.diff(inp.A_colptr.astype(np.int64)))
+    keyA = kmers_of * inp.n_reads + inp.A_rowids.astype(np.int64)
+    keyB = inp.B_rowids.astype(np.int64) * inp.n_reads + reads_of
+    Av = np.empty_like(Bv)
+    Av[np.argsort(keyA, kind="stable")] = Bv[np.argsort(keyB, kind="stable")]
+    inp.A_values = Av
+    ol.assert_same(gpu_result(inp), ol.oracle_spgemm(inp))
+
+
+def test_gpu_panel_format_strand_in_rowids(small_inputs):
+    # the multi-GPU exchange format: strand bit in bit 31 of B.rowids, strand_B = NULL, device-resident inputs
+    import torch
+    from bella_b200 import spgemm
+    inp = small_inputs
+    want = ol.oracle_spgemm(inp)
+    strand = np.unpackbits(inp.B_strand, bitorder="little")[:inp.nnz].astype(np.uint32)
+    dev = torch.device("cuda", 0)
+    t = lambda a, dt: torch.from_numpy(a.view(dt)).to(dev)
+    colptr, rows = t(inp.B_colptr, np.int32), t(inp.B_rowids | (strand << 31), np.int32)
+    vals, lens = t(inp.B_values, np.int16), t(inp.read_len, np.int32)
+    g = spgemm.OverlapSpGEMM(0)
+    g.set_inputs_device(inp.n_reads, inp.n_kmers, inp.nnz, (colptr, rows, vals), lens, None, inp.kmer_size, inp.bin_size)
+    flops, flopC, colptrC = g.symbolic()
+    r = g.numeric(aux=True)
+    g.close()
+    ol.assert_same(ol.Result(flopC, colptrC, *r), want)
