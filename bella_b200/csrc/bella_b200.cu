@@ -225,14 +225,14 @@ Params make_params(bella_b200_handle* h)
 	return P;
 }
 
-template <int CAP>
+template <int CAP, int NT>
 int launch_group(bella_b200_handle* h, const Params& P, const uint32_t* list, uint32_t count, uint32_t l1cap, int ctas_per_sm)
 {
 	if (!count) return 0;
 	const size_t smem = GF<CAP>::bytes(l1cap);
-	CK(cudaFuncSetAttribute(k_group_fold<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	CK(cudaFuncSetAttribute(k_group_fold<CAP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	uint32_t grid = count < 148u * ctas_per_sm ? count : 148u * ctas_per_sm;
-	k_group_fold<CAP><<<grid, GF_THREADS, smem, h->stream>>>(P, list, count, l1cap);
+	k_group_fold<CAP, NT><<<grid, NT, smem, h->stream>>>(P, list, count, l1cap);
 	LAUNCHED();
 	return 0;
 }
@@ -291,9 +291,9 @@ int run_symbolic(bella_b200_handle* h)
 	uint32_t span = h->n < (1u << MAX_SPAN_SHIFT) ? h->n : (1u << MAX_SPAN_SHIFT);
 	const uint32_t l1cap = (span + 1023 + 32) / 1024 + 1;
 	const uint32_t* lists = h->lists.as<uint32_t>();
-	if (int rc = launch_group<2048>(h, P, lists, cc[0], l1cap, 4)) return rc;
-	if (int rc = launch_group<4096>(h, P, lists + (size_t)ucap, cc[1], l1cap, 2)) return rc;
-	if (int rc = launch_group<8192>(h, P, lists + (size_t)2 * ucap, cc[2], l1cap, 1)) return rc;
+	if (int rc = launch_group<2048, 256>(h, P, lists, cc[0], l1cap, 4)) return rc;
+	if (int rc = launch_group<4096, 512>(h, P, lists + (size_t)ucap, cc[1], l1cap, 2)) return rc;
+	if (int rc = launch_group<8192, 1024>(h, P, lists + (size_t)2 * ucap, cc[2], l1cap, 1)) return rc;
 	if (cc[3]) {
 		k_huge_pair<<<cc[3] < 148u ? cc[3] : 148u, 1024, 0, h->stream>>>(P, lists + (size_t)3 * ucap, cc[3]);
 		LAUNCHED();

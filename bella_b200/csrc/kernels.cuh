@@ -481,20 +481,14 @@ __device__ __forceinline__ uint4 pack_result(uint32_t row, const PairResult& r)
 
 // one thread, P <= SHORT_FOLD, products in fold order (hv = h | v<<16, ov = overlap estimate)
 template <bool EXACT>
-__device__ __forceinline__ PairResult fold_short(const uint32_t* hvp, const uint16_t* ovp, uint32_t np, uint32_t K, int BIN)
+__device__ __forceinline__ PairResult fold_short(const uint32_t (&hv)[SHORT_FOLD], const uint16_t (&ov)[SHORT_FOLD], uint32_t np, uint32_t K, int BIN)
 {
 	constexpr int CAP = SHORT_FOLD;
 	const uint32_t lim = far_limit<EXACT>(K);
-	uint32_t hv[CAP];
-	uint16_t ov[CAP];
 	bool linear = true;
 #pragma unroll
-	for (int a = 0; a < CAP; ++a) {
-		if (a < (int)np) {
-			hv[a] = hvp[a]; ov[a] = ovp[a];
-			if (a) linear &= abs((int)ov[a] - (int)ov[a - 1]) < BIN;
-		} else { hv[a] = 0; ov[a] = 0; }
-	}
+	for (int a = 1; a < CAP; ++a)
+		if (a < (int)np) linear &= abs((int)ov[a] - (int)ov[a - 1]) < BIN;
 	PairResult R;
 	uint32_t csum = 0;
 	if (np == 1) { R.count = 1; R.hv = hv[0]; R.nbins = 1; R.sup = 1; R.ov = ov[0]; return R; }
@@ -632,50 +626,6 @@ __device__ PairResult fold_cta(const uint32_t* hv, const uint16_t* ov, uint16_t*
 constexpr uint32_t WSCR_WORDS = 192;       // per-warp scratch: position bitmap [128] + its prefix u16[128]
 constexpr uint32_t JR_BITMAP_MAX = 4096;   // columns of B up to this length rank through the bitmap
 
-// One warp orders the products of a pair (rec, arrival order) by their position in B's column into
-// hv/ov.  The positions of one pair are distinct, so a bitmap over them ranks in O(len + L/32).
-__device__ __forceinline__ void warp_rank_pair(const uint64_t* rec, uint32_t* hv, uint16_t* ov, uint32_t len, uint32_t L, uint32_t* scr,
-		uint32_t lane)
-{
-	if (L <= JR_BITMAP_MAX) {
-		const uint32_t Lw = (L + 31) >> 5;
-		uint16_t* jpre = (uint16_t*)(scr + 128);
-		for (uint32_t w = lane; w < Lw; w += 32) scr[w] = 0;
-		__syncwarp();
-		for (uint32_t y = lane; y < len; y += 32) {
-			const uint32_t jr = (uint32_t)(rec[y] >> 48);
-			atomicOr(&scr[jr >> 5], 1u << (jr & 31));
-		}
-		__syncwarp();
-		uint32_t carry = 0;
-		for (uint32_t w0 = 0; w0 < Lw; w0 += 32) {
-			const uint32_t w = w0 + lane;
-			const uint32_t c = w < Lw ? __popc(scr[w]) : 0;
-			uint32_t v = c;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, v, o); if (lane >= (uint32_t)o) v += y; }
-			if (w < Lw) jpre[w] = (uint16_t)(carry + v - c);
-			carry += __shfl_sync(FULL, v, 31);
-		}
-		__syncwarp();
-		for (uint32_t y = lane; y < len; y += 32) {
-			const uint64_t r = rec[y];
-			const uint32_t jr = (uint32_t)(r >> 48);
-			const uint32_t rank = jpre[jr >> 5] + __popc(scr[jr >> 5] & ((1u << (jr & 31)) - 1u));
-			hv[rank] = (uint32_t)r; ov[rank] = (uint16_t)(r >> 32);
-		}
-	} else {
-		for (uint32_t y = lane; y < len; y += 32) {
-			const uint64_t r = rec[y];
-			const uint32_t jr = (uint32_t)(r >> 48);
-			uint32_t rank = 0;
-			for (uint32_t z = 0; z < len; ++z) rank += ((uint32_t)(rec[z] >> 48) < jr);
-			hv[rank] = (uint32_t)r; ov[rank] = (uint16_t)(r >> 32);
-		}
-	}
-	__syncwarp();
-}
-
 // One warp folds a pair of P > SHORT_FOLD products (hv/ov in fold order; hv + P0 is the pair's slice of a
 // 16-byte aligned array, see fold_linear_rounds).  `own` is the pair's own 8*P-byte scratch.
 template <bool EXACT>
@@ -703,19 +653,123 @@ __device__ __forceinline__ PairResult warp_fold_pair(const uint32_t* hv, const u
 
 // ================================ group + fold ==============================================
 
+// exclusive scan by contiguous per-thread chunks: out[i] = sum_{j<i} val(j), out[n] = total (returned).
+// Three barriers whatever n is; `out` may alias the array val() reads (each element is read before
+// it is written, by the same thread).  s_tmp needs 33 words.
+template <class T, class F>
+__device__ __forceinline__ uint32_t block_scan_chunked(T* out, uint32_t n, F val, uint32_t* s_tmp)
+{
+	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+	const uint32_t per = ((n + blockDim.x - 1) / blockDim.x) | 1u;     // odd stride: no bank conflicts
+	const uint32_t i0 = min(tid * per, n), i1 = min(i0 + per, n);
+	uint32_t sum = 0;
+	for (uint32_t i = i0; i < i1; ++i) sum += val(i);
+	uint32_t incl = sum;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+	if (lane == 31) s_tmp[wid] = incl;
+	__syncthreads();
+	if (wid == 0) {
+		uint32_t w = lane < nw ? s_tmp[lane] : 0, ws = w;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, ws, o); if (lane >= (uint32_t)o) ws += y; }
+		s_tmp[lane] = ws - w;
+		if (lane == 31) s_tmp[32] = ws;
+	}
+	__syncthreads();
+	uint32_t run = s_tmp[wid] + incl - sum;
+	for (uint32_t i = i0; i < i1; ++i) { const uint32_t v = val(i); out[i] = (T)run; run += v; }
+	const uint32_t total = s_tmp[32];
+	if (tid == 0) out[n] = (T)total;
+	__syncthreads();
+	return total;
+}
+
+// sorting network for 8 keys (19 compare-exchanges)
+__device__ __forceinline__ void cex(uint64_t& a, uint64_t& b) { const uint64_t lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
+__device__ __forceinline__ void sort8(uint64_t (&k)[8])
+{
+	cex(k[0], k[1]); cex(k[2], k[3]); cex(k[4], k[5]); cex(k[6], k[7]);
+	cex(k[0], k[2]); cex(k[1], k[3]); cex(k[4], k[6]); cex(k[5], k[7]);
+	cex(k[1], k[2]); cex(k[5], k[6]); cex(k[0], k[4]); cex(k[3], k[7]);
+	cex(k[1], k[5]); cex(k[2], k[6]);
+	cex(k[1], k[4]); cex(k[3], k[6]);
+	cex(k[2], k[4]); cex(k[3], k[5]);
+	cex(k[3], k[4]);
+}
+
 template <int CAP>
 struct GF {
-	static constexpr size_t PROD = 0;                                  // u64[CAP]  raw -> packed -> fin
-	static constexpr size_t REC = PROD + 8 * (size_t)CAP;              // u64[CAP]  bits u32[CAP] + pre2 u16[CAP+2] | recA | par u16[CAP] + sup u32[CAP]
-	static constexpr size_t PID = REC + 8 * (size_t)CAP + 16;          // u16[CAP]  pair of the arrival slot | long-pair list
-	static constexpr size_t CNT = PID + 2 * (size_t)CAP;               // u16[CAP+2] per pair count -> poff
+	static constexpr size_t PROD = 0;                                  // u64[CAP]  raw -> packed (h, jr, pair, slot); later hv u32[CAP] + ov u16[CAP] of the long pairs
+	static constexpr size_t REC = PROD + 8 * (size_t)CAP;              // u64[CAP]  bits u32[CAP] + pre u16[CAP+2], then the products sorted by pair
+	static constexpr size_t CNT = REC + 8 * (size_t)CAP + 16;          // u16[CAP+2] per pair count -> offsets
 	static constexpr size_t ROW = CNT + 2 * (size_t)CAP + 16;          // u32[CAP]  row id of the pair
-	static constexpr size_t L1 = ROW + 4 * (size_t)CAP;                // u32[l1cap+1] bitmap words + u32[l1cap+2] prefix
+	static constexpr size_t LST = ROW + 4 * (size_t)CAP;               // u16[CAP/8] pairs longer than SHORT_FOLD
+	static constexpr size_t L1 = LST + 2 * ((size_t)CAP / 8);          // u32[l1cap+1] level-1 bitmap + u32[l1cap+2] prefix (two-level units only)
 	static size_t bytes(uint32_t l1cap) { return L1 + 8 * ((size_t)l1cap + 2); }
 };
 
-template <int CAP>
-__global__ void __launch_bounds__(GF_THREADS) k_group_fold(Params P, const uint32_t* __restrict__ list, uint32_t count, uint32_t l1cap)
+// multiply of one product (overlapop) -> key ordered by the position in B's column:
+// jrank(16)<<48 | overlap(16)<<32 | v(16)<<16 | h(16)
+__device__ __forceinline__ uint64_t product_key(const Params& P, uint64_t rec, uint32_t j0, int lenH, int lenV, bool& wide)
+{
+	const uint32_t h = (uint32_t)rec & 0xFFFFu, jr = ((uint32_t)rec >> 16), sH = (uint32_t)(rec >> 32) & 1u;
+	const uint32_t jg = j0 + jr;
+	const uint32_t v = P.B_values[jg], sV = strand_of(P.B_strand, P.B_rowids, jg);
+	const uint32_t ov = overlap_estimate(lenH, lenV, h, v, sH == sV, P.K);
+	wide |= max(h, v) > 65535u - P.K;                              // positions this large need the 32-bit far test
+	return ((uint64_t)jr << 48) | ((uint64_t)ov << 32) | (uint64_t)(h | (v << 16));
+}
+
+// One warp: multiply the products of a long pair (rec, arrival order) and store them in fold order
+// (position in B's column) as hv/ov.  The positions of one pair are distinct, so a bitmap over
+// them ranks in O(len + L/32).  Returns (warp-uniform) whether a position needs the exact far test.
+__device__ __forceinline__ bool warp_prepare_pair(const Params& P, const uint64_t* rec, uint32_t* hv, uint16_t* ov, uint32_t len, uint32_t j0,
+		uint32_t L, int lenH, int lenV, uint32_t* scr, uint32_t lane)
+{
+	bool wide = false;
+	if (L <= JR_BITMAP_MAX) {
+		const uint32_t Lw = (L + 31) >> 5;
+		uint16_t* jpre = (uint16_t*)(scr + 128);
+		for (uint32_t w = lane; w < Lw; w += 32) scr[w] = 0;
+		__syncwarp();
+		for (uint32_t y = lane; y < len; y += 32) {
+			const uint32_t jr = ((uint32_t)rec[y] >> 16);
+			atomicOr(&scr[jr >> 5], 1u << (jr & 31));
+		}
+		__syncwarp();
+		uint32_t carry = 0;
+		for (uint32_t w0 = 0; w0 < Lw; w0 += 32) {
+			const uint32_t w = w0 + lane;
+			const uint32_t c = w < Lw ? __popc(scr[w]) : 0;
+			uint32_t v = c;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, v, o); if (lane >= (uint32_t)o) v += y; }
+			if (w < Lw) jpre[w] = (uint16_t)(carry + v - c);
+			carry += __shfl_sync(FULL, v, 31);
+		}
+		__syncwarp();
+		for (uint32_t y = lane; y < len; y += 32) {
+			const uint64_t k = product_key(P, rec[y], j0, lenH, lenV, wide);
+			const uint32_t jr = (uint32_t)(k >> 48);
+			const uint32_t rank = jpre[jr >> 5] + __popc(scr[jr >> 5] & ((1u << (jr & 31)) - 1u));
+			hv[rank] = (uint32_t)k; ov[rank] = (uint16_t)(k >> 32);
+		}
+	} else {
+		for (uint32_t y = lane; y < len; y += 32) {
+			const uint64_t k = product_key(P, rec[y], j0, lenH, lenV, wide);
+			const uint32_t jr = (uint32_t)(k >> 48);
+			uint32_t rank = 0;
+			for (uint32_t z = 0; z < len; ++z) rank += (((uint32_t)rec[z] >> 16) < jr);
+			hv[rank] = (uint32_t)k; ov[rank] = (uint16_t)(k >> 32);
+		}
+	}
+	__syncwarp();
+	return __any_sync(FULL, wide);
+}
+
+template <int CAP, int NT>
+__global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __restrict__ list, uint32_t count, uint32_t l1cap)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) uint64_t s_bar;
@@ -723,18 +777,19 @@ __global__ void __launch_bounds__(GF_THREADS) k_group_fold(Params P, const uint3
 	__shared__ uint32_t s_nlong, s_nhuge, s_next, s_wide;
 	__shared__ uint32_t s_part[3];
 	__shared__ uint16_t hugelist[8];
-	__shared__ uint32_t wscr[(GF_THREADS / 32) * WSCR_WORDS];
+	__shared__ uint32_t wscr[(NT / 32) * WSCR_WORDS];
 	uint64_t* prodS = (uint64_t*)(smem + GF<CAP>::PROD);
-	uint64_t* recA = (uint64_t*)(smem + GF<CAP>::REC);
+	uint32_t* hvL = (uint32_t*)(smem + GF<CAP>::PROD);
+	uint16_t* ovL = (uint16_t*)(smem + GF<CAP>::PROD + 4 * (size_t)CAP);
+	uint64_t* sorted = (uint64_t*)(smem + GF<CAP>::REC);
 	uint32_t* bits = (uint32_t*)(smem + GF<CAP>::REC);
-	uint16_t* pre2 = (uint16_t*)(smem + GF<CAP>::REC + 4 * (size_t)CAP);
-	uint16_t* pid = (uint16_t*)(smem + GF<CAP>::PID);
+	uint16_t* pre = (uint16_t*)(smem + GF<CAP>::REC + 4 * (size_t)CAP);
 	uint16_t* cnt = (uint16_t*)(smem + GF<CAP>::CNT);
 	uint32_t* rowS = (uint32_t*)(smem + GF<CAP>::ROW);
+	uint16_t* longlist = (uint16_t*)(smem + GF<CAP>::LST);
 	uint32_t* l1 = (uint32_t*)(smem + GF<CAP>::L1);
 	uint32_t* l1pre = l1 + l1cap + 1;
 	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	constexpr uint32_t NT = GF_THREADS, NW = GF_THREADS / 32;
 	const uint32_t K = P.K;
 	const int BIN = (int)P.BIN;
 
@@ -756,93 +811,85 @@ __global__ void __launch_bounds__(GF_THREADS) k_group_fold(Params P, const uint3
 			r1 = min(r1, (bk + 1) << ci.sh);
 		}
 		const uint32_t rbase = r0 & ~31u;
-		const uint32_t l1w = ((r1 - rbase + 1023) >> 10);       // level-1 words (each covers 1024 rows)
-		if (Fi > (uint32_t)CAP || l1w > l1cap) { if (tid == 0) { set_err(P.err, -5); P.unnz[u] = 0; } continue; }
+		const uint32_t words = (r1 - rbase + 31) >> 5;              // 32-row words the unit spans
+		const bool two = words > (uint32_t)CAP;                     // too many for a direct bitmap: index the occupied words
+		const uint32_t l1w = (words + 31) >> 5;
+		if (Fi > (uint32_t)CAP || (two && l1w > l1cap)) { if (tid == 0) { set_err(P.err, -5); P.unnz[u] = 0; } continue; }
 
 		// --- stage the unit's products: one bulk async copy, overlapped with clearing the tables ---
 		if (tid == 0) {
 			fence_proxy_async();
 			bulk_load(prodS, P.raw + base, ((Fi + 1) & ~1u) * 8u, &s_bar);
 		}
-		for (uint32_t s = tid; s <= l1w; s += NT) l1[s] = 0;
+		if (two) { for (uint32_t s = tid; s <= l1w; s += NT) l1[s] = 0; }
+		const uint32_t nclear = two ? min(Fi, (uint32_t)CAP) : words;
+		for (uint32_t s = tid; s < nclear; s += NT) bits[s] = 0;
 		for (uint32_t s = tid; s < ((Fi + 3) >> 1); s += NT) ((uint32_t*)cnt)[s] = 0;
-		if (tid == 0) { s_nlong = 0; s_nhuge = 0; s_next = 0; s_wide = (K > 16383u); }
+		if (tid == 0) { s_nlong = 0; s_nhuge = 0; s_next = 0; s_wide = 0; }
 		mbar_wait(&s_bar, phase);
 		phase ^= 1;
 		__syncthreads();                                           // tables cleared by all threads before anyone sets a bit
 
-		// level 1: which 32-row words are occupied
+		// --- distinct rows (== estimateNNZ_Hash) and the pair index, rows ascending ---
+		uint32_t nwords = words;
+		if (two) {
+			for (uint32_t x = tid; x < Fi; x += NT) {
+				const uint32_t rel = ent_row(prodS[x]) - rbase;
+				atomicOr(&l1[rel >> 10], 1u << ((rel >> 5) & 31));
+			}
+			__syncthreads();
+			nwords = block_scan_chunked<uint32_t>(l1pre, l1w, [&](uint32_t w) { return (uint32_t)__popc(l1[w]); }, s_tmp);
+		}
+		auto word_of = [&](uint32_t rel) {
+			const uint32_t w = rel >> 5;
+			return two ? l1pre[w >> 5] + __popc(l1[w >> 5] & ((1u << (w & 31)) - 1u)) : w;
+		};
 		for (uint32_t x = tid; x < Fi; x += NT) {
 			const uint32_t rel = ent_row(prodS[x]) - rbase;
-			atomicOr(&l1[rel >> 10], 1u << ((rel >> 5) & 31));
+			atomicOr(&bits[word_of(rel)], 1u << (rel & 31));
 		}
 		__syncthreads();
-		block_popc_scan<uint32_t>(l1, l1pre, l1w, s_tmp);
-		const uint32_t Q = l1pre[l1w];
-		for (uint32_t s = tid; s < Q; s += NT) bits[s] = 0;
-		__syncthreads();
-		// level 2: the occupied words themselves
-		for (uint32_t x = tid; x < Fi; x += NT) {
-			const uint32_t rel = ent_row(prodS[x]) - rbase, w = rel >> 5;
-			const uint32_t q = l1pre[w >> 5] + __popc(l1[w >> 5] & ((1u << (w & 31)) - 1u));
-			atomicOr(&bits[q], 1u << (rel & 31));
-		}
-		__syncthreads();
-		block_popc_scan<uint16_t>(bits, pre2, Q, s_tmp);
-		const uint32_t Z = pre2[Q];                                // distinct rows == nnz of this unit
-		// pair index (rows ascending), arrival slot inside the pair
+		const uint32_t Z = block_scan_chunked<uint16_t>(pre, nwords, [&](uint32_t w) { return (uint32_t)__popc(bits[w]); }, s_tmp);
 		for (uint32_t x = tid; x < Fi; x += NT) {
 			const uint64_t r = prodS[x];
-			const uint32_t row = ent_row(r), rel = row - rbase, w = rel >> 5;
-			const uint32_t q = l1pre[w >> 5] + __popc(l1[w >> 5] & ((1u << (w & 31)) - 1u));
-			const uint32_t p = pre2[q] + __popc(bits[q] & ((1u << (rel & 31)) - 1u));
+			const uint32_t row = ent_row(r), rel = row - rbase, q = word_of(rel);
+			const uint32_t p = pre[q] + __popc(bits[q] & ((1u << (rel & 31)) - 1u));
 			const uint32_t a = atomic_add16(cnt, p, 1u);
 			rowS[p] = row;
-			prodS[x] = ((r >> 32) & 0xFFFFFFFFull) | ((uint64_t)p << 32) | ((uint64_t)a << 46) | ((uint64_t)((uint32_t)r >> 31) << 60);
+			// h(16) | jrank(16)<<16 | strandH<<32 | pair(14)<<34 | slot(14)<<48
+			prodS[x] = ((r >> 32) & 0xFFFFFFFFull) | ((uint64_t)((uint32_t)r >> 31) << 32) | ((uint64_t)p << 34) | ((uint64_t)a << 48);
 		}
 		__syncthreads();
-		block_excl_scan<uint16_t>(cnt, Z, s_tmp);                   // cnt -> poff, poff[Z] = Fi
+		block_scan_chunked<uint16_t>(cnt, Z, [&](uint32_t p) { return (uint32_t)cnt[p]; }, s_tmp);     // counts -> offsets, poff[Z] = Fi
 		const uint16_t* poff = cnt;
-		// multiply (overlap estimate) and placement in arrival order
-		const uint32_t j0 = P.B_colptr[i];
-		const int lenV = (int)P.read_len[i];
 		for (uint32_t x = tid; x < Fi; x += NT) {
 			const uint64_t t = prodS[x];
-			const uint32_t h = (uint32_t)t & 0xFFFFu, jr = ((uint32_t)t >> 16), p = (uint32_t)(t >> 32) & 0x3FFFu;
-			const uint32_t a = (uint32_t)(t >> 46) & 0x3FFFu, sH = (uint32_t)(t >> 60) & 1u;
-			const uint32_t jg = j0 + jr;
-			const uint32_t v = P.B_values[jg], sV = strand_of(P.B_strand, P.B_rowids, jg);
-			const uint32_t ov = overlap_estimate((int)P.read_len[rowS[p]], lenV, h, v, sH == sV, K);
-			const uint32_t y0 = poff[p] + a;
-			if (max(h, v) > 65535u - K) s_wide = 1;                   // positions this large need the 32-bit far test
-			recA[y0] = (uint64_t)(h | (v << 16)) | ((uint64_t)ov << 32) | ((uint64_t)jr << 48);
-			pid[y0] = (uint16_t)p;
+			sorted[poff[(uint32_t)(t >> 34) & 0x3FFFu] + ((uint32_t)(t >> 48) & 0x3FFFu)] = t & 0x1FFFFFFFFull;
 		}
 		__syncthreads();
-		// fold order inside the pair = position in B's column.  Short pairs: one thread per product.
-		uint32_t* hvF = (uint32_t*)prodS;
-		uint16_t* ovF = (uint16_t*)(smem + GF<CAP>::PROD + 4 * (size_t)CAP);
-		for (uint32_t y = tid; y < Fi; y += NT) {
-			const uint32_t p = pid[y], s0 = poff[p], len = poff[p + 1] - s0;
-			if (len > SHORT_FOLD) continue;
-			const uint64_t r = recA[y];
-			const uint32_t jr = (uint32_t)(r >> 48);
-			uint32_t rank = 0;
-			for (uint32_t z = s0; z < s0 + len; ++z) rank += ((uint32_t)(recA[z] >> 48) < jr);
-			hvF[s0 + rank] = (uint32_t)r; ovF[s0 + rank] = (uint16_t)(r >> 32);
-		}
-		__syncthreads();
-		// --- fold: short pairs by one thread each, the others are queued for the warps ---
-		const bool wide = s_wide != 0;
-		uint16_t* longlist = pid;
+
+		// --- short pairs: one thread multiplies, orders (position in B's column) and folds its pair in registers ---
+		const uint32_t j0 = P.B_colptr[i];
+		const int lenV = (int)P.read_len[i];
 		uint4* out = P.out + base;
 		for (uint32_t p = tid; p < Z; p += NT) {
 			const uint32_t s0 = poff[p], len = poff[p + 1] - s0;
-			if (len <= SHORT_FOLD)
-				out[p] = pack_result(rowS[p], wide ? fold_short<true>(hvF + s0, ovF + s0, len, K, BIN) : fold_short<false>(hvF + s0, ovF + s0, len, K, BIN));
-			else longlist[atomicAdd(&s_nlong, 1u)] = (uint16_t)p;
+			if (len > SHORT_FOLD) { longlist[atomicAdd(&s_nlong, 1u)] = (uint16_t)p; continue; }
+			const uint32_t row = rowS[p];
+			const int lenH = (int)P.read_len[row];
+			uint64_t key[SHORT_FOLD];
+			bool wide = K > 16383u;
+#pragma unroll
+			for (int q = 0; q < (int)SHORT_FOLD; ++q) key[q] = q < (int)len ? product_key(P, sorted[s0 + q], j0, lenH, lenV, wide) : ~0ull;
+			if (len > 1) sort8(key);
+			uint32_t hv[SHORT_FOLD];
+			uint16_t ov[SHORT_FOLD];
+#pragma unroll
+			for (int q = 0; q < (int)SHORT_FOLD; ++q) { hv[q] = (uint32_t)key[q]; ov[q] = (uint16_t)(key[q] >> 32); }
+			out[p] = pack_result(row, wide ? fold_short<true>(hv, ov, len, K, BIN) : fold_short<false>(hv, ov, len, K, BIN));
 		}
 		__syncthreads();
+		// --- long pairs: one warp each, taken from a queue ---
 		const uint32_t nlong = s_nlong;
 		const uint32_t Lcol = P.B_colptr[i + 1] - j0;
 		uint32_t* scr = wscr + wid * WSCR_WORDS;
@@ -853,28 +900,32 @@ __global__ void __launch_bounds__(GF_THREADS) k_group_fold(Params P, const uint3
 			if (q >= nlong) break;
 			const uint32_t p = longlist[q], s0 = poff[p], len = poff[p + 1] - s0;
 			if (len > 1024) { if (lane == 0) hugelist[atomicAdd(&s_nhuge, 1u)] = (uint16_t)p; continue; }
-			warp_rank_pair(recA + s0, hvF + s0, ovF + s0, len, Lcol, scr, lane);
-			PairResult R = wide ? warp_fold_pair<true>(hvF + s0, ovF + s0, recA + s0, len, K, BIN, lane)
-			                    : warp_fold_pair<false>(hvF + s0, ovF + s0, recA + s0, len, K, BIN, lane);
-			if (lane == 0) out[p] = pack_result(rowS[p], R);
+			const uint32_t row = rowS[p];
+			const bool wide = warp_prepare_pair(P, sorted + s0, hvL + s0, ovL + s0, len, j0, Lcol, (int)P.read_len[row], lenV, scr, lane) || K > 16383u;
+			PairResult R = wide ? warp_fold_pair<true>(hvL + s0, ovL + s0, sorted + s0, len, K, BIN, lane)
+			                    : warp_fold_pair<false>(hvL + s0, ovL + s0, sorted + s0, len, K, BIN, lane);
+			if (lane == 0) out[p] = pack_result(row, R);
 		}
 		__syncthreads();
 		const uint32_t nhuge = s_nhuge;                             // at most CAP/1024 pairs: the whole CTA takes each
 		for (uint32_t q = 0; q < nhuge; ++q) {
 			const uint32_t p = hugelist[q], s0 = poff[p], len = poff[p + 1] - s0;
+			const uint32_t row = rowS[p];
+			const int lenH = (int)P.read_len[row];
 			for (uint32_t y = tid; y < len; y += NT) {
-				const uint64_t r = recA[s0 + y];
-				const uint32_t jr = (uint32_t)(r >> 48);
+				bool wide = false;
+				const uint64_t k = product_key(P, sorted[s0 + y], j0, lenH, lenV, wide);
+				const uint32_t jr = (uint32_t)(k >> 48);
 				uint32_t rank = 0;
-				for (uint32_t z = s0; z < s0 + len; ++z) rank += ((uint32_t)(recA[z] >> 48) < jr);
-				hvF[s0 + rank] = (uint32_t)r; ovF[s0 + rank] = (uint16_t)(r >> 32);
+				for (uint32_t z = s0; z < s0 + len; ++z) rank += (((uint32_t)sorted[z] >> 16) < jr);
+				hvL[s0 + rank] = (uint32_t)k; ovL[s0 + rank] = (uint16_t)(k >> 32);
 			}
 			if (tid < 3) s_part[tid] = 0;
 			__syncthreads();
-			uint16_t* par = (uint16_t*)(recA + s0);
-			uint32_t* sup = (uint32_t*)(recA + s0) + ((len + 1) >> 1);
-			PairResult R = fold_cta(hvF + s0, ovF + s0, par, sup, len, K, BIN, s_part);
-			if (tid == 0) out[p] = pack_result(rowS[p], R);
+			uint16_t* par = (uint16_t*)(sorted + s0);
+			uint32_t* sup = (uint32_t*)(sorted + s0) + ((len + 1) >> 1);
+			PairResult R = fold_cta(hvL + s0, ovL + s0, par, sup, len, K, BIN, s_part);
+			if (tid == 0) out[p] = pack_result(row, R);
 			__syncthreads();
 		}
 		if (tid == 0) P.unnz[u] = Z;
