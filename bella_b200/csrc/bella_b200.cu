@@ -66,7 +66,7 @@ struct bella_b200_handle {
 	DevBuf boff, bcur, part, Aent, Acolptr, flop32;
 	// plan
 	uint32_t ucap = 0, U = 0, round = 0;
-	DevBuf nunits, ubase, shv, refine, colinfo, ucol, ucount, uptr, ucur, lists, unnz, uoff;
+	DevBuf nunits, ubase, shv, refine, colinfo, ucol, ucount, uptr, ucur, lists, redo, unnz, uoff;
 	// products and results
 	DevBuf raw, out, colptrC, rowsC, countC, posH, posV, aux;
 	DevBuf meta, errflag, cubtmp;
@@ -226,14 +226,24 @@ Params make_params(bella_b200_handle* h)
 }
 
 template <int CAP, int NT>
-int launch_group(bella_b200_handle* h, const Params& P, const uint32_t* list, uint32_t count, uint32_t l1cap, int ctas_per_sm)
+int launch_group(bella_b200_handle* h, const Params& P, int cls, uint32_t count, uint32_t l1cap, int ctas_per_sm)
 {
-	if (!count) return 0;
+	// fast instance over the class list, then the exact instance over whatever the fast one handed back
+	const uint32_t ucap = h->ucap;
+	const uint32_t* list = h->lists.as<uint32_t>() + (size_t)cls * ucap;
+	uint32_t* redo = h->redo.as<uint32_t>() + (size_t)cls * (ucap + 1);
+	uint32_t* redo_count = redo + ucap;
+	const uint32_t* class_count = &h->meta.as<Meta>()->class_count[cls];
 	const size_t smem = GF<CAP>::bytes(l1cap);
-	CK(cudaFuncSetAttribute(k_group_fold<CAP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	uint32_t grid = count < 148u * ctas_per_sm ? count : 148u * ctas_per_sm;
-	k_group_fold<CAP, NT><<<grid, NT, smem, h->stream>>>(P, list, count, l1cap);
-	LAUNCHED();
+	CK(cudaFuncSetAttribute(k_group_fold<CAP, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	CK(cudaFuncSetAttribute(k_group_fold<CAP, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	if (count) {
+		uint32_t grid = count < 148u * ctas_per_sm ? count : 148u * ctas_per_sm;
+		k_group_fold<CAP, NT, false><<<grid, NT, smem, h->stream>>>(P, list, class_count, l1cap, redo, redo_count);
+		LAUNCHED();
+		k_group_fold<CAP, NT, true><<<148, NT, smem, h->stream>>>(P, redo, redo_count, l1cap, nullptr, nullptr);
+		LAUNCHED();
+	}
 	return 0;
 }
 
@@ -291,9 +301,12 @@ int run_symbolic(bella_b200_handle* h)
 	uint32_t span = h->n < (1u << MAX_SPAN_SHIFT) ? h->n : (1u << MAX_SPAN_SHIFT);
 	const uint32_t l1cap = (span + 1023 + 32) / 1024 + 1;
 	const uint32_t* lists = h->lists.as<uint32_t>();
-	if (int rc = launch_group<2048, 256>(h, P, lists, cc[0], l1cap, 4)) return rc;
-	if (int rc = launch_group<4096, 512>(h, P, lists + (size_t)ucap, cc[1], l1cap, 2)) return rc;
-	if (int rc = launch_group<8192, 1024>(h, P, lists + (size_t)2 * ucap, cc[2], l1cap, 1)) return rc;
+	ENSURE(h->redo, sizeof(uint32_t) * (size_t)NCLASS * ((size_t)ucap + 1));
+	for (int c = 0; c < NCLASS; ++c)
+		CK(cudaMemsetAsync(h->redo.as<uint32_t>() + (size_t)c * (ucap + 1) + ucap, 0, sizeof(uint32_t), h->stream));
+	if (int rc = launch_group<2048, 256>(h, P, 0, cc[0], l1cap, 4)) return rc;
+	if (int rc = launch_group<4096, 512>(h, P, 1, cc[1], l1cap, 2)) return rc;
+	if (int rc = launch_group<8192, 1024>(h, P, 2, cc[2], l1cap, 1)) return rc;
 	if (cc[3]) {
 		k_huge_pair<<<cc[3] < 148u ? cc[3] : 148u, 1024, 0, h->stream>>>(P, lists + (size_t)3 * ucap, cc[3]);
 		LAUNCHED();
@@ -399,7 +412,7 @@ int bella_b200_destroy(bella_b200_handle* h)
 	cudaStreamSynchronize(h->stream);
 	DevBuf* bufs[] = {&h->oB_colptr, &h->oB_rowids, &h->oB_values, &h->oB_strand, &h->o_len, &h->boff, &h->bcur, &h->part,
 		&h->Aent, &h->Acolptr, &h->flop32, &h->nunits, &h->ubase, &h->shv, &h->refine, &h->colinfo, &h->ucol, &h->ucount,
-		&h->uptr, &h->ucur, &h->lists, &h->unnz, &h->uoff, &h->raw, &h->out, &h->colptrC, &h->rowsC, &h->countC, &h->posH, &h->posV,
+		&h->uptr, &h->ucur, &h->lists, &h->redo, &h->unnz, &h->uoff, &h->raw, &h->out, &h->colptrC, &h->rowsC, &h->countC, &h->posH, &h->posV,
 		&h->aux, &h->meta, &h->errflag, &h->cubtmp};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& e : h->ev) if (e) cudaEventDestroy(e);

@@ -563,8 +563,10 @@ __device__ __forceinline__ void fold_forest(const uint32_t* hv, const uint16_t* 
 	}
 }
 
-// linear case, one warp's share: rounds r0 = first, first + step, ... of 32 products s; every later
-// product t is tested against the 32 lanes at once (t broadcast from memory, four per 16-byte load).
+// linear case, one warp's share: rounds r0 = first, first + step, ... of 32 products s (one per lane).
+// Every later product t is broadcast from memory and tested against the 32 lanes at once; per block
+// of 32 t's a lane collects the "near" bits and its first near t ends its walk:
+//     c_s = (first near t > s, or P) - s - 1,   s survives iff there is none.
 template <bool EXACT>
 __device__ __forceinline__ void fold_linear_rounds(const uint32_t* hv, uint32_t P, uint32_t K, uint32_t first, uint32_t step,
 		uint32_t& csum, uint32_t& surv)
@@ -572,25 +574,25 @@ __device__ __forceinline__ void fold_linear_rounds(const uint32_t* hv, uint32_t 
 	const uint32_t lane = threadIdx.x & 31, lim = far_limit<EXACT>(K);
 	for (uint32_t r0 = first; r0 < P; r0 += step) {
 		const uint32_t s = r0 + lane;
-		bool alive = s < P;
-		const FarKey key = far_key<EXACT>(alive ? hv[s] : 0u, K);
-		const uint32_t tend = min(r0 + 32, P);
-		for (uint32_t t = r0 + 1; t < tend; ++t) {
-			const bool f = is_far<EXACT>(hv[t], key, lim);
-			if (t > s) { alive = alive && f; csum += alive; }
+		const bool valid = s < P;
+		const FarKey key = far_key<EXACT>(valid ? hv[s] : 0u, K);
+		bool alive = valid;
+		uint32_t tfirst = P;
+		for (uint32_t tb = r0; tb < P; tb += 32) {
+			uint32_t near = 0;
+			if (tb + 32 <= P) {
+#pragma unroll
+				for (int c = 0; c < 32; ++c)
+					if (!is_far<EXACT>(hv[tb + c], key, lim)) near |= 1u << c;
+			} else {
+				for (uint32_t c = 0; tb + c < P; ++c)
+					if (!is_far<EXACT>(hv[tb + c], key, lim)) near |= 1u << c;
+			}
+			if (tb == r0) near &= ~((2u << lane) - 1u);              // only t > s
+			if (alive && near) { tfirst = tb + __ffs(near) - 1; alive = false; }
+			if (!__any_sync(FULL, alive)) break;
 		}
-		uint32_t t = tend;
-		if (!__any_sync(FULL, alive)) continue;
-		for (; t < P && ((uintptr_t)(hv + t) & 15u); ++t) { alive = alive && is_far<EXACT>(hv[t], key, lim); csum += alive; }
-		for (; t + 4 <= P; t += 4) {
-			const uint4 q = *reinterpret_cast<const uint4*>(hv + t);
-			alive = alive && is_far<EXACT>(q.x, key, lim); csum += alive;
-			alive = alive && is_far<EXACT>(q.y, key, lim); csum += alive;
-			alive = alive && is_far<EXACT>(q.z, key, lim); csum += alive;
-			alive = alive && is_far<EXACT>(q.w, key, lim); csum += alive;
-		}
-		for (; t < P; ++t) { alive = alive && is_far<EXACT>(hv[t], key, lim); csum += alive; }
-		surv += alive;
+		if (valid) { csum += tfirst - s - 1; surv += alive; }
 	}
 	for (int o = 16; o; o >>= 1) { csum += __shfl_xor_sync(FULL, csum, o); surv += __shfl_xor_sync(FULL, surv, o); }
 }
@@ -768,9 +770,13 @@ __device__ __forceinline__ bool warp_prepare_pair(const Params& P, const uint64_
 	return __any_sync(FULL, wide);
 }
 
-template <int CAP, int NT>
-__global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __restrict__ list, uint32_t count, uint32_t l1cap)
+// EXACT = false is the fast kernel (packed 16-bit far test); a unit in which a position is too large for
+// it is appended to `redo` and done again by the EXACT = true instance (launched with redo as its list).
+template <int CAP, int NT, bool EXACT>
+__global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __restrict__ list, const uint32_t* __restrict__ count_ptr,
+		uint32_t l1cap, uint32_t* __restrict__ redo, uint32_t* __restrict__ redo_count)
 {
+	const uint32_t count = *count_ptr;
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) uint64_t s_bar;
 	__shared__ uint32_t s_tmp[34];
@@ -868,44 +874,49 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 		}
 		__syncthreads();
 
-		// --- short pairs: one thread multiplies, orders (position in B's column) and folds its pair in registers ---
+		// --- fold.  Queue: first the pairs longer than SHORT_FOLD (one warp each), then tiles of 32 pairs whose
+		//     short members are multiplied, ordered (position in B's column) and folded by one thread each ---
 		const uint32_t j0 = P.B_colptr[i];
 		const int lenV = (int)P.read_len[i];
 		uint4* out = P.out + base;
-		for (uint32_t p = tid; p < Z; p += NT) {
-			const uint32_t s0 = poff[p], len = poff[p + 1] - s0;
-			if (len > SHORT_FOLD) { longlist[atomicAdd(&s_nlong, 1u)] = (uint16_t)p; continue; }
-			const uint32_t row = rowS[p];
-			const int lenH = (int)P.read_len[row];
-			uint64_t key[SHORT_FOLD];
-			bool wide = K > 16383u;
-#pragma unroll
-			for (int q = 0; q < (int)SHORT_FOLD; ++q) key[q] = q < (int)len ? product_key(P, sorted[s0 + q], j0, lenH, lenV, wide) : ~0ull;
-			if (len > 1) sort8(key);
-			uint32_t hv[SHORT_FOLD];
-			uint16_t ov[SHORT_FOLD];
-#pragma unroll
-			for (int q = 0; q < (int)SHORT_FOLD; ++q) { hv[q] = (uint32_t)key[q]; ov[q] = (uint16_t)(key[q] >> 32); }
-			out[p] = pack_result(row, wide ? fold_short<true>(hv, ov, len, K, BIN) : fold_short<false>(hv, ov, len, K, BIN));
-		}
+		for (uint32_t p = tid; p < Z; p += NT)
+			if ((uint32_t)(poff[p + 1] - poff[p]) > SHORT_FOLD) longlist[atomicAdd(&s_nlong, 1u)] = (uint16_t)p;
 		__syncthreads();
-		// --- long pairs: one warp each, taken from a queue ---
-		const uint32_t nlong = s_nlong;
+		const uint32_t nlong = s_nlong, nitems = nlong + ((Z + 31) >> 5);
 		const uint32_t Lcol = P.B_colptr[i + 1] - j0;
 		uint32_t* scr = wscr + wid * WSCR_WORDS;
+		bool wide = false;
 		for (;;) {
 			uint32_t q = 0;
 			if (lane == 0) q = atomicAdd(&s_next, 1u);
 			q = __shfl_sync(FULL, q, 0);
-			if (q >= nlong) break;
-			const uint32_t p = longlist[q], s0 = poff[p], len = poff[p + 1] - s0;
-			if (len > 1024) { if (lane == 0) hugelist[atomicAdd(&s_nhuge, 1u)] = (uint16_t)p; continue; }
-			const uint32_t row = rowS[p];
-			const bool wide = warp_prepare_pair(P, sorted + s0, hvL + s0, ovL + s0, len, j0, Lcol, (int)P.read_len[row], lenV, scr, lane) || K > 16383u;
-			PairResult R = wide ? warp_fold_pair<true>(hvL + s0, ovL + s0, sorted + s0, len, K, BIN, lane)
-			                    : warp_fold_pair<false>(hvL + s0, ovL + s0, sorted + s0, len, K, BIN, lane);
-			if (lane == 0) out[p] = pack_result(row, R);
+			if (q >= nitems) break;
+			if (q < nlong) {
+				const uint32_t p = longlist[q], s0 = poff[p], len = poff[p + 1] - s0;
+				if (len > 1024) { if (lane == 0) hugelist[atomicAdd(&s_nhuge, 1u)] = (uint16_t)p; continue; }
+				const uint32_t row = rowS[p];
+				wide |= warp_prepare_pair(P, sorted + s0, hvL + s0, ovL + s0, len, j0, Lcol, (int)P.read_len[row], lenV, scr, lane);
+				PairResult R = warp_fold_pair<EXACT>(hvL + s0, ovL + s0, sorted + s0, len, K, BIN, lane);
+				if (lane == 0) out[p] = pack_result(row, R);
+			} else {
+				const uint32_t p = ((q - nlong) << 5) + lane;
+				if (p >= Z) continue;
+				const uint32_t s0 = poff[p], len = poff[p + 1] - s0;
+				if (len > SHORT_FOLD) continue;
+				const uint32_t row = rowS[p];
+				const int lenH = (int)P.read_len[row];
+				uint64_t key[SHORT_FOLD];
+#pragma unroll
+				for (int k = 0; k < (int)SHORT_FOLD; ++k) key[k] = k < (int)len ? product_key(P, sorted[s0 + k], j0, lenH, lenV, wide) : ~0ull;
+				if (len > 1) sort8(key);
+				uint32_t hv[SHORT_FOLD];
+				uint16_t ov[SHORT_FOLD];
+#pragma unroll
+				for (int k = 0; k < (int)SHORT_FOLD; ++k) { hv[k] = (uint32_t)key[k]; ov[k] = (uint16_t)(key[k] >> 32); }
+				out[p] = pack_result(row, fold_short<EXACT>(hv, ov, len, K, BIN));
+			}
 		}
+		if (!EXACT && (wide || K > 16383u)) s_wide = 1;
 		__syncthreads();
 		const uint32_t nhuge = s_nhuge;                             // at most CAP/1024 pairs: the whole CTA takes each
 		for (uint32_t q = 0; q < nhuge; ++q) {
@@ -913,8 +924,9 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 			const uint32_t row = rowS[p];
 			const int lenH = (int)P.read_len[row];
 			for (uint32_t y = tid; y < len; y += NT) {
-				bool wide = false;
-				const uint64_t k = product_key(P, sorted[s0 + y], j0, lenH, lenV, wide);
+				bool w2 = false;
+				const uint64_t k = product_key(P, sorted[s0 + y], j0, lenH, lenV, w2);
+				if (!EXACT && w2) s_wide = 1;
 				const uint32_t jr = (uint32_t)(k >> 48);
 				uint32_t rank = 0;
 				for (uint32_t z = s0; z < s0 + len; ++z) rank += (((uint32_t)sorted[z] >> 16) < jr);
@@ -928,7 +940,10 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 			if (tid == 0) out[p] = pack_result(row, R);
 			__syncthreads();
 		}
-		if (tid == 0) P.unnz[u] = Z;
+		if (tid == 0) {
+			P.unnz[u] = Z;
+			if (!EXACT && s_wide) redo[atomicAdd(redo_count, 1u)] = u;
+		}
 		__syncthreads();
 	}
 }
