@@ -63,6 +63,12 @@ struct bella_b200_handle {
 	DevBuf oB_colptr, oB_rowids, oB_values, oB_strand, o_len;
 	// transpose
 	uint32_t W = 0, NB = 0;                    // k-mers per bucket, buckets
+	uint32_t klo = 0, khi = 0;                 // k-mer range this handle transposes ([0, m) unless multi-GPU)
+	// multi-GPU product exchange (borrowed device pointers, valid during bella_b200_mg_finish)
+	const uint64_t *mg_recv = nullptr, *mg_segoff = nullptr, *mg_recvbase = nullptr;
+	const uint32_t* mg_counts = nullptr;
+	int mg_world = 0;
+	DevBuf mg_colinfo, mg_ucur;
 	DevBuf boff, bcur, part, Aent, Acolptr, flop32;
 	// plan
 	uint32_t ucap = 0, U = 0, round = 0;
@@ -131,39 +137,39 @@ int report_device_error(bella_b200_handle* h, int e)
 	return fail(h, BELLA_B200_ERR_INTERNAL, "device-side error %d", e);
 }
 
-// transpose: B (read-major) -> Aent (k-mer-major, columns sorted by read id) + per-column product counts
-int run_transpose(bella_b200_handle* h)
+// transpose: B (read-major) -> Aent (k-mer-major, columns sorted by read id) for the k-mers [klo, khi)
+// and the reads >= row_lo, + the product counts of the output columns [cnt_lo, cnt_hi) into flop_out
+int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32_t cnt_hi, uint32_t* flop_out)
 {
-	const uint32_t n = h->n, m = h->m;
+	const uint32_t n = h->n, ml = h->khi - h->klo;
 	const uint64_t nnz = h->nnzB;
-	const uint32_t ncols = h->hi - h->lo;
-	ENSURE(h->flop32, sizeof(uint32_t) * ((size_t)ncols + 1));
-	ENSURE(h->Acolptr, sizeof(uint32_t) * ((size_t)m + 2));
+	const uint32_t ncols = cnt_hi - cnt_lo;
+	ENSURE(h->Acolptr, sizeof(uint32_t) * ((size_t)ml + 2));
 	ENSURE(h->Aent, sizeof(uint64_t) * (nnz + 2));
-	CK(cudaMemsetAsync(h->flop32.p, 0, sizeof(uint32_t) * ((size_t)ncols + 1), h->stream));
-	if (!nnz || !m || !ncols) {
-		CK(cudaMemsetAsync(h->Acolptr.p, 0, sizeof(uint32_t) * ((size_t)m + 2), h->stream));
+	CK(cudaMemsetAsync(flop_out, 0, sizeof(uint32_t) * (size_t)ncols, h->stream));
+	if (!nnz || !ml || !ncols) {
+		CK(cudaMemsetAsync(h->Acolptr.p, 0, sizeof(uint32_t) * ((size_t)ml + 2), h->stream));
 		return 0;
 	}
 	if (!h->W) {
-		double avg = (double)nnz / (double)m;
+		double avg = (double)nnz / (double)h->m;
 		double w = 0.6 * BUCKET_CAP / (avg > 0.25 ? avg : 0.25);
 		h->W = (uint32_t)(w < 1 ? 1 : w > BUCKET_WMAX ? BUCKET_WMAX : w);
 	}
 	const uint32_t W = h->W;
-	const uint32_t NB = (uint32_t)(((uint64_t)m + W - 1) / W);
+	const uint32_t NB = (uint32_t)(((uint64_t)ml + W - 1) / W);
 	h->NB = NB;
 	ENSURE(h->bcur, sizeof(uint32_t) * ((size_t)NB + 2));
 	ENSURE(h->boff, sizeof(uint32_t) * ((size_t)NB + 2));
 	ENSURE(h->part, sizeof(uint4) * (size_t)NB * BUCKET_CAP);
 	CK(cudaMemsetAsync(h->bcur.p, 0, sizeof(uint32_t) * ((size_t)NB + 2), h->stream));
-	k_partition<<<grid_for((uint64_t)(n - h->lo) * 32, 256), 256, 0, h->stream>>>(n, h->lo, h->dB_colptr, h->dB_rowids, h->dB_values,
-		h->dB_strand, W, h->bcur.as<uint32_t>(), h->part.as<uint4>(), h->errflag.as<int>());
+	k_partition<<<grid_for((uint64_t)(n - row_lo) * 32, 256), 256, 0, h->stream>>>(n, row_lo, h->klo, h->khi, h->dB_colptr, h->dB_rowids,
+		h->dB_values, h->dB_strand, W, h->bcur.as<uint32_t>(), h->part.as<uint4>(), h->errflag.as<int>());
 	LAUNCHED();
 	if (int rc = exclusive_scan(h, h->bcur.as<uint32_t>(), h->boff.as<uint32_t>(), NB + 1)) return rc;
 	CK(cudaFuncSetAttribute(k_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BUCKET_SMEM));
-	k_bucket<<<NB < 148u * 12 ? NB : 148u * 12, 256, BUCKET_SMEM, h->stream>>>(m, h->lo, h->hi, W, NB, h->boff.as<uint32_t>(),
-		h->part.as<uint4>(), h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), h->flop32.as<uint32_t>(), h->errflag.as<int>());
+	k_bucket<<<NB < 148u * 12 ? NB : 148u * 12, 256, BUCKET_SMEM, h->stream>>>(h->klo, ml, cnt_lo, cnt_hi, W, NB, h->boff.as<uint32_t>(),
+		h->part.as<uint4>(), h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), flop_out, h->errflag.as<int>());
 	LAUNCHED();
 	return 0;
 }
@@ -198,8 +204,14 @@ int run_plan(bella_b200_handle* h)
 	k_units_init<<<grid_for(ncols, 256), 256, 0, h->stream>>>(ncols, ucap, h->flop32.as<uint32_t>(), h->ubase.as<uint32_t>(), h->shv.as<uint8_t>(),
 		h->colinfo.as<ColInfo>(), h->ucol.as<uint32_t>(), h->ucount.as<uint32_t>(), h->meta.as<Meta>(), h->errflag.as<int>());
 	LAUNCHED();
-	k_count_units<<<grid_for(h->m, 256), 256, 0, h->stream>>>(h->m, h->lo, h->hi, h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(),
-		h->colinfo.as<ColInfo>(), h->ucount.as<uint32_t>(), h->meta.as<Meta>(), h->errflag.as<int>());
+	if (h->mg_recv) {
+		k_regroup<true><<<148 * 8, 256, 0, h->stream>>>(h->n, h->lo, ncols, (uint32_t)h->mg_world, h->mg_counts, h->mg_segoff, h->mg_recvbase,
+			h->mg_recv, h->colinfo.as<ColInfo>(), h->ucount.as<uint32_t>(), nullptr, nullptr, h->meta.as<Meta>(), h->errflag.as<int>());
+	} else {
+		const uint32_t ml = h->khi - h->klo;
+		k_count_units<<<grid_for(ml, 256), 256, 0, h->stream>>>(ml, h->lo, h->hi, h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(),
+			h->colinfo.as<ColInfo>(), h->ucount.as<uint32_t>(), h->meta.as<Meta>(), h->errflag.as<int>());
+	}
 	LAUNCHED();
 	{
 		auto padded = thrust::make_transform_iterator((const uint32_t*)h->ucount.as<uint32_t>(), PadEven());
@@ -247,26 +259,26 @@ int launch_group(bella_b200_handle* h, const Params& P, int cls, uint32_t count,
 	return 0;
 }
 
-// the whole symbolic phase; on return C's colptr and the per-unit results are on the device
-int run_symbolic(bella_b200_handle* h)
+// plan until it converges (bucket overflow -> narrower buckets and a new transpose; more units than the
+// arrays hold -> larger arrays; units that do not fit shared memory -> finer row ranges)
+int plan_loop(bella_b200_handle* h, bool own_transpose)
 {
 	const uint32_t ncols = h->hi - h->lo;
-	ENSURE(h->meta, sizeof(Meta));
-	ENSURE(h->errflag, sizeof(int));
 	ENSURE(h->refine, (size_t)ncols + 1);
 	ENSURE(h->colptrC, sizeof(uint32_t) * ((size_t)ncols + 1));
-	CK(cudaMemsetAsync(h->errflag.p, 0, sizeof(int), h->stream));
 	CK(cudaMemsetAsync(h->refine.p, 0, (size_t)ncols + 1, h->stream));
 	h->round = 0;
-	CK(cudaEventRecord(h->ev[0], h->stream));
-	bool need_transpose = true;
+	bool need_transpose = own_transpose;
 	for (int attempt = 0;; ++attempt) {
 		if (attempt > 40) return fail(h, BELLA_B200_ERR_INTERNAL, "planning did not converge");
-		if (need_transpose) { if (int rc = run_transpose(h)) return rc; CK(cudaEventRecord(h->ev[1], h->stream)); }
+		if (need_transpose) {
+			ENSURE(h->flop32, sizeof(uint32_t) * ((size_t)ncols + 1));
+			if (int rc = run_transpose(h, h->lo, h->lo, h->hi, h->flop32.as<uint32_t>())) return rc;
+		}
 		if (int rc = run_plan(h)) return rc;
 		int e = 0;
 		if (int rc = read_flags(h, &e)) return rc;
-		if (e == ERR_BUCKET) {
+		if (e == ERR_BUCKET && own_transpose) {
 			if (h->W <= 1) return fail(h, BELLA_B200_ERR_RANGE, "a k-mer occurs in more than %u reads", BUCKET_CAP);
 			h->W = h->W / 2;
 			need_transpose = true;
@@ -285,17 +297,18 @@ int run_symbolic(bella_b200_handle* h)
 	}
 	h->flops = h->hmeta.flops;
 	h->U = h->hmeta.n_units;
-	const uint64_t F = h->flops;
+	ENSURE(h->raw, sizeof(uint64_t) * (h->flops + h->U + 2));
+	ENSURE(h->out, sizeof(uint4) * (h->flops + h->U + 2));
+	return 0;
+}
+
+// group + fold over the unit regions, then C's colptr; ends with the one host synchronisation that returns nnz(C)
+int group_and_output(bella_b200_handle* h)
+{
+	const uint32_t ncols = h->hi - h->lo;
 	const uint32_t U = h->U, ucap = h->ucap;
 	const uint32_t* cc = h->hmeta.class_count;
-	ENSURE(h->raw, sizeof(uint64_t) * (F + U + 2));
-	ENSURE(h->out, sizeof(uint4) * (F + U + 2));
 	Params P = make_params(h);
-	CK(cudaEventRecord(h->ev[2], h->stream));
-	if (F) {
-		k_scatter<<<grid_for(h->m, 256), 256, 0, h->stream>>>(h->m, h->lo, h->hi, P.A_colptr, P.Aent, P.colinfo, P.ucur, P.raw);
-		LAUNCHED();
-	}
 	CK(cudaEventRecord(h->ev[3], h->stream));
 	// level-1 bitmap words a unit can need: light columns span at most n rows, heavy units at most 2^MAX_SPAN_SHIFT
 	uint32_t span = h->n < (1u << MAX_SPAN_SHIFT) ? h->n : (1u << MAX_SPAN_SHIFT);
@@ -323,12 +336,32 @@ int run_symbolic(bella_b200_handle* h)
 	CK(cudaStreamSynchronize(h->stream));
 	if (e) return report_device_error(h, e);
 	h->Z = z32;
-	CK(cudaEventElapsedTime(&h->t_ms[0], h->ev[0], h->ev[2]));    // transpose + plan
-	CK(cudaEventElapsedTime(&h->t_ms[7], h->ev[2], h->ev[3]));    // scatter
 	CK(cudaEventElapsedTime(&h->t_ms[1], h->ev[3], h->ev[4]));    // group + fold
 	CK(cudaEventElapsedTime(&h->t_ms[6], h->ev[4], h->ev[5]));    // scans + colptr
 	h->symbolic_done = true;
 	h->numeric_done = false;
+	return 0;
+}
+
+// the whole symbolic phase; on return C's colptr and the per-unit results are on the device
+int run_symbolic(bella_b200_handle* h)
+{
+	ENSURE(h->meta, sizeof(Meta));
+	ENSURE(h->errflag, sizeof(int));
+	CK(cudaMemsetAsync(h->errflag.p, 0, sizeof(int), h->stream));
+	h->klo = 0; h->khi = h->m;
+	h->mg_recv = nullptr;
+	CK(cudaEventRecord(h->ev[0], h->stream));
+	if (int rc = plan_loop(h, true)) return rc;
+	Params P = make_params(h);
+	CK(cudaEventRecord(h->ev[2], h->stream));
+	if (h->flops) {
+		k_scatter<<<grid_for(h->m, 256), 256, 0, h->stream>>>(h->m, h->lo, h->hi, P.A_colptr, P.Aent, P.colinfo, P.ucur, P.raw);
+		LAUNCHED();
+	}
+	if (int rc = group_and_output(h)) return rc;
+	CK(cudaEventElapsedTime(&h->t_ms[0], h->ev[0], h->ev[2]));    // transpose + plan
+	CK(cudaEventElapsedTime(&h->t_ms[7], h->ev[2], h->ev[3]));    // scatter
 	return 0;
 }
 
@@ -378,6 +411,8 @@ void reset_problem(bella_b200_handle* h, const bella_csc_view* B, uint16_t K, ui
 	h->n = B->cols; h->m = B->rows; h->nnzB = B->nnz;
 	h->lo = 0; h->hi = h->n; h->K = K; h->BIN = BIN;
 	h->W = 0;
+	h->klo = 0; h->khi = h->m;
+	h->mg_recv = nullptr;
 	h->have_inputs = true; h->symbolic_done = h->numeric_done = false;
 	h->flops = h->Z = 0;
 }
@@ -413,7 +448,7 @@ int bella_b200_destroy(bella_b200_handle* h)
 	DevBuf* bufs[] = {&h->oB_colptr, &h->oB_rowids, &h->oB_values, &h->oB_strand, &h->o_len, &h->boff, &h->bcur, &h->part,
 		&h->Aent, &h->Acolptr, &h->flop32, &h->nunits, &h->ubase, &h->shv, &h->refine, &h->colinfo, &h->ucol, &h->ucount,
 		&h->uptr, &h->ucur, &h->lists, &h->redo, &h->unnz, &h->uoff, &h->raw, &h->out, &h->colptrC, &h->rowsC, &h->countC, &h->posH, &h->posV,
-		&h->aux, &h->meta, &h->errflag, &h->cubtmp};
+		&h->aux, &h->meta, &h->errflag, &h->cubtmp, &h->mg_colinfo, &h->mg_ucur};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& e : h->ev) if (e) cudaEventDestroy(e);
 	if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -591,6 +626,96 @@ int bella_b200_set_stream(bella_b200_handle* h, void* stream)
 	if (h->own_stream) cudaStreamDestroy(h->stream);
 	h->stream = (cudaStream_t)stream;
 	h->own_stream = false;
+	return BELLA_B200_OK;
+}
+
+/* ---- multi-GPU: k-mer-range transposition + product exchange (bella_b200/distributed.py drives the collectives) ---- */
+
+int bella_b200_mg_transpose(bella_b200_handle* h, uint32_t kmer_lo, uint32_t kmer_hi, uint32_t* cnt_local_dev)
+{
+	if (!h || !h->have_inputs) return fail(h, BELLA_B200_ERR_ARG, "set_inputs first");
+	if (kmer_lo > kmer_hi || kmer_hi > h->m || !cnt_local_dev) return fail(h, BELLA_B200_ERR_ARG, "bad k-mer range [%u,%u) of %u", kmer_lo, kmer_hi, h->m);
+	CK(cudaSetDevice(h->device));
+	h->launches = 0;
+	ENSURE(h->meta, sizeof(Meta));
+	ENSURE(h->errflag, sizeof(int));
+	h->klo = kmer_lo; h->khi = kmer_hi;
+	h->mg_recv = nullptr;
+	h->symbolic_done = h->numeric_done = false;
+	CK(cudaEventRecord(h->ev[0], h->stream));
+	for (;;) {
+		CK(cudaMemsetAsync(h->errflag.p, 0, sizeof(int), h->stream));
+		if (int rc = run_transpose(h, 0, 0, h->n, cnt_local_dev)) return rc;
+		int e = 0;
+		CK(cudaMemcpyAsync(&e, h->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+		CK(cudaStreamSynchronize(h->stream));
+		if (e == ERR_BUCKET) {
+			if (h->W <= 1) return fail(h, BELLA_B200_ERR_RANGE, "a k-mer occurs in more than %u reads", BUCKET_CAP);
+			h->W = h->W / 2;
+			continue;
+		}
+		if (e) return report_device_error(h, e);
+		break;
+	}
+	CK(cudaEventRecord(h->ev[1], h->stream));
+	return BELLA_B200_OK;
+}
+
+int bella_b200_mg_scatter(bella_b200_handle* h, const uint64_t* sendoff_dev, uint64_t* sendbuf_dev)
+{
+	if (!h || !h->have_inputs || !sendoff_dev) return fail(h, BELLA_B200_ERR_ARG, "bella_b200_mg_transpose first");
+	CK(cudaSetDevice(h->device));
+	const uint32_t n = h->n, ml = h->khi - h->klo;
+	ENSURE(h->mg_colinfo, sizeof(ColInfo) * ((size_t)n + 1));
+	ENSURE(h->mg_ucur, sizeof(uint64_t) * ((size_t)n + 1));
+	if (n && ml && h->nnzB) {
+		k_mg_colinfo<<<grid_for(n, 256), 256, 0, h->stream>>>(n, sendoff_dev, h->mg_colinfo.as<ColInfo>(), h->mg_ucur.as<unsigned long long>());
+		LAUNCHED();
+		k_scatter<<<grid_for(ml, 256), 256, 0, h->stream>>>(ml, 0, n, h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), h->mg_colinfo.as<ColInfo>(),
+			h->mg_ucur.as<unsigned long long>(), sendbuf_dev);
+		LAUNCHED();
+	}
+	CK(cudaEventRecord(h->ev[2], h->stream));
+	return BELLA_B200_OK;
+}
+
+int bella_b200_mg_finish(bella_b200_handle* h, uint32_t col_lo, uint32_t col_hi, int world, const uint32_t* counts_all_dev,
+		const uint64_t* segoff_dev, const uint64_t* recvbase_dev, const uint64_t* recv_dev)
+{
+	if (!h || !h->have_inputs) return fail(h, BELLA_B200_ERR_ARG, "set_inputs first");
+	if (col_lo > col_hi || col_hi > h->n || world < 1 || !counts_all_dev || !segoff_dev || !recvbase_dev)
+		return fail(h, BELLA_B200_ERR_ARG, "bad arguments to bella_b200_mg_finish");
+	CK(cudaSetDevice(h->device));
+	h->lo = col_lo; h->hi = col_hi;
+	const uint32_t ncols = col_hi - col_lo;
+	h->mg_recv = recv_dev ? recv_dev : (const uint64_t*)h->errflag.p;     // non-null marks the exchange mode even when nothing was received
+	h->mg_counts = counts_all_dev; h->mg_segoff = segoff_dev; h->mg_recvbase = recvbase_dev; h->mg_world = world;
+	CK(cudaEventRecord(h->ev[6], h->stream));
+	ENSURE(h->flop32, sizeof(uint32_t) * ((size_t)ncols + 1));
+	if (ncols) {
+		k_mg_sum_counts<<<grid_for(ncols, 256), 256, 0, h->stream>>>(h->n, col_lo, ncols, (uint32_t)world, counts_all_dev, h->flop32.as<uint32_t>(),
+			h->errflag.as<int>());
+		LAUNCHED();
+	}
+	int rc = plan_loop(h, false);
+	if (!rc && h->flops) {
+		k_regroup<false><<<148 * 8, 256, 0, h->stream>>>(h->n, col_lo, ncols, (uint32_t)world, counts_all_dev, segoff_dev, recvbase_dev, h->mg_recv,
+			h->colinfo.as<ColInfo>(), nullptr, h->ucur.as<unsigned long long>(), h->raw.as<uint64_t>(), h->meta.as<Meta>(), h->errflag.as<int>());
+		++h->launches;
+	}
+	if (!rc) rc = group_and_output(h);
+	h->mg_recv = nullptr;
+	if (rc) return rc;
+	CK(cudaEventElapsedTime(&h->t_ms[0], h->ev[0], h->ev[1]));    // this GPU's share of the transpose
+	CK(cudaEventElapsedTime(&h->t_ms[7], h->ev[1], h->ev[2]));    // expansion into the send buffer
+	return BELLA_B200_OK;
+}
+
+int bella_b200_get_colptr(bella_b200_handle* h, uint32_t* colptrC_host)
+{
+	if (!h || !h->symbolic_done || !colptrC_host) return fail(h, BELLA_B200_ERR_ARG, "the symbolic phase has not run");
+	CK(cudaMemcpyAsync(colptrC_host, h->colptrC.p, sizeof(uint32_t) * ((size_t)(h->hi - h->lo) + 1), cudaMemcpyDeviceToHost, h->stream));
+	CK(cudaStreamSynchronize(h->stream));
 	return BELLA_B200_OK;
 }
 

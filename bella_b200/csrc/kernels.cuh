@@ -171,7 +171,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // One warp per read (column of B): its nonzeros go to their k-mer bucket (W consecutive k-mer ids,
 // a fixed-capacity region of BUCKET_CAP 16-byte records {k-mer id, -, entry}).  The write frontier is
 // one open sector per bucket, so the small stores merge in L2.  Rows below lo never matter.
-__global__ void __launch_bounds__(256) k_partition(uint32_t n, uint32_t lo, const uint32_t* __restrict__ Bcolptr,
+__global__ void __launch_bounds__(256) k_partition(uint32_t n, uint32_t lo, uint32_t klo, uint32_t khi, const uint32_t* __restrict__ Bcolptr,
 		const uint32_t* __restrict__ Brow, const uint16_t* __restrict__ Bval, const uint8_t* __restrict__ Bstrand,
 		uint32_t W, uint32_t* __restrict__ bcnt, uint4* __restrict__ part, int* err)
 {
@@ -182,15 +182,22 @@ __global__ void __launch_bounds__(256) k_partition(uint32_t n, uint32_t lo, cons
 		if (j1 - j0 > 65536u) { if (lane == 0) set_err(err, -4); continue; }
 		for (uint32_t jb = j0; jb < j1; jb += 128) {
 			uint32_t c[4], b[4], q[4];
+			bool mine[4];                                      // k-mers outside [klo, khi) belong to another GPU's transpose
 #pragma unroll
 			for (int u = 0; u < 4; ++u) {
 				uint32_t j = jb + u * 32 + lane;
-				if (j < j1) { c[u] = Brow[j]; b[u] = (Bstrand ? c[u] : c[u] & 0x7FFFFFFFu) / W; q[u] = atomicAdd(&bcnt[b[u]], 1u); }
+				mine[u] = false;
+				if (j < j1) {
+					c[u] = Brow[j];
+					const uint32_t kid = Bstrand ? c[u] : c[u] & 0x7FFFFFFFu;
+					mine[u] = kid >= klo && kid < khi;
+					if (mine[u]) { b[u] = (kid - klo) / W; q[u] = atomicAdd(&bcnt[b[u]], 1u); }
+				}
 			}
 #pragma unroll
 			for (int u = 0; u < 4; ++u) {
 				uint32_t j = jb + u * 32 + lane;
-				if (j < j1) {
+				if (mine[u]) {
 					if (q[u] >= BUCKET_CAP) { set_err(err, -6); continue; }
 					const uint32_t st = Bstrand ? getbit(Bstrand, j) : c[u] >> 31;
 					const uint64_t e = (uint64_t)i | ((uint64_t)st << 31) | ((uint64_t)Bval[j] << 32) | ((uint64_t)(j - j0) << 48);
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(256) k_partition(uint32_t n, uint32_t lo, cons
 
 // One CTA per bucket: counting sort by k-mer in shared memory, each column sorted by read id,
 // coalesced write of Aent and A's colptr, product counts per output column.
-__global__ void __launch_bounds__(256) k_bucket(uint32_t m, uint32_t lo, uint32_t hi, uint32_t W, uint32_t nb,
+__global__ void __launch_bounds__(256) k_bucket(uint32_t klo, uint32_t m, uint32_t lo, uint32_t hi, uint32_t W, uint32_t nb,
 		const uint32_t* __restrict__ boff, const uint4* __restrict__ part,
 		uint32_t* __restrict__ Acolptr, uint64_t* __restrict__ Aent, uint32_t* __restrict__ flop32, const int* err)
 {
@@ -216,13 +223,13 @@ __global__ void __launch_bounds__(256) k_bucket(uint32_t m, uint32_t lo, uint32_
 	if (*err != 0) return;                                     // a bucket overflowed: the host retries with narrower buckets
 	for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
 		const uint32_t o0 = boff[b], size = boff[b + 1] - o0;
-		const uint32_t kbase = b * W, kw = min(W, m - kbase);
+		const uint32_t kbase = b * W, kw = min(W, m - kbase);      // k-mer ids are klo + kbase + k; A's colptr is local to [klo, klo + m)
 		const uint4* src = part + (size_t)b * BUCKET_CAP;
 		for (uint32_t k = tid; k <= kw; k += nt) off[k] = 0;
 		__syncthreads();
 		for (uint32_t x = tid; x < size; x += nt) {
 			const uint4 r = src[x];
-			const uint32_t k = r.x - kbase;
+			const uint32_t k = r.x - klo - kbase;
 			const uint32_t arr = atomicAdd(&off[k], 1u);
 			tmp[x] = k | (arr << 12);
 			E[x] = (uint64_t)r.z | ((uint64_t)r.w << 32);
@@ -997,6 +1004,66 @@ __global__ void __launch_bounds__(1024) k_huge_pair(Params P, const uint32_t* __
 		__syncthreads();
 		if (tid == 0) { P.out[base] = pack_result(row, R); P.unnz[u] = 1; }
 		__syncthreads();
+	}
+}
+
+// ================================ multi-GPU product exchange ================================
+// Each GPU transposes a k-mer range and expands its products for ALL output columns into a send
+// buffer ordered by column; after the all-to-all a GPU holds, for each of its columns, one segment
+// per source GPU.  k_regroup moves the segments into the unit regions the group kernel expects
+// (COUNT = true only counts the products per unit of the heavy columns, for the planner).
+
+__global__ void k_mg_colinfo(uint32_t n, const uint64_t* __restrict__ sendoff, ColInfo* __restrict__ colinfo, unsigned long long* __restrict__ ucur)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		colinfo[i] = ColInfo{i, 31u};
+		ucur[i] = sendoff[i];
+	}
+}
+
+__global__ void k_mg_sum_counts(uint32_t n, uint32_t lo, uint32_t ncols, uint32_t world, const uint32_t* __restrict__ counts_all,
+		uint32_t* __restrict__ flop32, int* err)
+{
+	for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < ncols; li += gridDim.x * blockDim.x) {
+		unsigned long long f = 0;
+		for (uint32_t s = 0; s < world; ++s) f += counts_all[(size_t)s * n + lo + li];
+		if (f > 0xFFFFFFFFull) { set_err(err, -4); f = 0; }
+		flop32[li] = (uint32_t)f;
+	}
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_regroup(uint32_t n, uint32_t lo, uint32_t ncols, uint32_t world, const uint32_t* __restrict__ counts_all,
+		const uint64_t* __restrict__ segoff, const uint64_t* __restrict__ recvbase, const uint64_t* __restrict__ recv,
+		const ColInfo* __restrict__ colinfo, uint32_t* __restrict__ ucount, unsigned long long* __restrict__ ucur, uint64_t* __restrict__ raw,
+		const Meta* meta, const int* err)
+{
+	if (*err != 0) return;
+	if (COUNT && meta->n_heavy_cols == 0) return;
+	const uint32_t lane = threadIdx.x & 31;
+	const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	const uint64_t nseg = (uint64_t)world * ncols;
+	for (uint64_t sg = warp; sg < nseg; sg += nwarps) {
+		const uint32_t s = (uint32_t)(sg / ncols), li = (uint32_t)(sg % ncols);
+		const uint32_t cnt = counts_all[(size_t)s * n + lo + li];
+		if (!cnt) continue;
+		const ColInfo ci = colinfo[li];
+		const uint64_t* src = recv + recvbase[s] + segoff[(size_t)s * (ncols + 1) + li];
+		if (ci.sh == 31) {
+			if (COUNT) continue;
+			unsigned long long q = 0;
+			if (lane == 0) q = atomicAdd(&ucur[ci.ubase], (unsigned long long)cnt);
+			q = __shfl_sync(FULL, q, 0);
+			for (uint32_t t = lane; t < cnt; t += 32) raw[q + t] = src[t];
+		} else {
+			const uint32_t i = lo + li;
+			for (uint32_t t = lane; t < cnt; t += 32) {
+				const uint64_t r = src[t];
+				const uint32_t u = unit_of(ci, i, ent_row(r));
+				if (COUNT) atomicAdd(&ucount[u], 1u);
+				else raw[atomicAdd(&ucur[u], 1ull)] = r;
+			}
+		}
 	}
 }
 

@@ -4,12 +4,17 @@ Layout (the reference has no distributed code, so there is no call
   * A is row-sharded: rank r owns the reads [read_lo_r, read_hi_r) -- equivalently the columns of
     B = A^T of those reads -- as a *compressed column panel*: per nonzero the k-mer id with the strand
     bit in bit 31 (u32) and the position (u16), plus per read its k-mer count and length.
-  * per batch ONE all-gather of the panels (NCCL over NVLink) gives every rank the whole B;
-  * output columns are independent (overlap.hpp:286-287), so every rank then runs the single-GPU
-    path (bella_b200_set_inputs_device + set_column_range + symbolic/numeric) on its own contiguous
-    column range.  Ranges are balanced on the product estimate  len_i * (n-1-i)  (the strictly lower
-    triangle makes low column ids heavier; the reference balances its stages on the nnz prefix,
-    overlap.hpp:703-710).  Outputs are disjoint column ranges: no reduction, the caller concatenates.
+  * per batch ONE all-gather of the panels (NCCL over NVLink) gives every rank the whole B.
+  * the transpose of B is split by k-mer range: rank r builds A's columns for its k-mers only and
+    expands the kept products of those k-mers -- for every output column -- into a send buffer
+    ordered by output column (bella_b200_mg_transpose / _mg_scatter);
+  * output columns are independent (overlap.hpp:286-287) and owned in contiguous ranges balanced on
+    the exact product counts (an all-gather of the per-column counts, 4 bytes per read and rank); one
+    all-to-all moves every product (8 bytes) to the owner of its column;
+  * the owner regroups what it received and runs the group + fold kernels on its columns
+    (bella_b200_mg_finish).  Outputs are disjoint column ranges: no reduction, the caller concatenates.
+(`mode="replicate"` keeps the first version: after the all-gather every rank transposes all reads at or
+above its first column itself and no products are exchanged.)
 
 Everything in this file is host-side plumbing on torch tensors (CPU tensors with gloo in the unit
 tests, CUDA tensors with NCCL on the box); the arithmetic is in libbella_b200.so.
@@ -155,11 +160,53 @@ def column_ranges(colptr64, world, rho=RHO):
     return bounds
 
 
+def kmer_ranges(n_kmers, world):
+    """k-mer ranges transposed by the ranks (k-mer ids are hash-order ids: uniform)."""
+    return [int(n_kmers * r // world) for r in range(world + 1)]
+
+
+def owner_ranges(total_counts, world):
+    """Contiguous output-column ranges with about equal product counts. total_counts: int64 [n]. -> world+1 ints"""
+    n = total_counts.numel()
+    if n == 0:
+        return [0] * (world + 1)
+    pre = torch.cumsum(total_counts.to(torch.float64), 0)
+    total = pre[-1]
+    targets = total * torch.arange(1, world, dtype=torch.float64, device=pre.device) / world
+    cuts = torch.searchsorted(pre, targets, right=False).tolist() if world > 1 else []
+    bounds = [0] + [int(c) + 1 for c in cuts] + [n]
+    for k in range(1, len(bounds)):
+        bounds[k] = min(max(bounds[k], bounds[k - 1]), n)
+    bounds[-1] = n
+    return bounds
+
+
+def exchange_plan(counts_all, bounds, rank):
+    """counts_all int32 [world][n] (every rank's per-column product counts), bounds = owner ranges.
+    -> (in_splits, out_splits as python lists, segoff int64 [world][ncols+1], recvbase int64 [world])"""
+    world, n = counts_all.shape
+    C = torch.zeros((world, n + 1), dtype=torch.int64, device=counts_all.device)
+    torch.cumsum(counts_all.to(torch.int64), 1, out=C[:, 1:])
+    b = torch.tensor(bounds, dtype=torch.int64, device=counts_all.device)
+    Cb = C[:, b]                                            # [world][world+1]
+    seg = (Cb[:, 1:] - Cb[:, :-1]).cpu()                    # seg[s][d] = products rank s sends to rank d
+    in_splits = [int(x) for x in seg[:, rank]]
+    out_splits = [int(x) for x in seg[rank, :]]
+    lo, hi = bounds[rank], bounds[rank + 1]
+    segoff = (C[:, lo:hi + 1] - C[:, lo:lo + 1]).contiguous()
+    rb = [0]
+    for x in in_splits[:-1]:
+        rb.append(rb[-1] + x)
+    recvbase = torch.tensor(rb, dtype=torch.int64, device=counts_all.device)
+    return in_splits, out_splits, segoff, recvbase
+
+
 class ShardedOverlapSpGEMM:
     """One instance per rank.  load_shard() once; step() per batch: all-gather + local SpGEMM of this rank's columns."""
 
-    def __init__(self, device_index):
+    def __init__(self, device_index, mode="exchange"):
         from . import spgemm
+        self.mode = mode
         self.dev = torch.device("cuda", device_index)
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.g = spgemm.OverlapSpGEMM(device_index)
@@ -191,6 +238,8 @@ class ShardedOverlapSpGEMM:
         """-> (Z of this rank's columns, products, (col_lo, col_hi)[, host results when fetch=True])"""
         gathered = all_gather_panels(self.panel, self.max_bytes)
         B = unpack_panels(gathered, self.shapes)
+        if self.mode == "exchange":
+            return self._step_exchange(gathered, B, fetch)
         bounds = column_ranges(B["colptr64"], self.world)
         lo, hi = bounds[self.rank], bounds[self.rank + 1]
         n = B["read_len"].numel()
@@ -205,6 +254,35 @@ class ShardedOverlapSpGEMM:
             return int(colptrC[hi - lo]), flops, (lo, hi), (colptrC[:hi - lo + 1],) + res
         Z, flops = self.g.run_resident()
         return Z, flops, (lo, hi)
+
+    def _step_exchange(self, gathered, B, fetch):
+        n, nnz = B["read_len"].numel(), B["rowids"].numel()
+        g, dev = self.g, self.dev
+        g.set_inputs_device(n, self.n_kmers, nnz, (B["colptr"], B["rowids"], B["values"]), B["read_len"], None,
+                            self.kmer_size, self.bin_size)
+        kr = kmer_ranges(self.n_kmers, self.world)
+        cnt_local = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        g.mg_transpose(kr[self.rank], kr[self.rank + 1], cnt_local)
+        counts_all = torch.empty((self.world, n), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(counts_all.view(-1), cnt_local[:n].contiguous())
+        sendoff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(cnt_local[:n].to(torch.int64), 0, out=sendoff[1:])
+        bounds = owner_ranges(counts_all.to(torch.int64).sum(0), self.world)
+        in_splits, out_splits, segoff, recvbase = exchange_plan(counts_all, bounds, self.rank)
+        send = torch.empty(max(sum(out_splits), 1), dtype=torch.int64, device=dev)
+        g.mg_scatter(sendoff, send)
+        recv = torch.empty(max(sum(in_splits), 1), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(recv[:sum(in_splits)], send[:sum(out_splits)], in_splits, out_splits)
+        lo, hi = bounds[self.rank], bounds[self.rank + 1]
+        self.keep = (gathered, B, counts_all, segoff, recvbase, send, recv, cnt_local, sendoff)
+        g.mg_finish(lo, hi, self.world, counts_all, segoff, recvbase, recv)
+        flops = sum(in_splits)
+        if fetch:
+            colptrC = g.get_colptr(pinned=True)
+            res = g.numeric(pinned=True)
+            return int(colptrC[hi - lo]), flops, (lo, hi), (colptrC[:hi - lo + 1],) + res
+        g.numeric_device()
+        return int(g.result_nnz()), flops, (lo, hi)
 
     def close(self):
         self.g.close()

@@ -47,6 +47,10 @@ def lib():
         L.bella_b200_stream.argtypes = [H]
         L.bella_b200_stream.restype = vp
         L.bella_b200_set_stream.argtypes = [H, vp]
+        L.bella_b200_mg_transpose.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, vp]
+        L.bella_b200_mg_scatter.argtypes = [H, vp, vp]
+        L.bella_b200_mg_finish.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, vp, vp, vp, vp]
+        L.bella_b200_get_colptr.argtypes = [H, vp]
         _lib = L
     return _lib
 
@@ -55,7 +59,8 @@ EXPORTS = ["bella_b200_create", "bella_b200_destroy", "bella_b200_last_error", "
            "bella_b200_set_inputs_device", "bella_b200_set_column_range", "bella_b200_symbolic",
            "bella_b200_numeric", "bella_b200_numeric_aux", "bella_b200_numeric_device",
            "bella_b200_result_device", "bella_b200_run_resident", "bella_b200_get_timings", "bella_b200_stream",
-           "bella_b200_set_stream"]
+           "bella_b200_set_stream", "bella_b200_mg_transpose", "bella_b200_mg_scatter", "bella_b200_mg_finish",
+           "bella_b200_get_colptr"]
 
 
 class BellaB200Error(RuntimeError):
@@ -180,6 +185,32 @@ class OverlapSpGEMM:
             self._check(self._L.bella_b200_numeric_aux(self._h, c0, c1, _ptr(a[0]), _ptr(a[1]), _ptr(a[2])), "bella_b200_numeric_aux")
             out = out + (np.ascontiguousarray(a[:, :z].T),)
         return out
+
+    # ---- multi-GPU stages (device tensors / pointers; bella_b200/distributed.py runs the collectives between them) ----
+    def mg_transpose(self, kmer_lo, kmer_hi, cnt_local):
+        self._check(self._L.bella_b200_mg_transpose(self._h, kmer_lo, kmer_hi, _ptr(cnt_local)), "bella_b200_mg_transpose")
+
+    def mg_scatter(self, sendoff, sendbuf):
+        self._check(self._L.bella_b200_mg_scatter(self._h, _ptr(sendoff), _ptr(sendbuf)), "bella_b200_mg_scatter")
+
+    def mg_finish(self, col_lo, col_hi, world, counts_all, segoff, recvbase, recv):
+        self._check(self._L.bella_b200_mg_finish(self._h, col_lo, col_hi, world, _ptr(counts_all), _ptr(segoff), _ptr(recvbase), _ptr(recv)),
+                    "bella_b200_mg_finish")
+        self.lo, self.hi = col_lo, col_hi
+
+    def get_colptr(self, pinned=False):
+        colptrC = self._host("colptrC", np.uint32, self.hi - self.lo + 1, pinned)
+        self._check(self._L.bella_b200_get_colptr(self._h, _ptr(colptrC)), "bella_b200_get_colptr")
+        self.colptrC = colptrC
+        return colptrC
+
+    def result_nnz(self):
+        z = ctypes.c_uint64(0)
+        self._check(self._L.bella_b200_result_device(self._h, None, None, None, None, None, ctypes.byref(z)), "bella_b200_result_device")
+        return z.value
+
+    def numeric_device(self):
+        self._check(self._L.bella_b200_numeric_device(self._h), "bella_b200_numeric_device")
 
     def run_resident(self):
         """layout + symbolic + numeric on device-resident inputs, no result copy. -> (nnzC, flops)"""

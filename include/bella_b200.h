@@ -132,6 +132,27 @@ void* bella_b200_stream(bella_b200_handle* h);
  * stream).  The handle does not take ownership. */
 int bella_b200_set_stream(bella_b200_handle* h, void* stream);
 
+/* ---- multi-GPU, one handle (process) per GPU; the caller runs the collectives between the calls.
+ * After the all-gather of the B panel every GPU holds the whole B (bella_b200_set_inputs_device).  It then
+ *   mg_transpose : transposes only the k-mers [kmer_lo, kmer_hi) (all reads) and writes, per output column of
+ *                  the WHOLE matrix, how many kept products those k-mers contribute: cnt_local_dev u32[n] (device)
+ *   mg_scatter   : expands those products into sendbuf_dev (device, 8 bytes each) ordered by output column;
+ *                  sendoff_dev u64[n+1] (device) is the exclusive scan of cnt_local_dev
+ *   -- the caller all-gathers the counts and exchanges the products (all-to-all) so that the owner of an
+ *      output column range receives, per source GPU, that range's products in column order --
+ *   mg_finish    : for the columns [col_lo, col_hi) this GPU owns: counts_all_dev u32[world][n] (every GPU's
+ *                  cnt_local), recv_dev = the received products, source-major; recvbase_dev u64[world] = offset of
+ *                  each source's block in recv_dev; segoff_dev u64[world][ncols+1] = per source the exclusive scan
+ *                  of its counts over the owned columns.  Runs the plan, group + fold and leaves the handle in
+ *                  the state bella_b200_symbolic leaves it in (bella_b200_numeric / _numeric_device / _get_colptr).
+ * All pointers are device pointers on the handle's GPU and stay valid during the call. */
+int bella_b200_mg_transpose(bella_b200_handle* h, uint32_t kmer_lo, uint32_t kmer_hi, uint32_t* cnt_local_dev);
+int bella_b200_mg_scatter(bella_b200_handle* h, const uint64_t* sendoff_dev, uint64_t* sendbuf_dev);
+int bella_b200_mg_finish(bella_b200_handle* h, uint32_t col_lo, uint32_t col_hi, int world, const uint32_t* counts_all_dev,
+		const uint64_t* segoff_dev, const uint64_t* recvbase_dev, const uint64_t* recv_dev);
+/* colptrC of the handle's column range to HOST memory ([col_hi-col_lo+1]) once the symbolic phase has run. */
+int bella_b200_get_colptr(bella_b200_handle* h, uint32_t* colptrC_host);
+
 #ifdef __cplusplus
 }
 #endif
