@@ -91,6 +91,35 @@ def all_gather_panels(panel, max_bytes):
     return out
 
 
+def all_gather_sections(panel, shapes):
+    """The same exchange without the repacking copy: every section of every rank's panel lands directly at
+    its place in the final arrays (uneven all-gather = one grouped NCCL broadcast per rank and section).
+    -> the dict unpack_panels returns"""
+    dev = panel.device
+    n = sum(a for a, _ in shapes)
+    nnz = sum(b for _, b in shapes)
+    rank = dist.get_rank()
+    rows = torch.empty(nnz, dtype=torch.int32, device=dev)
+    vals = torch.empty(nnz, dtype=torch.int16, device=dev)
+    cnts = torch.empty(n, dtype=torch.int32, device=dev)
+    lens = torch.empty(n, dtype=torch.int32, device=dev)
+    off, _ = panel_layout(*shapes[rank])
+    n_r, nnz_r = shapes[rank]
+    mine = {"rowids": panel[off["rowids"]:off["rowids"] + 4 * nnz_r], "values": panel[off["values"]:off["values"] + 2 * nnz_r],
+            "counts": panel[off["counts"]:off["counts"] + 4 * n_r], "read_len": panel[off["read_len"]:off["read_len"] + 4 * n_r]}
+    works = []
+    for key, full, per, width in (("rowids", rows, 1, 4), ("values", vals, 1, 2), ("counts", cnts, 0, 4), ("read_len", lens, 0, 4)):
+        sizes = [s[per] * width for s in shapes]              # bytes: NCCL has no 16-bit integer type
+        outs = list(torch.split(full.view(torch.uint8), sizes))
+        works.append(dist.all_gather(outs, mine[key], async_op=True))
+    for w in works:
+        w.wait()
+    counts = cnts.to(torch.int64)
+    colptr64 = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(counts, 0, out=colptr64[1:])
+    return {"colptr64": colptr64, "colptr": colptr64.to(torch.int32), "rowids": rows, "values": vals, "read_len": lens}
+
+
 def unpack_panels(gathered, shapes):
     """(world, max_bytes) uint8 + per-rank (n_r, nnz_r) -> B of all reads as tensors on the same device:
     colptr int32 [n+1] (uint32 bit pattern), rowids int32 [nnz] (strand in bit 31), values int16 [nnz], read_len int32 [n]"""
@@ -170,26 +199,34 @@ def owner_ranges(total_counts, world):
     n = total_counts.numel()
     if n == 0:
         return [0] * (world + 1)
-    pre = torch.cumsum(total_counts.to(torch.float64), 0)
-    total = pre[-1]
-    targets = total * torch.arange(1, world, dtype=torch.float64, device=pre.device) / world
-    cuts = torch.searchsorted(pre, targets, right=False).tolist() if world > 1 else []
-    bounds = [0] + [int(c) + 1 for c in cuts] + [n]
-    for k in range(1, len(bounds)):
-        bounds[k] = min(max(bounds[k], bounds[k - 1]), n)
-    bounds[-1] = n
-    return bounds
+    return [int(x) for x in _owner_bounds(torch.cumsum(total_counts.to(torch.float64), 0), world).tolist()]
 
 
-def exchange_plan(counts_all, bounds, rank):
-    """counts_all int32 [world][n] (every rank's per-column product counts), bounds = owner ranges.
-    -> (in_splits, out_splits as python lists, segoff int64 [world][ncols+1], recvbase int64 [world])"""
+def _owner_bounds(pre, world):
+    """pre = inclusive prefix of the per-column totals (float64 [n]) -> int64 [world+1] bounds, on pre's device"""
+    n = pre.numel()
+    targets = pre[-1] * torch.arange(1, world, dtype=torch.float64, device=pre.device) / world
+    cuts = torch.searchsorted(pre, targets, right=False) + 1
+    cuts = torch.cummax(torch.clamp(cuts, max=n), 0).values if world > 1 else cuts
+    z = torch.zeros(1, dtype=torch.int64, device=pre.device)
+    return torch.cat([z, cuts.to(torch.int64), z + n])
+
+
+def exchange_plan(counts_all, rank):
+    """counts_all int32 [world][n]: every rank's per-column product counts.  One device->host copy.
+    -> (bounds list, in_splits, out_splits, segoff int64 [world][ncols+1], recvbase int64 [world], sendoff int64 [n+1])"""
     world, n = counts_all.shape
-    C = torch.zeros((world, n + 1), dtype=torch.int64, device=counts_all.device)
-    torch.cumsum(counts_all.to(torch.int64), 1, out=C[:, 1:])
-    b = torch.tensor(bounds, dtype=torch.int64, device=counts_all.device)
+    dev = counts_all.device
+    C = torch.zeros((world, n + 1), dtype=torch.int64, device=dev)
+    torch.cumsum(counts_all, 1, out=C[:, 1:])
+    if n == 0:
+        z = torch.zeros((world, 1), dtype=torch.int64, device=dev)
+        return [0] * (world + 1), [0] * world, [0] * world, z, torch.zeros(world, dtype=torch.int64, device=dev), C[rank]
+    b = _owner_bounds(C[:, 1:].sum(0).to(torch.float64), world)
     Cb = C[:, b]                                            # [world][world+1]
-    seg = (Cb[:, 1:] - Cb[:, :-1]).cpu()                    # seg[s][d] = products rank s sends to rank d
+    host = torch.cat([b.view(1, -1), Cb]).cpu()             # the one synchronising copy
+    bounds = [int(x) for x in host[0]]
+    seg = host[1:, 1:] - host[1:, :-1]                      # seg[s][d] = products rank s sends to rank d
     in_splits = [int(x) for x in seg[:, rank]]
     out_splits = [int(x) for x in seg[rank, :]]
     lo, hi = bounds[rank], bounds[rank + 1]
@@ -197,8 +234,8 @@ def exchange_plan(counts_all, bounds, rank):
     rb = [0]
     for x in in_splits[:-1]:
         rb.append(rb[-1] + x)
-    recvbase = torch.tensor(rb, dtype=torch.int64, device=counts_all.device)
-    return in_splits, out_splits, segoff, recvbase
+    recvbase = torch.tensor(rb, dtype=torch.int64, device=dev)
+    return bounds, in_splits, out_splits, segoff, recvbase, C[rank]
 
 
 class ShardedOverlapSpGEMM:
@@ -213,6 +250,9 @@ class ShardedOverlapSpGEMM:
         self.g.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
         self.panel = None
         self.keep = None
+        import os
+        self._profile = os.environ.get("BELLA_MG_PROFILE") == "1"
+        self.prof = {}
 
     def load_shard(self, inp, pinned=False):
         """Take this rank's reads of `inp`, pack the panel and make it device resident."""
@@ -236,8 +276,15 @@ class ShardedOverlapSpGEMM:
 
     def step(self, fetch=False):
         """-> (Z of this rank's columns, products, (col_lo, col_hi)[, host results when fetch=True])"""
-        gathered = all_gather_panels(self.panel, self.max_bytes)
-        B = unpack_panels(gathered, self.shapes)
+        if self._profile:
+            import time
+            torch.cuda.synchronize(self.dev)
+            self._t0 = time.perf_counter()
+        if dist.get_backend() == "nccl":
+            gathered, B = None, all_gather_sections(self.panel, self.shapes)
+        else:
+            gathered = all_gather_panels(self.panel, self.max_bytes)
+            B = unpack_panels(gathered, self.shapes)
         if self.mode == "exchange":
             return self._step_exchange(gathered, B, fetch)
         bounds = column_ranges(B["colptr64"], self.world)
@@ -255,27 +302,40 @@ class ShardedOverlapSpGEMM:
         Z, flops = self.g.run_resident()
         return Z, flops, (lo, hi)
 
+    def _tick(self, name):
+        """BELLA_MG_PROFILE=1: per-stage wall times (device synchronised), kept in self.prof."""
+        if not self._profile:
+            return
+        import time
+        torch.cuda.synchronize(self.dev)
+        now = time.perf_counter()
+        self.prof[name] = self.prof.get(name, 0.0) + (now - self._t0) * 1e3
+        self._t0 = now
+
     def _step_exchange(self, gathered, B, fetch):
         n, nnz = B["read_len"].numel(), B["rowids"].numel()
         g, dev = self.g, self.dev
+        self._tick("allgather+unpack")
         g.set_inputs_device(n, self.n_kmers, nnz, (B["colptr"], B["rowids"], B["values"]), B["read_len"], None,
                             self.kmer_size, self.bin_size)
         kr = kmer_ranges(self.n_kmers, self.world)
         cnt_local = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         g.mg_transpose(kr[self.rank], kr[self.rank + 1], cnt_local)
+        self._tick("mg_transpose")
         counts_all = torch.empty((self.world, n), dtype=torch.int32, device=dev)
         dist.all_gather_into_tensor(counts_all.view(-1), cnt_local[:n].contiguous())
-        sendoff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(cnt_local[:n].to(torch.int64), 0, out=sendoff[1:])
-        bounds = owner_ranges(counts_all.to(torch.int64).sum(0), self.world)
-        in_splits, out_splits, segoff, recvbase = exchange_plan(counts_all, bounds, self.rank)
+        bounds, in_splits, out_splits, segoff, recvbase, sendoff = exchange_plan(counts_all, self.rank)
+        self._tick("counts+plan")
         send = torch.empty(max(sum(out_splits), 1), dtype=torch.int64, device=dev)
         g.mg_scatter(sendoff, send)
+        self._tick("mg_scatter")
         recv = torch.empty(max(sum(in_splits), 1), dtype=torch.int64, device=dev)
         dist.all_to_all_single(recv[:sum(in_splits)], send[:sum(out_splits)], in_splits, out_splits)
+        self._tick("all_to_all")
         lo, hi = bounds[self.rank], bounds[self.rank + 1]
         self.keep = (gathered, B, counts_all, segoff, recvbase, send, recv, cnt_local, sendoff)
         g.mg_finish(lo, hi, self.world, counts_all, segoff, recvbase, recv)
+        self._tick("mg_finish")
         flops = sum(in_splits)
         if fetch:
             colptrC = g.get_colptr(pinned=True)
