@@ -16,6 +16,7 @@
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -61,6 +62,12 @@ struct bella_b200_handle {
 	const uint16_t* dB_values = nullptr;
 	const uint8_t* dB_strand = nullptr;
 	DevBuf oB_colptr, oB_rowids, oB_values, oB_strand, o_len;
+	// chunked upload of host inputs, overlapped with the transpose (bella_b200_set_inputs)
+	static constexpr int MAX_CHUNKS = 8;
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t chunk_ev[MAX_CHUNKS]{}, copy_begin = nullptr, copy_end = nullptr;
+	uint32_t chunk_lo[MAX_CHUNKS + 1]{};
+	int n_chunks = 0;                          // > 0: reads [chunk_lo[c], chunk_lo[c+1]) are on the device once chunk_ev[c] has fired
 	// transpose
 	uint32_t W = 0, NB = 0;                    // k-mers per bucket, buckets
 	uint32_t klo = 0, khi = 0;                 // k-mer range this handle transposes ([0, m) unless multi-GPU)
@@ -163,9 +170,21 @@ int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32
 	ENSURE(h->boff, sizeof(uint32_t) * ((size_t)NB + 2));
 	ENSURE(h->part, sizeof(uint4) * (size_t)NB * BUCKET_CAP);
 	CK(cudaMemsetAsync(h->bcur.p, 0, sizeof(uint32_t) * ((size_t)NB + 2), h->stream));
-	k_partition<<<grid_for((uint64_t)(n - row_lo) * 32, 256), 256, 0, h->stream>>>(n, row_lo, h->klo, h->khi, h->dB_colptr, h->dB_rowids,
-		h->dB_values, h->dB_strand, W, h->bcur.as<uint32_t>(), h->part.as<uint4>(), h->errflag.as<int>());
-	LAUNCHED();
+	if (h->n_chunks > 0) {
+		// host inputs are still arriving chunk by chunk: partition each range of reads as soon as it is on the device
+		for (int c = 0; c < h->n_chunks; ++c) {
+			const uint32_t c0 = h->chunk_lo[c] > row_lo ? h->chunk_lo[c] : row_lo, c1 = h->chunk_lo[c + 1];
+			CK(cudaStreamWaitEvent(h->stream, h->chunk_ev[c], 0));
+			if (c0 >= c1) continue;
+			k_partition<<<grid_for((uint64_t)(c1 - c0) * 32, 256), 256, 0, h->stream>>>(c1, c0, h->klo, h->khi, h->dB_colptr, h->dB_rowids,
+				h->dB_values, h->dB_strand, W, h->bcur.as<uint32_t>(), h->part.as<uint4>(), h->errflag.as<int>());
+			LAUNCHED();
+		}
+	} else {
+		k_partition<<<grid_for((uint64_t)(n - row_lo) * 32, 256), 256, 0, h->stream>>>(n, row_lo, h->klo, h->khi, h->dB_colptr, h->dB_rowids,
+			h->dB_values, h->dB_strand, W, h->bcur.as<uint32_t>(), h->part.as<uint4>(), h->errflag.as<int>());
+		LAUNCHED();
+	}
 	if (int rc = exclusive_scan(h, h->bcur.as<uint32_t>(), h->boff.as<uint32_t>(), NB + 1)) return rc;
 	CK(cudaFuncSetAttribute(k_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BUCKET_SMEM));
 	k_bucket<<<NB < 148u * 12 ? NB : 148u * 12, 256, BUCKET_SMEM, h->stream>>>(h->klo, ml, cnt_lo, cnt_hi, W, NB, h->boff.as<uint32_t>(),
@@ -384,14 +403,6 @@ int run_numeric(bella_b200_handle* h)
 	return 0;
 }
 
-int copy_in(bella_b200_handle* h, DevBuf& buf, const void* src, size_t bytes, const void** dst)
-{
-	ENSURE(buf, bytes + 16);
-	CK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
-	*dst = buf.p;
-	return 0;
-}
-
 int validate_views(bella_b200_handle* h, const bella_csc_view* A, const bella_csc_view* B, const uint32_t* read_len,
 		const uint8_t* sB)
 {
@@ -436,6 +447,9 @@ int bella_b200_create(bella_b200_handle** out, int device)
 	h->device = device;
 	if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return BELLA_B200_ERR_CUDA; }
 	for (auto& e : h->ev) cudaEventCreate(&e);
+	cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+	for (auto& e : h->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+	cudaEventCreate(&h->copy_begin); cudaEventCreate(&h->copy_end);
 	*out = h;
 	return BELLA_B200_OK;
 }
@@ -451,6 +465,10 @@ int bella_b200_destroy(bella_b200_handle* h)
 		&h->aux, &h->meta, &h->errflag, &h->cubtmp, &h->mg_colinfo, &h->mg_ucur};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+	for (auto& e : h->chunk_ev) if (e) cudaEventDestroy(e);
+	if (h->copy_begin) cudaEventDestroy(h->copy_begin);
+	if (h->copy_end) cudaEventDestroy(h->copy_end);
+	if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
 	if (h->own_stream) cudaStreamDestroy(h->stream);
 	delete h;
 	return BELLA_B200_OK;
@@ -464,18 +482,47 @@ int bella_b200_set_inputs(bella_b200_handle* h, const bella_csc_view* A, const b
 	(void)strand_A;
 	if (int rc = validate_views(h, A, B, read_len, strand_B)) return rc;
 	CK(cudaSetDevice(h->device));
+	CK(cudaStreamSynchronize(h->copy_stream));                  // a previous upload must not be overwritten mid-flight
 	reset_problem(h, B, kmer_size, bin_size);
-	CK(cudaEventRecord(h->ev[10], h->stream));
-	const void* p;
-	if (int rc = copy_in(h, h->oB_colptr, B->colptr, sizeof(uint32_t) * ((size_t)B->cols + 1), &p)) return rc; h->dB_colptr = (const uint32_t*)p;
-	if (int rc = copy_in(h, h->oB_rowids, B->rowids, sizeof(uint32_t) * (size_t)B->nnz, &p)) return rc; h->dB_rowids = (const uint32_t*)p;
-	if (int rc = copy_in(h, h->oB_values, B->values, sizeof(uint16_t) * (size_t)B->nnz, &p)) return rc; h->dB_values = (const uint16_t*)p;
-	h->dB_strand = nullptr;
-	if (strand_B) { if (int rc = copy_in(h, h->oB_strand, strand_B, ((size_t)B->nnz + 7) / 8, &p)) return rc; h->dB_strand = (const uint8_t*)p; }
-	if (int rc = copy_in(h, h->o_len, read_len, sizeof(uint32_t) * (size_t)B->cols, &p)) return rc; h->d_len = (const uint32_t*)p;
-	CK(cudaEventRecord(h->ev[11], h->stream));
-	CK(cudaStreamSynchronize(h->stream));
-	CK(cudaEventElapsedTime(&h->t_ms[3], h->ev[10], h->ev[11]));
+	const size_t n = B->cols, nnz = B->nnz;
+	ENSURE(h->oB_colptr, sizeof(uint32_t) * (n + 1) + 16);
+	ENSURE(h->oB_rowids, sizeof(uint32_t) * nnz + 16);
+	ENSURE(h->oB_values, sizeof(uint16_t) * nnz + 16);
+	ENSURE(h->o_len, sizeof(uint32_t) * n + 16);
+	if (strand_B) ENSURE(h->oB_strand, (nnz + 7) / 8 + 16);
+	h->dB_colptr = h->oB_colptr.as<uint32_t>(); h->dB_rowids = h->oB_rowids.as<uint32_t>(); h->dB_values = h->oB_values.as<uint16_t>();
+	h->dB_strand = strand_B ? h->oB_strand.as<uint8_t>() : nullptr; h->d_len = h->o_len.as<uint32_t>();
+	// The upload runs on its own stream in up to MAX_CHUNKS ranges of reads of about equal nnz; the transpose
+	// (bella_b200_symbolic) consumes each range as soon as it has landed.  The host arrays must therefore stay
+	// valid until bella_b200_symbolic returns (page-locked memory makes the copies truly asynchronous).
+	cudaStream_t cs = h->copy_stream;
+	CK(cudaEventRecord(h->copy_begin, cs));
+	CK(cudaMemcpyAsync(h->oB_colptr.p, B->colptr, sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, cs));
+	CK(cudaMemcpyAsync(h->o_len.p, read_len, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, cs));
+	int nc = nnz >= (1u << 22) ? bella_b200_handle::MAX_CHUNKS : 1;
+	h->chunk_lo[0] = 0;
+	for (int c = 1; c < nc; ++c) {
+		const uint32_t target = (uint32_t)((uint64_t)nnz * c / nc);
+		const uint32_t* it = std::lower_bound(B->colptr, B->colptr + n + 1, target);
+		uint32_t r = (uint32_t)(it - B->colptr);
+		if (r > n) r = (uint32_t)n;
+		h->chunk_lo[c] = r < h->chunk_lo[c - 1] ? h->chunk_lo[c - 1] : r;
+	}
+	h->chunk_lo[nc] = (uint32_t)n;
+	for (int c = 0; c < nc; ++c) {
+		const size_t j0 = B->colptr[h->chunk_lo[c]], j1 = B->colptr[h->chunk_lo[c + 1]];
+		if (j1 > j0) {
+			CK(cudaMemcpyAsync(h->oB_rowids.as<uint32_t>() + j0, B->rowids + j0, sizeof(uint32_t) * (j1 - j0), cudaMemcpyHostToDevice, cs));
+			CK(cudaMemcpyAsync(h->oB_values.as<uint16_t>() + j0, B->values + j0, sizeof(uint16_t) * (j1 - j0), cudaMemcpyHostToDevice, cs));
+			if (strand_B) {
+				const size_t b0 = j0 / 8, b1 = (j1 + 7) / 8;        // whole bytes: neighbouring chunks rewrite a shared byte with the same value
+				CK(cudaMemcpyAsync(h->oB_strand.as<uint8_t>() + b0, strand_B + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
+			}
+		}
+		CK(cudaEventRecord(h->chunk_ev[c], cs));
+	}
+	CK(cudaEventRecord(h->copy_end, cs));
+	h->n_chunks = nc;
 	return BELLA_B200_OK;
 }
 
@@ -487,6 +534,7 @@ int bella_b200_set_inputs_device(bella_b200_handle* h, const bella_csc_view* A, 
 	CK(cudaSetDevice(h->device));
 	reset_problem(h, B, kmer_size, bin_size);
 	h->dB_colptr = B->colptr; h->dB_rowids = B->rowids; h->dB_values = B->values; h->dB_strand = strand_B; h->d_len = read_len;
+	h->n_chunks = 0;
 	h->t_ms[3] = 0;
 	return BELLA_B200_OK;
 }
@@ -504,7 +552,17 @@ static int do_symbolic(bella_b200_handle* h)
 {
 	CK(cudaSetDevice(h->device));
 	h->launches = 0;
-	return run_symbolic(h);
+	if (h->n_chunks > 0) {
+		// small arrays (colptr, read lengths) first: everything that follows reads them
+		CK(cudaStreamWaitEvent(h->stream, h->copy_begin, 0));
+		CK(cudaStreamWaitEvent(h->stream, h->chunk_ev[0], 0));
+	}
+	int rc = run_symbolic(h);
+	if (h->n_chunks > 0) {
+		CK(cudaStreamSynchronize(h->copy_stream));
+		CK(cudaEventElapsedTime(&h->t_ms[3], h->copy_begin, h->copy_end));
+	}
+	return rc;
 }
 
 int bella_b200_symbolic(bella_b200_handle* h, uint64_t* flops, uint32_t* flopC, uint32_t* colptrC)

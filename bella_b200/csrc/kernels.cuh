@@ -171,7 +171,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // One warp per read (column of B): its nonzeros go to their k-mer bucket (W consecutive k-mer ids,
 // a fixed-capacity region of BUCKET_CAP 16-byte records {k-mer id, -, entry}).  The write frontier is
 // one open sector per bucket, so the small stores merge in L2.  Rows below lo never matter.
-__global__ void __launch_bounds__(256) k_partition(uint32_t n, uint32_t lo, uint32_t klo, uint32_t khi, const uint32_t* __restrict__ Bcolptr,
+__global__ void __launch_bounds__(256) k_partition(uint32_t n, uint32_t lo, uint32_t klo, uint32_t khi, const uint32_t* __restrict__ Bcolptr,   // reads [lo, n)
 		const uint32_t* __restrict__ Brow, const uint16_t* __restrict__ Bval, const uint8_t* __restrict__ Bstrand,
 		uint32_t W, uint32_t* __restrict__ bcnt, uint4* __restrict__ part, int* err)
 {

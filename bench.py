@@ -286,8 +286,19 @@ def run_b200_arm(args, w):
               "k_scatter": 8 * nz + 4 * mk + 8 * flops,
               "k_group_fold": 8 * flops + 2 * nz + 16 * Z,
               "output(k_compact)": 16 * Z + 16 * Z}
+    # DRAM bytes of the same kernels from the committed ncu capture (profiles/traffic.json), per step, for this workload only
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("workload") == workload_name(w):
+            traffic = tj["dram_bytes_per_step"].get(dom)
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": kbytes[dom] / (kern[dom] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-            "peak_source": peak_src, "traffic": None,
+            "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes": int(kbytes[dom]),
+            "note": "kernel duration = CUDA events on the launching stream around the kernel's launches (all capacity classes), averaged "
+                    "over the timed steps; k_group_fold is warp-issue bound (the far tests of the fold), not HBM bound: see DESIGN.md 3-4",
             "whole_step": {"algorithmic_bytes": alg, "achieved": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak},
             "phase_ms": {k: float(v) for k, v in kern.items()}}
     roof["frac"] = roof["achieved"] / peak

@@ -57,7 +57,10 @@ int bella_b200_create(bella_b200_handle** out, int device);
 int bella_b200_destroy(bella_b200_handle* h);
 const char* bella_b200_last_error(const bella_b200_handle* h);
 
-/* Inputs from HOST memory (copied to the device here).  Replaces the `A, B, reads, bpars` arguments
+/* Inputs from HOST memory.  The copy to the device is started here on the handle's own copy stream, in a few
+ * ranges of reads, and bella_b200_symbolic consumes each range as soon as it has landed (the transpose overlaps
+ * the upload): the host arrays must stay valid and unchanged until bella_b200_symbolic has returned.
+ * Page-locked host memory makes the copies truly asynchronous; pageable memory works, without the overlap.  Replaces the `A, B, reads, bpars` arguments
  * of HashSpGEMM (include/overlap.hpp:650-652): read_len[n] and the strand bits stand in for `reads`,
  * kmer_size/bin_size for BELLApars.{kmerSize,binSize}.  strand bits are bit-packed, LSB first, one
  * bit per nonzero in that matrix's array order.  strand_B may be NULL: then bit 31 of every
