@@ -486,6 +486,42 @@ __device__ __forceinline__ uint4 pack_result(uint32_t row, const PairResult& r)
 	return make_uint4(row, (r.count & 0xFFFFu) | (r.nbins << 16), r.hv, (r.sup & 0xFFFFu) | (r.ov << 16));
 }
 
+// the rare case of fold_short: consecutive overlap estimates further apart than binSize (several bins).
+// Out of line and rolled: it keeps the hot kernel's instruction footprint small.
+template <bool EXACT>
+__device__ __noinline__ PairResult fold_short_forest(const uint32_t (&hvr)[SHORT_FOLD], const uint16_t (&ovr)[SHORT_FOLD], uint32_t np, uint32_t K, int BIN)
+{
+	constexpr int CAP = SHORT_FOLD;
+	const uint32_t lim = far_limit<EXACT>(K);
+	uint32_t hv[CAP];
+	uint16_t ov[CAP];
+	uint8_t par[CAP], sup[CAP];
+#pragma unroll
+	for (int a = 0; a < CAP; ++a) { hv[a] = hvr[a]; ov[a] = ovr[a]; }
+#pragma unroll 1
+	for (uint32_t b = 0; b < np; ++b) {
+		uint32_t t = b + 1;
+		while (t < np && abs((int)ov[t] - (int)ov[b]) >= BIN) ++t;
+		par[b] = t < np ? (uint8_t)t : (uint8_t)0xFF;
+		sup[b] = 0;
+	}
+	uint32_t csum = 0;
+#pragma unroll 1
+	for (uint32_t s = 0; s < np; ++s) {
+		const FarKey key = far_key<EXACT>(hv[s], K);
+		uint32_t a = par[s], last = s;
+		while (a != 0xFF && is_far<EXACT>(hv[a], key, lim)) { ++csum; last = a; a = par[a]; }
+		if (a == 0xFF) ++sup[last];
+	}
+	uint32_t best = 0, bt = 0, nb = 0;
+#pragma unroll 1
+	for (uint32_t t = 0; t < np; ++t)
+		if (par[t] == 0xFF) { ++nb; if (sup[t] >= best) { best = sup[t]; bt = t; } }
+	PairResult R;
+	R.count = (np + csum) & 0xFFFFu; R.hv = hv[bt]; R.nbins = nb; R.sup = best; R.ov = ov[bt];
+	return R;
+}
+
 // one thread, P <= SHORT_FOLD, products in fold order (hv = h | v<<16, ov = overlap estimate)
 template <bool EXACT>
 __device__ __forceinline__ PairResult fold_short(const uint32_t (&hv)[SHORT_FOLD], const uint16_t (&ov)[SHORT_FOLD], uint32_t np, uint32_t K, int BIN)
@@ -517,33 +553,13 @@ __device__ __forceinline__ PairResult fold_short(const uint32_t (&hv)[SHORT_FOLD
 		R.count = (np + csum) & 0xFFFFu; R.hv = last_hv; R.nbins = 1; R.sup = surv; R.ov = last_ov;
 		return R;
 	}
-	uint8_t par[CAP], sup[CAP];
-#pragma unroll
-	for (int b = 0; b < CAP; ++b) {
-		par[b] = 0xFF; sup[b] = 0;
-		if (b < (int)np) {
-#pragma unroll
-			for (int t = CAP - 1; t > b; --t)
-				if (t < (int)np && abs((int)ov[t] - (int)ov[b]) < BIN) par[b] = (uint8_t)t;
-		}
-	}
-	for (uint32_t s = 0; s < np; ++s) {
-		const FarKey key = far_key<EXACT>(hv[s], K);
-		uint32_t a = par[s], last = s;
-		while (a != 0xFF && is_far<EXACT>(hv[a], key, lim)) { ++csum; last = a; a = par[a]; }
-		if (a == 0xFF) ++sup[last];
-	}
-	uint32_t best = 0, bt = 0, nb = 0;
-	for (uint32_t t = 0; t < np; ++t)
-		if (par[t] == 0xFF) { ++nb; if (sup[t] >= best) { best = sup[t]; bt = t; } }
-	R.count = (np + csum) & 0xFFFFu; R.hv = hv[bt]; R.nbins = nb; R.sup = best; R.ov = ov[bt];
-	return R;
+	return fold_short_forest<EXACT>(hv, ov, np, K, BIN);
 }
 
 // The forest part shared by the cooperative folds: parents, ancestor walks, best root.
 // Threads tid0, tid0+stride, ... of the group take the products; sync() separates the phases.
 template <class Sync>
-__device__ __forceinline__ void fold_forest(const uint32_t* hv, const uint16_t* ov, uint16_t* par, uint32_t* sup, uint32_t P, uint32_t K,
+__device__ __noinline__ void fold_forest(const uint32_t* hv, const uint16_t* ov, uint16_t* par, uint32_t* sup, uint32_t P, uint32_t K,
 		int BIN, uint32_t tid0, uint32_t stride, Sync sync, uint32_t& csum, uint32_t& nroots, uint32_t& best)
 {
 	const uint32_t lim = far_limit<true>(K);
@@ -588,9 +604,14 @@ __device__ __forceinline__ void fold_linear_rounds(const uint32_t* hv, uint32_t 
 		for (uint32_t tb = r0; tb < P; tb += 32) {
 			uint32_t near = 0;
 			if (tb + 32 <= P) {
+#pragma unroll 1
+				for (uint32_t c0 = 0; c0 < 32; c0 += 8) {
+					uint32_t m = 0;
 #pragma unroll
-				for (int c = 0; c < 32; ++c)
-					if (!is_far<EXACT>(hv[tb + c], key, lim)) near |= 1u << c;
+					for (int c = 0; c < 8; ++c)
+						if (!is_far<EXACT>(hv[tb + c0 + c], key, lim)) m |= 1u << c;
+					near |= m << c0;
+				}
 			} else {
 				for (uint32_t c = 0; tb + c < P; ++c)
 					if (!is_far<EXACT>(hv[tb + c], key, lim)) near |= 1u << c;
@@ -606,11 +627,12 @@ __device__ __forceinline__ void fold_linear_rounds(const uint32_t* hv, uint32_t 
 
 // Whole-CTA fold of one pair (hv/ov/par/sup in shared or global memory, hv 16-byte aligned at
 // index 0).  part[0..2] (shared, zeroed by the caller) combines the warps.  All threads return the result.
-__device__ PairResult fold_cta(const uint32_t* hv, const uint16_t* ov, uint16_t* par, uint32_t* sup, uint32_t P, uint32_t K, int BIN,
+__device__ __noinline__ PairResult fold_cta(const uint32_t* hv, const uint16_t* ov, uint16_t* par, uint32_t* sup, uint32_t P, uint32_t K, int BIN,
 		uint32_t* part)
 {
 	const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
 	bool lin = true;
+#pragma unroll 1
 	for (uint32_t t = 1 + tid; t < P; t += blockDim.x) lin &= abs((int)ov[t] - (int)ov[t - 1]) < BIN;
 	const bool linear = (bool)__syncthreads_and(lin);
 	uint32_t csum = 0;
@@ -642,6 +664,7 @@ __device__ __forceinline__ PairResult warp_fold_pair(const uint32_t* hv, const u
 		uint32_t lane)
 {
 	bool lin = true;
+#pragma unroll 1
 	for (uint32_t t = 1 + lane; t < P; t += 32) lin &= abs((int)ov[t] - (int)ov[t - 1]) < BIN;
 	const bool linear = __all_sync(FULL, lin);
 	uint32_t csum = 0;
@@ -672,6 +695,7 @@ __device__ __forceinline__ uint32_t block_scan_chunked(T* out, uint32_t n, F val
 	const uint32_t per = ((n + blockDim.x - 1) / blockDim.x) | 1u;     // odd stride: no bank conflicts
 	const uint32_t i0 = min(tid * per, n), i1 = min(i0 + per, n);
 	uint32_t sum = 0;
+	#pragma unroll 1
 	for (uint32_t i = i0; i < i1; ++i) sum += val(i);
 	uint32_t incl = sum;
 #pragma unroll
@@ -687,6 +711,7 @@ __device__ __forceinline__ uint32_t block_scan_chunked(T* out, uint32_t n, F val
 	}
 	__syncthreads();
 	uint32_t run = s_tmp[wid] + incl - sum;
+	#pragma unroll 1
 	for (uint32_t i = i0; i < i1; ++i) { const uint32_t v = val(i); out[i] = (T)run; run += v; }
 	const uint32_t total = s_tmp[32];
 	if (tid == 0) out[n] = (T)total;
@@ -740,14 +765,17 @@ __device__ __forceinline__ bool warp_prepare_pair(const Params& P, const uint64_
 	if (L <= JR_BITMAP_MAX) {
 		const uint32_t Lw = (L + 31) >> 5;
 		uint16_t* jpre = (uint16_t*)(scr + 128);
+		#pragma unroll 1
 		for (uint32_t w = lane; w < Lw; w += 32) scr[w] = 0;
 		__syncwarp();
+		#pragma unroll 1
 		for (uint32_t y = lane; y < len; y += 32) {
 			const uint32_t jr = ((uint32_t)rec[y] >> 16);
 			atomicOr(&scr[jr >> 5], 1u << (jr & 31));
 		}
 		__syncwarp();
 		uint32_t carry = 0;
+		#pragma unroll 1
 		for (uint32_t w0 = 0; w0 < Lw; w0 += 32) {
 			const uint32_t w = w0 + lane;
 			const uint32_t c = w < Lw ? __popc(scr[w]) : 0;
@@ -758,6 +786,7 @@ __device__ __forceinline__ bool warp_prepare_pair(const Params& P, const uint64_
 			carry += __shfl_sync(FULL, v, 31);
 		}
 		__syncwarp();
+		#pragma unroll 1
 		for (uint32_t y = lane; y < len; y += 32) {
 			const uint64_t k = product_key(P, rec[y], j0, lenH, lenV, wide);
 			const uint32_t jr = (uint32_t)(k >> 48);
@@ -765,10 +794,12 @@ __device__ __forceinline__ bool warp_prepare_pair(const Params& P, const uint64_
 			hv[rank] = (uint32_t)k; ov[rank] = (uint16_t)(k >> 32);
 		}
 	} else {
+		#pragma unroll 1
 		for (uint32_t y = lane; y < len; y += 32) {
 			const uint64_t k = product_key(P, rec[y], j0, lenH, lenV, wide);
 			const uint32_t jr = (uint32_t)(k >> 48);
 			uint32_t rank = 0;
+			#pragma unroll 1
 			for (uint32_t z = 0; z < len; ++z) rank += (((uint32_t)rec[z] >> 16) < jr);
 			hv[rank] = (uint32_t)k; ov[rank] = (uint16_t)(k >> 32);
 		}
@@ -810,6 +841,7 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 	__syncthreads();
 	uint32_t phase = 0;
 
+	#pragma unroll 1
 	for (uint32_t it = blockIdx.x; it < count; it += gridDim.x) {
 		const uint32_t u = list[it];
 		const uint32_t li = P.ucol[u], i = P.lo + li;
@@ -836,7 +868,9 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 		}
 		if (two) { for (uint32_t s = tid; s <= l1w; s += NT) l1[s] = 0; }
 		const uint32_t nclear = two ? min(Fi, (uint32_t)CAP) : words;
+		#pragma unroll 1
 		for (uint32_t s = tid; s < nclear; s += NT) bits[s] = 0;
+		#pragma unroll 1
 		for (uint32_t s = tid; s < ((Fi + 3) >> 1); s += NT) ((uint32_t*)cnt)[s] = 0;
 		if (tid == 0) { s_nlong = 0; s_nhuge = 0; s_next = 0; s_wide = 0; }
 		mbar_wait(&s_bar, phase);
@@ -846,6 +880,7 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 		// --- distinct rows (== estimateNNZ_Hash) and the pair index, rows ascending ---
 		uint32_t nwords = words;
 		if (two) {
+			#pragma unroll 1
 			for (uint32_t x = tid; x < Fi; x += NT) {
 				const uint32_t rel = ent_row(prodS[x]) - rbase;
 				atomicOr(&l1[rel >> 10], 1u << ((rel >> 5) & 31));
@@ -857,12 +892,14 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 			const uint32_t w = rel >> 5;
 			return two ? l1pre[w >> 5] + __popc(l1[w >> 5] & ((1u << (w & 31)) - 1u)) : w;
 		};
+		#pragma unroll 1
 		for (uint32_t x = tid; x < Fi; x += NT) {
 			const uint32_t rel = ent_row(prodS[x]) - rbase;
 			atomicOr(&bits[word_of(rel)], 1u << (rel & 31));
 		}
 		__syncthreads();
 		const uint32_t Z = block_scan_chunked<uint16_t>(pre, nwords, [&](uint32_t w) { return (uint32_t)__popc(bits[w]); }, s_tmp);
+		#pragma unroll 1
 		for (uint32_t x = tid; x < Fi; x += NT) {
 			const uint64_t r = prodS[x];
 			const uint32_t row = ent_row(r), rel = row - rbase, q = word_of(rel);
@@ -875,6 +912,7 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 		__syncthreads();
 		block_scan_chunked<uint16_t>(cnt, Z, [&](uint32_t p) { return (uint32_t)cnt[p]; }, s_tmp);     // counts -> offsets, poff[Z] = Fi
 		const uint16_t* poff = cnt;
+		#pragma unroll 1
 		for (uint32_t x = tid; x < Fi; x += NT) {
 			const uint64_t t = prodS[x];
 			sorted[poff[(uint32_t)(t >> 34) & 0x3FFFu] + ((uint32_t)(t >> 48) & 0x3FFFu)] = t & 0x1FFFFFFFFull;
@@ -886,6 +924,7 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 		const uint32_t j0 = P.B_colptr[i];
 		const int lenV = (int)P.read_len[i];
 		uint4* out = P.out + base;
+		#pragma unroll 1
 		for (uint32_t p = tid; p < Z; p += NT)
 			if ((uint32_t)(poff[p + 1] - poff[p]) > SHORT_FOLD) longlist[atomicAdd(&s_nlong, 1u)] = (uint16_t)p;
 		__syncthreads();
@@ -913,8 +952,10 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 				const uint32_t row = rowS[p];
 				const int lenH = (int)P.read_len[row];
 				uint64_t key[SHORT_FOLD];
+#pragma unroll 1
+				for (uint32_t k = 0; k < len; ++k) sorted[s0 + k] = product_key(P, sorted[s0 + k], j0, lenH, lenV, wide);   // in place (own slots)
 #pragma unroll
-				for (int k = 0; k < (int)SHORT_FOLD; ++k) key[k] = k < (int)len ? product_key(P, sorted[s0 + k], j0, lenH, lenV, wide) : ~0ull;
+				for (int k = 0; k < (int)SHORT_FOLD; ++k) key[k] = k < (int)len ? sorted[s0 + k] : ~0ull;
 				if (len > 1) sort8(key);
 				uint32_t hv[SHORT_FOLD];
 				uint16_t ov[SHORT_FOLD];
@@ -926,16 +967,19 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 		if (!EXACT && (wide || K > 16383u)) s_wide = 1;
 		__syncthreads();
 		const uint32_t nhuge = s_nhuge;                             // at most CAP/1024 pairs: the whole CTA takes each
+		#pragma unroll 1
 		for (uint32_t q = 0; q < nhuge; ++q) {
 			const uint32_t p = hugelist[q], s0 = poff[p], len = poff[p + 1] - s0;
 			const uint32_t row = rowS[p];
 			const int lenH = (int)P.read_len[row];
+			#pragma unroll 1
 			for (uint32_t y = tid; y < len; y += NT) {
 				bool w2 = false;
 				const uint64_t k = product_key(P, sorted[s0 + y], j0, lenH, lenV, w2);
 				if (!EXACT && w2) s_wide = 1;
 				const uint32_t jr = (uint32_t)(k >> 48);
 				uint32_t rank = 0;
+				#pragma unroll 1
 				for (uint32_t z = s0; z < s0 + len; ++z) rank += (((uint32_t)sorted[z] >> 16) < jr);
 				hvL[s0 + rank] = (uint32_t)k; ovL[s0 + rank] = (uint16_t)(k >> 32);
 			}
