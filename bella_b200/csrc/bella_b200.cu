@@ -87,6 +87,7 @@ struct bella_b200_handle {
 	uint64_t flops = 0, Z = 0;
 	cudaEvent_t ev[12]{};
 	float t_ms[8]{};
+	float t_scans = 0, t_mg_scatter = 0;
 	int launches = 0;
 };
 
@@ -170,6 +171,7 @@ int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32
 	ENSURE(h->boff, sizeof(uint32_t) * ((size_t)NB + 2));
 	ENSURE(h->part, sizeof(uint4) * (size_t)NB * BUCKET_CAP);
 	CK(cudaMemsetAsync(h->bcur.p, 0, sizeof(uint32_t) * ((size_t)NB + 2), h->stream));
+	CK(cudaEventRecord(h->ev[8], h->stream));
 	if (h->n_chunks > 0) {
 		// host inputs are still arriving chunk by chunk: partition each range of reads as soon as it is on the device
 		for (int c = 0; c < h->n_chunks; ++c) {
@@ -185,6 +187,7 @@ int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32
 			h->dB_values, h->dB_strand, W, h->bcur.as<uint32_t>(), h->part.as<uint4>(), h->errflag.as<int>());
 		LAUNCHED();
 	}
+	CK(cudaEventRecord(h->ev[9], h->stream));
 	if (int rc = exclusive_scan(h, h->bcur.as<uint32_t>(), h->boff.as<uint32_t>(), NB + 1)) return rc;
 	CK(cudaFuncSetAttribute(k_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BUCKET_SMEM));
 	k_bucket<<<NB < 148u * 12 ? NB : 148u * 12, 256, BUCKET_SMEM, h->stream>>>(h->klo, ml, cnt_lo, cnt_hi, W, NB, h->boff.as<uint32_t>(),
@@ -356,7 +359,7 @@ int group_and_output(bella_b200_handle* h)
 	if (e) return report_device_error(h, e);
 	h->Z = z32;
 	CK(cudaEventElapsedTime(&h->t_ms[1], h->ev[3], h->ev[4]));    // group + fold
-	CK(cudaEventElapsedTime(&h->t_ms[6], h->ev[4], h->ev[5]));    // scans + colptr
+	CK(cudaEventElapsedTime(&h->t_scans, h->ev[4], h->ev[5]));    // scans + colptr
 	h->symbolic_done = true;
 	h->numeric_done = false;
 	return 0;
@@ -379,7 +382,10 @@ int run_symbolic(bella_b200_handle* h)
 		LAUNCHED();
 	}
 	if (int rc = group_and_output(h)) return rc;
-	CK(cudaEventElapsedTime(&h->t_ms[0], h->ev[0], h->ev[2]));    // transpose + plan
+	if (h->nnzB && h->m && h->hi > h->lo) {
+		CK(cudaEventElapsedTime(&h->t_ms[0], h->ev[8], h->ev[9]));    // k_partition (includes waiting for the upload when it is still running)
+		CK(cudaEventElapsedTime(&h->t_ms[6], h->ev[9], h->ev[2]));    // k_bucket + plan
+	} else h->t_ms[0] = h->t_ms[6] = 0;
 	CK(cudaEventElapsedTime(&h->t_ms[7], h->ev[2], h->ev[3]));    // scatter
 	return 0;
 }
@@ -590,6 +596,8 @@ int bella_b200_numeric_device(bella_b200_handle* h)
 	CK(cudaEventRecord(h->ev[7], h->stream));
 	CK(cudaStreamSynchronize(h->stream));
 	CK(cudaEventElapsedTime(&h->t_ms[2], h->ev[6], h->ev[7]));
+	h->t_ms[2] += h->t_scans;                                  // output = C's colptr scans + compaction
+	h->t_scans = 0;
 	return BELLA_B200_OK;
 }
 
@@ -726,6 +734,7 @@ int bella_b200_mg_scatter(bella_b200_handle* h, const uint64_t* sendoff_dev, uin
 	const uint32_t n = h->n, ml = h->khi - h->klo;
 	ENSURE(h->mg_colinfo, sizeof(ColInfo) * ((size_t)n + 1));
 	ENSURE(h->mg_ucur, sizeof(uint64_t) * ((size_t)n + 1));
+	CK(cudaEventRecord(h->ev[10], h->stream));
 	if (n && ml && h->nnzB) {
 		k_mg_colinfo<<<grid_for(n, 256), 256, 0, h->stream>>>(n, sendoff_dev, h->mg_colinfo.as<ColInfo>(), h->mg_ucur.as<unsigned long long>());
 		LAUNCHED();
@@ -734,6 +743,8 @@ int bella_b200_mg_scatter(bella_b200_handle* h, const uint64_t* sendoff_dev, uin
 		LAUNCHED();
 	}
 	CK(cudaEventRecord(h->ev[2], h->stream));
+	CK(cudaEventSynchronize(h->ev[2]));
+	CK(cudaEventElapsedTime(&h->t_mg_scatter, h->ev[10], h->ev[2]));
 	return BELLA_B200_OK;
 }
 
@@ -764,8 +775,11 @@ int bella_b200_mg_finish(bella_b200_handle* h, uint32_t col_lo, uint32_t col_hi,
 	if (!rc) rc = group_and_output(h);
 	h->mg_recv = nullptr;
 	if (rc) return rc;
-	CK(cudaEventElapsedTime(&h->t_ms[0], h->ev[0], h->ev[1]));    // this GPU's share of the transpose
-	CK(cudaEventElapsedTime(&h->t_ms[7], h->ev[1], h->ev[2]));    // expansion into the send buffer
+	if (h->nnzB && h->khi > h->klo && h->n) {
+		CK(cudaEventElapsedTime(&h->t_ms[0], h->ev[8], h->ev[9]));    // k_partition of this GPU's k-mer range
+		CK(cudaEventElapsedTime(&h->t_ms[6], h->ev[9], h->ev[1]));    // k_bucket
+	} else h->t_ms[0] = h->t_ms[6] = 0;
+	h->t_ms[7] = h->t_mg_scatter;
 	return BELLA_B200_OK;
 }
 

@@ -221,8 +221,8 @@ class OverlapSpGEMM:
     def timings(self):
         t = (ctypes.c_float * 8)()
         self._L.bella_b200_get_timings(self._h, t)
-        return {"transpose_ms": t[0], "group_fold_ms": t[1], "output_ms": t[2] + t[6], "h2d_ms": t[3], "d2h_ms": t[4],
-                "launches": int(t[5]), "scatter_ms": t[7]}
+        return {"partition_ms": t[0], "bucket_plan_ms": t[6], "transpose_ms": t[0] + t[6], "scatter_ms": t[7], "group_fold_ms": t[1],
+                "output_ms": t[2], "h2d_ms": t[3], "d2h_ms": t[4], "launches": int(t[5])}
 
 
 def overlap_spgemm(inp, device=0, with_A=False, aux=False):

@@ -233,12 +233,12 @@ def run_b200_arm(args, w):
     torch.cuda.synchronize()
     ev0.record(stream)
     launches = 0
-    phase = np.zeros(4)
+    phase = np.zeros(5)
     for _ in range(args.steps):
         Z, flops = resident_step()
         t = g.timings()
         launches += t["launches"]
-        phase += [t["transpose_ms"], t["scatter_ms"], t["group_fold_ms"], t["output_ms"]]
+        phase += [t["partition_ms"], t["bucket_plan_ms"], t["scatter_ms"], t["group_fold_ms"], t["output_ms"]]
     ev1.record(stream)
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / args.steps
@@ -278,13 +278,14 @@ def run_b200_arm(args, w):
     # ---- roofline of the dominant kernel ----
     peak, peak_src = measured_peak()
     alg = algorithmic_bytes(inp, Z, flops)
-    kern = {"transpose(k_partition+k_bucket)": phase[0], "k_scatter": phase[1], "k_group_fold": phase[2], "output(k_compact)": phase[3]}
+    kern = {"k_partition": phase[0], "k_bucket(+plan)": phase[1], "k_scatter": phase[2], "k_group_fold": phase[3], "output(k_compact)": phase[4]}
     dom = max(kern, key=kern.get)
-    # per-kernel algorithmic bytes (DESIGN.md)
+    # per-kernel algorithmic bytes (DESIGN.md 3)
     nz, mk = inp.nnz, inp.n_kmers
-    kbytes = {"transpose(k_partition+k_bucket)": 6 * nz + nz // 8 + 4 * inp.n_reads + 8 * nz + 4 * mk,
+    kbytes = {"k_partition": 6 * nz + nz // 8 + 4 * inp.n_reads + 16 * nz,
+              "k_bucket(+plan)": 16 * nz + 8 * nz + 4 * mk,
               "k_scatter": 8 * nz + 4 * mk + 8 * flops,
-              "k_group_fold": 8 * flops + 2 * nz + 16 * Z,
+              "k_group_fold": 8 * flops + 2 * flops + 4 * Z + 16 * Z,
               "output(k_compact)": 16 * Z + 16 * Z}
     # DRAM bytes of the same kernels from the committed ncu capture (profiles/traffic.json), per step, for this workload only
     traffic = None

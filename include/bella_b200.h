@@ -124,9 +124,9 @@ int bella_b200_result_device(bella_b200_handle* h, const uint32_t** colptrC, con
 int bella_b200_run_resident(bella_b200_handle* h, uint64_t* nnzC_out, uint64_t* flops_out);
 
 /* Timings of the last pass in milliseconds (CUDA events on the handle's stream):
- *   [0] transpose + plan (B -> A, product counts, units)   [1] group + fold kernels
- *   [2] output compaction         [3] host->device copies   [4] device->host copies
- *   [5] kernels launched (count)  [6] output scans          [7] scatter kernel */
+ *   [0] k_partition   [1] k_group_fold (all capacity classes)   [2] output (C's colptr scans + k_compact)
+ *   [3] host->device copies   [4] device->host copies   [5] kernels launched (count)
+ *   [6] k_bucket + plan kernels   [7] k_scatter */
 int bella_b200_get_timings(bella_b200_handle* h, float* ms8);
 
 /* cudaStream_t of the handle as an opaque pointer (so a caller can order its own work after it). */
