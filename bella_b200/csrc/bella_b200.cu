@@ -64,7 +64,8 @@ struct bella_b200_handle {
 	DevBuf oB_colptr, oB_rowids, oB_values, oB_strand, o_len;
 	// chunked upload of host inputs, overlapped with the transpose (bella_b200_set_inputs)
 	static constexpr int MAX_CHUNKS = 8;
-	cudaStream_t copy_stream = nullptr;
+	cudaStream_t copy_stream = nullptr, aux_stream = nullptr;   // aux: the larger group classes run beside the 2048 class
+	cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
 	cudaEvent_t chunk_ev[MAX_CHUNKS]{}, copy_begin = nullptr, copy_end = nullptr;
 	uint32_t chunk_lo[MAX_CHUNKS + 1]{};
 	int n_chunks = 0;                          // > 0: reads [chunk_lo[c], chunk_lo[c+1]) are on the device once chunk_ev[c] has fired
@@ -260,7 +261,7 @@ Params make_params(bella_b200_handle* h)
 }
 
 template <int CAP, int NT>
-int launch_group(bella_b200_handle* h, const Params& P, int cls, uint32_t count, uint32_t l1cap, int ctas_per_sm)
+int launch_group(bella_b200_handle* h, const Params& P, int cls, uint32_t count, uint32_t l1cap, int ctas_per_sm, cudaStream_t st)
 {
 	// fast instance over the class list, then the exact instance over whatever the fast one handed back
 	const uint32_t ucap = h->ucap;
@@ -273,9 +274,9 @@ int launch_group(bella_b200_handle* h, const Params& P, int cls, uint32_t count,
 	CK(cudaFuncSetAttribute(k_group_fold<CAP, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	if (count) {
 		uint32_t grid = count < 148u * ctas_per_sm ? count : 148u * ctas_per_sm;
-		k_group_fold<CAP, NT, false><<<grid, NT, smem, h->stream>>>(P, list, class_count, l1cap, redo, redo_count);
+		k_group_fold<CAP, NT, false><<<grid, NT, smem, st>>>(P, list, class_count, l1cap, redo, redo_count);
 		LAUNCHED();
-		k_group_fold<CAP, NT, true><<<148, NT, smem, h->stream>>>(P, redo, redo_count, l1cap, nullptr, nullptr);
+		k_group_fold<CAP, NT, true><<<148, NT, smem, st>>>(P, redo, redo_count, l1cap, nullptr, nullptr);
 		LAUNCHED();
 	}
 	return 0;
@@ -339,13 +340,18 @@ int group_and_output(bella_b200_handle* h)
 	ENSURE(h->redo, sizeof(uint32_t) * (size_t)NCLASS * ((size_t)ucap + 1));
 	for (int c = 0; c < NCLASS; ++c)
 		CK(cudaMemsetAsync(h->redo.as<uint32_t>() + (size_t)c * (ucap + 1) + ucap, 0, sizeof(uint32_t), h->stream));
-	if (int rc = launch_group<2048, 256>(h, P, 0, cc[0], l1cap, 4)) return rc;
-	if (int rc = launch_group<4096, 512>(h, P, 1, cc[1], l1cap, 2)) return rc;
-	if (int rc = launch_group<8192, 1024>(h, P, 2, cc[2], l1cap, 1)) return rc;
+	// the larger classes (few, long-running CTAs) start first on a second stream; the 2048 class fills the rest of the GPU
+	CK(cudaEventRecord(h->aux_fork, h->stream));
+	CK(cudaStreamWaitEvent(h->aux_stream, h->aux_fork, 0));
+	if (int rc = launch_group<8192, 1024>(h, P, 2, cc[2], l1cap, 1, h->aux_stream)) return rc;
+	if (int rc = launch_group<4096, 512>(h, P, 1, cc[1], l1cap, 2, h->aux_stream)) return rc;
 	if (cc[3]) {
-		k_huge_pair<<<cc[3] < 148u ? cc[3] : 148u, 1024, 0, h->stream>>>(P, lists + (size_t)3 * ucap, cc[3]);
+		k_huge_pair<<<cc[3] < 148u ? cc[3] : 148u, 1024, 0, h->aux_stream>>>(P, lists + (size_t)3 * ucap, cc[3]);
 		LAUNCHED();
 	}
+	CK(cudaEventRecord(h->aux_join, h->aux_stream));
+	if (int rc = launch_group<2048, 256>(h, P, 0, cc[0], l1cap, 4, h->stream)) return rc;
+	CK(cudaStreamWaitEvent(h->stream, h->aux_join, 0));
 	CK(cudaEventRecord(h->ev[4], h->stream));
 	if (int rc = exclusive_scan(h, h->unnz.as<uint32_t>(), h->uoff.as<uint32_t>(), U + 1)) return rc;
 	k_colptr<<<grid_for(ncols + 1, 256), 256, 0, h->stream>>>(ncols, h->ubase.as<uint32_t>(), h->uoff.as<uint32_t>(), h->colptrC.as<uint32_t>());
@@ -454,6 +460,8 @@ int bella_b200_create(bella_b200_handle** out, int device)
 	if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return BELLA_B200_ERR_CUDA; }
 	for (auto& e : h->ev) cudaEventCreate(&e);
 	cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+	cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+	cudaEventCreateWithFlags(&h->aux_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->aux_join, cudaEventDisableTiming);
 	for (auto& e : h->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
 	cudaEventCreate(&h->copy_begin); cudaEventCreate(&h->copy_end);
 	*out = h;
@@ -475,6 +483,9 @@ int bella_b200_destroy(bella_b200_handle* h)
 	if (h->copy_begin) cudaEventDestroy(h->copy_begin);
 	if (h->copy_end) cudaEventDestroy(h->copy_end);
 	if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+	if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
+	if (h->aux_fork) cudaEventDestroy(h->aux_fork);
+	if (h->aux_join) cudaEventDestroy(h->aux_join);
 	if (h->own_stream) cudaStreamDestroy(h->stream);
 	delete h;
 	return BELLA_B200_OK;

@@ -36,7 +36,7 @@ constexpr int NCLASS = 3;
 constexpr uint32_t CLASS_CAP[NCLASS] = {2048, 4096, 8192};
 constexpr uint32_t UNIT_CAP = 8192;        // products per unit (largest shared-memory class)
 constexpr uint32_t BUCKET_CAP = 4096;      // entries per transpose bucket
-constexpr uint32_t BUCKET_WMAX = 4096;     // k-mers per transpose bucket
+constexpr uint32_t BUCKET_WMAX = 2048;     // k-mers per transpose bucket
 constexpr uint32_t MAX_SPAN_SHIFT = 22;    // a unit covers at most 2^22 rows (two-level bitmap: 4097 words)
 constexpr uint32_t SHORT_FOLD = 8;         // pairs up to this many products are folded by one thread
 constexpr int GF_THREADS = 256;
