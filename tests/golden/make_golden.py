@@ -14,6 +14,11 @@ Fixtures:
   repeats       reads from a genome with diverged tandem repeats, u=60, binSize 200: several bins per
                 pair, bins merging and re-splitting (exercises the orphan / near-bin paths of chainop)
   build_csc     tuples -> B (CSC ctor + MergeDuplicates) -> A (Transpose, 1 thread) of the reference
+  heavy_units   250 reads x 5 kb, e=0.01, 40x, u=80: up to 188 k products per column, hundreds per pair (the GPU splits
+                such columns into row-range units)
+  huge_pair     24 reads x 14 kb, e=0.002, 8x, u=40: read pairs sharing more than 8192 k-mers (more than fits shared memory)
+  ragged        160 reads of 300..30 000 bp (log-uniform), 10 % substitutions, both strands: ragged columns, short reads
+                with a handful of k-mers next to very long ones
 """
 import os
 import sys
@@ -80,6 +85,36 @@ def save_repeats():
     save("repeats", inp, ol.ref_spgemm(inp, nthreads=1))
 
 
+def ragged_reads(seed=9, n_reads=160, genome_len=90000, err=0.10):
+    rng = np.random.default_rng(seed)
+    B = np.frombuffer(b"ACGT", dtype=np.uint8)
+    genome = rng.integers(0, 4, genome_len)
+    comp = np.array([3, 2, 1, 0])
+    reads = []
+    for r in range(n_reads):
+        L = int(np.exp(rng.uniform(np.log(300), np.log(30000))))
+        s0 = int(rng.integers(0, genome_len - L))
+        t = genome[s0:s0 + L].copy()
+        mut = rng.random(L) < err
+        t[mut] = (t[mut] + rng.integers(1, 4, int(mut.sum()))) % 4
+        if rng.random() < 0.5:
+            t = comp[t[::-1]]
+        reads.append(B[t].tobytes().decode())
+    return reads
+
+
+def main_round1_additions():
+    """Fixtures added later in round 1 (the earlier files stay byte-identical)."""
+    assert ol.have_ref(), "build oracle/_ref first (make -C oracle ref)"
+    inp = fe.synthetic(250, 5000, coverage=40.0, err=0.01, seed=13, hi=80)
+    save("heavy_units", inp, ol.ref_spgemm(inp, nthreads=1))
+    inp = fe.synthetic(24, 14000, coverage=8.0, err=0.002, seed=17, hi=40)
+    save("huge_pair", inp, ol.ref_spgemm(inp, nthreads=1))
+    s, o = fe.reads_from_strings(ragged_reads())
+    inp = fe.build_matrices(s, o)
+    save("ragged", inp, ol.ref_spgemm(inp, nthreads=1))
+
+
 def main():
     assert ol.have_ref(), "build oracle/_ref first (make -C oracle ref)"
     names, reads = fe.read_fastq("/root/reference/sanitytests/reversecomptest.fastq")
@@ -116,4 +151,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "additions":
+        main_round1_additions()
+    else:
+        main()
+        main_round1_additions()

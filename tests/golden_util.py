@@ -7,7 +7,7 @@ from bella_b200.frontend import OverlapInputs
 from oracle_lib import Result
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-SPGEMM_FIXTURES = ["sanity", "tiny_clr", "tiny_hifi", "tiny_bin50", "repeats"]
+SPGEMM_FIXTURES = ["sanity", "tiny_clr", "tiny_hifi", "tiny_bin50", "repeats", "heavy_units", "huge_pair", "ragged"]
 
 
 def load(name):

@@ -151,3 +151,24 @@ def test_gpu_panel_format_strand_in_rowids(small_inputs):
     r = g.numeric(aux=True)
     g.close()
     ol.assert_same(ol.Result(flopC, colptrC, *r), want)
+
+
+def test_gpu_ragged_edge_inputs():
+    # one read; reads without any reliable k-mer between overlapping ones (empty columns of B, rows that never occur)
+    from bella_b200 import frontend as fe
+    rng = np.random.default_rng(5)
+    bases = np.frombuffer(b"ACGT", dtype=np.uint8)
+    genome = rng.integers(0, 4, 6000)
+    rd = lambda a, b: bases[genome[a:b]].tobytes().decode()
+    lone = bases[rng.integers(0, 4, 900)].tobytes().decode()
+    cases = [[rd(0, 3000)],                                                     # n = 1: nothing to overlap with
+             [rd(0, 3000), lone, rd(1000, 4000), lone[::-1], rd(2000, 5000), rd(100, 140)]]   # unrelated and very short reads in between
+    for reads in cases:
+        s, o = fe.reads_from_strings(reads)
+        inp = fe.build_matrices(s, o)
+        want = ol.oracle_spgemm(inp) if inp.nnz else None
+        got = gpu_result(inp)
+        if want is None:
+            assert int(got.colptrC[-1]) == 0
+        else:
+            ol.assert_same(got, want)
