@@ -212,6 +212,10 @@ def _owner_bounds(pre, world):
     return torch.cat([z, cuts.to(torch.int64), z + n])
 
 
+UNIT_OVERHEAD = 320     # products: what one more (non-empty) column costs the group + fold stage, measured on 4 x B200
+                        # (two ranks with equal products, 7 k vs 24 k columns: 1.04 vs 1.34 ms)
+
+
 def exchange_plan(counts_all, rank):
     """counts_all int32 [world][n]: every rank's per-column product counts.  One device->host copy.
     -> (bounds list, in_splits, out_splits, segoff int64 [world][ncols+1], recvbase int64 [world], sendoff int64 [n+1])"""
@@ -222,7 +226,10 @@ def exchange_plan(counts_all, rank):
     if n == 0:
         z = torch.zeros((world, 1), dtype=torch.int64, device=dev)
         return [0] * (world + 1), [0] * world, [0] * world, z, torch.zeros(world, dtype=torch.int64, device=dev), C[rank]
-    b = _owner_bounds(C[:, 1:].sum(0).to(torch.float64), world)
+    # owner ranges equalise  products + UNIT_OVERHEAD per non-empty column  (both prefix sums are monotone)
+    tot_pre = C[:, 1:].sum(0)
+    nonempty_pre = torch.cumsum((counts_all.sum(0) > 0).to(torch.int64), 0)
+    b = _owner_bounds((tot_pre + UNIT_OVERHEAD * nonempty_pre).to(torch.float64), world)
     Cb = C[:, b]                                            # [world][world+1]
     host = torch.cat([b.view(1, -1), Cb]).cpu()             # the one synchronising copy
     bounds = [int(x) for x in host[0]]
