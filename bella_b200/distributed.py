@@ -19,6 +19,8 @@ above its first column itself and no products are exchanged.)
 Everything in this file is host-side plumbing on torch tensors (CPU tensors with gloo in the unit
 tests, CUDA tensors with NCCL on the box); the arithmetic is in libbella_b200.so.
 """
+import sys
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -368,17 +370,22 @@ def bench_multi(args, w, inp, rank, world, local, METRIC, UNIT, workload, ClockS
         dist.barrier()
         torch.cuda.synchronize(dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         ev0.record(stream)
         out = None
-        for _ in range(steps):
+        for k in range(steps):
             out = fn()
+            marks[k].record(stream)
         ev1.record(stream)
         torch.cuda.synchronize(dev)
+        if rank == 0:       # per-step device times, for the log only
+            per = [(ev0 if k == 0 else marks[k - 1]).elapsed_time(marks[k]) for k in range(steps)]
+            print("[bench] per-step ms (rank 0): " + " ".join(f"{x:.2f}" for x in per), file=sys.stderr, flush=True)
         ms = torch.tensor([ev0.elapsed_time(ev1) / steps], dtype=torch.float64, device=dev)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms[0]), out
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3) + 2):       # two more than asked: the first exchanges also set up NCCL's peer channels
         sh.step()
     sampler = ClockSampler(local)
     if rank == 0:
