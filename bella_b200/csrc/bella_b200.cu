@@ -88,7 +88,7 @@ struct bella_b200_handle {
 	uint64_t flops = 0, Z = 0;
 	cudaEvent_t ev[12]{};
 	float t_ms[8]{};
-	float t_scans = 0, t_mg_scatter = 0;
+	float t_scans = 0;
 	int launches = 0;
 };
 
@@ -754,8 +754,6 @@ int bella_b200_mg_scatter(bella_b200_handle* h, const uint64_t* sendoff_dev, uin
 		LAUNCHED();
 	}
 	CK(cudaEventRecord(h->ev[2], h->stream));
-	CK(cudaEventSynchronize(h->ev[2]));
-	CK(cudaEventElapsedTime(&h->t_mg_scatter, h->ev[10], h->ev[2]));
 	return BELLA_B200_OK;
 }
 
@@ -790,7 +788,7 @@ int bella_b200_mg_finish(bella_b200_handle* h, uint32_t col_lo, uint32_t col_hi,
 		CK(cudaEventElapsedTime(&h->t_ms[0], h->ev[8], h->ev[9]));    // k_partition of this GPU's k-mer range
 		CK(cudaEventElapsedTime(&h->t_ms[6], h->ev[9], h->ev[1]));    // k_bucket
 	} else h->t_ms[0] = h->t_ms[6] = 0;
-	h->t_ms[7] = h->t_mg_scatter;
+	CK(cudaEventElapsedTime(&h->t_ms[7], h->ev[10], h->ev[2]));    // expansion into the send buffer
 	return BELLA_B200_OK;
 }
 

@@ -428,7 +428,7 @@ def bench_multi(args, w, inp, rank, world, local, METRIC, UNIT, workload, ClockS
                 "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "u16/u32", "data": "synthetic",
                 "config": {"workload": workload, "n_kmers": inp.n_kmers, "nnz_A": inp.nnz, "products": Ft, "output_nnz": Zt,
-                           "parallelism": f"row-sharded x{world}, one all-gather of the B panel per step",
+                           "parallelism": f"row-sharded x{world}: all-gather of the B panel, transpose split by k-mer range, all-to-all of the products",
                            "l2": "inputs larger than L2, no flush"},
                 "clocks": clocks,
                 "e2e": {"value": Zt / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(d2h[0]),
