@@ -77,7 +77,6 @@ struct Meta {
 	unsigned int class_count[NCLASS + 1];   // + overflow
 	unsigned int n_heavy_cols;
 	unsigned int n_units;
-	unsigned int max_bucket;
 	unsigned int n_refine;
 };
 

@@ -80,3 +80,30 @@ def test_column_ranges_degenerate():
     assert bd.column_ranges(torch.zeros(1, dtype=torch.int64), 4) == [0, 0, 0, 0, 0]
     b = bd.column_ranges(torch.arange(0, 11, dtype=torch.int64) * 0, 2)      # all-empty reads
     assert b[0] == 0 and b[-1] == 10
+
+
+def test_exchange_plan_is_consistent_across_ranks():
+    # every rank derives the same owner ranges from the all-gathered counts, what rank s sends to rank d is what d
+    # expects from s, and the (source, column) segment offsets tile the receive buffer exactly
+    from bella_b200 import distributed as bd
+    torch.manual_seed(3)
+    world, n = 4, 3000
+    counts = torch.randint(0, 60, (world, n), dtype=torch.int32)
+    counts[:, 100:400] = 0                                   # a stretch of empty columns
+    plans = [bd.exchange_plan(counts, r) for r in range(world)]
+    bounds = plans[0][0]
+    assert bounds[0] == 0 and bounds[-1] == n and all(a <= b for a, b in zip(bounds[:-1], bounds[1:]))
+    tot = counts.to(torch.int64).sum(0)
+    cost = [int(tot[bounds[r]:bounds[r + 1]].sum()) + bd.UNIT_OVERHEAD * int((tot[bounds[r]:bounds[r + 1]] > 0).sum()) for r in range(world)]
+    assert max(cost) <= 1.05 * (sum(cost) / world) + 2 * (60 * world + bd.UNIT_OVERHEAD)
+    for r in range(world):
+        b, ins, outs, segoff, recvbase, sendoff = plans[r]
+        assert b == bounds
+        lo, hi = bounds[r], bounds[r + 1]
+        assert segoff.shape == (world, hi - lo + 1)
+        for s in range(world):
+            assert ins[s] == plans[s][2][r]                              # s -> r as seen from both sides
+            assert int(segoff[s, -1]) == ins[s]
+            np.testing.assert_array_equal(np.diff(segoff[s].numpy()), counts[s, lo:hi].numpy())
+        assert recvbase.tolist() == [sum(ins[:s]) for s in range(world)]
+        assert int(sendoff[-1]) == int(counts[r].sum()) and sendoff.numel() == n + 1
