@@ -77,6 +77,9 @@ struct bella_b200_handle {
 	const uint32_t* mg_counts = nullptr;
 	int mg_world = 0;
 	DevBuf mg_colinfo, mg_ucur;
+	// matrix construction from tuples (bella_b200_set_inputs_tuples)
+	DevBuf tp_kmer, tp_read, tp_pos, tp_strand, tp_rs, tp_re, tp_nruns, tp_cnt, tp_cp, tp_merged, tp_tmpK, tp_tmpV, tp_slab;
+	float t_build_ms = 0;
 	DevBuf boff, bcur, part, Aent, Acolptr, flop32;
 	// plan
 	uint32_t ucap = 0, U = 0, round = 0;
@@ -375,7 +378,7 @@ int group_and_output(bella_b200_handle* h)
 int run_symbolic(bella_b200_handle* h)
 {
 	ENSURE(h->meta, sizeof(Meta));
-	ENSURE(h->errflag, sizeof(int));
+	ENSURE(h->errflag, 4 * sizeof(int));
 	CK(cudaMemsetAsync(h->errflag.p, 0, sizeof(int), h->stream));
 	h->klo = 0; h->khi = h->m;
 	h->mg_recv = nullptr;
@@ -476,7 +479,8 @@ int bella_b200_destroy(bella_b200_handle* h)
 	DevBuf* bufs[] = {&h->oB_colptr, &h->oB_rowids, &h->oB_values, &h->oB_strand, &h->o_len, &h->boff, &h->bcur, &h->part,
 		&h->Aent, &h->Acolptr, &h->flop32, &h->nunits, &h->ubase, &h->shv, &h->refine, &h->colinfo, &h->ucol, &h->ucount,
 		&h->uptr, &h->ucur, &h->lists, &h->redo, &h->unnz, &h->uoff, &h->raw, &h->out, &h->colptrC, &h->rowsC, &h->countC, &h->posH, &h->posV,
-		&h->aux, &h->meta, &h->errflag, &h->cubtmp, &h->mg_colinfo, &h->mg_ucur};
+		&h->aux, &h->meta, &h->errflag, &h->cubtmp, &h->mg_colinfo, &h->mg_ucur, &h->tp_kmer, &h->tp_read, &h->tp_pos, &h->tp_strand,
+		&h->tp_rs, &h->tp_re, &h->tp_nruns, &h->tp_cnt, &h->tp_cp, &h->tp_merged, &h->tp_tmpK, &h->tp_tmpV, &h->tp_slab};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& e : h->ev) if (e) cudaEventDestroy(e);
 	for (auto& e : h->chunk_ev) if (e) cudaEventDestroy(e);
@@ -715,7 +719,7 @@ int bella_b200_mg_transpose(bella_b200_handle* h, uint32_t kmer_lo, uint32_t kme
 	CK(cudaSetDevice(h->device));
 	h->launches = 0;
 	ENSURE(h->meta, sizeof(Meta));
-	ENSURE(h->errflag, sizeof(int));
+	ENSURE(h->errflag, 4 * sizeof(int));
 	h->klo = kmer_lo; h->khi = kmer_hi;
 	h->mg_recv = nullptr;
 	h->symbolic_done = h->numeric_done = false;
@@ -797,6 +801,128 @@ int bella_b200_get_colptr(bella_b200_handle* h, uint32_t* colptrC_host)
 	if (!h || !h->symbolic_done || !colptrC_host) return fail(h, BELLA_B200_ERR_ARG, "the symbolic phase has not run");
 	CK(cudaMemcpyAsync(colptrC_host, h->colptrC.p, sizeof(uint32_t) * ((size_t)(h->hi - h->lo) + 1), cudaMemcpyDeviceToHost, h->stream));
 	CK(cudaStreamSynchronize(h->stream));
+	return BELLA_B200_OK;
+}
+
+/* ---- matrix construction on the device: tuples -> B (reference src/CSC.cpp:422-479 + MergeDuplicates :301-420) ---- */
+
+int bella_b200_set_inputs_tuples(bella_b200_handle* h, uint32_t n_kmers, uint32_t n_reads, uint64_t ntuples, const uint32_t* t_kmer,
+		const uint32_t* t_read, const uint16_t* t_pos, const uint8_t* t_strand, const uint32_t* read_len, uint16_t kmer_size, uint16_t bin_size)
+{
+	if (!h) return BELLA_B200_ERR_ARG;
+	if (!read_len || (ntuples && (!t_kmer || !t_read || !t_pos || !t_strand))) return fail(h, BELLA_B200_ERR_ARG, "tuple arrays, strand bits and read_len are required");
+	if (ntuples > 0xFFFFFFFFull) return fail(h, BELLA_B200_ERR_RANGE, "more than 2^32-1 tuples (CSC<uint32_t,...> cannot index them either)");
+	if (n_reads > 0x7FFFFFFFu || n_kmers > 0x80000000u) return fail(h, BELLA_B200_ERR_RANGE, "more than 2^31-1 reads or 2^31 k-mers");
+	CK(cudaSetDevice(h->device));
+	CK(cudaStreamSynchronize(h->copy_stream));
+	const size_t T = (size_t)ntuples, n = n_reads;
+	ENSURE(h->meta, sizeof(Meta));
+	ENSURE(h->errflag, 4 * sizeof(int));
+	ENSURE(h->tp_kmer, sizeof(uint32_t) * T + 16); ENSURE(h->tp_read, sizeof(uint32_t) * T + 16);
+	ENSURE(h->tp_pos, sizeof(uint16_t) * T + 16); ENSURE(h->tp_strand, (T + 7) / 8 + 16);
+	ENSURE(h->tp_rs, sizeof(uint32_t) * (n + 1)); ENSURE(h->tp_re, sizeof(uint32_t) * (n + 1)); ENSURE(h->tp_nruns, sizeof(uint32_t) * (n + 1));
+	ENSURE(h->tp_cnt, sizeof(uint32_t) * (n + 2)); ENSURE(h->tp_cp, sizeof(uint32_t) * (n + 2)); ENSURE(h->tp_merged, sizeof(uint32_t) * (n + 2));
+	ENSURE(h->tp_tmpK, sizeof(uint32_t) * T + 16); ENSURE(h->tp_tmpV, sizeof(uint16_t) * T + 16);
+	ENSURE(h->oB_colptr, sizeof(uint32_t) * (n + 2)); ENSURE(h->oB_rowids, sizeof(uint32_t) * T + 16); ENSURE(h->oB_values, sizeof(uint16_t) * T + 16);
+	ENSURE(h->o_len, sizeof(uint32_t) * n + 16);
+	cudaStream_t st = h->stream;
+	CK(cudaEventRecord(h->ev[10], st));
+	CK(cudaMemcpyAsync(h->tp_kmer.p, t_kmer, sizeof(uint32_t) * T, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(h->tp_read.p, t_read, sizeof(uint32_t) * T, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(h->tp_pos.p, t_pos, sizeof(uint16_t) * T, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(h->tp_strand.p, t_strand, (T + 7) / 8, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(h->o_len.p, read_len, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+	CK(cudaEventRecord(h->ev[11], st));
+	CK(cudaMemsetAsync(h->errflag.p, 0, 4 * sizeof(int), st));
+	CK(cudaMemsetAsync(h->tp_nruns.p, 0, sizeof(uint32_t) * (n + 1), st));
+	CK(cudaMemsetAsync(h->tp_cnt.p, 0, sizeof(uint32_t) * (n + 2), st));
+	CK(cudaMemsetAsync(h->tp_merged.p, 0, sizeof(uint32_t) * (n + 2), st));
+	uint32_t nnz = 0;
+	if (T && n) {
+		k_tuple_runs<<<grid_for(T, 256), 256, 0, st>>>(T, h->tp_read.as<uint32_t>(), n_reads, h->tp_rs.as<uint32_t>(), h->tp_re.as<uint32_t>(),
+			h->tp_nruns.as<uint32_t>(), h->errflag.as<int>());
+		LAUNCHED();
+		k_tuple_counts<<<grid_for(n, 256), 256, 0, st>>>(n_reads, h->tp_rs.as<uint32_t>(), h->tp_re.as<uint32_t>(), h->tp_nruns.as<uint32_t>(),
+			h->tp_cnt.as<uint32_t>(), h->errflag.as<int>());
+		LAUNCHED();
+		int maxcnt = 0;
+		CK(cudaMemcpyAsync(&maxcnt, h->errflag.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+		if (int rc = exclusive_scan(h, h->tp_cnt.as<uint32_t>(), h->tp_cp.as<uint32_t>(), n_reads + 1)) return rc;
+		CK(cudaStreamSynchronize(st));
+		constexpr int HT = 2048, WARPS = 12;
+		const size_t smem = (size_t)WARPS * 2 * HT * sizeof(uint32_t);
+		CK(cudaFuncSetAttribute(k_merge_duplicates<HT, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		k_merge_duplicates<HT, WARPS><<<148, WARPS * 32, smem, st>>>(n_reads, h->tp_rs.as<uint32_t>(), h->tp_cnt.as<uint32_t>(), h->tp_cp.as<uint32_t>(),
+			h->tp_kmer.as<uint32_t>(), h->tp_pos.as<uint16_t>(), h->tp_strand.as<uint8_t>(), h->tp_tmpK.as<uint32_t>(), h->tp_tmpV.as<uint16_t>(),
+			h->tp_merged.as<uint32_t>(), false, nullptr, 0);
+		LAUNCHED();
+		if (maxcnt > HT) {
+			// reads with more than HT tuples: their tables (up to 65536 slots) live in a global slab
+			uint32_t big_ht = 16;
+			while (big_ht < (uint32_t)maxcnt) big_ht <<= 1;
+			const uint32_t big_ctas = 74;
+			ENSURE(h->tp_slab, sizeof(uint32_t) * (size_t)big_ctas * WARPS * 2 * big_ht);
+			k_merge_duplicates<HT, WARPS><<<big_ctas, WARPS * 32, smem, st>>>(n_reads, h->tp_rs.as<uint32_t>(), h->tp_cnt.as<uint32_t>(),
+				h->tp_cp.as<uint32_t>(), h->tp_kmer.as<uint32_t>(), h->tp_pos.as<uint16_t>(), h->tp_strand.as<uint8_t>(), h->tp_tmpK.as<uint32_t>(),
+				h->tp_tmpV.as<uint16_t>(), h->tp_merged.as<uint32_t>(), true, h->tp_slab.as<uint32_t>(), big_ht);
+			LAUNCHED();
+		}
+		if (int rc = exclusive_scan(h, h->tp_merged.as<uint32_t>(), h->oB_colptr.as<uint32_t>(), n_reads + 1)) return rc;
+		k_compact_B<<<grid_for((uint64_t)n * 32, 256), 256, 0, st>>>(n_reads, h->tp_cp.as<uint32_t>(), h->oB_colptr.as<uint32_t>(),
+			h->tp_tmpK.as<uint32_t>(), h->tp_tmpV.as<uint16_t>(), h->oB_rowids.as<uint32_t>(), h->oB_values.as<uint16_t>());
+		LAUNCHED();
+		int e = 0;
+		CK(cudaMemcpyAsync(&nnz, h->oB_colptr.as<uint32_t>() + n_reads, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(&e, h->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+		CK(cudaEventRecord(h->ev[9], st));
+		CK(cudaStreamSynchronize(st));
+		if (e == -8) return fail(h, BELLA_B200_ERR_ARG, "the tuples of a read must be contiguous (the order BELLA's tuple emission produces, src/main.cpp:393-416)");
+		if (e == -1) return fail(h, BELLA_B200_ERR_ARG, "a tuple names a read id >= n_reads");
+		if (e) return report_device_error(h, e);
+		CK(cudaEventElapsedTime(&h->t_build_ms, h->ev[11], h->ev[9]));
+		CK(cudaEventElapsedTime(&h->t_ms[3], h->ev[10], h->ev[11]));
+	} else {
+		CK(cudaMemsetAsync(h->oB_colptr.p, 0, sizeof(uint32_t) * (n + 2), st));
+		CK(cudaStreamSynchronize(st));
+	}
+	bella_csc_view B{n_kmers, n_reads, nnz, h->oB_colptr.as<uint32_t>(), h->oB_rowids.as<uint32_t>(), h->oB_values.as<uint16_t>()};
+	reset_problem(h, &B, kmer_size, bin_size);
+	h->dB_colptr = B.colptr; h->dB_rowids = B.rowids; h->dB_values = B.values; h->dB_strand = nullptr; h->d_len = h->o_len.as<uint32_t>();
+	h->n_chunks = 0;
+	return BELLA_B200_OK;
+}
+
+int bella_b200_get_B(bella_b200_handle* h, uint32_t* nnz, uint32_t* colptr_host, uint32_t* rowids_host, uint16_t* values_host, uint8_t* strand_host,
+		float* build_ms)
+{
+	if (!h || !h->have_inputs) return fail(h, BELLA_B200_ERR_ARG, "set_inputs first");
+	CK(cudaSetDevice(h->device));
+	CK(cudaStreamSynchronize(h->copy_stream));
+	const size_t nz = h->nnzB;
+	if (nnz) *nnz = (uint32_t)nz;
+	if (build_ms) *build_ms = h->t_build_ms;
+	if (colptr_host) CK(cudaMemcpyAsync(colptr_host, h->dB_colptr, sizeof(uint32_t) * ((size_t)h->n + 1), cudaMemcpyDeviceToHost, h->stream));
+	if (values_host && nz) CK(cudaMemcpyAsync(values_host, h->dB_values, sizeof(uint16_t) * nz, cudaMemcpyDeviceToHost, h->stream));
+	std::vector<uint32_t> rows;
+	std::vector<uint8_t> bits;
+	if ((rowids_host || strand_host) && nz) {
+		rows.resize(nz);
+		CK(cudaMemcpyAsync(rows.data(), h->dB_rowids, sizeof(uint32_t) * nz, cudaMemcpyDeviceToHost, h->stream));
+		if (h->dB_strand && strand_host) {
+			bits.resize((nz + 7) / 8);
+			CK(cudaMemcpyAsync(bits.data(), h->dB_strand, (nz + 7) / 8, cudaMemcpyDeviceToHost, h->stream));
+		}
+	}
+	CK(cudaStreamSynchronize(h->stream));
+	const bool packed = h->dB_strand == nullptr;                   // strand bit in bit 31 of the row ids
+	if (strand_host && nz) memset(strand_host, 0, (nz + 7) / 8);
+	for (size_t j = 0; j < rows.size(); ++j) {
+		if (rowids_host) rowids_host[j] = packed ? rows[j] & 0x7FFFFFFFu : rows[j];
+		if (strand_host) {
+			const uint32_t b = packed ? rows[j] >> 31 : (bits[j >> 3] >> (j & 7)) & 1u;
+			if (b) strand_host[j >> 3] |= (uint8_t)(1u << (j & 7));
+		}
+	}
 	return BELLA_B200_OK;
 }
 

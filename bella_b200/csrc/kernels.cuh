@@ -1110,6 +1110,113 @@ __global__ void __launch_bounds__(256) k_regroup(uint32_t n, uint32_t lo, uint32
 	}
 }
 
+// ================================ matrix construction (tuples -> B) =========================
+// The reference builds B = CSC(tuples (k-mer id, read id, position), ..., keep-p1, needsort = false)
+// (src/main.cpp:476-480): a stable counting sort of the tuples by read (src/CSC.cpp:432-475), then
+// MergeDuplicates per column (src/CSC.cpp:301-420): table of ht = pow2 >= max(16, column nnz) slots,
+// slot = (key * 107) & (ht - 1) in 32-bit arithmetic, linear probing, tuples inserted in order, a repeated
+// k-mer keeps the LAST position, and the column is the table read out in slot order.  That order is the
+// fold order of the SpGEMM, so it is reproduced exactly: one warp per read, lane 0 replays the insertions
+// in shared memory (the slot of a key depends on every earlier insertion; there is nothing to parallelise
+// inside a read), all lanes compact.  BELLA emits the tuples of a read contiguously and in position order
+// (src/main.cpp:393-416), which is what the stable sort preserves; the runs are used in place.
+
+// run boundaries: rs[read] = first tuple of the read's run, re[read] = one past its last, nruns[read] counts runs
+__global__ void k_tuple_runs(uint64_t T, const uint32_t* __restrict__ t_read, uint32_t n, uint32_t* __restrict__ rs, uint32_t* __restrict__ re,
+		uint32_t* __restrict__ nruns, int* err)
+{
+	for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < T; t += (uint64_t)gridDim.x * blockDim.x) {
+		const uint32_t r = t_read[t];
+		if (r >= n) { set_err(err, -1); continue; }
+		if (t == 0 || t_read[t - 1] != r) { rs[r] = (uint32_t)t; atomicAdd(&nruns[r], 1u); }
+		if (t + 1 == T || t_read[t + 1] != r) re[r] = (uint32_t)(t + 1);
+	}
+}
+
+__global__ void k_tuple_counts(uint32_t n, const uint32_t* __restrict__ rs, const uint32_t* __restrict__ re, const uint32_t* __restrict__ nruns,
+		uint32_t* __restrict__ cnt, int* err)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t k = nruns[i];
+		if (k > 1) set_err(err, -8);                               // the tuples of a read are not contiguous
+		const uint32_t c = k ? re[i] - rs[i] : 0;
+		cnt[i] = c;
+		if (c > 65536u) set_err(err, -4);
+		if (c > 2048u) atomicMax(err + 1, (int)c);                  // err[1]: the longest read, when one exceeds the shared-memory table
+	}
+}
+
+// HT = slots of the shared-memory table per warp (reads with more tuples use the global slab: slab != nullptr)
+template <int HT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_merge_duplicates(uint32_t n, const uint32_t* __restrict__ rs, const uint32_t* __restrict__ cnt,
+		const uint32_t* __restrict__ cp, const uint32_t* __restrict__ t_kmer, const uint16_t* __restrict__ t_pos, const uint8_t* __restrict__ t_strand,
+		uint32_t* __restrict__ tmpK, uint16_t* __restrict__ tmpV, uint32_t* __restrict__ merged, bool big, uint32_t* __restrict__ slab, uint32_t slab_ht)
+{
+	extern __shared__ __align__(16) uint32_t msm[];
+	const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const uint32_t gw = blockIdx.x * WARPS + w, nw = gridDim.x * WARPS;
+	uint32_t* keys = big ? slab + (size_t)gw * 2 * slab_ht : msm + (size_t)w * 2 * HT;
+	uint32_t* vals = keys + (big ? slab_ht : (uint32_t)HT);
+	for (uint32_t i = gw; i < n; i += nw) {
+		const uint32_t c = cnt[i];
+		uint32_t ht = 16;
+		while (ht < c) ht <<= 1;
+		if ((ht > (uint32_t)HT) != big) continue;                   // the other launch takes this read
+		if (c == 0) { if (lane == 0) merged[i] = 0; continue; }
+		for (uint32_t s = lane; s < ht; s += 32) keys[s] = 0xFFFFFFFFu;
+		__syncwarp();
+		const uint32_t t0 = rs[i], mask = ht - 1;
+		// lanes fetch 32 tuples at a time, lane 0 replays the insertions in tuple order
+		for (uint32_t b = 0; b < c; b += 32) {
+			const uint32_t t = t0 + b + lane;
+			uint32_t k = 0, v = 0;
+			if (b + lane < c) { k = t_kmer[t]; v = (uint32_t)t_pos[t] | (getbit(t_strand, t) << 16); }
+			const uint32_t m = min(32u, c - b);
+			for (uint32_t q = 0; q < m; ++q) {
+				const uint32_t key = __shfl_sync(FULL, k, q), val = __shfl_sync(FULL, v, q);
+				if (lane == 0) {
+					uint32_t h = (key * 107u) & mask;
+					for (;;) {
+						const uint32_t cur = keys[h];
+						if (cur == key) { vals[h] = val; break; }               // addop returns the new value: last position wins
+						if (cur == 0xFFFFFFFFu) { keys[h] = key; vals[h] = val; break; }
+						h = (h + 1) & mask;
+					}
+				}
+			}
+		}
+		if (big) __threadfence_block();
+		__syncwarp();
+		// compaction in slot order into the read's pre-merge region
+		uint32_t outp = cp[i], total = 0;
+		for (uint32_t s0 = 0; s0 < ht; s0 += 32) {
+			const uint32_t key = keys[s0 + lane];
+			const uint32_t bal = __ballot_sync(FULL, key != 0xFFFFFFFFu);
+			if (key != 0xFFFFFFFFu) {
+				const uint32_t o = outp + total + __popc(bal & ((1u << lane) - 1u));
+				const uint32_t v = vals[s0 + lane];
+				tmpK[o] = key | ((v >> 16) << 31);                        // strand bit rides in bit 31 (panel format)
+				tmpV[o] = (uint16_t)v;
+			}
+			total += __popc(bal);
+		}
+		if (lane == 0) merged[i] = total;
+		__syncwarp();
+	}
+}
+
+// warp per read: pre-merge region -> final CSC position
+__global__ void __launch_bounds__(256) k_compact_B(uint32_t n, const uint32_t* __restrict__ cp, const uint32_t* __restrict__ Bcolptr,
+		const uint32_t* __restrict__ tmpK, const uint16_t* __restrict__ tmpV, uint32_t* __restrict__ Brow, uint16_t* __restrict__ Bval)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t i = warp; i < n; i += nwarps) {
+		const uint32_t src = cp[i], dst = Bcolptr[i], c = Bcolptr[i + 1] - dst;
+		for (uint32_t x = lane; x < c; x += 32) { Brow[dst + x] = tmpK[src + x]; Bval[dst + x] = tmpV[src + x]; }
+	}
+}
+
 // ================================ output ====================================================
 
 __global__ void k_colptr(uint32_t ncols, const uint32_t* __restrict__ ubase, const uint32_t* __restrict__ uoff, uint32_t* __restrict__ colptrC)

@@ -51,6 +51,8 @@ def lib():
         L.bella_b200_mg_scatter.argtypes = [H, vp, vp]
         L.bella_b200_mg_finish.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, vp, vp, vp, vp]
         L.bella_b200_get_colptr.argtypes = [H, vp]
+        L.bella_b200_set_inputs_tuples.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, vp, vp, vp, vp, vp, ctypes.c_uint16, ctypes.c_uint16]
+        L.bella_b200_get_B.argtypes = [H, ctypes.POINTER(ctypes.c_uint32), vp, vp, vp, vp, ctypes.POINTER(ctypes.c_float)]
         _lib = L
     return _lib
 
@@ -60,7 +62,7 @@ EXPORTS = ["bella_b200_create", "bella_b200_destroy", "bella_b200_last_error", "
            "bella_b200_numeric", "bella_b200_numeric_aux", "bella_b200_numeric_device",
            "bella_b200_result_device", "bella_b200_run_resident", "bella_b200_get_timings", "bella_b200_stream",
            "bella_b200_set_stream", "bella_b200_mg_transpose", "bella_b200_mg_scatter", "bella_b200_mg_finish",
-           "bella_b200_get_colptr"]
+           "bella_b200_get_colptr", "bella_b200_set_inputs_tuples", "bella_b200_get_B"]
 
 
 class BellaB200Error(RuntimeError):
@@ -185,6 +187,25 @@ class OverlapSpGEMM:
             self._check(self._L.bella_b200_numeric_aux(self._h, c0, c1, _ptr(a[0]), _ptr(a[1]), _ptr(a[2])), "bella_b200_numeric_aux")
             out = out + (np.ascontiguousarray(a[:, :z].T),)
         return out
+
+    # ---- matrix construction on the device ("next" row f2) ----
+    def set_inputs_tuples(self, n_kmers, n_reads, t_kmer, t_read, t_pos, t_strand, read_len, kmer_size=17, bin_size=500):
+        """Host tuples (k-mer id, read id, position; one strand bit per tuple) -> B on the device, in the reference's order."""
+        self._keep = (t_kmer, t_read, t_pos, t_strand, read_len)
+        self._check(self._L.bella_b200_set_inputs_tuples(self._h, n_kmers, n_reads, len(t_kmer), _ptr(t_kmer), _ptr(t_read), _ptr(t_pos),
+                                                         _ptr(t_strand), _ptr(read_len), kmer_size, bin_size), "bella_b200_set_inputs_tuples")
+        self.n, self.m, self.lo, self.hi = n_reads, n_kmers, 0, n_reads
+
+    def get_B(self):
+        """-> (colptr, rowids, values, strand bits, build_ms) of the handle's B, on the host"""
+        nnz, ms = ctypes.c_uint32(0), ctypes.c_float(0)
+        self._check(self._L.bella_b200_get_B(self._h, ctypes.byref(nnz), None, None, None, None, ctypes.byref(ms)), "bella_b200_get_B")
+        z = nnz.value
+        colptr = np.zeros(self.n + 1, dtype=np.uint32)
+        rows, vals = np.zeros(max(z, 1), dtype=np.uint32), np.zeros(max(z, 1), dtype=np.uint16)
+        strand = np.zeros((z + 7) // 8 + 8, dtype=np.uint8)
+        self._check(self._L.bella_b200_get_B(self._h, None, _ptr(colptr), _ptr(rows), _ptr(vals), _ptr(strand), None), "bella_b200_get_B")
+        return colptr, rows[:z], vals[:z], strand, ms.value
 
     # ---- multi-GPU stages (device tensors / pointers; bella_b200/distributed.py runs the collectives between them) ----
     def mg_transpose(self, kmer_lo, kmer_hi, cnt_local):

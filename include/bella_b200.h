@@ -156,6 +156,20 @@ int bella_b200_mg_finish(bella_b200_handle* h, uint32_t col_lo, uint32_t col_hi,
 /* colptrC of the handle's column range to HOST memory ([col_hi-col_lo+1]) once the symbolic phase has run. */
 int bella_b200_get_colptr(bella_b200_handle* h, uint32_t* colptrC_host);
 
+/* ---- "next" row f2: matrix construction on the device.
+ * Replaces  CSC<IT,NT> transpmat(alltuples, nkmer, numReads, keep-p1, needsort=false)  (src/main.cpp:476-480 ->
+ * src/CSC.cpp:422-479: counting sort by read, then MergeDuplicates :301-420) and  transpmat.Transpose()
+ * (src/main.cpp:489).  Tuples are (k-mer id, read id, position) in HOST memory, the tuples of one read contiguous and in
+ * position order (what src/main.cpp:393-416 emits; anything else is refused), t_strand one bit per tuple (LSB first).
+ * B comes out in exactly the reference's order -- the hash-slot order of MergeDuplicates, which is the fold order of
+ * the SpGEMM -- stays on the device, and the handle is left as after bella_b200_set_inputs. */
+int bella_b200_set_inputs_tuples(bella_b200_handle* h, uint32_t n_kmers, uint32_t n_reads, uint64_t ntuples, const uint32_t* t_kmer,
+		const uint32_t* t_read, const uint16_t* t_pos, const uint8_t* t_strand, const uint32_t* read_len, uint16_t kmer_size, uint16_t bin_size);
+/* The handle's B back to HOST memory (any pointer may be NULL; call with NULLs first for nnz): colptr [n+1], rowids/values
+ * [nnz], strand bits [(nnz+7)/8]; build_ms = device time of the last bella_b200_set_inputs_tuples without its upload. */
+int bella_b200_get_B(bella_b200_handle* h, uint32_t* nnz, uint32_t* colptr_host, uint32_t* rowids_host, uint16_t* values_host,
+		uint8_t* strand_host, float* build_ms);
+
 #ifdef __cplusplus
 }
 #endif
