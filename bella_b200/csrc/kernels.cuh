@@ -1166,23 +1166,35 @@ __global__ void __launch_bounds__(WARPS * 32) k_merge_duplicates(uint32_t n, con
 		for (uint32_t s = lane; s < ht; s += 32) keys[s] = 0xFFFFFFFFu;
 		__syncwarp();
 		const uint32_t t0 = rs[i], mask = ht - 1;
-		// lanes fetch 32 tuples at a time, lane 0 replays the insertions in tuple order
+		// 32 tuples at a time.  Every lane probes read-only for its slot (the first empty slot at or after its home,
+		// or the slot already holding its key); slots found by one lane only cannot lie on another lane's probe
+		// path (a path crosses occupied slots only), so the lanes before the first one that shares its slot with an
+		// earlier lane commit together and give exactly the sequential result; the rest probe again.
 		for (uint32_t b = 0; b < c; b += 32) {
 			const uint32_t t = t0 + b + lane;
-			uint32_t k = 0, v = 0;
-			if (b + lane < c) { k = t_kmer[t]; v = (uint32_t)t_pos[t] | (getbit(t_strand, t) << 16); }
+			const bool have = b + lane < c;
+			uint32_t key = 0, val = 0;
+			if (have) { key = t_kmer[t]; val = (uint32_t)t_pos[t] | (getbit(t_strand, t) << 16); }
+			uint32_t start = 0;
 			const uint32_t m = min(32u, c - b);
-			for (uint32_t q = 0; q < m; ++q) {
-				const uint32_t key = __shfl_sync(FULL, k, q), val = __shfl_sync(FULL, v, q);
-				if (lane == 0) {
-					uint32_t h = (key * 107u) & mask;
+			while (start < m) {
+				const bool act = lane >= start && lane < m;
+				uint32_t h = (key * 107u) & mask;
+				if (act) {
 					for (;;) {
 						const uint32_t cur = keys[h];
-						if (cur == key) { vals[h] = val; break; }               // addop returns the new value: last position wins
-						if (cur == 0xFFFFFFFFu) { keys[h] = key; vals[h] = val; break; }
+						if (cur == key || cur == 0xFFFFFFFFu) break;
 						h = (h + 1) & mask;
 					}
 				}
+				const uint32_t actmask = __ballot_sync(FULL, act);
+				uint32_t same = act ? __match_any_sync(actmask, h) : 0u;
+				const bool loser = act && (uint32_t)(__ffs(same) - 1) != lane;
+				const uint32_t losers = __ballot_sync(FULL, loser);
+				const uint32_t stop = losers ? (uint32_t)(__ffs(losers) - 1) : m;
+				if (act && lane < stop) { keys[h] = key; vals[h] = val; }          // a repeated k-mer keeps the LAST position (addop returns the new value)
+				__syncwarp();
+				start = stop;
 			}
 		}
 		if (big) __threadfence_block();
