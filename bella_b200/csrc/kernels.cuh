@@ -4,7 +4,7 @@
 // shared memory" stages, so that every HBM access is either a coalesced stream or a small store
 // to one of a few thousand write frontiers that live in L2 (DESIGN.md has the traffic model):
 //
-//   transpose  k_bucket_hist / k_partition   B's nonzeros (read-major) -> buckets of consecutive k-mer ids
+//   transpose  k_partition                   B's nonzeros (read-major) -> fixed-capacity buckets of consecutive k-mer ids
 //              k_bucket                      one CTA per bucket: counting sort by k-mer, columns sorted by
 //                                            read id, written as packed entries `Aent` + A's colptr, and the
 //                                            per-output-column product count == estimateFLOP
@@ -15,15 +15,19 @@
 //   scatter    k_scatter                     outer-product expansion on the A side: k-mer column
 //                                            (r0<r1<..) emits the kept products (col r_a, row r_b), a<b,
 //                                            into the unit's region (one 8-byte record per product)
-//   group+fold k_group_fold<CAP>             one CTA per unit: region staged into shared memory with one
-//                                            bulk async copy (TMA 1-D), distinct rows through a two-level
-//                                            bitmap (== estimateNNZ_Hash, overlap.hpp:205-276), products
+//   group+fold k_group_fold<CAP,NT,EXACT>    one CTA per unit: region staged into shared memory with one
+//                                            bulk async copy (TMA 1-D), distinct rows through a bitmap (two
+//                                            levels when the unit spans more rows than CAP words cover;
+//                                            == estimateNNZ_Hash, overlap.hpp:205-276), products
 //                                            grouped by pair in B-column order (== LocalSpGEMM's visiting
 //                                            order, overlap.hpp:306-341), then the semiring fold
 //                                            (chain.hpp:74-150) and choose() (common.h:162-170) without
 //                                            leaving shared memory
 //              k_huge_pair                   a single pair with more products than fit in shared memory
 //   output     k_colptr / k_compact          per-unit results -> C in CSC order, rows ascending
+//   multi-GPU  k_mg_colinfo / k_mg_sum_counts / k_regroup   send-buffer cursors, summed counts, received segments -> unit regions
+//   build      k_tuple_runs / k_tuple_counts / k_merge_duplicates / k_compact_B   tuples -> B in the reference's
+//                                            MergeDuplicates order (src/CSC.cpp:301-479; "next" row f2)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
