@@ -31,6 +31,7 @@
 #include <cstdlib>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "bella_b200.h"
@@ -65,47 +66,13 @@ inline int strand_bit(const std::string& s, size_t p, size_t k)
 
 } // namespace bella_b200_shim
 
-template <typename IT, typename NT, typename FT, typename MultiplyOperation, typename AddOperation>
-void HashSpGEMM_b200(const CSC<IT, NT>& A, const CSC<IT, NT>& B, MultiplyOperation, AddOperation, const readVector_& reads,
-		FT& getvaluetype, char* filename, const BELLApars& bpars, const double& ratiophi, int device = 0)
+namespace bella_b200_shim {
+
+// symbolic phase, the reference's stage loop and RunPairWiseAlignments on a handle whose inputs are set
+template <typename IT, typename FT>
+void run_stages(bella_b200_handle* h, IT n, const readVector_& reads, char* filename, const BELLApars& bpars, const double& ratiophi)
 {
-	static_assert(sizeof(IT) == 4 && sizeof(NT) == 2, "the B200 path is built for CSC<uint32_t, unsigned short> (KMERINDEX = uint32_t)");
-	using namespace bella_b200_shim;
-	(void)getvaluetype;
-	if (bpars.useHOPC) { std::fprintf(stderr, "bella_b200: --hopc is not supported by the B200 overlap path\n"); std::exit(1); }
-
-	const IT n = B.cols;
-	// reads -> read lengths + one strand bit per nonzero of B (replaces `reads` inside the multiply)
-	std::vector<uint32_t> read_len(n);
-	std::vector<uint8_t> strandB((size_t(B.nnz) + 7) / 8 + 8, 0);
-	int bad = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(| : bad)
-	for (int64_t i = 0; i < int64_t(n); ++i) {
-		const std::string& s = reads[i].seq;
-		read_len[i] = uint32_t(s.size());
-		for (IT j = B.colptr[i]; j < B.colptr[i + 1]; ++j) {
-			const int bit = strand_bit(s, B.values[j], bpars.kmerSize);
-			if (bit < 0) { bad = 1; continue; }
-			if (bit) {
-#pragma omp atomic
-				strandB[j >> 3] |= uint8_t(1u << (j & 7));
-			}
-		}
-	}
-	if (bad) {
-		std::fprintf(stderr, "bella_b200: a k-mer window contains a character other than upper-case ACGT (or runs past its read); "
-			"the strand-bit form of checkstrand does not cover it\n");
-		std::exit(1);
-	}
-
-	bella_b200_handle* h = nullptr;
-	int rc = bella_b200_create(&h, device);
-	if (rc) die(nullptr, "bella_b200_create (no usable sm_100 device; there is no CPU fallback)", rc);
-	bella_csc_view vA{A.rows, A.cols, A.nnz, A.colptr, A.rowids, A.values};
-	bella_csc_view vB{B.rows, B.cols, B.nnz, B.colptr, B.rowids, B.values};
-	rc = bella_b200_set_inputs(h, &vA, &vB, read_len.data(), nullptr, strandB.data(), bpars.kmerSize, bpars.binSize);
-	if (rc) die(h, "bella_b200_set_inputs", rc);
-
+	int rc;
 	// symbolic phase (overlap.hpp:667-679)
 	uint64_t flops64 = 0;
 	IT* colptrC = new IT[size_t(n) + 1];
@@ -164,6 +131,88 @@ void HashSpGEMM_b200(const CSC<IT, NT>& A, const CSC<IT, NT>& B, MultiplyOperati
 	}
 	delete[] colptrC;
 	delete[] colStart;
+}
+
+} // namespace bella_b200_shim
+
+template <typename IT, typename NT, typename FT, typename MultiplyOperation, typename AddOperation>
+void HashSpGEMM_b200(const CSC<IT, NT>& A, const CSC<IT, NT>& B, MultiplyOperation, AddOperation, const readVector_& reads,
+		FT& getvaluetype, char* filename, const BELLApars& bpars, const double& ratiophi, int device = 0)
+{
+	static_assert(sizeof(IT) == 4 && sizeof(NT) == 2, "the B200 path is built for CSC<uint32_t, unsigned short> (KMERINDEX = uint32_t)");
+	using namespace bella_b200_shim;
+	(void)getvaluetype;
+	if (bpars.useHOPC) { std::fprintf(stderr, "bella_b200: --hopc is not supported by the B200 overlap path\n"); std::exit(1); }
+
+	const IT n = B.cols;
+	// reads -> read lengths + one strand bit per nonzero of B (replaces `reads` inside the multiply)
+	std::vector<uint32_t> read_len(n);
+	std::vector<uint8_t> strandB((size_t(B.nnz) + 7) / 8 + 8, 0);
+	int bad = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(| : bad)
+	for (int64_t i = 0; i < int64_t(n); ++i) {
+		const std::string& s = reads[i].seq;
+		read_len[i] = uint32_t(s.size());
+		for (IT j = B.colptr[i]; j < B.colptr[i + 1]; ++j) {
+			const int bit = strand_bit(s, B.values[j], bpars.kmerSize);
+			if (bit < 0) { bad = 1; continue; }
+			if (bit) {
+#pragma omp atomic
+				strandB[j >> 3] |= uint8_t(1u << (j & 7));
+			}
+		}
+	}
+	if (bad) {
+		std::fprintf(stderr, "bella_b200: a k-mer window contains a character other than upper-case ACGT (or runs past its read); "
+			"the strand-bit form of checkstrand does not cover it\n");
+		std::exit(1);
+	}
+
+	bella_b200_handle* h = nullptr;
+	int rc = bella_b200_create(&h, device);
+	if (rc) die(nullptr, "bella_b200_create (no usable sm_100 device; there is no CPU fallback)", rc);
+	bella_csc_view vA{A.rows, A.cols, A.nnz, A.colptr, A.rowids, A.values};
+	bella_csc_view vB{B.rows, B.cols, B.nnz, B.colptr, B.rowids, B.values};
+	rc = bella_b200_set_inputs(h, &vA, &vB, read_len.data(), nullptr, strandB.data(), bpars.kmerSize, bpars.binSize);
+	if (rc) die(h, "bella_b200_set_inputs", rc);
+	run_stages<IT, FT>(h, n, reads, filename, bpars, ratiophi);
+	bella_b200_destroy(h);
+}
+
+// "Next" row f2: the same, starting from the tuples BELLA emits (src/main.cpp:393-416), i.e. replacing
+//   CSC<IT,NT> transpmat(alltuples, nkmer, numReads, keep-p1, false);  spmat = transpmat.Transpose();  HashSpGEMM(...)
+// (src/main.cpp:476-525).  B is built on the device in the reference's MergeDuplicates order (src/CSC.cpp:301-479).
+template <typename IT, typename NT, typename FT>
+void OverlapFromTuples_b200(const std::vector<std::tuple<IT, IT, NT>>& tuples, IT nkmer, IT nreads, const readVector_& reads,
+		FT& getvaluetype, char* filename, const BELLApars& bpars, const double& ratiophi, int device = 0)
+{
+	static_assert(sizeof(IT) == 4 && sizeof(NT) == 2, "the B200 path is built for CSC<uint32_t, unsigned short> (KMERINDEX = uint32_t)");
+	using namespace bella_b200_shim;
+	(void)getvaluetype;
+	if (bpars.useHOPC) { std::fprintf(stderr, "bella_b200: --hopc is not supported by the B200 overlap path\n"); std::exit(1); }
+	const size_t T = tuples.size();
+	std::vector<uint32_t> tk(T), tr(T), read_len(nreads);
+	std::vector<uint16_t> tp(T);
+	std::vector<uint8_t> strand((T + 7) / 8 + 8, 0);
+	for (IT i = 0; i < nreads; ++i) read_len[i] = uint32_t(reads[i].seq.size());
+	int bad = 0;
+#pragma omp parallel for reduction(| : bad)
+	for (int64_t t = 0; t < int64_t(T); ++t) {
+		tk[t] = std::get<0>(tuples[t]); tr[t] = std::get<1>(tuples[t]); tp[t] = std::get<2>(tuples[t]);
+		const int bit = tr[t] < nreads ? strand_bit(reads[tr[t]].seq, tp[t], bpars.kmerSize) : -1;
+		if (bit < 0) { bad = 1; continue; }
+		if (bit) {
+#pragma omp atomic
+			strand[t >> 3] |= uint8_t(1u << (t & 7));
+		}
+	}
+	if (bad) { std::fprintf(stderr, "bella_b200: a tuple's k-mer window is outside its read or contains a character other than upper-case ACGT\n"); std::exit(1); }
+	bella_b200_handle* h = nullptr;
+	int rc = bella_b200_create(&h, device);
+	if (rc) die(nullptr, "bella_b200_create (no usable sm_100 device; there is no CPU fallback)", rc);
+	rc = bella_b200_set_inputs_tuples(h, nkmer, nreads, T, tk.data(), tr.data(), tp.data(), strand.data(), read_len.data(), bpars.kmerSize, bpars.binSize);
+	if (rc) die(h, "bella_b200_set_inputs_tuples", rc);
+	run_stages<IT, FT>(h, nreads, reads, filename, bpars, ratiophi);
 	bella_b200_destroy(h);
 }
 

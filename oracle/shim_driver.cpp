@@ -78,7 +78,10 @@ Mat* make_csc(IT rows, IT cols, IT nnz, const IT* colptr, const IT* rowids, cons
 }
 } // namespace
 
-// which: 1 = reference HashSpGEMM -> out_ref, 2 = HashSpGEMM_b200 -> out_b200, 3 = both.
+// which: bit 0 = reference HashSpGEMM -> out_ref, bit 1 = HashSpGEMM_b200 -> out_b200,
+// bit 2 = OverlapFromTuples_b200 -> out_b200 (tuples = B's entries read by read in position order, what
+// src/main.cpp:393-416 emits; the reference arm then also rebuilds B with its own CSC constructor from those
+// tuples, src/main.cpp:476-480, so both sides start from the tuples).
 // memory_mb sizes the stage loop (overlap.hpp:682-710): a small value forces several stages.
 extern "C" int shim_compare(IT n_reads, IT n_kmers, IT nnz, const IT* A_colptr, const IT* A_rowids, const NT* A_values,
 		const IT* B_colptr, const IT* B_rowids, const NT* B_values, const char* seqs, const uint64_t* seq_off,
@@ -118,9 +121,33 @@ extern "C" int shim_compare(IT n_reads, IT n_kmers, IT nnz, const IT* A_colptr, 
 		chainop(m1, m2, bpars, readname1, readname2);
 		return m1;
 	};
+	std::vector<std::tuple<IT, IT, NT>> tuples;
+	if (which & 4) {
+		tuples.reserve(nnz);
+		for (IT i = 0; i < n_reads; ++i) {
+			std::vector<std::pair<NT, IT>> col;
+			for (IT j = B_colptr[i]; j < B_colptr[i + 1]; ++j) col.emplace_back(B_values[j], B_rowids[j]);
+			std::sort(col.begin(), col.end());
+			for (auto& e : col) tuples.emplace_back(e.second, i, e.first);
+		}
+		// the reference's own matrix construction from the same tuples (src/main.cpp:476-489)
+		std::vector<std::tuple<IT, IT, NT>> copy(tuples);
+		Mat* B2 = new Mat(copy, n_kmers, n_reads, [] (unsigned short int& p1, unsigned short int& p2) { return p1; }, false);
+		delete B; B = B2;
+		// A = B.Transpose(); transpose.h:35 writes one past its colptr, so call the routine on a padded array
+		std::vector<IT> acolptr(size_t(n_kmers) + 2);
+		Mat* A2 = new Mat(B->nnz, n_reads, n_kmers);
+		csr2csc_atomic_nosort(B->cols, B->rows, B->nnz, B->colptr, B->rowids, B->values, acolptr.data(), A2->rowids, A2->values);
+		memcpy(A2->colptr, acolptr.data(), sizeof(IT) * (size_t(n_kmers) + 1));
+		delete A; A = A2;
+	}
 	if (which & 1) {
 		remove(out_ref);
 		HashSpGEMM(*A, *B, multop, addop, reads, getvaluetype, (char*)out_ref, bpars, ratiophi);
+	}
+	if (which & 4) {
+		remove(out_b200);
+		OverlapFromTuples_b200<IT, NT>(tuples, n_kmers, n_reads, reads, getvaluetype, (char*)out_b200, bpars, ratiophi);
 	}
 	if (which & 2) {
 		remove(out_b200);

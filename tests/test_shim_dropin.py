@@ -51,3 +51,14 @@ def test_shim_writes_the_reference_output_file(small_inputs, tmp_path):
     ref, got = _lines(out_ref), _lines(out_b200)
     assert len(ref) > 1000
     assert got == ref
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(SHIM_SO), reason="oracle/_ref/libbella_shim_test.so not built (needs the reference tree)")
+def test_tuples_shim_writes_the_reference_output_file(small_inputs, tmp_path):
+    # "next" row f2 at the reference's own boundary: from the tuples, the reference runs its CSC constructor
+    # (MergeDuplicates) + Transpose + HashSpGEMM; the shim's OverlapFromTuples_b200 builds B on the device
+    out_ref, out_b200 = _run(small_inputs, tmp_path, 8000.0, 1 | 4)
+    ref, got = _lines(out_ref), _lines(out_b200)
+    assert len(ref) > 1000
+    assert got == ref
