@@ -172,3 +172,12 @@ def test_gpu_ragged_edge_inputs():
             assert int(got.colptrC[-1]) == 0
         else:
             ol.assert_same(got, want)
+
+
+def test_gpu_many_reads_two_level_row_bitmap():
+    # more than 65 536 reads: a light column's rows span more 32-row words than the direct bitmap of the
+    # smallest class holds, so the pair index goes through the two-level bitmap
+    from bella_b200 import frontend as fe
+    inp = fe.synthetic(70000, 1000, coverage=20.0, seed=41)
+    assert inp.n_reads > 65536 + 2048
+    ol.assert_same(gpu_result(inp), ol.oracle_spgemm(inp))
