@@ -151,10 +151,11 @@ int report_device_error(bella_b200_handle* h, int e)
 
 // transpose: B (read-major) -> Aent (k-mer-major, columns sorted by read id) for the k-mers [klo, khi)
 // and the reads >= row_lo, + the product counts of the output columns [cnt_lo, cnt_hi) into flop_out
-int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32_t cnt_hi, uint32_t* flop_out)
+int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32_t cnt_hi, uint32_t* flop_out,
+		const uint32_t* rec = nullptr, uint64_t nrec = 0)
 {
 	const uint32_t n = h->n, ml = h->khi - h->klo;
-	const uint64_t nnz = h->nnzB;
+	const uint64_t nnz = rec ? nrec : h->nnzB;                     // route mode: the nonzeros are the received records
 	const uint32_t ncols = cnt_hi - cnt_lo;
 	ENSURE(h->Acolptr, sizeof(uint32_t) * ((size_t)ml + 2));
 	ENSURE(h->Aent, sizeof(uint64_t) * (nnz + 2));
@@ -164,7 +165,7 @@ int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32
 		return 0;
 	}
 	if (!h->W) {
-		double avg = (double)nnz / (double)h->m;
+		double avg = rec ? (double)nnz / (double)ml : (double)nnz / (double)h->m;
 		double w = 0.6 * BUCKET_CAP / (avg > 0.25 ? avg : 0.25);
 		h->W = (uint32_t)(w < 1 ? 1 : w > BUCKET_WMAX ? BUCKET_WMAX : w);
 	}
@@ -176,7 +177,11 @@ int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32
 	ENSURE(h->part, sizeof(uint4) * (size_t)NB * BUCKET_CAP);
 	CK(cudaMemsetAsync(h->bcur.p, 0, sizeof(uint32_t) * ((size_t)NB + 2), h->stream));
 	CK(cudaEventRecord(h->ev[8], h->stream));
-	if (h->n_chunks > 0) {
+	if (rec) {
+		k_partition_rec<<<grid_for(nrec, 256), 256, 0, h->stream>>>(nrec, rec, h->klo, h->khi, W, h->bcur.as<uint32_t>(), h->part.as<uint4>(),
+			h->errflag.as<int>());
+		LAUNCHED();
+	} else if (h->n_chunks > 0) {
 		// host inputs are still arriving chunk by chunk: partition each range of reads as soon as it is on the device
 		for (int c = 0; c < h->n_chunks; ++c) {
 			const uint32_t c0 = h->chunk_lo[c] > row_lo ? h->chunk_lo[c] : row_lo, c1 = h->chunk_lo[c + 1];
@@ -750,7 +755,7 @@ int bella_b200_mg_scatter(bella_b200_handle* h, const uint64_t* sendoff_dev, uin
 	ENSURE(h->mg_colinfo, sizeof(ColInfo) * ((size_t)n + 1));
 	ENSURE(h->mg_ucur, sizeof(uint64_t) * ((size_t)n + 1));
 	CK(cudaEventRecord(h->ev[10], h->stream));
-	if (n && ml && h->nnzB) {
+	if (n && ml) {
 		k_mg_colinfo<<<grid_for(n, 256), 256, 0, h->stream>>>(n, sendoff_dev, h->mg_colinfo.as<ColInfo>(), h->mg_ucur.as<unsigned long long>());
 		LAUNCHED();
 		k_scatter<<<grid_for(ml, 256), 256, 0, h->stream>>>(ml, 0, n, h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), h->mg_colinfo.as<ColInfo>(),
@@ -923,6 +928,71 @@ int bella_b200_get_B(bella_b200_handle* h, uint32_t* nnz, uint32_t* colptr_host,
 			if (b) strand_host[j >> 3] |= (uint8_t)(1u << (j & 7));
 		}
 	}
+	return BELLA_B200_OK;
+}
+
+/* route mode (bella_b200/distributed.py, mode "route"): k-mer-partitioned records instead of an all-gather of B */
+int bella_b200_mg_route(bella_b200_handle* h, uint32_t n_local, uint32_t read_base, const uint32_t* colptr_local_dev, const uint32_t* rowids_dev,
+		const uint16_t* values_dev, uint32_t kmers_per_rank, int world, uint32_t* send_dev, uint64_t* send_counts_host)
+{
+	if (!h || world < 1 || world > 64 || !kmers_per_rank || !send_counts_host || (n_local && (!colptr_local_dev || !rowids_dev || !values_dev || !send_dev)))
+		return fail(h, BELLA_B200_ERR_ARG, "bad arguments to bella_b200_mg_route");
+	CK(cudaSetDevice(h->device));
+	ENSURE(h->mg_ucur, sizeof(uint64_t) * 2 * 64 + sizeof(uint64_t) * ((size_t)h->n + 1));
+	unsigned long long* counts = h->mg_ucur.as<unsigned long long>();
+	unsigned long long* cursor = counts + 64;
+	CK(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * 128, h->stream));
+	for (int d = 0; d < world; ++d) send_counts_host[d] = 0;
+	if (!n_local) return BELLA_B200_OK;
+	k_route_count<<<grid_for((uint64_t)n_local * 32, 256), 256, 0, h->stream>>>(n_local, colptr_local_dev, rowids_dev, kmers_per_rank, (uint32_t)world, counts);
+	LAUNCHED();
+	unsigned long long hc[64];
+	CK(cudaMemcpyAsync(hc, counts, sizeof(uint64_t) * world, cudaMemcpyDeviceToHost, h->stream));
+	CK(cudaStreamSynchronize(h->stream));
+	unsigned long long off[64], run = 0;
+	for (int d = 0; d < world; ++d) { off[d] = run; run += hc[d]; send_counts_host[d] = hc[d]; }
+	CK(cudaMemcpyAsync(cursor, off, sizeof(uint64_t) * world, cudaMemcpyHostToDevice, h->stream));
+	k_route_fill<<<grid_for((uint64_t)n_local * 32, 256), 256, 0, h->stream>>>(n_local, read_base, colptr_local_dev, rowids_dev, values_dev,
+		kmers_per_rank, (uint32_t)world, cursor, send_dev);
+	LAUNCHED();
+	CK(cudaStreamSynchronize(h->stream));                           // `off` lives on this stack frame
+	return BELLA_B200_OK;
+}
+
+int bella_b200_mg_transpose_records(bella_b200_handle* h, const uint32_t* rec_dev, uint64_t nrec, uint32_t kmer_lo, uint32_t kmer_hi,
+		uint32_t* cnt_local_dev)
+{
+	if (!h || !h->have_inputs) return fail(h, BELLA_B200_ERR_ARG, "set_inputs first");
+	if (kmer_lo > kmer_hi || kmer_hi > h->m || !cnt_local_dev || (nrec && !rec_dev)) return fail(h, BELLA_B200_ERR_ARG, "bad arguments to bella_b200_mg_transpose_records");
+	CK(cudaSetDevice(h->device));
+	h->launches = 0;
+	ENSURE(h->meta, sizeof(Meta));
+	ENSURE(h->errflag, 4 * sizeof(int));
+	h->klo = kmer_lo; h->khi = kmer_hi;
+	h->mg_recv = nullptr;
+	h->symbolic_done = h->numeric_done = false;
+	CK(cudaEventRecord(h->ev[0], h->stream));
+	if (!nrec) {
+		CK(cudaMemsetAsync(cnt_local_dev, 0, sizeof(uint32_t) * (size_t)h->n, h->stream));
+		ENSURE(h->Acolptr, sizeof(uint32_t) * ((size_t)(kmer_hi - kmer_lo) + 2));
+		CK(cudaMemsetAsync(h->Acolptr.p, 0, sizeof(uint32_t) * ((size_t)(kmer_hi - kmer_lo) + 2), h->stream));
+		CK(cudaEventRecord(h->ev[8], h->stream)); CK(cudaEventRecord(h->ev[9], h->stream));
+	}
+	for (; nrec;) {
+		CK(cudaMemsetAsync(h->errflag.p, 0, sizeof(int), h->stream));
+		if (int rc = run_transpose(h, 0, 0, h->n, cnt_local_dev, rec_dev, nrec)) return rc;
+		int e = 0;
+		CK(cudaMemcpyAsync(&e, h->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+		CK(cudaStreamSynchronize(h->stream));
+		if (e == ERR_BUCKET) {
+			if (h->W <= 1) return fail(h, BELLA_B200_ERR_RANGE, "a k-mer occurs in more than %u reads", BUCKET_CAP);
+			h->W = h->W / 2;
+			continue;
+		}
+		if (e) return report_device_error(h, e);
+		break;
+	}
+	CK(cudaEventRecord(h->ev[1], h->stream));
 	return BELLA_B200_OK;
 }
 

@@ -1114,6 +1114,74 @@ __global__ void __launch_bounds__(256) k_regroup(uint32_t n, uint32_t lo, uint32
 	}
 }
 
+// ---- multi-GPU "route" mode: instead of all-gathering B, every GPU sends each of its nonzeros to the GPU that
+// transposes that k-mer range (12-byte records {k-mer id | strand<<31, read id, pos | jrank<<16}) ----
+
+// nonzeros of this GPU's reads per destination (warp per read, lanes with the same destination vote together)
+__global__ void __launch_bounds__(256) k_route_count(uint32_t n_local, const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ rowids,
+		uint32_t kpr, uint32_t world, unsigned long long* __restrict__ counts)
+{
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t i = warp; i < n_local; i += nwarps) {
+		const uint32_t j0 = colptr[i], j1 = colptr[i + 1];
+		for (uint32_t jb = j0; jb < j1; jb += 32) {
+			const uint32_t j = jb + lane;
+			const bool have = j < j1;
+			const uint32_t dest = have ? min((rowids[j] & 0x7FFFFFFFu) / kpr, world - 1) : 0xFFFFFFFFu;
+			const uint32_t act = __ballot_sync(FULL, have);
+			if (have) {
+				const uint32_t same = __match_any_sync(act, dest);
+				if ((uint32_t)(__ffs(same) - 1) == lane) atomicAdd(&counts[dest], (unsigned long long)__popc(same));
+			}
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) k_route_fill(uint32_t n_local, uint32_t read_base, const uint32_t* __restrict__ colptr,
+		const uint32_t* __restrict__ rowids, const uint16_t* __restrict__ values, uint32_t kpr, uint32_t world,
+		unsigned long long* __restrict__ cursor, uint32_t* __restrict__ send)
+{
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t i = warp; i < n_local; i += nwarps) {
+		const uint32_t j0 = colptr[i], j1 = colptr[i + 1];
+		for (uint32_t jb = j0; jb < j1; jb += 32) {
+			const uint32_t j = jb + lane;
+			const bool have = j < j1;
+			const uint32_t c = have ? rowids[j] : 0;
+			const uint32_t dest = have ? min((c & 0x7FFFFFFFu) / kpr, world - 1) : 0xFFFFFFFFu;
+			const uint32_t act = __ballot_sync(FULL, have);
+			if (have) {
+				const uint32_t same = __match_any_sync(act, dest);
+				const uint32_t leader = __ffs(same) - 1;
+				unsigned long long base = 0;
+				if (leader == lane) base = atomicAdd(&cursor[dest], (unsigned long long)__popc(same));
+				base = __shfl_sync(same, base, leader);
+				const unsigned long long q = base + __popc(same & ((1u << lane) - 1u));
+				send[3 * q + 0] = c;
+				send[3 * q + 1] = read_base + i;
+				send[3 * q + 2] = (uint32_t)values[j] | ((j - j0) << 16);
+			}
+		}
+	}
+}
+
+// received records -> k-mer buckets (the same fixed-capacity layout k_partition fills)
+__global__ void __launch_bounds__(256) k_partition_rec(uint64_t nrec, const uint32_t* __restrict__ rec, uint32_t klo, uint32_t khi, uint32_t W,
+		uint32_t* __restrict__ bcnt, uint4* __restrict__ part, int* err)
+{
+	for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < nrec; t += (uint64_t)gridDim.x * blockDim.x) {
+		const uint32_t c = rec[3 * t], kid = c & 0x7FFFFFFFu, rd = rec[3 * t + 1], pj = rec[3 * t + 2];
+		if (kid < klo || kid >= khi) { set_err(err, -5); continue; }
+		const uint32_t b = (kid - klo) / W;
+		const uint32_t q = atomicAdd(&bcnt[b], 1u);
+		if (q >= BUCKET_CAP) { set_err(err, -6); continue; }
+		const uint64_t e = (uint64_t)rd | ((uint64_t)(c >> 31) << 31) | ((uint64_t)(pj & 0xFFFFu) << 32) | ((uint64_t)(pj >> 16) << 48);
+		part[(size_t)b * BUCKET_CAP + q] = make_uint4(kid, 0u, (uint32_t)e, (uint32_t)(e >> 32));
+	}
+}
+
 // ================================ matrix construction (tuples -> B) =========================
 // The reference builds B = CSC(tuples (k-mer id, read id, position), ..., keep-p1, needsort = false)
 // (src/main.cpp:476-480): a stable counting sort of the tuples by read (src/CSC.cpp:432-475), then

@@ -181,8 +181,9 @@ UNIT_OVERHEAD = 320     # products: what one more (non-empty) column costs the g
                         # (two ranks with equal products, 7 k vs 24 k columns: 1.04 vs 1.34 ms)
 
 
-def exchange_plan(counts_all, rank):
+def exchange_plan(counts_all, rank, fixed_bounds=None):
     """counts_all int32 [world][n]: every rank's per-column product counts.  One device->host copy.
+    fixed_bounds: owner ranges given by the caller (route mode: a rank owns the columns of its own reads).
     -> (bounds list, in_splits, out_splits, segoff int64 [world][ncols+1], recvbase int64 [world], sendoff int64 [n+1])"""
     world, n = counts_all.shape
     dev = counts_all.device
@@ -192,9 +193,12 @@ def exchange_plan(counts_all, rank):
         z = torch.zeros((world, 1), dtype=torch.int64, device=dev)
         return [0] * (world + 1), [0] * world, [0] * world, z, torch.zeros(world, dtype=torch.int64, device=dev), C[rank]
     # owner ranges equalise  products + UNIT_OVERHEAD per non-empty column  (both prefix sums are monotone)
-    tot_pre = C[:, 1:].sum(0)
-    nonempty_pre = torch.cumsum((counts_all.sum(0) > 0).to(torch.int64), 0)
-    b = _owner_bounds((tot_pre + UNIT_OVERHEAD * nonempty_pre).to(torch.float64), world)
+    if fixed_bounds is not None:
+        b = torch.tensor(fixed_bounds, dtype=torch.int64, device=dev)
+    else:
+        tot_pre = C[:, 1:].sum(0)
+        nonempty_pre = torch.cumsum((counts_all.sum(0) > 0).to(torch.int64), 0)
+        b = _owner_bounds((tot_pre + UNIT_OVERHEAD * nonempty_pre).to(torch.float64), world)
     Cb = C[:, b]                                            # [world][world+1]
     host = torch.cat([b.view(1, -1), Cb]).cpu()             # the one synchronising copy
     bounds = [int(x) for x in host[0]]
@@ -228,8 +232,20 @@ class ShardedOverlapSpGEMM:
 
     def load_shard(self, inp, pinned=False):
         """Take this rank's reads of `inp`, pack the panel and make it device resident."""
-        cuts = shard_bounds(inp.B_colptr, self.world)
+        if self.mode == "route":
+            # a rank owns the output columns of its own reads: shards balanced on the estimated products + the per-column
+            # overhead of the group + fold stage (the same weights the exchange mode balances exactly, but up front)
+            lens = np.diff(inp.B_colptr.astype(np.int64)).astype(np.float64)
+            n = inp.n_reads
+            w = 1.83 * lens * (np.arange(n - 1, -1, -1, dtype=np.float64) / max(n - 1, 1)) + UNIT_OVERHEAD * (lens > 0)
+            pre = np.cumsum(w)
+            cuts = [0] + [int(np.searchsorted(pre, pre[-1] * r / self.world)) + 1 for r in range(1, self.world)] + [n]
+            cuts = [min(max(c, 0), n) for c in np.maximum.accumulate(cuts)]
+        else:
+            cuts = shard_bounds(inp.B_colptr, self.world)
+        self.cuts = cuts
         r0, r1 = cuts[self.rank], cuts[self.rank + 1]
+        self.r0, self.r1 = r0, r1
         host = pack_panel(inp, r0, r1)
         n_r, nnz_r = r1 - r0, int(inp.B_colptr[r1]) - int(inp.B_colptr[r0])
         self.shapes = exchange_sizes(n_r, nnz_r, self.dev)
@@ -240,6 +256,14 @@ class ShardedOverlapSpGEMM:
         if pinned:
             self.host_panel = self.host_panel.pin_memory()
         self.panel = self.host_panel.to(self.dev)
+        if self.mode == "route":
+            off, _ = panel_layout(n_r, nnz_r)
+            p = self.panel
+            self.loc = {"rowids": p[off["rowids"]:off["rowids"] + 4 * nnz_r].view(torch.int32),
+                        "values": p[off["values"]:off["values"] + 2 * nnz_r].view(torch.int16),
+                        "counts": p[off["counts"]:off["counts"] + 4 * n_r].view(torch.int32),
+                        "read_len": p[off["read_len"]:off["read_len"] + 4 * n_r].view(torch.int32)}
+            self.nnz_local = nnz_r
         return r0, r1
 
     def upload(self):
@@ -248,6 +272,8 @@ class ShardedOverlapSpGEMM:
 
     def step(self, fetch=False):
         """-> (Z of this rank's columns, products, (col_lo, col_hi)[, host results when fetch=True])"""
+        if self.mode == "route":
+            return self._step_route(fetch)
         if self._profile:
             import time
             torch.cuda.synchronize(self.dev)
@@ -315,6 +341,65 @@ class ShardedOverlapSpGEMM:
         g.numeric_device()
         return int(g.result_nnz()), flops, (lo, hi)
 
+    def _step_route(self, fetch):
+        """No all-gather of B: the nonzeros go to the rank that transposes their k-mer range (all-to-all of 12-byte
+        records), the products to the rank that owns their column (all-to-all of 8-byte records); a rank owns the
+        columns of its own reads, so B's values stay where they are."""
+        if self._profile:
+            import time
+            torch.cuda.synchronize(self.dev)
+            self._t0 = time.perf_counter()
+        g, dev, world, rank = self.g, self.dev, self.world, self.rank
+        r0, r1, n_r = self.r0, self.r1, self.r1 - self.r0
+        n = self.cuts[-1]
+        # read lengths of every read (4 bytes per read) + this rank's local colptr
+        lens_pad = torch.zeros(max(b - a for a, b in zip(self.cuts[:-1], self.cuts[1:])), dtype=torch.int32, device=dev)
+        lens_pad[:n_r] = self.loc["read_len"]
+        gathered = torch.empty((world, lens_pad.numel()), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(gathered.view(-1), lens_pad)
+        read_len = torch.cat([gathered[s, :self.cuts[s + 1] - self.cuts[s]] for s in range(world)])
+        colptr_local = torch.zeros(n_r + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(self.loc["counts"].to(torch.int64), 0, out=colptr_local[1:])
+        colptr_local = colptr_local.to(torch.int32)
+        # the handle sees B through pointers shifted so that the GLOBAL read id indexes colptr
+        g.set_inputs_device(n, self.n_kmers, self.nnz_local, (colptr_local.data_ptr() - 4 * r0, self.loc["rowids"], self.loc["values"]),
+                            read_len, None, self.kmer_size, self.bin_size)
+        kpr = (self.n_kmers + world - 1) // world
+        send = torch.empty(3 * max(self.nnz_local, 1), dtype=torch.int32, device=dev)
+        out_counts = g.mg_route(n_r, r0, colptr_local, self.loc["rowids"], self.loc["values"], kpr, world, send)
+        self._tick("route")
+        oc = torch.tensor(out_counts, dtype=torch.int64, device=dev)
+        ic = torch.empty_like(oc)
+        dist.all_to_all_single(ic, oc)
+        in_counts = [int(x) for x in ic.tolist()]
+        nrec = sum(in_counts)
+        recv = torch.empty(3 * max(nrec, 1), dtype=torch.int32, device=dev)
+        dist.all_to_all_single(recv[:3 * nrec], send[:3 * sum(out_counts)], [3 * x for x in in_counts], [3 * x for x in out_counts])
+        self._tick("all_to_all records")
+        cnt_local = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        g.mg_transpose_records(recv, nrec, min(rank * kpr, self.n_kmers), min((rank + 1) * kpr, self.n_kmers), cnt_local)
+        self._tick("mg_transpose")
+        counts_all = torch.empty((world, n), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(counts_all.view(-1), cnt_local[:n].contiguous())
+        bounds, in_splits, out_splits, segoff, recvbase, sendoff = exchange_plan(counts_all, rank, fixed_bounds=self.cuts)
+        self._tick("counts+plan")
+        psend = torch.empty(max(sum(out_splits), 1), dtype=torch.int64, device=dev)
+        g.mg_scatter(sendoff, psend)
+        self._tick("mg_scatter")
+        precv = torch.empty(max(sum(in_splits), 1), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(precv[:sum(in_splits)], psend[:sum(out_splits)], in_splits, out_splits)
+        self._tick("all_to_all products")
+        self.keep = (read_len, colptr_local, send, recv, counts_all, segoff, recvbase, psend, precv, cnt_local, sendoff, gathered)
+        g.mg_finish(r0, r1, world, counts_all, segoff, recvbase, precv)
+        self._tick("mg_finish")
+        flops = sum(in_splits)
+        if fetch:
+            colptrC = g.get_colptr(pinned=True)
+            res = g.numeric(pinned=True)
+            return int(colptrC[r1 - r0]), flops, (r0, r1), (colptrC[:r1 - r0 + 1],) + res
+        g.numeric_device()
+        return int(g.result_nnz()), flops, (r0, r1)
+
     def close(self):
         self.g.close()
 
@@ -323,8 +408,10 @@ def bench_multi(args, w, inp, rank, world, local, METRIC, UNIT, workload, ClockS
     """bench.py body for N > 1 (launched under torchrun): strong scaling of the N=1 workload."""
     import json
     import time
+    import os
     dev = torch.device("cuda", local)
-    sh = ShardedOverlapSpGEMM(local)
+    mode = os.environ.get("BELLA_MG_MODE", "exchange")      # "route" (no all-gather of B) is opt-in until it has been run on 8 GPUs
+    sh = ShardedOverlapSpGEMM(local, mode=mode)
     sh.load_shard(inp, pinned=True)
     stream = torch.cuda.current_stream(dev)
 
@@ -391,7 +478,9 @@ def bench_multi(args, w, inp, rank, world, local, METRIC, UNIT, workload, ClockS
                 "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "u16/u32", "data": "synthetic",
                 "config": {"workload": workload, "n_kmers": inp.n_kmers, "nnz_A": inp.nnz, "products": Ft, "output_nnz": Zt,
-                           "parallelism": f"row-sharded x{world}: all-gather of the B panel, transpose split by k-mer range, all-to-all of the products",
+                           "parallelism": (f"row-sharded x{world}: all-gather of the B panel, transpose split by k-mer range, all-to-all of the products"
+                                           if mode != "route" else
+                                           f"row-sharded x{world}: all-to-all of k-mer-partitioned records, transpose per k-mer range, all-to-all of the products"),
                            "l2": "inputs larger than L2, no flush"},
                 "clocks": clocks,
                 "e2e": {"value": Zt / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(d2h[0]),

@@ -51,6 +51,8 @@ def lib():
         L.bella_b200_mg_scatter.argtypes = [H, vp, vp]
         L.bella_b200_mg_finish.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, vp, vp, vp, vp]
         L.bella_b200_get_colptr.argtypes = [H, vp]
+        L.bella_b200_mg_route.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp, ctypes.c_uint32, ctypes.c_int, vp, ctypes.POINTER(ctypes.c_uint64)]
+        L.bella_b200_mg_transpose_records.argtypes = [H, vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, vp]
         L.bella_b200_set_inputs_tuples.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, vp, vp, vp, vp, vp, ctypes.c_uint16, ctypes.c_uint16]
         L.bella_b200_get_B.argtypes = [H, ctypes.POINTER(ctypes.c_uint32), vp, vp, vp, vp, ctypes.POINTER(ctypes.c_float)]
         _lib = L
@@ -62,7 +64,8 @@ EXPORTS = ["bella_b200_create", "bella_b200_destroy", "bella_b200_last_error", "
            "bella_b200_numeric", "bella_b200_numeric_aux", "bella_b200_numeric_device",
            "bella_b200_result_device", "bella_b200_run_resident", "bella_b200_get_timings", "bella_b200_stream",
            "bella_b200_set_stream", "bella_b200_mg_transpose", "bella_b200_mg_scatter", "bella_b200_mg_finish",
-           "bella_b200_get_colptr", "bella_b200_set_inputs_tuples", "bella_b200_get_B"]
+           "bella_b200_get_colptr", "bella_b200_set_inputs_tuples", "bella_b200_get_B", "bella_b200_mg_route",
+           "bella_b200_mg_transpose_records"]
 
 
 class BellaB200Error(RuntimeError):
@@ -210,6 +213,17 @@ class OverlapSpGEMM:
     # ---- multi-GPU stages (device tensors / pointers; bella_b200/distributed.py runs the collectives between them) ----
     def mg_transpose(self, kmer_lo, kmer_hi, cnt_local):
         self._check(self._L.bella_b200_mg_transpose(self._h, kmer_lo, kmer_hi, _ptr(cnt_local)), "bella_b200_mg_transpose")
+
+    def mg_route(self, n_local, read_base, colptr_local, rowids, values, kmers_per_rank, world, send):
+        """-> per-destination record counts (python list)"""
+        counts = (ctypes.c_uint64 * world)()
+        self._check(self._L.bella_b200_mg_route(self._h, n_local, read_base, _ptr(colptr_local), _ptr(rowids), _ptr(values), kmers_per_rank,
+                                                world, _ptr(send), counts), "bella_b200_mg_route")
+        return [int(x) for x in counts]
+
+    def mg_transpose_records(self, rec, nrec, kmer_lo, kmer_hi, cnt_local):
+        self._check(self._L.bella_b200_mg_transpose_records(self._h, _ptr(rec), nrec, kmer_lo, kmer_hi, _ptr(cnt_local)),
+                    "bella_b200_mg_transpose_records")
 
     def mg_scatter(self, sendoff, sendbuf):
         self._check(self._L.bella_b200_mg_scatter(self._h, _ptr(sendoff), _ptr(sendbuf)), "bella_b200_mg_scatter")
