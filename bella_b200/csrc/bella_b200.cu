@@ -944,7 +944,8 @@ int bella_b200_mg_route(bella_b200_handle* h, uint32_t n_local, uint32_t read_ba
 	CK(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * 128, h->stream));
 	for (int d = 0; d < world; ++d) send_counts_host[d] = 0;
 	if (!n_local) return BELLA_B200_OK;
-	k_route_count<<<grid_for((uint64_t)n_local * 32, 256), 256, 0, h->stream>>>(n_local, colptr_local_dev, rowids_dev, kmers_per_rank, (uint32_t)world, counts);
+	const int rgrid = n_local < 148u * 8 ? (int)n_local : 148 * 8;
+	k_route_count<<<rgrid, 256, 0, h->stream>>>(n_local, colptr_local_dev, rowids_dev, kmers_per_rank, (uint32_t)world, counts);
 	LAUNCHED();
 	unsigned long long hc[64];
 	CK(cudaMemcpyAsync(hc, counts, sizeof(uint64_t) * world, cudaMemcpyDeviceToHost, h->stream));
@@ -952,7 +953,7 @@ int bella_b200_mg_route(bella_b200_handle* h, uint32_t n_local, uint32_t read_ba
 	unsigned long long off[64], run = 0;
 	for (int d = 0; d < world; ++d) { off[d] = run; run += hc[d]; send_counts_host[d] = hc[d]; }
 	CK(cudaMemcpyAsync(cursor, off, sizeof(uint64_t) * world, cudaMemcpyHostToDevice, h->stream));
-	k_route_fill<<<grid_for((uint64_t)n_local * 32, 256), 256, 0, h->stream>>>(n_local, read_base, colptr_local_dev, rowids_dev, values_dev,
+	k_route_fill<<<rgrid, 256, 0, h->stream>>>(n_local, read_base, colptr_local_dev, rowids_dev, values_dev,
 		kmers_per_rank, (uint32_t)world, cursor, send_dev);
 	LAUNCHED();
 	CK(cudaStreamSynchronize(h->stream));                           // `off` lives on this stack frame

@@ -1117,13 +1117,14 @@ __global__ void __launch_bounds__(256) k_regroup(uint32_t n, uint32_t lo, uint32
 // ---- multi-GPU "route" mode: instead of all-gathering B, every GPU sends each of its nonzeros to the GPU that
 // transposes that k-mer range (12-byte records {k-mer id | strand<<31, read id, pos | jrank<<16}) ----
 
-// nonzeros of this GPU's reads per destination (warp per read, lanes with the same destination vote together)
-__global__ void __launch_bounds__(256) k_route_count(uint32_t n_local, const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ rowids,
-		uint32_t kpr, uint32_t world, unsigned long long* __restrict__ counts)
+// One CTA per contiguous range of this GPU's reads; warp per read, lanes with the same destination vote together and
+// the CTA keeps its per-destination counters in shared memory, so the few global counters (one per destination GPU)
+// see one atomic per CTA instead of one per warp.
+__device__ __forceinline__ void route_count_cta(uint32_t i0, uint32_t i1, const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ rowids,
+		uint32_t kpr, uint32_t world, uint32_t* s_cnt)
 {
-	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-	for (uint32_t i = warp; i < n_local; i += nwarps) {
+	const uint32_t w = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31;
+	for (uint32_t i = i0 + w; i < i1; i += nw) {
 		const uint32_t j0 = colptr[i], j1 = colptr[i + 1];
 		for (uint32_t jb = j0; jb < j1; jb += 32) {
 			const uint32_t j = jb + lane;
@@ -1132,19 +1133,42 @@ __global__ void __launch_bounds__(256) k_route_count(uint32_t n_local, const uin
 			const uint32_t act = __ballot_sync(FULL, have);
 			if (have) {
 				const uint32_t same = __match_any_sync(act, dest);
-				if ((uint32_t)(__ffs(same) - 1) == lane) atomicAdd(&counts[dest], (unsigned long long)__popc(same));
+				if ((uint32_t)(__ffs(same) - 1) == lane) atomicAdd(&s_cnt[dest], (uint32_t)__popc(same));
 			}
 		}
 	}
+}
+
+__global__ void __launch_bounds__(256) k_route_count(uint32_t n_local, const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ rowids,
+		uint32_t kpr, uint32_t world, unsigned long long* __restrict__ counts)
+{
+	__shared__ uint32_t s_cnt[64];
+	if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t i0 = (uint32_t)((uint64_t)n_local * blockIdx.x / gridDim.x), i1 = (uint32_t)((uint64_t)n_local * (blockIdx.x + 1) / gridDim.x);
+	route_count_cta(i0, i1, colptr, rowids, kpr, world, s_cnt);
+	__syncthreads();
+	if (threadIdx.x < world && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(256) k_route_fill(uint32_t n_local, uint32_t read_base, const uint32_t* __restrict__ colptr,
 		const uint32_t* __restrict__ rowids, const uint16_t* __restrict__ values, uint32_t kpr, uint32_t world,
 		unsigned long long* __restrict__ cursor, uint32_t* __restrict__ send)
 {
-	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-	for (uint32_t i = warp; i < n_local; i += nwarps) {
+	__shared__ uint32_t s_cnt[64];
+	__shared__ unsigned long long s_base[64];
+	if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t i0 = (uint32_t)((uint64_t)n_local * blockIdx.x / gridDim.x), i1 = (uint32_t)((uint64_t)n_local * (blockIdx.x + 1) / gridDim.x);
+	route_count_cta(i0, i1, colptr, rowids, kpr, world, s_cnt);           // how much this CTA sends to every destination
+	__syncthreads();
+	if (threadIdx.x < world) {
+		s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]) : 0ull;
+		s_cnt[threadIdx.x] = 0;                                             // becomes the CTA's cursor inside its reservation
+	}
+	__syncthreads();
+	const uint32_t w = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31;
+	for (uint32_t i = i0 + w; i < i1; i += nw) {
 		const uint32_t j0 = colptr[i], j1 = colptr[i + 1];
 		for (uint32_t jb = j0; jb < j1; jb += 32) {
 			const uint32_t j = jb + lane;
@@ -1155,10 +1179,10 @@ __global__ void __launch_bounds__(256) k_route_fill(uint32_t n_local, uint32_t r
 			if (have) {
 				const uint32_t same = __match_any_sync(act, dest);
 				const uint32_t leader = __ffs(same) - 1;
-				unsigned long long base = 0;
-				if (leader == lane) base = atomicAdd(&cursor[dest], (unsigned long long)__popc(same));
-				base = __shfl_sync(same, base, leader);
-				const unsigned long long q = base + __popc(same & ((1u << lane) - 1u));
+				uint32_t off = 0;
+				if (leader == lane) off = atomicAdd(&s_cnt[dest], (uint32_t)__popc(same));
+				off = __shfl_sync(same, off, leader);
+				const unsigned long long q = s_base[dest] + off + __popc(same & ((1u << lane) - 1u));
 				send[3 * q + 0] = c;
 				send[3 * q + 1] = read_base + i;
 				send[3 * q + 2] = (uint32_t)values[j] | ((j - j0) << 16);
