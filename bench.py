@@ -3,15 +3,18 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-A "step" is one whole pass of the hot path (device layout + symbolic + numeric) over the workload
+A "step" is one whole pass of the hot path (device transpose of B + symbolic + numeric) over the workload
 BASELINE.json quotes the metric on: configs[1], "synthetic 50k PacBio reads x 10 kb, e=0.15, k=17"
 (genome 16.67 Mb, 30x, [l,u]=[2,8], seed 2), matrices built once by the host front end
-(bella_b200/csrc/frontend.cpp) outside the timed region.
+(bella_b200/csrc/frontend.cpp) outside the timed region.  With --gpus N > 1 (under torchrun) the same workload is
+row-sharded over the N GPUs (bella_b200/distributed.py, strong scaling).
 
-  value         output nnz / s with A, B (raw CSC arrays), strand bits and read lengths resident in HBM
+  value         output nnz / s with B (raw CSC arrays), strand bits and read lengths resident in HBM
+                (A == B^T is derived on the device, so it is not an input)
   e2e           the same through the host-buffer C-ABI calls (set_inputs -> symbolic -> numeric):
-                H2D of every input and D2H of colptrC/rowids/count/posH/posV inside the timed region
-  roofline      dominant kernel: algorithmic bytes / its CUDA-event duration vs the measured HBM peak
+                H2D of every input from page-locked memory and D2H of colptrC/rowids/count/posH/posV inside the timed region
+  roofline      dominant kernel: algorithmic bytes (DESIGN.md 3) / its CUDA-event duration vs the measured HBM peak;
+                traffic = its DRAM bytes per step from the committed ncu launch list (profiles/traffic.json)
   cpu_baseline  the reference's own OpenMP estimateFLOP+estimateNNZ_Hash+LocalSpGEMM (oracle/_ref, kind
                 "reference") or the C port (oracle/, kind "port") on a bounded column-prefix sample
 --impl reference times that CPU path alone (all host threads) and prints the same line shape.
