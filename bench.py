@@ -115,13 +115,19 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def gathered_entries(inp):
+    """E of SURVEY.md 8d: A entries gathered before the triangular filter = sum over k-mers of degree^2."""
+    d = np.diff(inp.A_colptr.astype(np.int64))
+    return int((d * d).sum())
+
+
 def algorithmic_bytes(inp, Z, flops):
-    """SURVEY.md 8d / DESIGN.md: bytes the path must move once, whatever the implementation:
-    stream B (u32 id + u16 pos) and its colptr, two A-colptr words per B nonzero, the gathered A
-    entries that survive the row>col filter (u32 id + u16 pos each), read lengths and strand bits,
-    and the output (u32 row + 3 x u16) with its colptr."""
+    """SURVEY.md 8d / BASELINE.md 3: bytes the path must move once, whatever the implementation
+    (14.25 nnz + 6 E + 10 Z + 12 n): stream B (u32 id + u16 pos) and its colptr, two A-colptr words per B nonzero,
+    the gathered A segments (u32 id + u16 pos per entry, E entries), read lengths and strand bits, and the
+    output (u32 row + 3 x u16) with its colptr."""
     nz, n = inp.nnz, inp.n_reads
-    return 6 * nz + 4 * (n + 1) + 8 * nz + 6 * flops + 4 * n + nz // 4 + 10 * Z + 4 * (n + 1)
+    return 6 * nz + 4 * (n + 1) + 8 * nz + 6 * gathered_entries(inp) + 4 * n + nz // 4 + 10 * Z + 4 * (n + 1)
 
 
 def measured_peak():
@@ -303,7 +309,8 @@ def run_b200_arm(args, w):
             "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes": int(kbytes[dom]),
             "note": "kernel duration = CUDA events on the launching stream around the kernel's launches (all capacity classes), averaged "
                     "over the timed steps; k_group_fold is warp-issue bound (the far tests of the fold), not HBM bound: see DESIGN.md 3-4",
-            "whole_step": {"algorithmic_bytes": alg, "achieved": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak},
+            "whole_step": {"algorithmic_bytes": alg, "achieved": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                           "frac_of_nominal_8TBs": alg / (ms * 1e-3) / 8e12},
             "phase_ms": {k: float(v) for k, v in kern.items()}}
     roof["frac"] = roof["achieved"] / peak
 
