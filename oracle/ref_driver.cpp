@@ -275,6 +275,26 @@ int64_t bella_ref_build(IT n_kmers, IT n_reads, uint64_t ntuples,
 	return nnz;
 }
 
+// "Next" row f1: the reference's CPU seed-and-extend, alignSeqAn (include/align.hpp:93-139) ->
+// seqan::extendSeed(..., GappedXDrop) with Score(1,-1,-1).  One call per candidate pair; out6[p] =
+// { score, strand char, begH, endH, begV, endV } (H coordinates on the reverse complement when strand == 'c').
+int bella_ref_align(uint64_t n_pairs, const IT* rows, const IT* cols, const NT* posH, const NT* posV,
+		const char* seqs, const uint64_t* seq_off, int kmer_len, int xdrop, int32_t* out6)
+{
+	Quiet q;
+#pragma omp parallel for schedule(dynamic, 16)
+	for (int64_t p = 0; p < (int64_t)n_pairs; ++p) {
+		std::string row(seqs + seq_off[rows[p]], seqs + seq_off[rows[p] + 1]);
+		std::string col(seqs + seq_off[cols[p]], seqs + seq_off[cols[p] + 1]);
+		seqAnResult r = alignSeqAn(row, col, (int)row.length(), posH[p], posV[p], xdrop, kmer_len, false, false, false);
+		int32_t* o = out6 + 6 * p;
+		o[0] = r.score; o[1] = r.strand[0];
+		o[2] = (int32_t)beginPositionH(r.seed); o[3] = (int32_t)endPositionH(r.seed);
+		o[4] = (int32_t)beginPositionV(r.seed); o[5] = (int32_t)endPositionV(r.seed);
+	}
+	return 0;
+}
+
 int bella_ref_max_threads(void) { return omp_get_max_threads(); }
 
 } // extern "C"

@@ -17,6 +17,8 @@ Fixtures:
   heavy_units   250 reads x 5 kb, e=0.01, 40x, u=80: up to 188 k products per column, hundreds per pair (the GPU splits
                 such columns into row-range units)
   huge_pair     24 reads x 14 kb, e=0.002, 8x, u=40: read pairs sharing more than 8192 k-mers (more than fits shared memory)
+  xdrop         "next" row f1: (score, strand, begH, endH, begV, endV) of the reference's alignSeqAn (gapped X-drop) on
+                3000 candidate pairs of the tiny_clr reads
   ragged        160 reads of 300..30 000 bp (log-uniform), 10 % substitutions, both strands: ragged columns, short reads
                 with a handful of k-mers next to very long ones
 """
@@ -113,6 +115,20 @@ def main_round1_additions():
     s, o = fe.reads_from_strings(ragged_reads())
     inp = fe.build_matrices(s, o)
     save("ragged", inp, ol.ref_spgemm(inp, nthreads=1))
+    save_xdrop()
+
+
+def save_xdrop():
+    """"Next" row f1: the reference's alignSeqAn (gapped X-drop, x = 7) on 3000 candidate pairs of the tiny_clr reads."""
+    inp = fe.synthetic(300, 3000, seed=101)
+    r = ol.oracle_spgemm(inp, want_aux=False)
+    cols = np.repeat(np.arange(inp.n_reads, dtype=np.uint32), np.diff(r.colptrC.astype(np.int64)))
+    idx = np.sort(np.random.default_rng(1).choice(r.nnz, 3000, replace=False))
+    rows, cols, pH, pV = r.rowids[idx], cols[idx], r.posH[idx], r.posV[idx]
+    ref = ol.ref_align(inp, rows, cols, pH, pV, 7)
+    np.savez_compressed(os.path.join(HERE, "xdrop.npz"), n_reads=inp.n_reads, k=inp.kmer_size, xdrop=7, seqs=inp.seqs, seq_off=inp.seq_off,
+                        rows=rows, cols=cols, posH=pH, posV=pV, ref_out=ref)
+    print(f"xdrop: {len(rows)} pairs, scores {ref[:, 0].min()}..{ref[:, 0].max()}, {(ref[:, 1] == ord('c')).sum()} on the reverse strand")
 
 
 def main():

@@ -142,3 +142,26 @@ def assert_same(a, b, aux=True):
     np.testing.assert_array_equal(a.posV, b.posV)
     if aux and a.aux is not None and b.aux is not None:
         np.testing.assert_array_equal(a.aux, b.aux)
+
+
+# ---- "next" row f1: gapped X-drop seed-and-extend ------------------------------------------------
+
+def _align(fn, inp, rows, cols, posH, posV, xdrop):
+    rows = np.ascontiguousarray(rows, dtype=np.uint32); cols = np.ascontiguousarray(cols, dtype=np.uint32)
+    posH = np.ascontiguousarray(posH, dtype=np.uint16); posV = np.ascontiguousarray(posV, dtype=np.uint16)
+    out = np.zeros((len(rows), 6), dtype=np.int32)
+    rc = fn(ctypes.c_uint64(len(rows)), _p(rows), _p(cols), _p(posH), _p(posV), _p(inp.seqs), _p(inp.seq_off),
+            ctypes.c_int(inp.kmer_size), ctypes.c_int(xdrop), _p(out))
+    if rc != 0:
+        raise RuntimeError(f"alignment failed: {rc}")
+    return out
+
+
+def oracle_align(inp, rows, cols, posH, posV, xdrop=7):
+    """oracle/bella_oracle.c oracle_xdrop_align -> int32 [n][6] = score, strand char, begH, endH, begV, endV"""
+    return _align(oracle().oracle_xdrop_align, inp, rows, cols, posH, posV, xdrop)
+
+
+def ref_align(inp, rows, cols, posH, posV, xdrop=7):
+    """the reference's alignSeqAn (oracle/_ref) on the same pairs"""
+    return _align(ref().bella_ref_align, inp, rows, cols, posH, posV, xdrop)
