@@ -1,6 +1,7 @@
 """In-tree builds of the native libraries (no JIT cache: the built .so files travel with the repo).
 
   libbella_b200.so      bella_b200/csrc/bella_b200.cu  -- CUDA kernels (sm_100a) + the C-ABI (include/bella_b200.h)
+  libbella_xdrop.so     bella_b200/csrc/bella_xdrop.cu -- "next" row f1: X-drop seed-and-extend kernels + C-ABI (include/bella_xdrop.h)
   libbella_frontend.so  bella_b200/csrc/frontend.cpp   -- host front end (matrix construction, read simulator)
 """
 import os
@@ -11,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_CUDA = os.path.join(HERE, "libbella_b200.so")
+LIB_XDROP = os.path.join(HERE, "libbella_xdrop.so")
 LIB_FE = os.path.join(HERE, "libbella_frontend.so")
 
 NVCC_FLAGS = [
@@ -34,8 +36,7 @@ def _nvcc():
 
 
 def build_cuda(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
-    srcs.append(os.path.join(ROOT, "include", "bella_b200.h"))
+    srcs = [os.path.join(CSRC, "bella_b200.cu"), os.path.join(CSRC, "kernels.cuh"), os.path.join(ROOT, "include", "bella_b200.h")]
     if not force and not _stale(LIB_CUDA, srcs):
         return LIB_CUDA
     cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", LIB_CUDA,
@@ -44,6 +45,18 @@ def build_cuda(force=False, verbose=False):
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)
     return LIB_CUDA
+
+
+def build_xdrop(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, "bella_xdrop.cu"), os.path.join(CSRC, "xdrop.cuh"), os.path.join(ROOT, "include", "bella_xdrop.h")]
+    if not force and not _stale(LIB_XDROP, srcs):
+        return LIB_XDROP
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math"]
+    cmd = [_nvcc()] + flags + ["-I", os.path.join(ROOT, "include"), "-o", LIB_XDROP, srcs[0]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.run(cmd, check=True)
+    return LIB_XDROP
 
 
 def build_frontend(force=False):
@@ -58,3 +71,4 @@ def build_frontend(force=False):
 if __name__ == "__main__":
     build_frontend()
     build_cuda(verbose=True)
+    build_xdrop(verbose=True)

@@ -1,0 +1,411 @@
+// "Next" row f1: batched gapped X-drop seed-and-extend (the step right after the overlap SpGEMM).
+//
+// What it replaces: the reference's per-pair alignSeqAn -> seqan::extendSeed(.., GappedXDrop()) (include/align.hpp:93-139,
+// seqan/seqan/seeds/seeds_extension.h:622-843) and its CUDA port (loganGPU/functions.cuh:223-408, one 32-thread block per
+// alignment, anti-diagonals in global memory).  Same recurrence, same trimming rules, same "longest extension" rules, so
+// (score, strand, begH, endH, begV, endV) are identical per pair; the oracle is oracle/bella_oracle.c oracle_xdrop_align.
+//
+// Layout of one extension on the device (xd::Ext<G,T>): a group of G lanes owns the live window of the three anti-diagonals
+// in REGISTERS.  Column c of the DP matrix lives in slot c mod (G*T) = lane + G*t, so a column never moves between lanes
+// while the window slides; the left neighbour (column c-1) is one __shfl away.  The window [minCol-1, maxCol] of every step
+// must fit G*T slots -- when it does not (rare: 0.1 % of the extensions at x = 7 with G*T = 32) the extension is handed to
+// the wide path (xd::wide_extend: one warp, anti-diagonals in global scratch, any width).  Bases are staged through two
+// small shared-memory rings per group (query and database segment), refilled G bytes at a time.
+//
+// This header is compiled twice: by nvcc into the kernels of bella_xdrop.cu, and by g++ with XD_EMULATE defined into the
+// lane-thread emulator of tests/emu/xdrop_emu.cpp (32 host threads per warp, collectives through barriers), which checks
+// this very source against the oracle on the CPU.
+#pragma once
+#include <stdint.h>
+#include <limits.h>
+
+#ifdef XD_EMULATE
+#define XD_FN inline
+#else
+#define XD_FN __device__ __forceinline__
+#endif
+
+namespace xd {
+
+constexpr int UNDEF = INT_MIN + 1;        // seeds_extension.h:646 (minValue - gapCost, gapCost = -1)
+constexpr unsigned FULL = 0xffffffffu;
+
+#ifndef XD_EMULATE
+XD_FN int lane_id() { return (int)(threadIdx.x & 31); }
+XD_FN int shfl(unsigned mask, int v, int src, int width) { return __shfl_sync(mask, v, src, width); }
+XD_FN int rmax(unsigned mask, int v) { return __reduce_max_sync(mask, v); }
+XD_FN int rmin(unsigned mask, int v) { return __reduce_min_sync(mask, v); }
+XD_FN bool all(unsigned mask, bool p) { return __all_sync(mask, p) != 0; }
+XD_FN void wsync(unsigned mask) { __syncwarp(mask); }
+XD_FN int atomic_inc(int* p) { return atomicAdd(p, 1); }
+XD_FN char ldg(const char* p) { return __ldg(p); }
+#else
+int lane_id();                              // provided by the emulator
+int shfl(unsigned mask, int v, int src, int width);
+int rmax(unsigned mask, int v);
+int rmin(unsigned mask, int v);
+bool all(unsigned mask, bool p);
+void wsync(unsigned mask);
+int atomic_inc(int* p);
+inline char ldg(const char* p) { return *p; }
+#endif
+
+XD_FN int imax(int a, int b) { return a > b ? a : b; }
+XD_FN int imin(int a, int b) { return a < b ? a : b; }
+XD_FN char comp(char c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N'; }
+
+// One direction of one pair.  Index t of a segment counts AWAY from the seed: base t of the query (V) segment is
+// q[qstep * t], base r of the database (H) segment is d[dstep * r], complemented when the pair is on the reverse strand.
+struct Segs {
+	const char* q; const char* d;
+	int qstep, dstep, dcomp;
+	int qlen, dlen;
+};
+
+struct Pairs {                              // the candidate pairs, as the overlap SpGEMM emits them
+	const uint32_t* rows; const uint32_t* cols;      // H = row read, V = column read
+	const uint16_t* posH; const uint16_t* posV;      // seed k-mer
+	const char* seqs; const uint64_t* seq_off;       // reads, concatenated, 1 byte per base
+	int kmer_len, xdrop;
+	int n_jobs;                                      // 2 per pair: job 2p = left, 2p+1 = right
+};
+
+// per job: { score, H coordinate, V coordinate, flag }; left: begin positions, flag = reverse strand; right: end positions
+struct JobResult { int score, posH, posV, flag; };
+
+// Pair p, direction dir -> segments.  Every lane of the group computes the same values; `lane`/`G` only split the
+// seed comparison (twin(seedH) == seedV, align.hpp:110-113).  Returns false when the seed does not fit its reads.
+template <int G>
+XD_FN bool make_segs(const Pairs& P, int job, unsigned mask, int lane, Segs& s, int& reverse, int& baseH, int& baseV)
+{
+	const int p = job >> 1, right = job & 1;
+	const uint64_t oh = P.seq_off[P.rows[p]], ov = P.seq_off[P.cols[p]];
+	const char* H = P.seqs + oh; const int lenH = (int)(P.seq_off[P.rows[p] + 1] - oh);
+	const char* V = P.seqs + ov; const int lenV = (int)(P.seq_off[P.cols[p] + 1] - ov);
+	int i = P.posH[p];
+	const int j = P.posV[p], k = P.kmer_len;
+	if (i + k > lenH || j + k > lenV) return false;
+	bool same = true;
+	for (int t = lane; t < k; t += G) same = same && (comp(ldg(H + i + k - 1 - t)) == ldg(V + j + t));
+	reverse = all(mask, same) ? 1 : 0;
+	if (reverse) i = lenH - i - k;
+	const int begH = i, endH = i + k, begV = j, endV = j + k;
+	s.dcomp = reverse;
+	if (!right) {                               // prefixes, EXTEND_LEFT (seeds_extension.h:812-823)
+		s.qlen = begV; s.q = V + begV - 1; s.qstep = -1;
+		s.dlen = begH;
+		if (!reverse) { s.d = H + begH - 1; s.dstep = -1; } else { s.d = H + (lenH - begH); s.dstep = 1; }
+		baseH = begH; baseV = begV;
+	} else {                                    // suffixes, EXTEND_RIGHT (:825-840)
+		s.qlen = lenV - endV; s.q = V + endV; s.qstep = 1;
+		s.dlen = lenH - endH;
+		if (!reverse) { s.d = H + endH; s.dstep = 1; } else { s.d = H + (lenH - 1 - endH); s.dstep = -1; }
+		baseH = endH; baseV = endV;
+	}
+	return true;
+}
+
+XD_FN char load_q(const Segs& s, int t) { return ldg(s.q + (long)s.qstep * t); }
+XD_FN char load_d(const Segs& s, int r) { const char c = ldg(s.d + (long)s.dstep * r); return s.dcomp ? comp(c) : c; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Register-resident extension: G lanes, T cells per lane.
+// ------------------------------------------------------------------------------------------------------------------
+template <int G, int T>
+struct Ext {
+	static constexpr int GT = G * T;
+	static constexpr int RING = 2 * GT;         // >= GT + G - 3, power of two
+	static_assert((G & (G - 1)) == 0 && (T & (T - 1)) == 0 && GT >= 4, "G, T powers of two");
+
+	int v1[T], v2[T], v3[T];                    // anti-diagonals n-2, n-1, n at this lane's slots
+	int n, minCol, maxCol, best;                // group-uniform state (seeds_extension.h:650-660)
+	int off1, n1, off2, n2, off3, n3;
+	int qhi, dhi;                               // bases [.. , qhi) / [.., dhi) of the segments are in the rings
+	int rows, cols, xdrop;
+
+	XD_FN void init(const Segs& s, int xdrop_, int lane)
+	{
+		rows = s.dlen + 1; cols = s.qlen + 1; xdrop = xdrop_;
+		const int g0 = (1 > xdrop) ? UNDEF : -1;          // _initAntiDiags :462-485
+#pragma unroll
+		for (int t = 0; t < T; ++t) {
+			const int slot = t * G + lane;
+			v1[t] = UNDEF;
+			v2[t] = slot == 0 ? 0 : UNDEF;
+			v3[t] = slot <= 1 ? g0 : UNDEF;
+		}
+		n1 = 0; n2 = 1; n3 = 2; off1 = off2 = off3 = 0;
+		minCol = 1; maxCol = 2; n = 1; best = 0; qhi = dhi = 0;
+	}
+
+	XD_FN bool active() const { return minCol < maxCol; }
+
+	// One anti-diagonal (the body of the while loop, seeds_extension.h:662-745).  false: the window no longer fits.
+	XD_FN bool step(const Segs& s, unsigned mask, int lane, char* qring, char* dring)
+	{
+		++n;
+#pragma unroll
+		for (int t = 0; t < T; ++t) { v1[t] = v2[t]; v2[t] = v3[t]; }
+		n1 = n2; n2 = n3; off1 = off2; off2 = off3; off3 = minCol - 1;
+		n3 = maxCol + 1 - off3;
+		if (n3 > GT) return false;
+
+		if (n - minCol - 1 >= dhi) {                      // database bases up to row n - minCol - 1 are needed
+			wsync(mask);
+			const int r = dhi + lane;
+			if (r < s.dlen) dring[r & (RING - 1)] = load_d(s, r);
+			dhi += G;
+			wsync(mask);
+		}
+		if (maxCol - 2 >= qhi) {                          // query bases up to column maxCol - 1
+			wsync(mask);
+			const int c = qhi + lane;
+			if (c < s.qlen) qring[c & (RING - 1)] = load_q(s, c);
+			qhi += G;
+			wsync(mask);
+		}
+
+		const int lim = best - xdrop;
+		const bool edge = -n > lim;                       // antiDiagNo * gapCost > best - scoreDropOff (:507)
+		int m = UNDEF, lo_fail = INT_MAX, hi_fail = INT_MIN;
+#pragma unroll
+		for (int t = 0; t < T; ++t) {
+			const int slot = t * G + lane;
+			const int c = off3 + ((slot - off3) & (GT - 1));          // this slot's column in [minCol-1, minCol-1+GT)
+			int s2 = v2[t], s1 = v1[t];
+			if (T > 1 && lane == G - 1) { s2 = v2[(t + T - 1) % T]; s1 = v1[(t + T - 1) % T]; }   // what lane 0 reads is slot-1
+			const int up2 = shfl(mask, s2, (lane + G - 1) & (G - 1), G);   // a2[c-1]
+			const int up1 = shfl(mask, s1, (lane + G - 1) & (G - 1), G);   // a1[c-1]
+			int val = UNDEF;
+			if (c >= minCol && c < maxCol) {
+				const char qc = qring[(c - 1) & (RING - 1)], dc = dring[(n - c - 1) & (RING - 1)];
+				int tmp = imax(up2, v2[t]) - 1;
+				tmp = imax(tmp, up1 + (qc == dc ? 1 : -1));
+				if (tmp >= lim) { val = tmp; m = imax(m, tmp); }
+			} else if (edge && ((c == off3 && c == 0) || (c == maxCol && n == maxCol))) {
+				val = -n;                                     // first column / first row of the matrix (:509-512)
+			}
+			v3[t] = val;
+			if (c >= minCol && c <= maxCol && !(val == UNDEF && up2 == UNDEF)) lo_fail = imin(lo_fail, c);
+			if (c >= off3 && c < maxCol && !(val == UNDEF && v2[t] == UNDEF)) hi_fail = imax(hi_fail, c);
+		}
+		best = imax(best, rmax(mask, m));
+		const int lo = rmin(mask, lo_fail), hi = rmax(mask, hi_fail);
+		const int newMin = imin(lo, maxCol + 1);             // :723-727
+		const int newMax = (hi == INT_MIN ? off3 : hi + 1) + 1;   // :730-735
+		minCol = imax(newMin, n + 2 - rows);                 // :739
+		maxCol = imin(newMax, cols);                         // :741
+		return true;
+	}
+
+	// value of anti-diagonal `v` (whose window started at column `off`) at column col
+	XD_FN int at(const int (&v)[T], int col, unsigned mask, int lane) const
+	{
+		const int want = col & (GT - 1);
+		int x = INT_MIN;
+#pragma unroll
+		for (int t = 0; t < T; ++t) if (t * G + lane == want) x = v[t];
+		return rmax(mask, x);
+	}
+
+	// the longest extension (:747-843): score and the number of query columns / database rows it covers
+	XD_FN int finish(unsigned mask, int lane, int& ext_cols, int& ext_rows) const
+	{
+		int lcol = n3 + off3 - 2, lrow = n - lcol, lscore = at(v3, lcol, mask, lane);
+		if (lscore == UNDEF) {
+			const int e2 = at(v2, off2 + n2 - 2, mask, lane);
+			if (e2 != UNDEF) { lcol = n2 + off2 - 2; lrow = n - 1 - lcol; lscore = e2; }
+			else if (n2 > 2) {
+				const int e3 = at(v2, off2 + n2 - 3, mask, lane);
+				if (e3 != UNDEF) { lcol = n2 + off2 - 3; lrow = n - 1 - lcol; lscore = e3; }
+			}
+		}
+		if (lscore == UNDEF) {
+			int mx = INT_MIN;
+			int c1[T];
+#pragma unroll
+			for (int t = 0; t < T; ++t) {
+				c1[t] = off1 + ((t * G + lane - off1) & (GT - 1));
+				if (c1[t] - off1 < n1) mx = imax(mx, v1[t]);
+			}
+			mx = rmax(mask, mx);
+			if (mx > lscore) {
+				int cc = INT_MAX;
+#pragma unroll
+				for (int t = 0; t < T; ++t) if (c1[t] - off1 < n1 && v1[t] == mx) cc = imin(cc, c1[t]);
+				lcol = rmin(mask, cc); lrow = n - 2 - lcol; lscore = mx;
+			}
+		}
+		ext_cols = 0; ext_rows = 0;
+		if (lscore != UNDEF) { ext_cols = lcol; ext_rows = lrow; }
+		return lscore;
+	}
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// Wide path: one warp, anti-diagonals in global scratch (3 arrays of `cap` ints), any window width.
+// ------------------------------------------------------------------------------------------------------------------
+XD_FN int wide_extend(const Segs& s, int xdrop, int lane, int* scratch, int cap, int& ext_cols, int& ext_rows)
+{
+	const int cols = s.qlen + 1, rows = s.dlen + 1;
+	int *a1 = scratch, *a2 = scratch + cap, *a3 = scratch + 2 * cap;
+	int n1 = 0, n2 = 1, n3 = 2, off1 = 0, off2 = 0, off3 = 0;
+	int minCol = 1, maxCol = 2, n = 1, best = 0;
+	if (lane == 0) { a2[0] = 0; a3[0] = a3[1] = (1 > xdrop) ? UNDEF : -1; }
+	wsync(FULL);
+	while (minCol < maxCol) {
+		++n;
+		int* t = a1; a1 = a2; a2 = a3; a3 = t;
+		n1 = n2; n2 = n3; off1 = off2; off2 = off3; off3 = minCol - 1;
+		n3 = maxCol + 1 - off3;
+		const int lim = best - xdrop;
+		if (lane == 0) {
+			const bool edge = -n > lim;
+			a3[0] = (edge && off3 == 0) ? -n : UNDEF;
+			a3[maxCol - off3] = (edge && n == maxCol) ? -n : UNDEF;
+		}
+		int m = UNDEF;
+		for (int c = minCol + lane; c < maxCol; c += 32) {
+			const char qc = load_q(s, c - 1), dc = load_d(s, n - c - 1);
+			int tmp = imax(a2[c - off2 - 1], a2[c - off2]) - 1;
+			tmp = imax(tmp, a1[c - off1 - 1] + (qc == dc ? 1 : -1));
+			if (tmp < lim) tmp = UNDEF; else m = imax(m, tmp);
+			a3[c - off3] = tmp;
+		}
+		best = imax(best, rmax(FULL, m));
+		wsync(FULL);                                        // a3 is complete before anyone trims on it
+		while (minCol - off3 < n3 && a3[minCol - off3] == UNDEF && minCol - off2 - 1 < n2 && a2[minCol - off2 - 1] == UNDEF) ++minCol;
+		while (maxCol - off3 > 0 && a3[maxCol - off3 - 1] == UNDEF && a2[maxCol - off2 - 1] == UNDEF) --maxCol;
+		++maxCol;
+		minCol = imax(minCol, n + 2 - rows);
+		maxCol = imin(maxCol, cols);
+		wsync(FULL);                                        // everyone has read a1 before it is reused as a3
+	}
+	int lcol = n3 + off3 - 2, lrow = n - lcol, lscore = a3[lcol - off3];
+	if (lscore == UNDEF) {
+		if (a2[n2 - 2] != UNDEF) { lcol = n2 + off2 - 2; lrow = n - 1 - lcol; lscore = a2[lcol - off2]; }
+		else if (n2 > 2 && a2[n2 - 3] != UNDEF) { lcol = n2 + off2 - 3; lrow = n - 1 - lcol; lscore = a2[lcol - off2]; }
+	}
+	if (lscore == UNDEF) {
+		int mx = INT_MIN, cc = INT_MAX;
+		for (int i = lane; i < n1; i += 32) mx = imax(mx, a1[i]);
+		mx = rmax(FULL, mx);
+		if (mx > lscore) {
+			for (int i = lane; i < n1; i += 32) if (a1[i] == mx) cc = imin(cc, i + off1);
+			lcol = rmin(FULL, cc); lrow = n - 2 - lcol; lscore = mx;
+		}
+	}
+	wsync(FULL);                                            // the scratch may be reused by the next job
+	ext_cols = 0; ext_rows = 0;
+	if (lscore != UNDEF) { ext_cols = lcol; ext_rows = lrow; }
+	return lscore;
+}
+
+XD_FN void store_result(JobResult* res, int job, int lane0, int score, int ec, int er, int baseH, int baseV, int reverse)
+{
+	if (!lane0) return;
+	JobResult r;
+	r.score = score;
+	if (job & 1) { r.posH = baseH + er; r.posV = baseV + ec; r.flag = 0; }
+	else { r.posH = baseH - er; r.posV = baseV - ec; r.flag = reverse; }
+	res[job] = r;
+}
+
+// Per pair: the two halves joined (align.hpp:125-137) and the reference's adaptive-threshold test fused behind it
+// (PostAlignDecision, overlap.hpp:415-462, with its unsigned-short arithmetic).
+// out8 = { score, strand ('n' / 'c'), begH, endH, begV, endV, estimated overlap `ov`, passed }.
+XD_FN void compose(const Pairs& P, const JobResult* res, int p, double ratiophi, double delta, int fixed_threshold, int32_t* out8)
+{
+	const JobResult L = res[2 * p], R = res[2 * p + 1];
+	const int score = L.score + R.score + P.kmer_len;
+	const int begH = L.posH, begV = L.posV, endH = R.posH, endV = R.posV;
+	const int lenH = (int)(uint16_t)(P.seq_off[P.rows[p] + 1] - P.seq_off[P.rows[p]]);
+	const int lenV = (int)(uint16_t)(P.seq_off[P.cols[p] + 1] - P.seq_off[P.cols[p]]);
+	const uint16_t ovV = (uint16_t)(endV - begV), ovH = (uint16_t)(endH - begH);
+	const uint16_t minLeft = (uint16_t)imin(begV, begH), minRight = (uint16_t)imin(lenV - endV, lenH - endH);
+	const uint16_t ov = (uint16_t)((int)minLeft + (int)minRight + ((int)ovV + (int)ovH) / 2);
+	int passed;
+	if (fixed_threshold == -1) {
+		const float thr = (float)((1 - delta) * (ratiophi * (double)(float)ov));
+		passed = (float)score >= thr;
+	} else passed = score >= fixed_threshold;
+	int32_t* o = out8 + 8 * (long)p;
+	o[0] = score; o[1] = L.flag ? 'c' : 'n'; o[2] = begH; o[3] = endH; o[4] = begV; o[5] = endV; o[6] = ov; o[7] = passed;
+}
+
+struct Queue {
+	int* next;                                  // job counter
+	int* wide_count; int* wide_jobs;            // extensions whose window outgrew the registers
+	int* bad;                                   // set when a seed does not fit its reads
+};
+
+// A warp of the register kernel: 32/G groups, each pulling jobs until the queue is empty.  `rings` = this warp's
+// 32/G * 2 * RING bytes of shared memory.
+template <int G, int T>
+XD_FN void warp_main(const Pairs& P, const Queue& Q, JobResult* res, char* rings)
+{
+	typedef Ext<G, T> E;
+	const int wl = lane_id(), grp = wl / G, lane = wl & (G - 1);
+	const unsigned mask = G == 32 ? FULL : (((1u << (G & 31)) - 1u) << (grp * G));
+	char* qring = rings + grp * 2 * E::RING;
+	char* dring = qring + E::RING;
+	E e;
+	Segs s;
+	int job = 0, reverse = 0, baseH = 0, baseV = 0;
+	bool have = false, done = false;
+	for (;;) {
+		if (!have && !done) {
+			int j = 0;
+			if (lane == 0) j = atomic_inc(Q.next);
+			job = shfl(mask, j, 0, G);
+			if (job >= P.n_jobs) done = true;
+			else if (!make_segs<G>(P, job, mask, lane, s, reverse, baseH, baseV)) {
+				if (lane == 0) *Q.bad = 1;
+				store_result(res, job, lane == 0, 0, 0, 0, 0, 0, 0);
+			} else if (s.qlen == 0 || s.dlen == 0) {              // :635-636
+				store_result(res, job, lane == 0, 0, 0, 0, baseH, baseV, reverse);
+			} else {
+				e.init(s, P.xdrop, lane);
+				have = true;
+			}
+		}
+		if (all(FULL, done)) break;
+		if (have) {
+			if (e.active()) {
+				if (!e.step(s, mask, lane, qring, dring)) {
+					if (lane == 0) Q.wide_jobs[atomic_inc(Q.wide_count)] = job;
+					have = false;
+				}
+			} else {
+				int ec, er;
+				const int score = e.finish(mask, lane, ec, er);
+				store_result(res, job, lane == 0, score, ec, er, baseH, baseV, reverse);
+				have = false;
+			}
+		}
+	}
+}
+
+// A warp of the wide kernel: jobs from the overflow list (or, with list == nullptr, every job).
+XD_FN void wide_main(const Pairs& P, const int* list, int n_list, int* next, JobResult* res, int* scratch, int cap, int* bad)
+{
+	const int lane = lane_id();
+	for (;;) {
+		int j = 0;
+		if (lane == 0) j = atomic_inc(next);
+		j = shfl(FULL, j, 0, 32);
+		if (j >= n_list) break;
+		const int job = list ? list[j] : j;
+		Segs s;
+		int reverse, baseH, baseV, ec = 0, er = 0, score = 0;
+		if (!make_segs<32>(P, job, FULL, lane, s, reverse, baseH, baseV)) {
+			if (lane == 0) *bad = 1;
+			store_result(res, job, lane == 0, 0, 0, 0, 0, 0, 0);
+			continue;
+		}
+		if (s.qlen > 0 && s.dlen > 0) score = wide_extend(s, P.xdrop, lane, scratch, cap, ec, er);
+		store_result(res, job, lane == 0, score, ec, er, baseH, baseV, reverse);
+	}
+}
+
+}  // namespace xd

@@ -295,6 +295,66 @@ int bella_ref_align(uint64_t n_pairs, const IT* rows, const IT* cols, const NT* 
 	return 0;
 }
 
+// The reference's accept/reject step behind the alignment, PostAlignDecision (include/overlap.hpp:415-497), called as
+// RunPairWiseAlignments does (:574-577).  out8[p] = the six fields of bella_ref_align, then `ov` as the reference PRINTS it
+// (column 5 of its output line; -1 when the pair is rejected and nothing is printed), then passed (0/1).
+int bella_ref_align_post(uint64_t n_pairs, const IT* rows, const IT* cols, const NT* posH, const NT* posV,
+		const char* seqs, const uint64_t* seq_off, int kmer_len, int xdrop, double ratiophi, double delta, int fixed_threshold,
+		int32_t* out8)
+{
+	Quiet q;
+	BELLApars bpars;
+	bpars.kmerSize = (unsigned short)kmer_len; bpars.xDrop = (unsigned short)xdrop;
+	bpars.deltaChernoff = delta; bpars.fixedThreshold = (short)fixed_threshold; bpars.outputPaf = false;
+#pragma omp parallel for schedule(dynamic, 16)
+	for (int64_t p = 0; p < (int64_t)n_pairs; ++p) {
+		readType_ r1, r2;
+		r1.nametag = "H"; r2.nametag = "V";
+		r1.seq.assign(seqs + seq_off[rows[p]], seqs + seq_off[rows[p] + 1]);
+		r2.seq.assign(seqs + seq_off[cols[p]], seqs + seq_off[cols[p] + 1]);
+		seqAnResult r = alignSeqAn(r1.seq, r2.seq, (int)r1.seq.length(), posH[p], posV[p], xdrop, kmer_len, false, false, false);
+		std::stringstream line;
+		size_t outputted = 0, basesTrue = 0, basesFalse = 0;
+		bool passed = false;
+		// overlap.hpp:74-76 hard-defines __SIMD__, so PostAlignDecision takes a xavierResult: same fields, filled from the SeqAn seed
+		xavierResult xr;
+		xr.score = r.score; xr.strand = r.strand;
+		xr.seed = SeedX((int)beginPositionH(r.seed), (int)beginPositionV(r.seed), (int)endPositionH(r.seed), (int)endPositionV(r.seed));
+		PostAlignDecision(xr, r1, r2, bpars, ratiophi, 1, line, outputted, basesTrue, basesFalse, passed, 1);
+		int32_t* o = out8 + 8 * p;
+		o[0] = r.score; o[1] = r.strand[0];
+		o[2] = (int32_t)beginPositionH(r.seed); o[3] = (int32_t)endPositionH(r.seed);
+		o[4] = (int32_t)beginPositionV(r.seed); o[5] = (int32_t)endPositionV(r.seed);
+		o[6] = -1; o[7] = passed ? 1 : 0;
+		if (passed) {
+			std::string f; int col = 0; long ov = -1;
+			while (std::getline(line, f, '\t')) { if (++col == 5) { ov = atol(f.c_str()); break; } }
+			o[6] = (int32_t)ov;
+		}
+	}
+	return 0;
+}
+
+// What the reference's DEFAULT CPU build actually calls (overlap.hpp:74-76 defines __SIMD__ unconditionally): xavierAlign
+// (include/align.hpp:152-202), a fixed-band SIMD X-drop -- a different algorithm from alignSeqAn / LOGAN, kept here only to
+// quantify how far the two reference aligners are from each other.  Same out6 layout as bella_ref_align.
+int bella_ref_align_xavier(uint64_t n_pairs, const IT* rows, const IT* cols, const NT* posH, const NT* posV,
+		const char* seqs, const uint64_t* seq_off, int kmer_len, int xdrop, int32_t* out6)
+{
+	Quiet q;
+#pragma omp parallel for schedule(dynamic, 16)
+	for (int64_t p = 0; p < (int64_t)n_pairs; ++p) {
+		std::string row(seqs + seq_off[rows[p]], seqs + seq_off[rows[p] + 1]);
+		std::string col(seqs + seq_off[cols[p]], seqs + seq_off[cols[p] + 1]);
+		xavierResult r = xavierAlign(row, col, (int)row.length(), posH[p], posV[p], xdrop, kmer_len);
+		int32_t* o = out6 + 6 * p;
+		o[0] = r.score; o[1] = r.strand[0];
+		o[2] = getBeginPositionH(r.seed); o[3] = getEndPositionH(r.seed);
+		o[4] = getBeginPositionV(r.seed); o[5] = getEndPositionV(r.seed);
+	}
+	return 0;
+}
+
 int bella_ref_max_threads(void) { return omp_get_max_threads(); }
 
 } // extern "C"

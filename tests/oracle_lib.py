@@ -165,3 +165,34 @@ def oracle_align(inp, rows, cols, posH, posV, xdrop=7):
 def ref_align(inp, rows, cols, posH, posV, xdrop=7):
     """the reference's alignSeqAn (oracle/_ref) on the same pairs"""
     return _align(ref().bella_ref_align, inp, rows, cols, posH, posV, xdrop)
+
+
+def ref_align_xavier(inp, rows, cols, posH, posV, xdrop=7):
+    """the aligner the reference's default CPU build calls (xavierAlign, a different fixed-band algorithm); informational"""
+    return _align(ref().bella_ref_align_xavier, inp, rows, cols, posH, posV, xdrop)
+
+
+def oracle_align_post(inp, rows, cols, posH, posV, xdrop=7, ratiophi=0.5, delta=0.1, fixed_threshold=-1):
+    """oracle_xdrop_align + oracle_xdrop_post -> int32 [n][8] = the six alignment fields, ov, passed"""
+    a = oracle_align(inp, rows, cols, posH, posV, xdrop)
+    rows = np.ascontiguousarray(rows, dtype=np.uint32); cols = np.ascontiguousarray(cols, dtype=np.uint32)
+    post = np.zeros((len(rows), 2), dtype=np.int32)
+    rc = oracle().oracle_xdrop_post(ctypes.c_uint64(len(rows)), _p(rows), _p(cols), _p(inp.seq_off), _p(a),
+                                    ctypes.c_double(ratiophi), ctypes.c_double(delta), ctypes.c_int(fixed_threshold), _p(post))
+    if rc != 0:
+        raise RuntimeError(f"post-alignment decision failed: {rc}")
+    return np.concatenate([a, post], axis=1)
+
+
+def ref_align_post(inp, rows, cols, posH, posV, xdrop=7, ratiophi=0.5, delta=0.1, fixed_threshold=-1):
+    """the reference's alignSeqAn + PostAlignDecision -> int32 [n][8]; column 6 (ov) is -1 where the pair is rejected,
+    because the reference only prints it for accepted pairs"""
+    rows = np.ascontiguousarray(rows, dtype=np.uint32); cols = np.ascontiguousarray(cols, dtype=np.uint32)
+    posH = np.ascontiguousarray(posH, dtype=np.uint16); posV = np.ascontiguousarray(posV, dtype=np.uint16)
+    out = np.zeros((len(rows), 8), dtype=np.int32)
+    rc = ref().bella_ref_align_post(ctypes.c_uint64(len(rows)), _p(rows), _p(cols), _p(posH), _p(posV), _p(inp.seqs), _p(inp.seq_off),
+                                    ctypes.c_int(inp.kmer_size), ctypes.c_int(xdrop), ctypes.c_double(ratiophi), ctypes.c_double(delta),
+                                    ctypes.c_int(fixed_threshold), _p(out))
+    if rc != 0:
+        raise RuntimeError(f"reference post-alignment failed: {rc}")
+    return out

@@ -1,0 +1,117 @@
+"""CPU: the DEVICE source of the X-drop kernels (bella_b200/csrc/xdrop.cuh -- register path, overflow hand-over, wide
+path, the fused threshold test) compiled for the host under the lane-fiber emulator of tests/emu/ and compared with the
+oracle (oracle_xdrop_align + oracle_xdrop_post, both pinned against the reference in test_oracle_xdrop.py).  Same code
+the GPU runs, so logic errors show up here without a B200; the GPU parity tests are tests/test_xdrop_gpu.py."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_util
+import oracle_lib as ol
+from bella_b200 import frontend as fe
+
+EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+_emu = None
+
+
+def emu_lib():
+    global _emu
+    if _emu is None:
+        subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+        _emu = ctypes.CDLL(os.path.join(EMU_DIR, "_build", "libxdrop_emu.so"))
+    return _emu
+
+
+def _p(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def emu_align(inp, rows, cols, posH, posV, xdrop, lanes, cells, ratiophi=0.5, delta=0.1, fixed_threshold=-1, warps=8):
+    rows = np.ascontiguousarray(rows, dtype=np.uint32); cols = np.ascontiguousarray(cols, dtype=np.uint32)
+    posH = np.ascontiguousarray(posH, dtype=np.uint16); posV = np.ascontiguousarray(posV, dtype=np.uint16)
+    out = np.zeros((len(rows), 8), dtype=np.int32)
+    n_wide = ctypes.c_int(0)
+    rc = emu_lib().xdrop_emu_align(lanes, cells, ctypes.c_uint64(len(rows)), _p(rows), _p(cols), _p(posH), _p(posV), _p(inp.seqs),
+                                   _p(inp.seq_off), ctypes.c_uint32(len(inp.seq_off) - 1), ctypes.c_int(inp.kmer_size), ctypes.c_int(xdrop),
+                                   ctypes.c_double(ratiophi), ctypes.c_double(delta), ctypes.c_int(fixed_threshold), ctypes.c_int(warps),
+                                   _p(out), ctypes.byref(n_wide))
+    return rc, out, n_wide.value
+
+
+def candidate_pairs(inp, limit, seed=0):
+    r = ol.oracle_spgemm(inp, want_aux=False)
+    cols = np.repeat(np.arange(inp.n_reads, dtype=np.uint32), np.diff(r.colptrC.astype(np.int64)))
+    idx = np.arange(r.nnz)
+    if r.nnz > limit:
+        idx = np.sort(np.random.default_rng(seed).choice(r.nnz, limit, replace=False))
+    return r.rowids[idx], cols[idx], r.posH[idx], r.posV[idx]
+
+
+@pytest.fixture(scope="module")
+def reads():
+    inp = fe.synthetic(120, 1200, coverage=14.0, seed=31)
+    return inp, candidate_pairs(inp, 400, seed=3)
+
+
+# (lanes per extension, cells per lane, xdrop): every instantiation the library ships, (0,0) = wide path only
+@pytest.mark.parametrize("lanes,cells,xdrop", [(32, 1, 7), (32, 2, 15), (32, 4, 30), (16, 1, 3), (16, 2, 7), (0, 0, 7)])
+def test_device_source_matches_oracle(reads, lanes, cells, xdrop):
+    inp, pairs = reads
+    want = ol.oracle_align_post(inp, *pairs, xdrop, 0.55, 0.1, -1)
+    rc, got, _ = emu_align(inp, *pairs, xdrop, lanes, cells, 0.55, 0.1, -1)
+    assert rc == 0
+    np.testing.assert_array_equal(got, want)
+    assert want[:, 0].max() > 300 and (want[:, 1] == ord("c")).any() and (want[:, 1] == ord("n")).any()
+    assert 0 < want[:, 7].sum() < len(want) or xdrop != 7          # the threshold test separates the pairs
+
+
+def test_window_overflow_hands_over_to_the_wide_path(reads):
+    inp, pairs = reads
+    want = ol.oracle_align_post(inp, *pairs, 7, 0.55, 0.1, 200)
+    rc, got, n_wide = emu_align(inp, *pairs, 7, 16, 1, 0.55, 0.1, 200)     # 16 slots: a quarter of the extensions outgrow them
+    assert rc == 0 and n_wide > 20
+    np.testing.assert_array_equal(got, want)
+    rc, got, n_wide = emu_align(inp, *pairs, 25, 32, 1, 0.55, 0.1, 200)    # x = 25 needs ~34 columns: most go wide
+    assert rc == 0 and n_wide > len(want)
+    np.testing.assert_array_equal(got, ol.oracle_align_post(inp, *pairs, 25, 0.55, 0.1, 200))
+
+
+def test_low_error_reads_and_seeds_at_the_read_ends():
+    inp = fe.synthetic(60, 1500, coverage=15.0, err=0.02, seed=77, hi=40)       # extensions that run into the read ends
+    pairs = candidate_pairs(inp, 200)
+    rc, got, _ = emu_align(inp, *pairs, 7, 32, 1)
+    assert rc == 0
+    np.testing.assert_array_equal(got, ol.oracle_align_post(inp, *pairs, 7))
+    k, n = inp.kmer_size, 30
+    r = np.arange(1, n + 1, dtype=np.uint32)
+    c = np.zeros(n, dtype=np.uint32)
+    lens = inp.read_len
+    pH = np.where(np.arange(n) % 2 == 0, 0, lens[r] - k).astype(np.uint16)      # empty prefix / empty suffix
+    pV = np.where(np.arange(n) % 3 == 0, 0, lens[c] - k).astype(np.uint16)
+    for lanes, cells in ((32, 1), (16, 2), (0, 0)):
+        rc, got, _ = emu_align(inp, r, c, pH, pV, 7, lanes, cells)
+        assert rc == 0
+        np.testing.assert_array_equal(got, ol.oracle_align_post(inp, r, c, pH, pV, 7))
+
+
+def test_reference_golden_fixture():
+    z = np.load(os.path.join(golden_util.GOLDEN, "xdrop.npz"))
+    inp = fe.OverlapInputs(n_reads=int(z["n_reads"]), n_kmers=0, nnz=0, A_colptr=None, A_rowids=None, A_values=None, A_strand=None,
+                           B_colptr=None, B_rowids=None, B_values=None, B_strand=None, read_len=None, kmer_size=int(z["k"]),
+                           seqs=z["seqs"], seq_off=z["seq_off"])
+    sel = slice(0, 3000, 6)
+    rc, got, _ = emu_align(inp, z["rows"][sel], z["cols"][sel], z["posH"][sel], z["posV"][sel], int(z["xdrop"]), 32, 1)
+    assert rc == 0
+    np.testing.assert_array_equal(got[:, :6], z["ref_out"][sel])
+
+
+def test_seed_outside_its_read_is_reported(reads):
+    inp, pairs = reads
+    rows, cols, pH, pV = (a[:8].copy() for a in pairs)
+    pH[3] = inp.read_len[rows[3]] - 3
+    for lanes, cells in ((32, 1), (0, 0)):
+        rc, _, _ = emu_align(inp, rows, cols, pH, pV, 7, lanes, cells)
+        assert rc == -1
