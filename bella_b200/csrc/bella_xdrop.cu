@@ -7,7 +7,7 @@
 //   k_xdrop_compose  joins the two halves of each pair and applies the reference's threshold test
 //
 // Reads stay resident on the device between batches; seeds come as (row, col, posH, posV) arrays -- host pointers
-// (bella_xdrop_align) or the overlap SpGEMM's device result (bella_xdrop_align_device).
+// (bella_xdrop_align) or the overlap SpGEMM's device result (bella_xdrop_align_device / _align_csc_device).
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -111,7 +111,7 @@ void pick_shape(const bella_xdrop* h, int& G, int& T)
 }
 
 int run_batch(bella_xdrop* h, uint64_t n_pairs, const uint32_t* d_rows, const uint32_t* d_cols, const uint16_t* d_posH,
-		const uint16_t* d_posV, int32_t* d_out)
+		const uint16_t* d_posV, int32_t* d_out, const uint32_t* d_colptr = nullptr, int n_cols = 0)
 {
 	if (!h->seqs.p) return fail(h, BELLA_XDROP_EINVAL, "bella_xdrop_set_reads has not been called");
 	if (n_pairs > (1u << 30) - 1) return fail(h, BELLA_XDROP_EINVAL, "more than 2^30 - 1 pairs in one batch");
@@ -123,7 +123,7 @@ int run_batch(bella_xdrop* h, uint64_t n_pairs, const uint32_t* d_rows, const ui
 	XCUDA(h->ctr.reserve(4 * sizeof(int)));
 	int* ctr = (int*)h->ctr.p;                  // [0] queue, [1] wide count, [2] wide queue, [3] bad seed
 	XCUDA(cudaMemsetAsync(ctr, 0, 4 * sizeof(int), h->stream));
-	xd::Pairs P{d_rows, d_cols, d_posH, d_posV, (const char*)h->seqs.p, (const uint64_t*)h->seq_off.p, h->kmer_len, h->xdrop, n_jobs};
+	xd::Pairs P{d_rows, d_cols, d_posH, d_posV, (const char*)h->seqs.p, (const uint64_t*)h->seq_off.p, h->kmer_len, h->xdrop, n_jobs, d_colptr, n_cols};
 	xd::Queue Q{ctr, ctr + 1, (int*)h->wide.p, ctr + 3};
 	xd::JobResult* res = (xd::JobResult*)h->res.p;
 	int G, T;
@@ -237,12 +237,23 @@ int bella_xdrop_align_device(bella_xdrop* h, uint64_t n_pairs, const uint32_t* d
 	return run_batch(h, n_pairs, d_rows, d_cols, d_posH, d_posV, d_out);
 }
 
+int bella_xdrop_align_csc_device(bella_xdrop* h, uint32_t n_cols, const uint32_t* d_colptrC, uint64_t n_pairs, const uint32_t* d_rowids,
+		const uint16_t* d_posH, const uint16_t* d_posV, int32_t* d_out)
+{
+	if (!h) return BELLA_XDROP_EINVAL;
+	if (n_cols != h->n_reads) return fail(h, BELLA_XDROP_EINVAL, "the overlap matrix must have one column per read");
+	if (n_pairs && !d_colptrC) return fail(h, BELLA_XDROP_EINVAL, "null colptr");
+	XCUDA(cudaSetDevice(h->device));
+	return run_batch(h, n_pairs, d_rowids, nullptr, d_posH, d_posV, d_out, d_colptrC, (int)n_cols);
+}
+
 int bella_xdrop_align(bella_xdrop* h, uint64_t n_pairs, const uint32_t* rows, const uint32_t* cols,
 		const uint16_t* posH, const uint16_t* posV, int32_t* out)
 {
 	if (!h) return BELLA_XDROP_EINVAL;
 	if (n_pairs == 0) { h->launches = 0; return 0; }
 	if (!rows || !cols || !posH || !posV || !out) return fail(h, BELLA_XDROP_EINVAL, "null pair arrays");
+	if (!h->seqs.p) return fail(h, BELLA_XDROP_EINVAL, "bella_xdrop_set_reads has not been called");
 	XCUDA(cudaSetDevice(h->device));
 	for (uint64_t p = 0; p < n_pairs; ++p)
 		if (rows[p] >= h->n_reads || cols[p] >= h->n_reads) return fail(h, BELLA_XDROP_EINVAL, "read index out of range");

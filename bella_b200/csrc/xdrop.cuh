@@ -3,7 +3,7 @@
 // What it replaces: the reference's per-pair alignSeqAn -> seqan::extendSeed(.., GappedXDrop()) (include/align.hpp:93-139,
 // seqan/seqan/seeds/seeds_extension.h:622-843) and its CUDA port (loganGPU/functions.cuh:223-408, one 32-thread block per
 // alignment, anti-diagonals in global memory).  Same recurrence, same trimming rules, same "longest extension" rules, so
-// (score, strand, begH, endH, begV, endV) are identical per pair; the oracle is oracle/bella_oracle.c oracle_xdrop_align.
+// (score, strand, begH, endH, begV, endV) are identical per pair (the tests check it against the CPU restatement oracle_xdrop_align).
 //
 // Layout of one extension on the device (xd::Ext<G,T>): a group of G lanes owns the live window of the three anti-diagonals
 // in REGISTERS.  Column c of the DP matrix lives in slot c mod (G*T) = lane + G*t, so a column never moves between lanes
@@ -63,12 +63,24 @@ struct Segs {
 };
 
 struct Pairs {                              // the candidate pairs, as the overlap SpGEMM emits them
-	const uint32_t* rows; const uint32_t* cols;      // H = row read, V = column read
+	const uint32_t* rows; const uint32_t* cols;      // H = row read, V = column read; cols == nullptr: CSC form, see colptr
 	const uint16_t* posH; const uint16_t* posV;      // seed k-mer
 	const char* seqs; const uint64_t* seq_off;       // reads, concatenated, 1 byte per base
 	int kmer_len, xdrop;
 	int n_jobs;                                      // 2 per pair: job 2p = left, 2p+1 = right
+	const uint32_t* colptr; int n_cols;              // CSC form: pair p belongs to the column c with colptr[c] <= p < colptr[c+1]
 };
+
+XD_FN uint32_t pair_col(const Pairs& P, int p)
+{
+	if (P.cols) return P.cols[p];
+	int lo = 0, hi = P.n_cols;                       // colptr[lo] <= p < colptr[hi]
+	while (hi - lo > 1) {
+		const int mid = (lo + hi) >> 1;
+		if (P.colptr[mid] <= (uint32_t)p) lo = mid; else hi = mid;
+	}
+	return (uint32_t)lo;
+}
 
 // per job: { score, H coordinate, V coordinate, flag }; left: begin positions, flag = reverse strand; right: end positions
 struct JobResult { int score, posH, posV, flag; };
@@ -79,9 +91,10 @@ template <int G>
 XD_FN bool make_segs(const Pairs& P, int job, unsigned mask, int lane, Segs& s, int& reverse, int& baseH, int& baseV)
 {
 	const int p = job >> 1, right = job & 1;
-	const uint64_t oh = P.seq_off[P.rows[p]], ov = P.seq_off[P.cols[p]];
+	const uint32_t col = pair_col(P, p);
+	const uint64_t oh = P.seq_off[P.rows[p]], ov = P.seq_off[col];
 	const char* H = P.seqs + oh; const int lenH = (int)(P.seq_off[P.rows[p] + 1] - oh);
-	const char* V = P.seqs + ov; const int lenV = (int)(P.seq_off[P.cols[p] + 1] - ov);
+	const char* V = P.seqs + ov; const int lenV = (int)(P.seq_off[col + 1] - ov);
 	int i = P.posH[p];
 	const int j = P.posV[p], k = P.kmer_len;
 	if (i + k > lenH || j + k > lenV) return false;
@@ -320,7 +333,8 @@ XD_FN void compose(const Pairs& P, const JobResult* res, int p, double ratiophi,
 	const int score = L.score + R.score + P.kmer_len;
 	const int begH = L.posH, begV = L.posV, endH = R.posH, endV = R.posV;
 	const int lenH = (int)(uint16_t)(P.seq_off[P.rows[p] + 1] - P.seq_off[P.rows[p]]);
-	const int lenV = (int)(uint16_t)(P.seq_off[P.cols[p] + 1] - P.seq_off[P.cols[p]]);
+	const uint32_t col = pair_col(P, p);
+	const int lenV = (int)(uint16_t)(P.seq_off[col + 1] - P.seq_off[col]);
 	const uint16_t ovV = (uint16_t)(endV - begV), ovH = (uint16_t)(endH - begH);
 	const uint16_t minLeft = (uint16_t)imin(begV, begH), minRight = (uint16_t)imin(lenV - endV, lenH - endH);
 	const uint16_t ov = (uint16_t)((int)minLeft + (int)minRight + ((int)ovV + (int)ovH) / 2);

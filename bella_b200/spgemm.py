@@ -244,6 +244,16 @@ class OverlapSpGEMM:
         self._check(self._L.bella_b200_result_device(self._h, None, None, None, None, None, ctypes.byref(z)), "bella_b200_result_device")
         return z.value
 
+    def result_device(self):
+        """device pointers of the whole result after numeric_device() / run_resident():
+        -> dict(colptrC, rowids, count, posH, posV: int addresses; nnz).  Valid until the next pass on this handle."""
+        ptrs = [ctypes.c_void_p(0) for _ in range(5)]
+        z = ctypes.c_uint64(0)
+        self._check(self._L.bella_b200_result_device(self._h, *[ctypes.byref(p) for p in ptrs], ctypes.byref(z)), "bella_b200_result_device")
+        out = {k: (p.value or 0) for k, p in zip(("colptrC", "rowids", "count", "posH", "posV"), ptrs)}
+        out["nnz"] = z.value
+        return out
+
     def numeric_device(self):
         self._check(self._L.bella_b200_numeric_device(self._h), "bella_b200_numeric_device")
 

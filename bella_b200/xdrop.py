@@ -13,6 +13,7 @@ _lib = None
 FIELDS = ("score", "strand", "begH", "endH", "begV", "endV", "ov", "passed")
 EXPORTS = ["bella_xdrop_create", "bella_xdrop_destroy", "bella_xdrop_last_error", "bella_xdrop_set_reads",
            "bella_xdrop_set_params", "bella_xdrop_set_shape", "bella_xdrop_align", "bella_xdrop_align_device",
+           "bella_xdrop_align_csc_device",
            "bella_xdrop_get_stats", "bella_xdrop_stream", "bella_xdrop_sync"]
 
 
@@ -39,6 +40,7 @@ def lib():
         L.bella_xdrop_set_shape.argtypes = [H, ctypes.c_int, ctypes.c_int]
         L.bella_xdrop_align.argtypes = [H, ctypes.c_uint64, vp, vp, vp, vp, vp]
         L.bella_xdrop_align_device.argtypes = [H, ctypes.c_uint64, vp, vp, vp, vp, vp]
+        L.bella_xdrop_align_csc_device.argtypes = [H, ctypes.c_uint32, vp, ctypes.c_uint64, vp, vp, vp, vp]
         L.bella_xdrop_get_stats.argtypes = [H, ctypes.POINTER(ctypes.c_double)]
         L.bella_xdrop_stream.argtypes = [H]
         L.bella_xdrop_stream.restype = vp
@@ -98,6 +100,11 @@ class XdropAligner:
         """device pointers (ints or torch tensors); asynchronous on the handle's stream -- call sync()"""
         ptr = lambda a: ctypes.c_void_p(a.data_ptr() if hasattr(a, "data_ptr") else int(a))  # noqa: E731
         self._check(lib().bella_xdrop_align_device(self._h, n_pairs, ptr(d_rows), ptr(d_cols), ptr(d_posH), ptr(d_posV), ptr(d_out)))
+
+    def align_csc_device(self, n_cols, d_colptrC, n_pairs, d_rowids, d_posH, d_posV, d_out):
+        """the overlap SpGEMM's device result (OverlapSpGEMM.result_device()) in, int32 [n_pairs][8] on the device out"""
+        ptr = lambda a: ctypes.c_void_p(a.data_ptr() if hasattr(a, "data_ptr") else int(a))  # noqa: E731
+        self._check(lib().bella_xdrop_align_csc_device(self._h, n_cols, ptr(d_colptrC), n_pairs, ptr(d_rowids), ptr(d_posH), ptr(d_posV), ptr(d_out)))
 
     def sync(self):
         self._check(lib().bella_xdrop_sync(self._h))

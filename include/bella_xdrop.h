@@ -62,6 +62,12 @@ int bella_xdrop_align(bella_xdrop* h, uint64_t n_pairs, const uint32_t* rows, co
 int bella_xdrop_align_device(bella_xdrop* h, uint64_t n_pairs, const uint32_t* d_rows, const uint32_t* d_cols,
                              const uint16_t* d_posH, const uint16_t* d_posV, int32_t* d_out);
 
+/* Same, fed with the overlap SpGEMM's result exactly as bella_b200_result_device() hands it out (include/bella_b200.h):
+ * C in CSC form over all n_cols = n_reads columns, pair p = nonzero p, its V read = the column that holds it.  This is the
+ * loop nest of RunPairWiseAlignments (include/overlap.hpp:518-546) without the host in between. */
+int bella_xdrop_align_csc_device(bella_xdrop* h, uint32_t n_cols, const uint32_t* d_colptrC, uint64_t n_pairs,
+                                 const uint32_t* d_rowids, const uint16_t* d_posH, const uint16_t* d_posV, int32_t* d_out);
+
 /* stats[0] = milliseconds of the last batch's kernels (CUDA events), [1] = extensions that went through the wide path,
  * [2] = kernel launches of the last batch, [3] = lanes, [4] = cells per lane actually used. */
 int bella_xdrop_get_stats(bella_xdrop* h, double* stats5);

@@ -190,13 +190,13 @@ void run_wide(const xd::Pairs& P, const int* list, int n_list, xd::JobResult* re
 }
 
 }  // namespace
-// G = 0: everything through the wide path.  Returns 0, -1 for a seed outside its read, -2 for an unknown shape;
+// G = 0: everything through the wide path.  cols == nullptr: CSC form (colptr over n_cols columns).  Returns 0, -1 for a seed outside its read, -2 for an unknown shape;
 // *n_wide = extensions that left the register path.
 extern "C" int xdrop_emu_align(int G, int T, uint64_t n_pairs, const uint32_t* rows, const uint32_t* cols, const uint16_t* posH,
 		const uint16_t* posV, const char* seqs, const uint64_t* seq_off, uint32_t n_reads, int kmer_len, int xdrop,
-		double ratiophi, double delta, int fixed_threshold, int n_warps, int32_t* out8, int* n_wide)
+		double ratiophi, double delta, int fixed_threshold, int n_warps, int32_t* out8, int* n_wide, const uint32_t* colptr, int n_cols)
 {
-	xd::Pairs P{rows, cols, posH, posV, seqs, seq_off, kmer_len, xdrop, (int)(2 * n_pairs)};
+	xd::Pairs P{rows, cols, posH, posV, seqs, seq_off, kmer_len, xdrop, (int)(2 * n_pairs), colptr, n_cols};
 	std::vector<xd::JobResult> res(2 * n_pairs);
 	std::vector<int> wide(2 * n_pairs + 1);
 	int next = 0, wide_count = 0, bad = 0;

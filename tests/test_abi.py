@@ -9,10 +9,10 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    hdr = open(os.path.join(ROOT, "include", "bella_b200.h")).read()
+def declared_symbols(header="bella_b200.h", prefix="bella_b200_"):
+    hdr = open(os.path.join(ROOT, "include", header)).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(bella_b200_\w+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"\b(" + prefix + r"\w+)\s*\(", hdr)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -24,6 +24,16 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/bella_b200.h but not exported"
     assert sorted(spgemm.EXPORTS) == syms
+
+
+def test_xdrop_library_exports_every_declared_symbol():
+    from bella_b200 import _build, xdrop
+    L = ctypes.CDLL(_build.build_xdrop())
+    syms = declared_symbols("bella_xdrop.h", "bella_xdrop_")
+    assert len(syms) >= 10
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/bella_xdrop.h but not exported"
+    assert sorted(xdrop.EXPORTS) == syms
 
 
 def test_product_path_does_not_touch_the_oracle():
@@ -44,3 +54,6 @@ def test_no_cpu_fallback_without_gpu():
     from bella_b200 import spgemm
     with pytest.raises(spgemm.BellaB200Error):
         spgemm.OverlapSpGEMM(0)
+    from bella_b200 import xdrop
+    with pytest.raises(xdrop.BellaXdropError):
+        xdrop.XdropAligner(0)

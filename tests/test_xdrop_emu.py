@@ -29,15 +29,21 @@ def _p(a):
     return ctypes.c_void_p(a.ctypes.data)
 
 
-def emu_align(inp, rows, cols, posH, posV, xdrop, lanes, cells, ratiophi=0.5, delta=0.1, fixed_threshold=-1, warps=8):
-    rows = np.ascontiguousarray(rows, dtype=np.uint32); cols = np.ascontiguousarray(cols, dtype=np.uint32)
+def emu_align(inp, rows, cols, posH, posV, xdrop, lanes, cells, ratiophi=0.5, delta=0.1, fixed_threshold=-1, warps=8, colptr=None):
+    rows = np.ascontiguousarray(rows, dtype=np.uint32)
     posH = np.ascontiguousarray(posH, dtype=np.uint16); posV = np.ascontiguousarray(posV, dtype=np.uint16)
+    if colptr is None:
+        cols = np.ascontiguousarray(cols, dtype=np.uint32)
+        c_cols, c_colptr, n_cols = _p(cols), None, 0
+    else:                                                           # CSC form: the column of a pair comes from colptr
+        colptr = np.ascontiguousarray(colptr, dtype=np.uint32)
+        c_cols, c_colptr, n_cols = None, _p(colptr), len(colptr) - 1
     out = np.zeros((len(rows), 8), dtype=np.int32)
     n_wide = ctypes.c_int(0)
-    rc = emu_lib().xdrop_emu_align(lanes, cells, ctypes.c_uint64(len(rows)), _p(rows), _p(cols), _p(posH), _p(posV), _p(inp.seqs),
+    rc = emu_lib().xdrop_emu_align(lanes, cells, ctypes.c_uint64(len(rows)), _p(rows), c_cols, _p(posH), _p(posV), _p(inp.seqs),
                                    _p(inp.seq_off), ctypes.c_uint32(len(inp.seq_off) - 1), ctypes.c_int(inp.kmer_size), ctypes.c_int(xdrop),
                                    ctypes.c_double(ratiophi), ctypes.c_double(delta), ctypes.c_int(fixed_threshold), ctypes.c_int(warps),
-                                   _p(out), ctypes.byref(n_wide))
+                                   _p(out), ctypes.byref(n_wide), c_colptr, ctypes.c_int(n_cols))
     return rc, out, n_wide.value
 
 
@@ -106,6 +112,16 @@ def test_reference_golden_fixture():
     rc, got, _ = emu_align(inp, z["rows"][sel], z["cols"][sel], z["posH"][sel], z["posV"][sel], int(z["xdrop"]), 32, 1)
     assert rc == 0
     np.testing.assert_array_equal(got[:, :6], z["ref_out"][sel])
+
+
+def test_csc_form_takes_the_spgemm_result_as_it_is():
+    inp = fe.synthetic(40, 900, coverage=10.0, seed=9)
+    r = ol.oracle_spgemm(inp, want_aux=False)
+    assert (np.diff(r.colptrC.astype(np.int64)) == 0).any()        # empty columns are part of the case
+    cols = np.repeat(np.arange(inp.n_reads, dtype=np.uint32), np.diff(r.colptrC.astype(np.int64)))
+    rc, got, _ = emu_align(inp, r.rowids, None, r.posH, r.posV, 7, 32, 1, colptr=r.colptrC)
+    assert rc == 0
+    np.testing.assert_array_equal(got, ol.oracle_align_post(inp, r.rowids, cols, r.posH, r.posV, 7))
 
 
 def test_seed_outside_its_read_is_reported(reads):
