@@ -3,6 +3,7 @@
 //
 //   k_xdrop<G,T>     persistent CTAs of 8 warps; every group of G lanes pulls extensions (2 per pair) from one queue and
 //                    runs them with the anti-diagonals in registers; windows that outgrow G*T slots go to a list
+//   k_xdrop_thread<W> one THREAD per extension (small x: the window is too narrow for a warp), anti-diagonals in shared memory
 //   k_xdrop_wide     one warp per listed extension, anti-diagonals in global scratch
 //   k_xdrop_compose  joins the two halves of each pair and applies the reference's threshold test
 //
@@ -27,6 +28,15 @@ __global__ void __launch_bounds__(WARPS * 32) k_xdrop(xd::Pairs P, xd::Queue Q, 
 	constexpr int PER_WARP = (32 / G) * 2 * xd::Ext<G, T>::RING;
 	__shared__ char rings[WARPS * PER_WARP];
 	xd::warp_main<G, T>(P, Q, res, rings + (threadIdx.x >> 5) * PER_WARP);
+}
+
+// thread-per-extension kernel: NT threads, each with 2 anti-diagonals of W ints + 2 * W bases in shared memory
+template <int W>
+__global__ void k_xdrop_thread(xd::Pairs P, xd::Queue Q, xd::JobResult* res)
+{
+	extern __shared__ int smem_thread[];
+	const int nt = blockDim.x;
+	xd::thread_main<W>(P, Q, res, smem_thread, (char*)(smem_thread + 2 * W * nt), nt, threadIdx.x);
 }
 
 // list == nullptr: every job of the batch; otherwise the *n_list jobs the register kernel gave up on
@@ -100,6 +110,26 @@ int launch_reg(bella_xdrop* h, const xd::Pairs& P, const xd::Queue& Q, xd::JobRe
 	return 0;
 }
 
+template <int W>
+int launch_thread(bella_xdrop* h, const xd::Pairs& P, const xd::Queue& Q, xd::JobResult* res)
+{
+	// as many threads per SM as the shared memory holds (10 * W bytes each), in one CTA
+	int nt = (int)((size_t)(227 * 1024 - 1024) / (10 * W)) / 32 * 32;
+	if (nt > 1024) nt = 1024;
+	const size_t smem = (size_t)nt * 10 * W;
+	XCUDA(cudaFuncSetAttribute(k_xdrop_thread<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 0;
+	XCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xdrop_thread<W>, nt, smem));
+	if (per_sm < 1) return fail(h, BELLA_XDROP_ECUDA, "k_xdrop_thread does not fit an SM");
+	long grid = (long)h->sms * per_sm;
+	const long needed = ((long)P.n_jobs + nt - 1) / nt;
+	if (grid > needed) grid = needed;
+	k_xdrop_thread<W><<<(unsigned)grid, nt, smem, h->stream>>>(P, Q, res);
+	XCUDA(cudaGetLastError());
+	++h->launches;
+	return 0;
+}
+
 void pick_shape(const bella_xdrop* h, int& G, int& T)
 {
 	if (h->lanes >= 0) { G = h->lanes; T = h->cells; return; }
@@ -144,6 +174,11 @@ int run_batch(bella_xdrop* h, uint64_t n_pairs, const uint32_t* d_rows, const ui
 		else if (G == 32 && T == 4) rc = launch_reg<32, 4>(h, P, Q, res);
 		else if (G == 16 && T == 1) rc = launch_reg<16, 1>(h, P, Q, res);
 		else if (G == 16 && T == 2) rc = launch_reg<16, 2>(h, P, Q, res);
+		else if (G == 16 && T == 4) rc = launch_reg<16, 4>(h, P, Q, res);
+		else if (G == 8 && T == 4) rc = launch_reg<8, 4>(h, P, Q, res);
+		else if (G == 8 && T == 8) rc = launch_reg<8, 8>(h, P, Q, res);
+		else if (G == 1 && T == 64) rc = launch_thread<64>(h, P, Q, res);
+		else if (G == 1 && T == 32) rc = launch_thread<32>(h, P, Q, res);
 		else return fail(h, BELLA_XDROP_EINVAL, "unsupported shape (lanes, cells per lane)");
 		if (rc) return rc;
 		k_xdrop_wide<<<wide_grid, WARPS * 32, 0, h->stream>>>(P, (const int*)h->wide.p, ctr + 1, ctr + 2, res, (int*)h->scratch.p, cap, ctr + 3);
@@ -223,7 +258,9 @@ int bella_xdrop_set_shape(bella_xdrop* h, int lanes, int cells_per_lane)
 	if (!h) return BELLA_XDROP_EINVAL;
 	const bool ok = (lanes == -1 && cells_per_lane == -1) || (lanes == 0 && cells_per_lane == 0)
 		|| (lanes == 32 && (cells_per_lane == 1 || cells_per_lane == 2 || cells_per_lane == 4))
-		|| (lanes == 16 && (cells_per_lane == 1 || cells_per_lane == 2));
+		|| (lanes == 16 && (cells_per_lane == 1 || cells_per_lane == 2 || cells_per_lane == 4))
+		|| (lanes == 8 && (cells_per_lane == 4 || cells_per_lane == 8))
+		|| (lanes == 1 && (cells_per_lane == 32 || cells_per_lane == 64));
 	if (!ok) return fail(h, BELLA_XDROP_EINVAL, "unsupported shape (lanes, cells per lane)");
 	h->lanes = lanes; h->cells = cells_per_lane;
 	return 0;

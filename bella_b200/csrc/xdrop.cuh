@@ -400,6 +400,161 @@ XD_FN void warp_main(const Pairs& P, const Queue& Q, JobResult* res, char* rings
 	}
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Thread-per-extension path, for small x (BELLA's default x = 7: the live window is ~9 columns, far too narrow to feed
+// a warp).  Every lane runs its OWN extension with the plain sequential recurrence; 32 extensions advance per warp
+// instruction and there is no cross-lane traffic at all.  Per thread, in shared memory (slot-major, thread-minor, so a
+// warp's accesses never conflict on the score arrays): two anti-diagonals of W columns as rings indexed by column
+// (a3 is written over a1 in place, going down the columns: a3[c] needs a1[c-1], which is overwritten only afterwards) and
+// W bases of each segment.  What the final "longest extension" rule needs of a1 (its maximum and first position,
+// seeds_extension.h:783-790) is tracked while the anti-diagonal is produced.  A window wider than W goes to the wide path.
+// ------------------------------------------------------------------------------------------------------------------
+template <int W>
+struct ThreadExt {
+	int* sc; char* ch; int nt, tid;              // sc: 2 * W * nt ints, ch: 2 * W * nt bytes of shared memory
+	XD_FN int& S(int arr, int c) const { return sc[(arr * W + (c & (W - 1))) * nt + tid]; }
+	XD_FN char& QR(int t) const { return ch[(t & (W - 1)) * nt + tid]; }
+	XD_FN char& DR(int r) const { return ch[(W + (r & (W - 1))) * nt + tid]; }
+
+	int ia, ib;                                  // arrays holding a1 (becomes a3) and a2
+	int n, minCol, maxCol, best, off2, n2, off3, n3, qhi, dhi, rows, cols, xdrop;
+	int m1, c1, m2, c2, m3, c3;                  // maximum / its first column of anti-diagonals n-2, n-1, n
+
+	XD_FN void init(const Segs& s, int xdrop_)
+	{
+		rows = s.dlen + 1; cols = s.qlen + 1; xdrop = xdrop_;
+		const int g0 = (1 > xdrop) ? UNDEF : -1;
+		ia = 1; ib = 0;                                    // swapped at the start of the first step
+		S(0, 0) = 0; S(1, 0) = g0; S(1, 1) = g0;
+		m1 = UNDEF; c1 = 0; m2 = 0; c2 = 0; m3 = g0; c3 = 0;
+		n2 = 1; n3 = 2; off2 = off3 = 0;
+		minCol = 1; maxCol = 2; n = 1; best = 0; qhi = dhi = 0;
+	}
+
+	XD_FN bool active() const { return minCol < maxCol; }
+
+	XD_FN bool step(const Segs& s)
+	{
+		++n;
+		{ const int t = ia; ia = ib; ib = t; }
+		m1 = m2; c1 = c2; m2 = m3; c2 = c3;
+		n2 = n3; off2 = off3; off3 = minCol - 1;
+		n3 = maxCol + 1 - off3;
+		if (n3 > W) return false;
+		while (dhi <= n - minCol - 1) { DR(dhi) = load_d(s, dhi); ++dhi; }
+		while (qhi <= maxCol - 2) { QR(qhi) = load_q(s, qhi); ++qhi; }
+		const int lim = best - xdrop;
+		const bool edge = -n > lim;
+		int v = (edge && n == maxCol) ? -n : UNDEF;        // first row of the matrix (:511)
+		S(ia, maxCol) = v;
+		m3 = v; c3 = maxCol;
+		int a2c = S(ib, maxCol - 1);
+		for (int c = maxCol - 1; c >= minCol; --c) {
+			const int a2l = S(ib, c - 1), a1l = S(ia, c - 1);
+			int tmp = imax(a2l, a2c) - 1;
+			tmp = imax(tmp, a1l + (QR(c - 1) == DR(n - c - 1) ? 1 : -1));
+			v = tmp < lim ? UNDEF : tmp;
+			S(ia, c) = v;
+			if (v >= m3) { m3 = v; c3 = c; }
+			a2c = a2l;
+		}
+		v = (edge && off3 == 0) ? -n : UNDEF;              // first column of the matrix (:509)
+		S(ia, off3) = v;
+		if (v >= m3) { m3 = v; c3 = off3; }
+		best = imax(best, m3);
+		while (minCol - off3 < n3 && S(ia, minCol) == UNDEF && minCol - off2 - 1 < n2 && S(ib, minCol - 1) == UNDEF) ++minCol;
+		while (maxCol - off3 > 0 && S(ia, maxCol - 1) == UNDEF && S(ib, maxCol - 1) == UNDEF) --maxCol;
+		++maxCol;
+		minCol = imax(minCol, n + 2 - rows);
+		maxCol = imin(maxCol, cols);
+		return true;
+	}
+
+	XD_FN int finish(int& ext_cols, int& ext_rows) const
+	{
+		int lcol = n3 + off3 - 2, lrow = n - lcol, lscore = S(ia, lcol);
+		if (lscore == UNDEF) {
+			const int e2 = S(ib, off2 + n2 - 2);
+			if (e2 != UNDEF) { lcol = n2 + off2 - 2; lrow = n - 1 - lcol; lscore = e2; }
+			else if (n2 > 2) {
+				const int e3 = S(ib, off2 + n2 - 3);
+				if (e3 != UNDEF) { lcol = n2 + off2 - 3; lrow = n - 1 - lcol; lscore = e3; }
+			}
+		}
+		if (lscore == UNDEF && m1 > lscore) { lscore = m1; lcol = c1; lrow = n - 2 - lcol; }
+		ext_cols = 0; ext_rows = 0;
+		if (lscore != UNDEF) { ext_cols = lcol; ext_rows = lrow; }
+		return lscore;
+	}
+};
+
+// make_segs for a single thread (no group to split the seed comparison over)
+XD_FN bool make_segs_thread(const Pairs& P, int job, Segs& s, int& reverse, int& baseH, int& baseV)
+{
+	const int p = job >> 1, right = job & 1;
+	const uint32_t col = pair_col(P, p);
+	const uint64_t oh = P.seq_off[P.rows[p]], ov = P.seq_off[col];
+	const char* H = P.seqs + oh; const int lenH = (int)(P.seq_off[P.rows[p] + 1] - oh);
+	const char* V = P.seqs + ov; const int lenV = (int)(P.seq_off[col + 1] - ov);
+	int i = P.posH[p];
+	const int j = P.posV[p], k = P.kmer_len;
+	if (i + k > lenH || j + k > lenV) return false;
+	reverse = 1;
+	for (int t = 0; t < k; ++t) if (comp(ldg(H + i + k - 1 - t)) != ldg(V + j + t)) { reverse = 0; break; }
+	if (reverse) i = lenH - i - k;
+	const int begH = i, endH = i + k, begV = j, endV = j + k;
+	s.dcomp = reverse;
+	if (!right) {
+		s.qlen = begV; s.q = V + begV - 1; s.qstep = -1;
+		s.dlen = begH;
+		if (!reverse) { s.d = H + begH - 1; s.dstep = -1; } else { s.d = H + (lenH - begH); s.dstep = 1; }
+		baseH = begH; baseV = begV;
+	} else {
+		s.qlen = lenV - endV; s.q = V + endV; s.qstep = 1;
+		s.dlen = lenH - endH;
+		if (!reverse) { s.d = H + endH; s.dstep = 1; } else { s.d = H + (lenH - 1 - endH); s.dstep = -1; }
+		baseH = endH; baseV = endV;
+	}
+	return true;
+}
+
+// A thread of the thread-per-extension kernel; the only warp-wide operation is the "everybody done" vote.
+template <int W>
+XD_FN void thread_main(const Pairs& P, const Queue& Q, JobResult* res, int* sc, char* ch, int nt, int tid)
+{
+	ThreadExt<W> e;
+	e.sc = sc; e.ch = ch; e.nt = nt; e.tid = tid;
+	Segs s;
+	int job = 0, reverse = 0, baseH = 0, baseV = 0;
+	bool have = false, done = false;
+	for (;;) {
+		if (!have && !done) {
+			job = atomic_inc(Q.next);
+			if (job >= P.n_jobs) done = true;
+			else if (!make_segs_thread(P, job, s, reverse, baseH, baseV)) {
+				*Q.bad = 1;
+				store_result(res, job, true, 0, 0, 0, 0, 0, 0);
+			} else if (s.qlen == 0 || s.dlen == 0) {
+				store_result(res, job, true, 0, 0, 0, baseH, baseV, reverse);
+			} else {
+				e.init(s, P.xdrop);
+				have = true;
+			}
+		}
+		if (all(FULL, done)) break;
+		if (have) {
+			if (e.active()) {
+				if (!e.step(s)) { Q.wide_jobs[atomic_inc(Q.wide_count)] = job; have = false; }
+			} else {
+				int ec, er;
+				const int score = e.finish(ec, er);
+				store_result(res, job, true, score, ec, er, baseH, baseV, reverse);
+				have = false;
+			}
+		}
+	}
+}
+
 // A warp of the wide kernel: jobs from the overflow list (or, with list == nullptr, every job).
 XD_FN void wide_main(const Pairs& P, const int* list, int n_list, int* next, JobResult* res, int* scratch, int cap, int* bad)
 {

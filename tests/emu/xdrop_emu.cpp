@@ -182,6 +182,14 @@ void run_reg(const xd::Pairs& P, const xd::Queue& Q, xd::JobResult* res, int n_w
 	run_warps(n_warps, [&](int w) { xd::warp_main<G, T>(P, Q, res, rings[w].data()); });
 }
 
+template <int W>
+void run_thread(const xd::Pairs& P, const xd::Queue& Q, xd::JobResult* res, int n_warps)
+{
+	std::vector<std::vector<int>> sc(n_warps, std::vector<int>(2 * W * 32));
+	std::vector<std::vector<char>> ch(n_warps, std::vector<char>(2 * W * 32));
+	run_warps(n_warps, [&](int w) { xd::thread_main<W>(P, Q, res, sc[w].data(), ch[w].data(), 32, xd::lane_id()); });
+}
+
 void run_wide(const xd::Pairs& P, const int* list, int n_list, xd::JobResult* res, int cap, int* bad, int n_warps)
 {
 	std::vector<std::vector<int>> scratch(n_warps, std::vector<int>(3 * (size_t)cap));
@@ -211,6 +219,12 @@ extern "C" int xdrop_emu_align(int G, int T, uint64_t n_pairs, const uint32_t* r
 		else if (G == 16 && T == 1) run_reg<16, 1>(P, Q, res.data(), n_warps);
 		else if (G == 16 && T == 2) run_reg<16, 2>(P, Q, res.data(), n_warps);
 		else if (G == 8 && T == 1) run_reg<8, 1>(P, Q, res.data(), n_warps);
+		else if (G == 16 && T == 4) run_reg<16, 4>(P, Q, res.data(), n_warps);
+		else if (G == 8 && T == 4) run_reg<8, 4>(P, Q, res.data(), n_warps);
+		else if (G == 8 && T == 8) run_reg<8, 8>(P, Q, res.data(), n_warps);
+		else if (G == 1 && T == 64) run_thread<64>(P, Q, res.data(), n_warps);      // thread per extension, T = window slots
+		else if (G == 1 && T == 32) run_thread<32>(P, Q, res.data(), n_warps);
+		else if (G == 1 && T == 16) run_thread<16>(P, Q, res.data(), n_warps);
 		else return -2;
 		run_wide(P, wide.data(), wide_count, res.data(), cap, &bad, n_warps);
 	}
