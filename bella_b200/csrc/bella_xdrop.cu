@@ -133,8 +133,10 @@ int launch_thread(bella_xdrop* h, const xd::Pairs& P, const xd::Queue& Q, xd::Jo
 void pick_shape(const bella_xdrop* h, int& G, int& T)
 {
 	if (h->lanes >= 0) { G = h->lanes; T = h->cells; return; }
-	// the window is about xdrop + 9 columns wide (measured on CLR reads); wider ones take the wide path
-	if (h->xdrop <= 12) { G = 32; T = 1; }
+	// the live window is about 2 * xdrop columns wide on real overlaps (xdrop + 9 near the seed), with a tail several
+	// times that; whatever outgrows the chosen shape takes the wide path.  Measured on a B200 (profiles/xdrop_r01.md):
+	// at x = 7 one thread per extension beats every warp shape.
+	if (h->xdrop <= 12) { G = 1; T = 64; }
 	else if (h->xdrop <= 40) { G = 32; T = 2; }
 	else if (h->xdrop <= 100) { G = 32; T = 4; }
 	else { G = 0; T = 0; }
@@ -160,7 +162,11 @@ int run_batch(bella_xdrop* h, uint64_t n_pairs, const uint32_t* d_rows, const ui
 	pick_shape(h, G, T);
 	h->used_lanes = G; h->used_cells = T;
 	const int cap = h->max_len + 3;
-	const int wide_grid = h->sms;
+	// wide kernel: up to 4 CTAs per SM, as many as 1 GiB of anti-diagonal scratch allows (3 * cap ints per warp)
+	const size_t per_cta = (size_t)WARPS * 3 * cap * sizeof(int);
+	long per_sm_wide = (long)(((size_t)1 << 30) / per_cta / (size_t)h->sms);
+	per_sm_wide = per_sm_wide < 1 ? 1 : per_sm_wide > 4 ? 4 : per_sm_wide;
+	const int wide_grid = (int)(h->sms * per_sm_wide);
 	XCUDA(h->scratch.reserve((size_t)wide_grid * WARPS * 3 * cap * sizeof(int)));
 	XCUDA(cudaEventRecord(h->ev0, h->stream));
 	int rc = 0;

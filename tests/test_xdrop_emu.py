@@ -62,8 +62,10 @@ def reads():
     return inp, candidate_pairs(inp, 400, seed=3)
 
 
-# (lanes per extension, cells per lane, xdrop): every instantiation the library ships, (0,0) = wide path only
-@pytest.mark.parametrize("lanes,cells,xdrop", [(32, 1, 7), (32, 2, 15), (32, 4, 30), (16, 1, 3), (16, 2, 7), (0, 0, 7)])
+# (lanes per extension, cells per lane, xdrop): every instantiation the library ships; (1, W) = one thread per extension
+# with W window slots, (0,0) = wide path only
+@pytest.mark.parametrize("lanes,cells,xdrop", [(1, 64, 7), (1, 32, 7), (32, 1, 7), (32, 2, 15), (32, 4, 30), (16, 1, 3), (16, 2, 7), (16, 4, 15),
+                                                (8, 4, 7), (8, 8, 15), (0, 0, 7)])
 def test_device_source_matches_oracle(reads, lanes, cells, xdrop):
     inp, pairs = reads
     want = ol.oracle_align_post(inp, *pairs, xdrop, 0.55, 0.1, -1)
@@ -80,6 +82,9 @@ def test_window_overflow_hands_over_to_the_wide_path(reads):
     rc, got, n_wide = emu_align(inp, *pairs, 7, 16, 1, 0.55, 0.1, 200)     # 16 slots: a quarter of the extensions outgrow them
     assert rc == 0 and n_wide > 20
     np.testing.assert_array_equal(got, want)
+    rc, got, n_wide = emu_align(inp, *pairs, 7, 1, 16, 0.55, 0.1, 200)     # the thread-per-extension path hands over the same way
+    assert rc == 0 and n_wide > 20
+    np.testing.assert_array_equal(got, want)
     rc, got, n_wide = emu_align(inp, *pairs, 25, 32, 1, 0.55, 0.1, 200)    # x = 25 needs ~34 columns: most go wide
     assert rc == 0 and n_wide > len(want)
     np.testing.assert_array_equal(got, ol.oracle_align_post(inp, *pairs, 25, 0.55, 0.1, 200))
@@ -88,16 +93,17 @@ def test_window_overflow_hands_over_to_the_wide_path(reads):
 def test_low_error_reads_and_seeds_at_the_read_ends():
     inp = fe.synthetic(60, 1500, coverage=15.0, err=0.02, seed=77, hi=40)       # extensions that run into the read ends
     pairs = candidate_pairs(inp, 200)
-    rc, got, _ = emu_align(inp, *pairs, 7, 32, 1)
-    assert rc == 0
-    np.testing.assert_array_equal(got, ol.oracle_align_post(inp, *pairs, 7))
+    for lanes, cells in ((32, 1), (1, 64)):
+        rc, got, _ = emu_align(inp, *pairs, 7, lanes, cells)
+        assert rc == 0
+        np.testing.assert_array_equal(got, ol.oracle_align_post(inp, *pairs, 7))
     k, n = inp.kmer_size, 30
     r = np.arange(1, n + 1, dtype=np.uint32)
     c = np.zeros(n, dtype=np.uint32)
     lens = inp.read_len
     pH = np.where(np.arange(n) % 2 == 0, 0, lens[r] - k).astype(np.uint16)      # empty prefix / empty suffix
     pV = np.where(np.arange(n) % 3 == 0, 0, lens[c] - k).astype(np.uint16)
-    for lanes, cells in ((32, 1), (16, 2), (0, 0)):
+    for lanes, cells in ((1, 64), (32, 1), (16, 2), (0, 0)):
         rc, got, _ = emu_align(inp, r, c, pH, pV, 7, lanes, cells)
         assert rc == 0
         np.testing.assert_array_equal(got, ol.oracle_align_post(inp, r, c, pH, pV, 7))
@@ -109,9 +115,10 @@ def test_reference_golden_fixture():
                            B_colptr=None, B_rowids=None, B_values=None, B_strand=None, read_len=None, kmer_size=int(z["k"]),
                            seqs=z["seqs"], seq_off=z["seq_off"])
     sel = slice(0, 3000, 6)
-    rc, got, _ = emu_align(inp, z["rows"][sel], z["cols"][sel], z["posH"][sel], z["posV"][sel], int(z["xdrop"]), 32, 1)
-    assert rc == 0
-    np.testing.assert_array_equal(got[:, :6], z["ref_out"][sel])
+    for lanes, cells in ((32, 1), (1, 64)):
+        rc, got, _ = emu_align(inp, z["rows"][sel], z["cols"][sel], z["posH"][sel], z["posV"][sel], int(z["xdrop"]), lanes, cells)
+        assert rc == 0
+        np.testing.assert_array_equal(got[:, :6], z["ref_out"][sel])
 
 
 def test_csc_form_takes_the_spgemm_result_as_it_is():
@@ -119,15 +126,16 @@ def test_csc_form_takes_the_spgemm_result_as_it_is():
     r = ol.oracle_spgemm(inp, want_aux=False)
     assert (np.diff(r.colptrC.astype(np.int64)) == 0).any()        # empty columns are part of the case
     cols = np.repeat(np.arange(inp.n_reads, dtype=np.uint32), np.diff(r.colptrC.astype(np.int64)))
-    rc, got, _ = emu_align(inp, r.rowids, None, r.posH, r.posV, 7, 32, 1, colptr=r.colptrC)
-    assert rc == 0
-    np.testing.assert_array_equal(got, ol.oracle_align_post(inp, r.rowids, cols, r.posH, r.posV, 7))
+    for lanes, cells in ((32, 1), (1, 64)):
+        rc, got, _ = emu_align(inp, r.rowids, None, r.posH, r.posV, 7, lanes, cells, colptr=r.colptrC)
+        assert rc == 0
+        np.testing.assert_array_equal(got, ol.oracle_align_post(inp, r.rowids, cols, r.posH, r.posV, 7))
 
 
 def test_seed_outside_its_read_is_reported(reads):
     inp, pairs = reads
     rows, cols, pH, pV = (a[:8].copy() for a in pairs)
     pH[3] = inp.read_len[rows[3]] - 3
-    for lanes, cells in ((32, 1), (0, 0)):
+    for lanes, cells in ((32, 1), (1, 64), (0, 0)):
         rc, _, _ = emu_align(inp, rows, cols, pH, pV, 7, lanes, cells)
         assert rc == -1

@@ -38,7 +38,8 @@ def reads():
 
 
 # every instantiation the library ships; (0,0) = wide path only; (-1,-1) = chosen from xdrop
-@pytest.mark.parametrize("lanes,cells,xdrop", [(-1, -1, 7), (32, 1, 7), (32, 2, 15), (32, 4, 30), (16, 1, 3), (16, 2, 7), (0, 0, 7), (-1, -1, 25), (-1, -1, 120)])
+@pytest.mark.parametrize("lanes,cells,xdrop", [(-1, -1, 7), (1, 64, 7), (1, 32, 7), (32, 1, 7), (32, 2, 15), (32, 4, 30), (16, 1, 3), (16, 2, 7), (16, 4, 15), (8, 4, 7),
+                                                (8, 8, 15), (0, 0, 7), (-1, -1, 25), (-1, -1, 120)])
 def test_xdrop_matches_oracle(reads, lanes, cells, xdrop):
     inp, pairs = reads
     a = aligner(inp, xdrop, (lanes, cells))
@@ -47,23 +48,30 @@ def test_xdrop_matches_oracle(reads, lanes, cells, xdrop):
     np.testing.assert_array_equal(got, want)
     st = a.stats()
     assert st["launches"] == 3 - (st["lanes"] == 0) and st["kernel_ms"] > 0
+    if (lanes, cells) == (-1, -1):
+        assert (st["lanes"], st["cells_per_lane"]) == ((1, 64) if xdrop <= 12 else (32, 2) if xdrop <= 40 else (0, 0))
     a.close()
 
 
 def test_window_overflow_goes_through_the_wide_kernel(reads):
     inp, pairs = reads
-    a = aligner(inp, 7, (16, 1), fixed_threshold=200)
-    got = a.align(*pairs)
-    assert a.stats()["wide_extensions"] > 100                       # 16 slots: about a quarter of the extensions outgrow them
-    np.testing.assert_array_equal(got, ol.oracle_align_post(inp, *pairs, 7, 0.55, 0.1, 200))
-    a.close()
+    want = ol.oracle_align_post(inp, *pairs, 7, 0.55, 0.1, 200)
+    for shape, least in (((16, 1), 100), ((1, 32), 1)):             # 16 slots: about a quarter of the extensions outgrow them
+        a = aligner(inp, 7, shape, fixed_threshold=200)
+        got = a.align(*pairs)
+        assert a.stats()["wide_extensions"] >= least
+        np.testing.assert_array_equal(got, want)
+        a.close()
 
 
 def test_low_error_reads_and_seeds_at_the_read_ends():
     inp = fe.synthetic(150, 3000, coverage=20.0, err=0.02, seed=77, hi=40)
     pairs = candidate_pairs(inp, 1500)
+    for shape in ((-1, -1), (32, 1)):
+        a = aligner(inp, 7, shape)
+        np.testing.assert_array_equal(a.align(*pairs), ol.oracle_align_post(inp, *pairs, 7, 0.55, 0.1, -1))
+        a.close()
     a = aligner(inp)
-    np.testing.assert_array_equal(a.align(*pairs), ol.oracle_align_post(inp, *pairs, 7, 0.55, 0.1, -1))
     k, n = inp.kmer_size, 40
     r = np.arange(1, n + 1, dtype=np.uint32)
     c = np.zeros(n, dtype=np.uint32)
