@@ -196,3 +196,25 @@ def ref_align_post(inp, rows, cols, posH, posV, xdrop=7, ratiophi=0.5, delta=0.1
     if rc != 0:
         raise RuntimeError(f"reference post-alignment failed: {rc}")
     return out
+
+
+LOGAN = os.path.join(ROOT, "oracle", "_ref", "libbella_logan.so")
+
+
+def have_logan():
+    return os.path.exists(LOGAN)
+
+
+def logan_align(inp, rows, cols, posH, posV, xdrop=7):
+    """the reference's CUDA aligner (LOGAN, recompiled for sm_100a from /root/reference; needs a GPU)
+    -> (int32 [n][6] like ref_align, seconds spent in extendSeedL)"""
+    L = ctypes.CDLL(LOGAN)
+    rows = np.ascontiguousarray(rows, dtype=np.uint32); cols = np.ascontiguousarray(cols, dtype=np.uint32)
+    posH = np.ascontiguousarray(posH, dtype=np.uint16); posV = np.ascontiguousarray(posV, dtype=np.uint16)
+    out = np.zeros((len(rows), 6), dtype=np.int32)
+    sec = ctypes.c_double(0.0)
+    rc = L.bella_logan_align(ctypes.c_uint64(len(rows)), _p(rows), _p(cols), _p(posH), _p(posV), _p(inp.seqs), _p(inp.seq_off),
+                             ctypes.c_int(inp.kmer_size), ctypes.c_int(xdrop), _p(out), ctypes.byref(sec))
+    if rc != 0:
+        raise RuntimeError(f"LOGAN failed: {rc}")
+    return out, sec.value

@@ -134,3 +134,16 @@ def test_chained_behind_the_overlap_spgemm_on_the_device(small_inputs):
     want = ol.oracle_align_post(inp, want_c.rowids, cols, want_c.posH, want_c.posV, 7, 0.55, 0.1, -1)
     np.testing.assert_array_equal(out.cpu().numpy(), want)
     a.close()
+
+
+@pytest.mark.skipif(os.environ.get("BELLA_RUN_LOGAN") != "1" or not ol.have_logan(),
+                    reason="opt-in (BELLA_RUN_LOGAN=1): the reference's CUDA aligner recompiled for sm_100a as a second live reference; "
+                           "not yet run on a B200, so it does not gate the suite")
+def test_logan_recompiled_agrees(reads):
+    """LOGAN keeps its anti-diagonals in `short`, so it can only agree while scores stay below 32767 (true here)."""
+    inp, pairs = reads
+    got, seconds = ol.logan_align(inp, *pairs, 7)
+    want = ol.oracle_align(inp, *pairs, 7)
+    same = (got == want).all(axis=1).mean()
+    print(f"LOGAN vs oracle: {same:.4f} of {len(want)} pairs identical, {seconds:.3f} s in extendSeedL")
+    assert same > 0.99

@@ -1,6 +1,7 @@
 """Timing / profiling driver of the X-drop row: one batch of candidate pairs through several register shapes.
   python tools/xdrop_prof.py               timing of every shape (kernel ms by CUDA events) + parity against the oracle
   python tools/xdrop_prof.py --quick       the same for three shapes only
+  ... --logan                              also runs the reference's CUDA aligner (oracle/_ref/libbella_logan.so) on the batch
   python tools/xdrop_prof.py --prof G T    one un-warmed batch with shape (G,T), for ncu"""
 import json
 import os
@@ -48,5 +49,10 @@ for x, shapes in plan:
                     "parity": bool(np.array_equal(got[:, :6], w)), "cpu_oracle_s_x7": cpu_s})
         print(out[-1], flush=True)
         a.close()
+if "--logan" in sys.argv and ol.have_logan():                     # the bar of SURVEY.md 8f: the reference kernel on the same box
+    got, sec = ol.logan_align(big, *pairs, 7)
+    out.append({"xdrop": 7, "shape": "LOGAN (reference, recompiled sm_100a)", "pairs": n, "extendSeedL_s": sec,
+                "identical_to_oracle": float((got == want).all(axis=1).mean())})
+    print(out[-1], flush=True)
 name = "xdrop_shapes_quick_r01.json" if "--quick" in sys.argv else "xdrop_shapes_r01.json"
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", name), "w"), indent=1)
