@@ -30,6 +30,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_xdrop(xd::Pairs P, xd::Queue Q, 
 	xd::warp_main<G, T>(P, Q, res, rings + (threadIdx.x >> 5) * PER_WARP);
 }
 
+__global__ void k_xdrop_encode(char* seqs, size_t n)     // raw bases -> Dna5 codes, in place
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) seqs[i] = xd::dna5(seqs[i]);
+}
+
 // thread-per-extension kernel: NT threads, each with 2 anti-diagonals of W ints + 2 * W bases in shared memory
 template <int W>
 __global__ void k_xdrop_thread(xd::Pairs P, xd::Queue Q, xd::JobResult* res)
@@ -246,6 +251,10 @@ int bella_xdrop_set_reads(bella_xdrop* h, const char* seqs, const uint64_t* seq_
 	XCUDA(h->seq_off.reserve(((size_t)n_reads + 1) * sizeof(uint64_t)));
 	XCUDA(cudaMemcpyAsync(h->seqs.p, seqs, total, cudaMemcpyHostToDevice, h->stream));
 	XCUDA(cudaMemcpyAsync(h->seq_off.p, seq_off, ((size_t)n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+	if (total) {
+		k_xdrop_encode<<<h->sms * 8, 256, 0, h->stream>>>((char*)h->seqs.p, (size_t)total);
+		XCUDA(cudaGetLastError());
+	}
 	XCUDA(cudaStreamSynchronize(h->stream));
 	h->n_reads = n_reads; h->max_len = max_len;
 	return 0;

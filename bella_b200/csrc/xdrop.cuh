@@ -52,7 +52,15 @@ inline char ldg(const char* p) { return *p; }
 
 XD_FN int imax(int a, int b) { return a > b ? a : b; }
 XD_FN int imin(int a, int b) { return a < b ? a : b; }
-XD_FN char comp(char c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N'; }
+// Bases are Dna5 codes, as alignSeqAn sees them (seqan::Dna5String, align.hpp:97-100): SeqAn's char -> Dna5 table
+// (seqan/basic/alphabet_residue_tabs.h:113-140: A/a 0, C/c 1, G/g 2, T/t/U/u 3, anything else 4 = N), N matches N, the
+// reverse complement maps 0<->3, 1<->2, N->N.  The reads are encoded once when they are uploaded.
+XD_FN char dna5(char c)
+{
+	const char l = c | 0x20;
+	return l == 'a' ? 0 : l == 'c' ? 1 : l == 'g' ? 2 : (l == 't' || l == 'u') ? 3 : 4;
+}
+XD_FN char comp(char c) { return c < 4 ? (char)(3 - c) : c; }
 
 // One direction of one pair.  Index t of a segment counts AWAY from the seed: base t of the query (V) segment is
 // q[qstep * t], base r of the database (H) segment is d[dstep * r], complemented when the pair is on the reverse strand.
@@ -65,7 +73,7 @@ struct Segs {
 struct Pairs {                              // the candidate pairs, as the overlap SpGEMM emits them
 	const uint32_t* rows; const uint32_t* cols;      // H = row read, V = column read; cols == nullptr: CSC form, see colptr
 	const uint16_t* posH; const uint16_t* posV;      // seed k-mer
-	const char* seqs; const uint64_t* seq_off;       // reads, concatenated, 1 byte per base
+	const char* seqs; const uint64_t* seq_off;       // reads, concatenated, 1 byte per base, Dna5 codes (see dna5())
 	int kmer_len, xdrop;
 	int n_jobs;                                      // 2 per pair: job 2p = left, 2p+1 = right
 	const uint32_t* colptr; int n_cols;              // CSC form: pair p belongs to the column c with colptr[c] <= p < colptr[c+1]

@@ -204,7 +204,9 @@ extern "C" int xdrop_emu_align(int G, int T, uint64_t n_pairs, const uint32_t* r
 		const uint16_t* posV, const char* seqs, const uint64_t* seq_off, uint32_t n_reads, int kmer_len, int xdrop,
 		double ratiophi, double delta, int fixed_threshold, int n_warps, int32_t* out8, int* n_wide, const uint32_t* colptr, int n_cols)
 {
-	xd::Pairs P{rows, cols, posH, posV, seqs, seq_off, kmer_len, xdrop, (int)(2 * n_pairs), colptr, n_cols};
+	std::vector<char> coded(seq_off[n_reads]);                   // what k_xdrop_encode does on the device
+	for (size_t i = 0; i < coded.size(); ++i) coded[i] = xd::dna5(seqs[i]);
+	xd::Pairs P{rows, cols, posH, posV, coded.data(), seq_off, kmer_len, xdrop, (int)(2 * n_pairs), colptr, n_cols};
 	std::vector<xd::JobResult> res(2 * n_pairs);
 	std::vector<int> wide(2 * n_pairs + 1);
 	int next = 0, wide_count = 0, bad = 0;

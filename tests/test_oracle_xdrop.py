@@ -51,6 +51,22 @@ def test_xdrop_oracle_matches_reference_low_error_and_edges():
     np.testing.assert_array_equal(ol.oracle_align(inp, r, c, pH, pV, 7), ol.ref_align(inp, r, c, pH, pV, 7))
 
 
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref/libbella_ref.so not built (needs /root/reference)")
+def test_xdrop_oracle_follows_seqan_dna5_on_unusual_bases(small_inputs):
+    """alignSeqAn converts the reads to seqan::Dna5String: lower case == upper case, U == T, everything else is N and N matches N"""
+    import copy
+    rows, cols, pH, pV = candidate_pairs(small_inputs, limit=3000, seed=11)
+    dirty = copy.copy(small_inputs)
+    s = small_inputs.seqs.copy()
+    rng = np.random.default_rng(5)
+    idx = rng.choice(len(s), len(s) // 50, replace=False)
+    s[idx] = np.frombuffer(b"NnacgtRUuYx-", dtype=np.uint8)[rng.integers(0, 12, len(idx))]
+    dirty.seqs = s
+    want = ol.ref_align(dirty, rows, cols, pH, pV, 7)
+    np.testing.assert_array_equal(ol.oracle_align(dirty, rows, cols, pH, pV, 7), want)
+    assert (want != ol.ref_align(small_inputs, rows, cols, pH, pV, 7)).any()
+
+
 def test_xdrop_oracle_reproduces_reference_golden():
     z = np.load(GOLD)
     from bella_b200.frontend import OverlapInputs

@@ -121,6 +121,24 @@ def test_reference_golden_fixture():
         np.testing.assert_array_equal(got[:, :6], z["ref_out"][sel])
 
 
+def test_bases_are_dna5_as_seqan_sees_them(reads):
+    """N, lower case, U and IUPAC letters: alignSeqAn converts to seqan::Dna5 first (N matches N, 'a' == 'A')"""
+    import copy
+    inp, pairs = reads
+    dirty = copy.copy(inp)
+    s = inp.seqs.copy()
+    rng = np.random.default_rng(5)
+    idx = rng.choice(len(s), len(s) // 40, replace=False)
+    s[idx] = np.frombuffer(b"NnacgtRUuYx-", dtype=np.uint8)[rng.integers(0, 12, len(idx))]
+    dirty.seqs = s
+    want = ol.oracle_align_post(dirty, *pairs, 7)
+    assert (want[:, :6] != ol.oracle_align(inp, *pairs, 7)).any()
+    for lanes, cells in ((1, 64), (32, 1), (0, 0)):
+        rc, got, _ = emu_align(dirty, *pairs, 7, lanes, cells)
+        assert rc == 0
+        np.testing.assert_array_equal(got, want)
+
+
 def test_csc_form_takes_the_spgemm_result_as_it_is():
     inp = fe.synthetic(40, 900, coverage=10.0, seed=9)
     r = ol.oracle_spgemm(inp, want_aux=False)

@@ -83,6 +83,23 @@ def test_low_error_reads_and_seeds_at_the_read_ends():
     a.close()
 
 
+def test_bases_are_dna5_as_seqan_sees_them(reads):
+    """N, lower case, U and IUPAC letters: alignSeqAn converts to seqan::Dna5 first (N matches N, 'a' == 'A')"""
+    import copy
+    inp, pairs = reads
+    dirty = copy.copy(inp)
+    s = inp.seqs.copy()
+    rng = np.random.default_rng(5)
+    idx = rng.choice(len(s), len(s) // 40, replace=False)
+    s[idx] = np.frombuffer(b"NnacgtRUuYx-", dtype=np.uint8)[rng.integers(0, 12, len(idx))]
+    dirty.seqs = s
+    want = ol.oracle_align_post(dirty, *pairs, 7, 0.55, 0.1, -1)
+    for shape in ((-1, -1), (32, 1), (0, 0)):
+        a = aligner(dirty, 7, shape)
+        np.testing.assert_array_equal(a.align(*pairs), want)
+        a.close()
+
+
 def test_reference_golden_fixture():
     z = np.load(os.path.join(golden_util.GOLDEN, "xdrop.npz"))
     inp = fe.OverlapInputs(n_reads=int(z["n_reads"]), n_kmers=0, nnz=0, A_colptr=None, A_rowids=None, A_values=None, A_strand=None,
