@@ -10,6 +10,7 @@
 // Reads stay resident on the device between batches; seeds come as (row, col, posH, posV) arrays -- host pointers
 // (bella_xdrop_align) or the overlap SpGEMM's device result (bella_xdrop_align_device / _align_csc_device).
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <cstdio>
 #include <cstring>
@@ -42,6 +43,21 @@ __global__ void k_xdrop_thread(xd::Pairs P, xd::Queue Q, xd::JobResult* res)
 	extern __shared__ int smem_thread[];
 	const int nt = blockDim.x;
 	xd::thread_main<W>(P, Q, res, smem_thread, (char*)(smem_thread + 2 * W * nt), nt, threadIdx.x);
+}
+
+// packed-word form (opt-in until measured): one 32-bit word per cell carrying its two bases, NT a template constant
+template <int W, int NT>
+__global__ void __launch_bounds__(NT) k_xdrop_thread_packed(xd::Pairs P, xd::Queue Q, xd::JobResult* res, const int* order)
+{
+	extern __shared__ int smem_packed[];
+	xd::thread_main_packed<W, NT>(P, Q, res, smem_packed, threadIdx.x, order);
+}
+
+// longest-first schedule: key = 65535 - min(query segment, database segment), sorted ascending (plumbing: cub radix sort)
+__global__ void k_xdrop_estimate(xd::Pairs P, unsigned short* key, int* job)
+{
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j < P.n_jobs) { key[j] = (unsigned short)(65535 - xd::job_estimate(P, j)); job[j] = j; }
 }
 
 // list == nullptr: every job of the batch; otherwise the *n_list jobs the register kernel gave up on
@@ -80,7 +96,7 @@ struct bella_xdrop {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	std::string err;
-	Buf seqs, seq_off, rows, cols, posH, posV, out, res, wide, scratch, ctr;
+	Buf seqs, seq_off, rows, cols, posH, posV, out, res, wide, scratch, ctr, key_in, key_out, job_in, job_out, sort_tmp;
 	uint32_t n_reads = 0; int max_len = 0;
 	int kmer_len = 17, xdrop = 7, fixed_threshold = -1;
 	double ratiophi = 0.0, delta = 0.1;
@@ -130,6 +146,39 @@ int launch_thread(bella_xdrop* h, const xd::Pairs& P, const xd::Queue& Q, xd::Jo
 	const long needed = ((long)P.n_jobs + nt - 1) / nt;
 	if (grid > needed) grid = needed;
 	k_xdrop_thread<W><<<(unsigned)grid, nt, smem, h->stream>>>(P, Q, res);
+	XCUDA(cudaGetLastError());
+	++h->launches;
+	return 0;
+}
+
+template <int W, int NT>
+int launch_thread_packed(bella_xdrop* h, const xd::Pairs& P, const xd::Queue& Q, xd::JobResult* res, bool longest_first)
+{
+	const int* order = nullptr;
+	if (longest_first) {
+		const int n = P.n_jobs;
+		XCUDA(h->key_in.reserve((size_t)n * 2)); XCUDA(h->key_out.reserve((size_t)n * 2));
+		XCUDA(h->job_in.reserve((size_t)n * 4)); XCUDA(h->job_out.reserve((size_t)n * 4));
+		k_xdrop_estimate<<<(n + 255) / 256, 256, 0, h->stream>>>(P, (unsigned short*)h->key_in.p, (int*)h->job_in.p);
+		XCUDA(cudaGetLastError());
+		++h->launches;
+		size_t tmp = 0;
+		XCUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const unsigned short*)h->key_in.p, (unsigned short*)h->key_out.p,
+				(const int*)h->job_in.p, (int*)h->job_out.p, n, 0, 16, h->stream));
+		XCUDA(h->sort_tmp.reserve(tmp ? tmp : 1));
+		XCUDA(cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp, (const unsigned short*)h->key_in.p, (unsigned short*)h->key_out.p,
+				(const int*)h->job_in.p, (int*)h->job_out.p, n, 0, 16, h->stream));
+		order = (const int*)h->job_out.p;
+	}
+	const size_t smem = (size_t)2 * W * NT * sizeof(int);
+	XCUDA(cudaFuncSetAttribute(k_xdrop_thread_packed<W, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 0;
+	XCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xdrop_thread_packed<W, NT>, NT, smem));
+	if (per_sm < 1) return fail(h, BELLA_XDROP_ECUDA, "k_xdrop_thread_packed does not fit an SM");
+	long grid = (long)h->sms * per_sm;
+	const long needed = ((long)P.n_jobs + NT - 1) / NT;
+	if (grid > needed) grid = needed;
+	k_xdrop_thread_packed<W, NT><<<(unsigned)grid, NT, smem, h->stream>>>(P, Q, res, order);
 	XCUDA(cudaGetLastError());
 	++h->launches;
 	return 0;
@@ -190,6 +239,8 @@ int run_batch(bella_xdrop* h, uint64_t n_pairs, const uint32_t* d_rows, const ui
 		else if (G == 8 && T == 8) rc = launch_reg<8, 8>(h, P, Q, res);
 		else if (G == 1 && T == 64) rc = launch_thread<64>(h, P, Q, res);
 		else if (G == 1 && T == 32) rc = launch_thread<32>(h, P, Q, res);
+		else if ((G == 2 || G == 3) && T == 64) rc = launch_thread_packed<64, 128>(h, P, Q, res, G == 3);
+		else if ((G == 2 || G == 3) && T == 32) rc = launch_thread_packed<32, 128>(h, P, Q, res, G == 3);
 		else return fail(h, BELLA_XDROP_EINVAL, "unsupported shape (lanes, cells per lane)");
 		if (rc) return rc;
 		k_xdrop_wide<<<wide_grid, WARPS * 32, 0, h->stream>>>(P, (const int*)h->wide.p, ctr + 1, ctr + 2, res, (int*)h->scratch.p, cap, ctr + 3);
@@ -226,7 +277,8 @@ void bella_xdrop_destroy(bella_xdrop* h)
 	if (!h) return;
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->stream);
-	for (Buf* b : {&h->seqs, &h->seq_off, &h->rows, &h->cols, &h->posH, &h->posV, &h->out, &h->res, &h->wide, &h->scratch, &h->ctr}) b->release();
+	for (Buf* b : {&h->seqs, &h->seq_off, &h->rows, &h->cols, &h->posH, &h->posV, &h->out, &h->res, &h->wide, &h->scratch, &h->ctr,
+			&h->key_in, &h->key_out, &h->job_in, &h->job_out, &h->sort_tmp}) b->release();
 	cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
 	cudaStreamDestroy(h->stream);
 	delete h;
@@ -275,7 +327,7 @@ int bella_xdrop_set_shape(bella_xdrop* h, int lanes, int cells_per_lane)
 		|| (lanes == 32 && (cells_per_lane == 1 || cells_per_lane == 2 || cells_per_lane == 4))
 		|| (lanes == 16 && (cells_per_lane == 1 || cells_per_lane == 2 || cells_per_lane == 4))
 		|| (lanes == 8 && (cells_per_lane == 4 || cells_per_lane == 8))
-		|| (lanes == 1 && (cells_per_lane == 32 || cells_per_lane == 64));
+		|| ((lanes == 1 || lanes == 2 || lanes == 3) && (cells_per_lane == 32 || cells_per_lane == 64));
 	if (!ok) return fail(h, BELLA_XDROP_EINVAL, "unsupported shape (lanes, cells per lane)");
 	h->lanes = lanes; h->cells = cells_per_lane;
 	return 0;

@@ -496,6 +496,108 @@ struct ThreadExt {
 	}
 };
 
+// Second form of the thread-per-extension path (opt-in until measured): every cell is ONE 32-bit word
+//     score << 6 | q code << 3 | d code
+// that carries the two bases the cell was computed from -- the query base of its column and the database base of its
+// row.  The cell (c, row) of anti-diagonal n reads a2[c-1] (same row: its d code) and a2[c] (same column: its q code), so
+// the bases travel through the recurrence and the inner loop has no base loads at all: 2 shared loads + 1 store per
+// cell.  Only the two window ends fetch a new base from the reads per anti-diagonal.  The thread count NT is a template
+// constant (a power of two), so a ring slot's address is (c * NT) & (W * NT - 1).
+template <int W, int NT>
+struct ThreadExtP {
+	static constexpr int PUNDEF = -(1 << 24);   // below every real score, far from overflow when shifted by 6
+	int* sc; int tid;                            // sc: 2 * W * NT ints of shared memory
+	XD_FN int& S(int arr, int c) const { return sc[arr * (W * NT) + ((c * NT) & (W * NT - 1)) + tid]; }
+	static XD_FN int pack(int score, int q, int d) { return (int)(((unsigned)score << 6) | (unsigned)(q << 3) | (unsigned)d); }
+
+	int ia, ib;
+	int n, minCol, maxCol, best, off2, n2, off3, n3, rows, cols, xdrop;
+	int m1, c1, m2, c2, m3, c3;
+
+	XD_FN void init(const Segs& s, int xdrop_)
+	{
+		rows = s.dlen + 1; cols = s.qlen + 1; xdrop = xdrop_;
+		const int g0 = (1 > xdrop) ? PUNDEF : -1;
+		ia = 1; ib = 0;
+		const int q0 = load_q(s, 0), d0 = load_d(s, 0);   // both segments are non-empty here
+		S(0, 0) = pack(0, 0, 0);                         // cell (0,0)
+		S(1, 0) = pack(g0, 0, d0);                       // cell (0,1): row 1 -> d[0]
+		S(1, 1) = pack(g0, q0, 0);                       // cell (1,0): column 1 -> q[0]
+		m1 = PUNDEF; c1 = 0; m2 = 0; c2 = 0; m3 = g0; c3 = 0;
+		n2 = 1; n3 = 2; off2 = off3 = 0;
+		minCol = 1; maxCol = 2; n = 1; best = 0;
+	}
+
+	XD_FN bool active() const { return minCol < maxCol; }
+
+	XD_FN bool step(const Segs& s)
+	{
+		++n;
+		{ const int t = ia; ia = ib; ib = t; }
+		m1 = m2; c1 = c2; m2 = m3; c2 = c3;
+		n2 = n3; off2 = off3; off3 = minCol - 1;
+		n3 = maxCol + 1 - off3;
+		if (n3 > W) return false;
+		const int lim = best - xdrop;
+		const bool edge = -n > lim;
+		// running slot offset instead of one address computation per access: slot(c-1) = (slot(c) - NT) & (W*NT - 1)
+		int* const A = sc + ia * (W * NT) + tid;
+		const int* const B = sc + ib * (W * NT) + tid;
+		int o = ((maxCol - 1) * NT) & (W * NT - 1);
+		int a2c = B[o];                                  // cell (maxCol-1, n-maxCol): the row of the new top cell
+		{
+			const int qn = maxCol - 1 < s.qlen ? load_q(s, maxCol - 1) : 0;
+			const int v = (edge && n == maxCol) ? -n : PUNDEF;
+			A[(o + NT) & (W * NT - 1)] = pack(v, qn, a2c & 7);
+			m3 = v; c3 = maxCol;
+		}
+		int s2c = a2c >> 6;
+		for (int c = maxCol - 1; c >= minCol; --c) {
+			const int oc = o;
+			o = (o - NT) & (W * NT - 1);
+			const int a2l = B[o], a1l = A[o];
+			const int q = (a2c >> 3) & 7, d = a2l & 7, s2l = a2l >> 6;
+			int tmp = imax(s2l, s2c) - 1;
+			tmp = imax(tmp, (a1l >> 6) + (q == d ? 1 : -1));
+			const int v = tmp < lim ? PUNDEF : tmp;
+			A[oc] = pack(v, q, d);
+			if (v >= m3) { m3 = v; c3 = c; }
+			a2c = a2l; s2c = s2l;
+		}
+		{
+			const int dn = n - minCol < s.dlen ? load_d(s, n - minCol) : 0;     // the new bottom row n - off3
+			const int v = (edge && off3 == 0) ? -n : PUNDEF;
+			A[o] = pack(v, (a2c >> 3) & 7, dn);             // o is the slot of off3 and a2c is a2[off3]: same column
+			if (v >= m3) { m3 = v; c3 = off3; }
+		}
+		best = imax(best, m3);
+		while (minCol - off3 < n3 && (S(ia, minCol) >> 6) == PUNDEF && minCol - off2 - 1 < n2 && (S(ib, minCol - 1) >> 6) == PUNDEF) ++minCol;
+		while (maxCol - off3 > 0 && (S(ia, maxCol - 1) >> 6) == PUNDEF && (S(ib, maxCol - 1) >> 6) == PUNDEF) --maxCol;
+		++maxCol;
+		minCol = imax(minCol, n + 2 - rows);
+		maxCol = imin(maxCol, cols);
+		return true;
+	}
+
+	XD_FN int finish(int& ext_cols, int& ext_rows) const
+	{
+		int lcol = n3 + off3 - 2, lrow = n - lcol, lscore = S(ia, lcol) >> 6;
+		if (lscore == PUNDEF) {
+			const int e2 = S(ib, off2 + n2 - 2) >> 6;
+			if (e2 != PUNDEF) { lcol = n2 + off2 - 2; lrow = n - 1 - lcol; lscore = e2; }
+			else if (n2 > 2) {
+				const int e3 = S(ib, off2 + n2 - 3) >> 6;
+				if (e3 != PUNDEF) { lcol = n2 + off2 - 3; lrow = n - 1 - lcol; lscore = e3; }
+			}
+		}
+		if (lscore == PUNDEF && m1 > lscore) { lscore = m1; lcol = c1; lrow = n - 2 - lcol; }
+		ext_cols = 0; ext_rows = 0;
+		if (lscore == PUNDEF) return UNDEF;
+		ext_cols = lcol; ext_rows = lrow;
+		return lscore;
+	}
+};
+
 // make_segs for a single thread (no group to split the seed comparison over)
 XD_FN bool make_segs_thread(const Pairs& P, int job, Segs& s, int& reverse, int& baseH, int& baseV)
 {
@@ -526,12 +628,11 @@ XD_FN bool make_segs_thread(const Pairs& P, int job, Segs& s, int& reverse, int&
 	return true;
 }
 
-// A thread of the thread-per-extension kernel; the only warp-wide operation is the "everybody done" vote.
-template <int W>
-XD_FN void thread_main(const Pairs& P, const Queue& Q, JobResult* res, int* sc, char* ch, int nt, int tid)
+// A thread of the thread-per-extension kernels; the only warp-wide operation is the "everybody done" vote.
+// order != nullptr: the jobs are taken in that order (longest expected extension first, see k_xdrop_estimate).
+template <class E>
+XD_FN void thread_loop(E& e, const Pairs& P, const Queue& Q, JobResult* res, const int* order)
 {
-	ThreadExt<W> e;
-	e.sc = sc; e.ch = ch; e.nt = nt; e.tid = tid;
 	Segs s;
 	int job = 0, reverse = 0, baseH = 0, baseV = 0;
 	bool have = false, done = false;
@@ -539,14 +640,17 @@ XD_FN void thread_main(const Pairs& P, const Queue& Q, JobResult* res, int* sc, 
 		if (!have && !done) {
 			job = atomic_inc(Q.next);
 			if (job >= P.n_jobs) done = true;
-			else if (!make_segs_thread(P, job, s, reverse, baseH, baseV)) {
-				*Q.bad = 1;
-				store_result(res, job, true, 0, 0, 0, 0, 0, 0);
-			} else if (s.qlen == 0 || s.dlen == 0) {
-				store_result(res, job, true, 0, 0, 0, baseH, baseV, reverse);
-			} else {
-				e.init(s, P.xdrop);
-				have = true;
+			else {
+				if (order) job = order[job];
+				if (!make_segs_thread(P, job, s, reverse, baseH, baseV)) {
+					*Q.bad = 1;
+					store_result(res, job, true, 0, 0, 0, 0, 0, 0);
+				} else if (s.qlen == 0 || s.dlen == 0) {
+					store_result(res, job, true, 0, 0, 0, baseH, baseV, reverse);
+				} else {
+					e.init(s, P.xdrop);
+					have = true;
+				}
 			}
 		}
 		if (all(FULL, done)) break;
@@ -561,6 +665,31 @@ XD_FN void thread_main(const Pairs& P, const Queue& Q, JobResult* res, int* sc, 
 			}
 		}
 	}
+}
+
+template <int W>
+XD_FN void thread_main(const Pairs& P, const Queue& Q, JobResult* res, int* sc, char* ch, int nt, int tid, const int* order = nullptr)
+{
+	ThreadExt<W> e;
+	e.sc = sc; e.ch = ch; e.nt = nt; e.tid = tid;
+	thread_loop(e, P, Q, res, order);
+}
+
+template <int W, int NT>
+XD_FN void thread_main_packed(const Pairs& P, const Queue& Q, JobResult* res, int* sc, int tid, const int* order = nullptr)
+{
+	ThreadExtP<W, NT> e;
+	e.sc = sc; e.tid = tid;
+	thread_loop(e, P, Q, res, order);
+}
+
+// Expected length of a job = min(query segment, database segment): the sort key of the longest-first schedule.
+XD_FN int job_estimate(const Pairs& P, int job)
+{
+	Segs s;
+	int reverse, baseH, baseV;
+	if (!make_segs_thread(P, job, s, reverse, baseH, baseV)) return 0;
+	return imin(s.qlen, s.dlen);
 }
 
 // A warp of the wide kernel: jobs from the overflow list (or, with list == nullptr, every job).

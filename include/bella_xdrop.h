@@ -48,8 +48,9 @@ int bella_xdrop_set_reads(bella_xdrop* h, const char* seqs, const uint64_t* seq_
 int bella_xdrop_set_params(bella_xdrop* h, int kmer_len, int xdrop, double ratiophi, double delta_chernoff, int fixed_threshold);
 
 /* Lanes per extension and cells (window slots) per lane: (32,1) (32,2) (32,4) (16,1) (16,2) (16,4) (8,4) (8,8) = the
- * register kernel; (1,32) (1,64) = one thread per extension with the window in shared memory; (0,0) = everything through
- * the wide path; (-1,-1) = chosen from xdrop (default). */
+ * register kernel; (1,32) (1,64) = one thread per extension with the window in shared memory; (2,32) (2,64) = the same
+ * with one packed word per cell, (3,32) (3,64) = packed + longest extension first (both opt-in: not measured yet);
+ * (0,0) = everything through the wide path; (-1,-1) = chosen from xdrop (default). */
 int bella_xdrop_set_shape(bella_xdrop* h, int lanes, int cells_per_lane);
 
 /* One batch of candidate pairs: rows[p] = H read (row of C), cols[p] = V read (column of C), posH/posV = the seed k-mer the

@@ -64,7 +64,8 @@ def reads():
 
 # (lanes per extension, cells per lane, xdrop): every instantiation the library ships; (1, W) = one thread per extension
 # with W window slots, (0,0) = wide path only
-@pytest.mark.parametrize("lanes,cells,xdrop", [(1, 64, 7), (1, 32, 7), (32, 1, 7), (32, 2, 15), (32, 4, 30), (16, 1, 3), (16, 2, 7), (16, 4, 15),
+# (2, W) / (3, W) = the packed-word form of the thread path / the same with the longest-first job order
+@pytest.mark.parametrize("lanes,cells,xdrop", [(1, 64, 7), (1, 32, 7), (2, 64, 7), (3, 64, 7), (2, 32, 3), (3, 32, 15), (32, 1, 7), (32, 2, 15), (32, 4, 30), (16, 1, 3), (16, 2, 7), (16, 4, 15),
                                                 (8, 4, 7), (8, 8, 15), (0, 0, 7)])
 def test_device_source_matches_oracle(reads, lanes, cells, xdrop):
     inp, pairs = reads
@@ -82,9 +83,10 @@ def test_window_overflow_hands_over_to_the_wide_path(reads):
     rc, got, n_wide = emu_align(inp, *pairs, 7, 16, 1, 0.55, 0.1, 200)     # 16 slots: a quarter of the extensions outgrow them
     assert rc == 0 and n_wide > 20
     np.testing.assert_array_equal(got, want)
-    rc, got, n_wide = emu_align(inp, *pairs, 7, 1, 16, 0.55, 0.1, 200)     # the thread-per-extension path hands over the same way
-    assert rc == 0 and n_wide > 20
-    np.testing.assert_array_equal(got, want)
+    for lanes in (1, 3):                                                   # the thread-per-extension paths hand over the same way
+        rc, got, n_wide = emu_align(inp, *pairs, 7, lanes, 16, 0.55, 0.1, 200)
+        assert rc == 0 and n_wide > 20
+        np.testing.assert_array_equal(got, want)
     rc, got, n_wide = emu_align(inp, *pairs, 25, 32, 1, 0.55, 0.1, 200)    # x = 25 needs ~34 columns: most go wide
     assert rc == 0 and n_wide > len(want)
     np.testing.assert_array_equal(got, ol.oracle_align_post(inp, *pairs, 25, 0.55, 0.1, 200))
@@ -93,7 +95,7 @@ def test_window_overflow_hands_over_to_the_wide_path(reads):
 def test_low_error_reads_and_seeds_at_the_read_ends():
     inp = fe.synthetic(60, 1500, coverage=15.0, err=0.02, seed=77, hi=40)       # extensions that run into the read ends
     pairs = candidate_pairs(inp, 200)
-    for lanes, cells in ((32, 1), (1, 64)):
+    for lanes, cells in ((32, 1), (1, 64), (2, 64)):
         rc, got, _ = emu_align(inp, *pairs, 7, lanes, cells)
         assert rc == 0
         np.testing.assert_array_equal(got, ol.oracle_align_post(inp, *pairs, 7))
@@ -103,7 +105,7 @@ def test_low_error_reads_and_seeds_at_the_read_ends():
     lens = inp.read_len
     pH = np.where(np.arange(n) % 2 == 0, 0, lens[r] - k).astype(np.uint16)      # empty prefix / empty suffix
     pV = np.where(np.arange(n) % 3 == 0, 0, lens[c] - k).astype(np.uint16)
-    for lanes, cells in ((1, 64), (32, 1), (16, 2), (0, 0)):
+    for lanes, cells in ((1, 64), (3, 64), (32, 1), (16, 2), (0, 0)):
         rc, got, _ = emu_align(inp, r, c, pH, pV, 7, lanes, cells)
         assert rc == 0
         np.testing.assert_array_equal(got, ol.oracle_align_post(inp, r, c, pH, pV, 7))
@@ -133,7 +135,7 @@ def test_bases_are_dna5_as_seqan_sees_them(reads):
     dirty.seqs = s
     want = ol.oracle_align_post(dirty, *pairs, 7)
     assert (want[:, :6] != ol.oracle_align(inp, *pairs, 7)).any()
-    for lanes, cells in ((1, 64), (32, 1), (0, 0)):
+    for lanes, cells in ((1, 64), (2, 64), (32, 1), (0, 0)):
         rc, got, _ = emu_align(dirty, *pairs, 7, lanes, cells)
         assert rc == 0
         np.testing.assert_array_equal(got, want)
@@ -154,6 +156,6 @@ def test_seed_outside_its_read_is_reported(reads):
     inp, pairs = reads
     rows, cols, pH, pV = (a[:8].copy() for a in pairs)
     pH[3] = inp.read_len[rows[3]] - 3
-    for lanes, cells in ((32, 1), (1, 64), (0, 0)):
+    for lanes, cells in ((32, 1), (1, 64), (3, 64), (0, 0)):
         rc, _, _ = emu_align(inp, rows, cols, pH, pV, 7, lanes, cells)
         assert rc == -1
