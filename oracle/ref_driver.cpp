@@ -355,6 +355,50 @@ int bella_ref_align_xavier(uint64_t n_pairs, const IT* rows, const IT* cols, con
 	return 0;
 }
 
+// "Next" row f3: the reference's reliable k-mer selection, SplitCount (include/kmercount.hpp:466-677: HyperLogLog estimate
+// -> Bloom filter -> cuckoo hash counts -> keep l <= count <= u; what src/main.cpp:299-302 calls), run on a FASTQ file of
+// the reads, followed by the tuple emission loop of src/main.cpp:383-416 restated with the reference's own Kmer / rep() /
+// dictionary lookup.  K-mer ids are cuckoo iteration order (kmercount.hpp:650-659), i.e. arbitrary, so what is returned is
+// the id-free content: every reliable occurrence as (read, pos), in read / position order, and the number of distinct
+// reliable k-mers.  One thread: bloom_check_add is not atomic, with several threads two simultaneous first sightings of a
+// k-mer can both miss (a race in the reference, not part of its specification).
+int bella_ref_reliable_occurrences(const char* fastq_path, uint64_t fastq_size, uint32_t n_reads, const char* seqs, const uint64_t* seq_off,
+		int kmer_len, int lower, int upper, uint32_t* out_read, uint16_t* out_pos, uint64_t cap, uint64_t* n_out, uint64_t* n_kmers)
+{
+	Quiet q;
+	const int saved = omp_get_max_threads();
+	omp_set_num_threads(1);
+	BELLApars bpars;
+	bpars.kmerSize = (unsigned short)kmer_len;
+	bpars.SplitCount = 1;
+	Kmer::set_k(kmer_len);
+	std::vector<filedata> allfiles(1);
+	strncpy(allfiles[0].filename, fastq_path, MAX_FILE_PATH - 1);
+	allfiles[0].filename[MAX_FILE_PATH - 1] = 0;
+	allfiles[0].filesize = fastq_size;
+	CuckooDict<IT> countsreliable;
+	SplitCount(allfiles, countsreliable, lower, upper, (size_t)10000000, bpars);
+	omp_set_num_threads(saved);
+	*n_kmers = countsreliable.size();
+	uint64_t n = 0;
+	for (uint32_t r = 0; r < n_reads; ++r) {
+		const std::string seq(seqs + seq_off[r], seqs + seq_off[r + 1]);
+		const int len = (int)seq.length();
+		for (int j = 0; j <= len - kmer_len; ++j) {
+			std::string kmerstrfromfastq = seq.substr(j, kmer_len);
+			Kmer mykmer(kmerstrfromfastq.c_str(), kmerstrfromfastq.length());
+			Kmer lexsmall = mykmer.rep();
+			IT idx;
+			if (countsreliable.find(lexsmall, idx)) {
+				if (n < cap) { out_read[n] = r; out_pos[n] = (uint16_t)j; }
+				++n;
+			}
+		}
+	}
+	*n_out = n;
+	return n <= cap ? 0 : -1;
+}
+
 int bella_ref_max_threads(void) { return omp_get_max_threads(); }
 
 } // extern "C"

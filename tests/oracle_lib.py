@@ -218,3 +218,35 @@ def logan_align(inp, rows, cols, posH, posV, xdrop=7):
     if rc != 0:
         raise RuntimeError(f"LOGAN failed: {rc}")
     return out, sec.value
+
+
+# ---- "next" row f3: reliable k-mer selection -------------------------------------------------------
+
+def _occurrences(fn, head, inp, k, lower, upper):
+    total = int(len(inp.seqs))
+    out_read = np.zeros(total, dtype=np.uint32); out_pos = np.zeros(total, dtype=np.uint16)
+    n_out, n_kmers = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    rc = fn(*head, ctypes.c_uint32(inp.n_reads), _p(inp.seqs), _p(inp.seq_off), ctypes.c_int(k), ctypes.c_int(lower), ctypes.c_int(upper),
+            _p(out_read), _p(out_pos), ctypes.c_uint64(total), ctypes.byref(n_out), ctypes.byref(n_kmers))
+    if rc != 0:
+        raise RuntimeError(f"reliable k-mer selection failed: {rc}")
+    return out_read[:n_out.value].copy(), out_pos[:n_out.value].copy(), n_kmers.value
+
+
+def oracle_reliable_occurrences(inp, k, lower, upper):
+    """oracle_reliable_occurrences -> (read u32[], pos u16[], number of distinct reliable k-mers)"""
+    return _occurrences(oracle().oracle_reliable_occurrences, (), inp, k, lower, upper)
+
+
+def write_fastq(inp, path):
+    with open(path, "wb") as f:
+        for r in range(inp.n_reads):
+            s = inp.seqs[int(inp.seq_off[r]):int(inp.seq_off[r + 1])].tobytes()
+            f.write(b"@read%d\n" % r + s + b"\n+\n" + b"I" * len(s) + b"\n")
+    return os.path.getsize(path)
+
+
+def ref_reliable_occurrences(inp, k, lower, upper, fastq_path):
+    """the reference's SplitCount on a FASTQ of the reads + its tuple emission loop -> same triple"""
+    size = write_fastq(inp, fastq_path)
+    return _occurrences(ref().bella_ref_reliable_occurrences, (fastq_path.encode(), ctypes.c_uint64(size)), inp, k, lower, upper)
