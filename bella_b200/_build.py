@@ -2,6 +2,7 @@
 
   libbella_b200.so      bella_b200/csrc/bella_b200.cu  -- CUDA kernels (sm_100a) + the C-ABI (include/bella_b200.h)
   libbella_xdrop.so     bella_b200/csrc/bella_xdrop.cu -- "next" row f1: X-drop seed-and-extend kernels + C-ABI (include/bella_xdrop.h)
+  libbella_kmers.so     bella_b200/csrc/bella_kmers.cu -- "next" row f3: reliable k-mer selection + tuple emission (include/bella_kmers.h)
   libbella_frontend.so  bella_b200/csrc/frontend.cpp   -- host front end (matrix construction, read simulator)
 """
 import os
@@ -13,6 +14,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_CUDA = os.path.join(HERE, "libbella_b200.so")
 LIB_XDROP = os.path.join(HERE, "libbella_xdrop.so")
+LIB_KMERS = os.path.join(HERE, "libbella_kmers.so")
 LIB_FE = os.path.join(HERE, "libbella_frontend.so")
 
 NVCC_FLAGS = [
@@ -59,6 +61,18 @@ def build_xdrop(force=False, verbose=False):
     return LIB_XDROP
 
 
+def build_kmers(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, "bella_kmers.cu"), os.path.join(CSRC, "kmers.cuh"), os.path.join(ROOT, "include", "bella_kmers.h")]
+    if not force and not _stale(LIB_KMERS, srcs):
+        return LIB_KMERS
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math"]
+    cmd = [_nvcc()] + flags + ["-I", os.path.join(ROOT, "include"), "-o", LIB_KMERS, srcs[0]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.run(cmd, check=True)
+    return LIB_KMERS
+
+
 def build_frontend(force=False):
     src = os.path.join(CSRC, "frontend.cpp")
     if not force and not _stale(LIB_FE, [src]):
@@ -72,3 +86,4 @@ if __name__ == "__main__":
     build_frontend()
     build_cuda(verbose=True)
     build_xdrop(verbose=True)
+    build_kmers(verbose=True)

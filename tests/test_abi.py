@@ -36,6 +36,16 @@ def test_xdrop_library_exports_every_declared_symbol():
     assert sorted(xdrop.EXPORTS) == syms
 
 
+def test_kmers_library_exports_every_declared_symbol():
+    from bella_b200 import _build, kmers
+    L = ctypes.CDLL(_build.build_kmers())
+    syms = declared_symbols("bella_kmers.h", "bella_kmers_")
+    assert len(syms) >= 6
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/bella_kmers.h but not exported"
+    assert sorted(kmers.EXPORTS) == syms
+
+
 def test_product_path_does_not_touch_the_oracle():
     bad = []
     for d, _, files in os.walk(os.path.join(ROOT, "bella_b200")):
@@ -57,3 +67,6 @@ def test_no_cpu_fallback_without_gpu():
     from bella_b200 import xdrop
     with pytest.raises(xdrop.BellaXdropError):
         xdrop.XdropAligner(0)
+    from bella_b200 import kmers
+    with pytest.raises(kmers.BellaKmersError):
+        kmers.KmerCounter(0)

@@ -53,17 +53,6 @@ def test_xdrop_matches_oracle(reads, lanes, cells, xdrop):
     a.close()
 
 
-@pytest.mark.skipif(os.environ.get("BELLA_XDROP_UNMEASURED") != "1",
-                    reason="opt-in (BELLA_XDROP_UNMEASURED=1): shapes written after the round's GPU time was spent -- checked under the "
-                           "CPU lane emulator (test_xdrop_emu.py), not yet run on a B200, so they do not gate the suite")
-@pytest.mark.parametrize("lanes,cells,xdrop", [(2, 64, 7), (3, 64, 7), (2, 32, 7), (3, 32, 3)])
-def test_unmeasured_shapes_match_oracle(reads, lanes, cells, xdrop):
-    inp, pairs = reads
-    a = aligner(inp, xdrop, (lanes, cells))
-    np.testing.assert_array_equal(a.align(*pairs), ol.oracle_align_post(inp, *pairs, xdrop, 0.55, 0.1, -1))
-    a.close()
-
-
 def test_window_overflow_goes_through_the_wide_kernel(reads):
     inp, pairs = reads
     want = ol.oracle_align_post(inp, *pairs, 7, 0.55, 0.1, 200)
