@@ -159,3 +159,60 @@ def test_seed_outside_its_read_is_reported(reads):
     for lanes, cells in ((32, 1), (1, 64), (3, 64), (0, 0)):
         rc, _, _ = emu_align(inp, rows, cols, pH, pV, 7, lanes, cells)
         assert rc == -1
+
+
+def _inputs_from_strings(reads, k=17):
+    seqs = np.frombuffer("".join(reads).encode(), dtype=np.uint8).copy()
+    off = np.zeros(len(reads) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(r) for r in reads])
+    return fe.OverlapInputs(n_reads=len(reads), n_kmers=0, nnz=0, A_colptr=None, A_rowids=None, A_values=None, A_strand=None,
+                            B_colptr=None, B_rowids=None, B_values=None, B_strand=None,
+                            read_len=np.array([len(r) for r in reads], dtype=np.uint32), kmer_size=k, seqs=seqs, seq_off=off)
+
+
+@pytest.mark.parametrize("xdrop", [0, 1, 7, 200])
+def test_degenerate_reads_and_extreme_xdrop(xdrop):
+    """homopolymers, tandem repeats, reads of exactly k bases, exact reverse complements, arbitrary (non-matching) seeds,
+    x = 0 (the initial gap cells are undefined, seeds_extension.h:476) and x larger than any score: reference (when built),
+    oracle and every execution shape of the device source agree"""
+    rng = np.random.default_rng(1)
+    rnd = lambda n: "".join(rng.choice(list("ACGT"), n))  # noqa: E731
+    rc = lambda s: s[::-1].translate(str.maketrans("ACGT", "TGCA"))  # noqa: E731
+
+    def mutate(s, e):
+        out = []
+        for c in s:
+            u = rng.random()
+            if u < e / 3:
+                continue
+            out.append(rng.choice(list("ACGT")) if u < 2 * e / 3 else c)
+            if 2 * e / 3 <= u < e:
+                out.append(rng.choice(list("ACGT")))
+        return "".join(out)
+
+    base = rnd(700)
+    reads = [base, mutate(base, 0.1), rc(mutate(base, 0.1)), "A" * 300, "A" * 250 + "C" * 50, "AC" * 150, base[:17], base[:40], rnd(200),
+             base[100:500], rc(base[100:500])]
+    inp = _inputs_from_strings(reads)
+    rows, cols, pH, pV = [], [], [], []
+    for i in range(len(reads)):
+        for j in range(len(reads)):
+            if i == j:
+                continue
+            for _ in range(3):
+                rows.append(i); cols.append(j)
+                pH.append(int(rng.integers(0, len(reads[i]) - 16))); pV.append(int(rng.integers(0, len(reads[j]) - 16)))
+            rows += [i, i]; cols += [j, j]
+            pH += [0, len(reads[i]) - 17]; pV += [0, len(reads[j]) - 17]
+    for a in (0, 1, 150, 382, 383):                                   # exact reverse complements: twin(seedH) == seedV
+        rows.append(9); cols.append(10); pH.append(a); pV.append(400 - a - 17)
+        rows.append(10); cols.append(9); pH.append(400 - a - 17); pV.append(a)
+    pairs = (np.array(rows, dtype=np.uint32), np.array(cols, dtype=np.uint32), np.array(pH, dtype=np.uint16), np.array(pV, dtype=np.uint16))
+    want = ol.oracle_align_post(inp, *pairs, xdrop, 0.4, 0.1, -1)
+    assert (want[:, 1] == ord("c")).sum() >= 10 and want[:, 0].max() >= 400
+    if ol.have_ref():
+        np.testing.assert_array_equal(want[:, :6], ol.ref_align(inp, *pairs, xdrop))
+    for lanes, cells in ((1, 64), (2, 64), (32, 1), (32, 4), (16, 2), (0, 0)):
+        rc_, got, _ = emu_align(inp, *pairs, xdrop, lanes, cells, 0.4, 0.1, -1)
+        assert rc_ == 0
+        np.testing.assert_array_equal(got, want)
