@@ -53,6 +53,14 @@ __global__ void __launch_bounds__(NT) k_xdrop_thread_packed(xd::Pairs P, xd::Que
 	xd::thread_main_packed<W, NT>(P, Q, res, smem_packed, threadIdx.x, order);
 }
 
+// both live anti-diagonals of a column in one word: W words per thread (opt-in until measured)
+template <int W, int NT>
+__global__ void __launch_bounds__(NT) k_xdrop_thread_two(xd::Pairs P, xd::Queue Q, xd::JobResult* res, const int* order)
+{
+	extern __shared__ int smem_two[];
+	xd::thread_main_two<W, NT>(P, Q, res, smem_two, threadIdx.x, order);
+}
+
 // longest-first schedule: key = 65535 - min(query segment, database segment), sorted ascending (plumbing: cub radix sort)
 __global__ void k_xdrop_estimate(xd::Pairs P, unsigned short* key, int* job)
 {
@@ -151,8 +159,10 @@ int launch_thread(bella_xdrop* h, const xd::Pairs& P, const xd::Queue& Q, xd::Jo
 	return 0;
 }
 
-template <int W, int NT>
-int launch_thread_packed(bella_xdrop* h, const xd::Pairs& P, const xd::Queue& Q, xd::JobResult* res, bool longest_first)
+typedef void (*thread_kernel_t)(xd::Pairs, xd::Queue, xd::JobResult*, const int*);
+
+int launch_thread_ordered(bella_xdrop* h, thread_kernel_t kernel, int NT, size_t smem, const xd::Pairs& P, const xd::Queue& Q,
+		xd::JobResult* res, bool longest_first)
 {
 	const int* order = nullptr;
 	if (longest_first) {
@@ -170,18 +180,29 @@ int launch_thread_packed(bella_xdrop* h, const xd::Pairs& P, const xd::Queue& Q,
 				(const int*)h->job_in.p, (int*)h->job_out.p, n, 0, 16, h->stream));
 		order = (const int*)h->job_out.p;
 	}
-	const size_t smem = (size_t)2 * W * NT * sizeof(int);
-	XCUDA(cudaFuncSetAttribute(k_xdrop_thread_packed<W, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	XCUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int per_sm = 0;
-	XCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xdrop_thread_packed<W, NT>, NT, smem));
-	if (per_sm < 1) return fail(h, BELLA_XDROP_ECUDA, "k_xdrop_thread_packed does not fit an SM");
+	XCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NT, smem));
+	if (per_sm < 1) return fail(h, BELLA_XDROP_ECUDA, "the thread kernel does not fit an SM");
 	long grid = (long)h->sms * per_sm;
 	const long needed = ((long)P.n_jobs + NT - 1) / NT;
 	if (grid > needed) grid = needed;
-	k_xdrop_thread_packed<W, NT><<<(unsigned)grid, NT, smem, h->stream>>>(P, Q, res, order);
+	kernel<<<(unsigned)grid, NT, smem, h->stream>>>(P, Q, res, order);
 	XCUDA(cudaGetLastError());
 	++h->launches;
 	return 0;
+}
+
+template <int W, int NT>
+int launch_thread_packed(bella_xdrop* h, const xd::Pairs& P, const xd::Queue& Q, xd::JobResult* res, bool longest_first)
+{
+	return launch_thread_ordered(h, k_xdrop_thread_packed<W, NT>, NT, (size_t)2 * W * NT * sizeof(int), P, Q, res, longest_first);
+}
+
+template <int W, int NT>
+int launch_thread_two(bella_xdrop* h, const xd::Pairs& P, const xd::Queue& Q, xd::JobResult* res, bool longest_first)
+{
+	return launch_thread_ordered(h, k_xdrop_thread_two<W, NT>, NT, (size_t)W * NT * sizeof(int), P, Q, res, longest_first);
 }
 
 void pick_shape(const bella_xdrop* h, int& G, int& T)
@@ -241,6 +262,8 @@ int run_batch(bella_xdrop* h, uint64_t n_pairs, const uint32_t* d_rows, const ui
 		else if (G == 1 && T == 32) rc = launch_thread<32>(h, P, Q, res);
 		else if ((G == 2 || G == 3) && T == 64) rc = launch_thread_packed<64, 128>(h, P, Q, res, G == 3);
 		else if ((G == 2 || G == 3) && T == 32) rc = launch_thread_packed<32, 128>(h, P, Q, res, G == 3);
+		else if ((G == 4 || G == 5) && T == 64) rc = launch_thread_two<64, 256>(h, P, Q, res, G == 5);
+		else if ((G == 4 || G == 5) && T == 32) rc = launch_thread_two<32, 256>(h, P, Q, res, G == 5);
 		else return fail(h, BELLA_XDROP_EINVAL, "unsupported shape (lanes, cells per lane)");
 		if (rc) return rc;
 		k_xdrop_wide<<<wide_grid, WARPS * 32, 0, h->stream>>>(P, (const int*)h->wide.p, ctr + 1, ctr + 2, res, (int*)h->scratch.p, cap, ctr + 3);
@@ -327,7 +350,7 @@ int bella_xdrop_set_shape(bella_xdrop* h, int lanes, int cells_per_lane)
 		|| (lanes == 32 && (cells_per_lane == 1 || cells_per_lane == 2 || cells_per_lane == 4))
 		|| (lanes == 16 && (cells_per_lane == 1 || cells_per_lane == 2 || cells_per_lane == 4))
 		|| (lanes == 8 && (cells_per_lane == 4 || cells_per_lane == 8))
-		|| ((lanes == 1 || lanes == 2 || lanes == 3) && (cells_per_lane == 32 || cells_per_lane == 64));
+		|| (lanes >= 1 && lanes <= 5 && (cells_per_lane == 32 || cells_per_lane == 64));
 	if (!ok) return fail(h, BELLA_XDROP_EINVAL, "unsupported shape (lanes, cells per lane)");
 	h->lanes = lanes; h->cells = cells_per_lane;
 	return 0;

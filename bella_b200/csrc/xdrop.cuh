@@ -598,6 +598,126 @@ struct ThreadExtP {
 	}
 };
 
+// Third form (opt-in until measured): ONE 32-bit word per column slot holds BOTH live anti-diagonals of that column,
+//     [31:22] score field of half 1 | [21:12] score field of half 0 | [11:9] q code of the column | [8:6] d code of half 1 |
+//     [5:3] d code of half 0
+// so a cell costs one shared load and one store, and a thread needs W words (256 B at W = 64: 768 threads per SM).
+// Scores are stored relative to the drop-off limit of their own anti-diagonal: field = score - lim + 4, field 0 =
+// undefined (a defined score is >= lim when it is written, seeds_extension.h:704-710, and <= lim + x + 1).  At step n,
+// a2 lives in half n & 1 and a3 is written over a1 in the other half.  Decoding with the limit of the CURRENT step is
+// one add: an undefined cell decodes to <= -4, which no +1 brings back to >= 0, so it needs no special case.
+template <int W, int NT>
+struct ThreadExtQ {
+	int* sc; int tid;                            // sc: W * NT ints of shared memory
+	XD_FN int& S(int c) const { return sc[((c * NT) & (W * NT - 1)) + tid]; }
+
+	int n, minCol, maxCol, best, off2, n2, off3, n3, rows, cols, xdrop;
+	int lim2, lim3;                              // limits the anti-diagonals n-1 and n were encoded with
+	int m1, c1, m2, c2, m3, c3;                  // absolute maximum / its first column of anti-diagonals n-2, n-1, n
+
+	XD_FN void init(const Segs& s, int xdrop_)
+	{
+		rows = s.dlen + 1; cols = s.qlen + 1; xdrop = xdrop_;
+		const int lim = -xdrop;                          // best = 0 for the two initial anti-diagonals
+		const int g0f = (1 > xdrop) ? 0 : (-1 - lim + 4);
+		const int q0 = load_q(s, 0), d0 = load_d(s, 0);
+		// anti-diagonal 0 = cell (0,0) in half 1 (it is a1 at step 2); anti-diagonal 1 = cells (0,1), (1,0) in half 0
+		S(0) = ((0 - lim + 4) << 22) | (g0f << 12) | (d0 << 3);
+		S(1) = (g0f << 12) | (q0 << 9);
+		lim2 = lim; lim3 = lim;
+		m1 = UNDEF; c1 = 0; m2 = 0; c2 = 0; m3 = (1 > xdrop) ? UNDEF : -1; c3 = 0;
+		n2 = 1; n3 = 2; off2 = off3 = 0;
+		minCol = 1; maxCol = 2; n = 1; best = 0;
+	}
+
+	XD_FN bool active() const { return minCol < maxCol; }
+
+	template <int P>                             // P = n & 1: the half that holds a2
+	XD_FN void cells(const Segs& s, int lim)
+	{
+		constexpr int SH2 = P ? 22 : 12, SH3 = P ? 12 : 22;          // score fields of a2 and of a1/a3
+		constexpr int DS2 = P ? 6 : 3, DS3 = P ? 3 : 6;              // their d codes
+		constexpr unsigned KEEP = (1023u << SH2) | (7u << DS2) | (7u << 9);   // what a3's store leaves alone: a2's half and q
+		const int dec2 = 4 + (lim - lim3), dec1 = 4 + (lim - lim2); // lim3 / lim2 still describe anti-diagonals n-1 / n-2 here
+		const bool edge = -n > lim;
+		int o = ((maxCol - 1) * NT) & (W * NT - 1);
+		int* const A = sc + tid;
+		unsigned wc = (unsigned)A[o];                   // column maxCol-1
+		{
+			const unsigned top = (unsigned)A[(o + NT) & (W * NT - 1)];
+			const int qn = maxCol - 1 < s.qlen ? load_q(s, maxCol - 1) : 0;
+			const int v = (edge && n == maxCol) ? -n : UNDEF;
+			const unsigned f = v == UNDEF ? 0u : (unsigned)(v - lim + 4);
+			A[(o + NT) & (W * NT - 1)] = (int)((top & (1023u << SH2)) | ((top & (7u << DS2))) | ((unsigned)qn << 9) | (f << SH3) | (((wc >> DS2) & 7u) << DS3));
+			m3 = v; c3 = maxCol;
+		}
+		int x2c = (int)((wc >> SH2) & 1023u) - dec2;
+		for (int c = maxCol - 1; c >= minCol; --c) {
+			const int oc = o;
+			o = (o - NT) & (W * NT - 1);
+			const unsigned w = (unsigned)A[o];          // column c-1: a2[c-1] and a1[c-1]
+			const int x2l = (int)((w >> SH2) & 1023u) - dec2, x1l = (int)((w >> SH3) & 1023u) - dec1;
+			const unsigned q = (wc >> 9) & 7u, d = (w >> DS2) & 7u;
+			int tmp = imax(x2l, x2c) - 1;
+			tmp = imax(tmp, x1l + (q == d ? 1 : -1));
+			const unsigned f = tmp < 0 ? 0u : (unsigned)(tmp + 4);
+			A[oc] = (int)((wc & KEEP) | (f << SH3) | (d << DS3));
+			const int v = tmp < 0 ? UNDEF : tmp + lim;
+			if (v >= m3) { m3 = v; c3 = c; }
+			wc = w; x2c = x2l;
+		}
+		{
+			const int dn = n - minCol < s.dlen ? load_d(s, n - minCol) : 0;
+			const int v = (edge && off3 == 0) ? -n : UNDEF;
+			const unsigned f = v == UNDEF ? 0u : (unsigned)(v - lim + 4);
+			A[o] = (int)((wc & KEEP) | (f << SH3) | ((unsigned)dn << DS3));     // o is the slot of off3, wc its word
+			if (v >= m3) { m3 = v; c3 = off3; }
+		}
+	}
+
+	XD_FN bool undef3(int c) const { return ((((unsigned)S(c)) >> ((n & 1) ? 12 : 22)) & 1023u) == 0; }   // a3[c]
+	XD_FN bool undef2(int c) const { return ((((unsigned)S(c)) >> ((n & 1) ? 22 : 12)) & 1023u) == 0; }   // a2[c]
+
+	XD_FN bool step(const Segs& s)
+	{
+		++n;
+		m1 = m2; c1 = c2; m2 = m3; c2 = c3;
+		n2 = n3; off2 = off3; off3 = minCol - 1;
+		n3 = maxCol + 1 - off3;
+		if (n3 > W) return false;
+		const int lim = best - xdrop;
+		if (n & 1) cells<1>(s, lim); else cells<0>(s, lim);
+		lim2 = lim3; lim3 = lim;
+		best = imax(best, m3);
+		while (minCol - off3 < n3 && undef3(minCol) && minCol - off2 - 1 < n2 && undef2(minCol - 1)) ++minCol;
+		while (maxCol - off3 > 0 && undef3(maxCol - 1) && undef2(maxCol - 1)) --maxCol;
+		++maxCol;
+		minCol = imax(minCol, n + 2 - rows);
+		maxCol = imin(maxCol, cols);
+		return true;
+	}
+
+	XD_FN int score3(int c) const { const unsigned f = (((unsigned)S(c)) >> ((n & 1) ? 12 : 22)) & 1023u; return f ? (int)f - 4 + lim3 : UNDEF; }
+	XD_FN int score2(int c) const { const unsigned f = (((unsigned)S(c)) >> ((n & 1) ? 22 : 12)) & 1023u; return f ? (int)f - 4 + lim2 : UNDEF; }
+
+	XD_FN int finish(int& ext_cols, int& ext_rows) const
+	{
+		int lcol = n3 + off3 - 2, lrow = n - lcol, lscore = score3(lcol);
+		if (lscore == UNDEF) {
+			const int e2 = score2(off2 + n2 - 2);
+			if (e2 != UNDEF) { lcol = n2 + off2 - 2; lrow = n - 1 - lcol; lscore = e2; }
+			else if (n2 > 2) {
+				const int e3 = score2(off2 + n2 - 3);
+				if (e3 != UNDEF) { lcol = n2 + off2 - 3; lrow = n - 1 - lcol; lscore = e3; }
+			}
+		}
+		if (lscore == UNDEF && m1 > lscore) { lscore = m1; lcol = c1; lrow = n - 2 - lcol; }
+		ext_cols = 0; ext_rows = 0;
+		if (lscore != UNDEF) { ext_cols = lcol; ext_rows = lrow; }
+		return lscore;
+	}
+};
+
 // make_segs for a single thread (no group to split the seed comparison over)
 XD_FN bool make_segs_thread(const Pairs& P, int job, Segs& s, int& reverse, int& baseH, int& baseV)
 {
@@ -679,6 +799,14 @@ template <int W, int NT>
 XD_FN void thread_main_packed(const Pairs& P, const Queue& Q, JobResult* res, int* sc, int tid, const int* order = nullptr)
 {
 	ThreadExtP<W, NT> e;
+	e.sc = sc; e.tid = tid;
+	thread_loop(e, P, Q, res, order);
+}
+
+template <int W, int NT>
+XD_FN void thread_main_two(const Pairs& P, const Queue& Q, JobResult* res, int* sc, int tid, const int* order = nullptr)
+{
+	ThreadExtQ<W, NT> e;
 	e.sc = sc; e.tid = tid;
 	thread_loop(e, P, Q, res, order);
 }

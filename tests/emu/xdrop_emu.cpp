@@ -198,6 +198,13 @@ void run_thread_packed(const xd::Pairs& P, const xd::Queue& Q, xd::JobResult* re
 	run_warps(n_warps, [&](int w) { xd::thread_main_packed<W, 32>(P, Q, res, sc[w].data(), xd::lane_id(), order); });
 }
 
+template <int W>
+void run_thread_two(const xd::Pairs& P, const xd::Queue& Q, xd::JobResult* res, int n_warps, const int* order)
+{
+	std::vector<std::vector<int>> sc(n_warps, std::vector<int>(W * 32));
+	run_warps(n_warps, [&](int w) { xd::thread_main_two<W, 32>(P, Q, res, sc[w].data(), xd::lane_id(), order); });
+}
+
 void run_wide(const xd::Pairs& P, const int* list, int n_list, xd::JobResult* res, int cap, int* bad, int n_warps)
 {
 	std::vector<std::vector<int>> scratch(n_warps, std::vector<int>(3 * (size_t)cap));
@@ -235,17 +242,23 @@ extern "C" int xdrop_emu_align(int G, int T, uint64_t n_pairs, const uint32_t* r
 		else if (G == 1 && T == 64) run_thread<64>(P, Q, res.data(), n_warps);      // thread per extension, T = window slots
 		else if (G == 1 && T == 32) run_thread<32>(P, Q, res.data(), n_warps);
 		else if (G == 1 && T == 16) run_thread<16>(P, Q, res.data(), n_warps);
-		else if (G == 2 || G == 3) {                                                 // packed-word thread path; 3 = longest job first
+		else if (G == 2 || G == 3 || G == 4 || G == 5) {                             // packed thread paths; 3, 5 = longest job first
 			std::vector<int> order;
-			if (G == 3) {
+			if (G == 3 || G == 5) {
 				std::vector<int> est(P.n_jobs);
 				for (int j = 0; j < P.n_jobs; ++j) est[j] = xd::job_estimate(P, j);
 				order.resize(P.n_jobs);
 				for (int j = 0; j < P.n_jobs; ++j) order[j] = j;
 				std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return est[a] > est[b]; });
 			}
-			const int* ord = G == 3 ? order.data() : nullptr;
-			if (T == 64) run_thread_packed<64>(P, Q, res.data(), n_warps, ord);
+			const int* ord = (G == 3 || G == 5) ? order.data() : nullptr;
+			if (G >= 4) {                                                            // both anti-diagonals of a column in one word
+				if (T == 64) run_thread_two<64>(P, Q, res.data(), n_warps, ord);
+				else if (T == 32) run_thread_two<32>(P, Q, res.data(), n_warps, ord);
+				else if (T == 16) run_thread_two<16>(P, Q, res.data(), n_warps, ord);
+				else return -2;
+			}
+			else if (T == 64) run_thread_packed<64>(P, Q, res.data(), n_warps, ord);
 			else if (T == 32) run_thread_packed<32>(P, Q, res.data(), n_warps, ord);
 			else if (T == 16) run_thread_packed<16>(P, Q, res.data(), n_warps, ord);
 			else return -2;

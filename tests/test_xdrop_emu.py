@@ -64,8 +64,10 @@ def reads():
 
 # (lanes per extension, cells per lane, xdrop): every instantiation the library ships; (1, W) = one thread per extension
 # with W window slots, (0,0) = wide path only
-# (2, W) / (3, W) = the packed-word form of the thread path / the same with the longest-first job order
-@pytest.mark.parametrize("lanes,cells,xdrop", [(1, 64, 7), (1, 32, 7), (2, 64, 7), (3, 64, 7), (2, 32, 3), (3, 32, 15), (32, 1, 7), (32, 2, 15), (32, 4, 30), (16, 1, 3), (16, 2, 7), (16, 4, 15),
+# (2, W) / (3, W) = the packed-word form of the thread path / the same with the longest-first job order;
+# (4, W) / (5, W) = both anti-diagonals of a column in one word / the same with the longest-first job order
+@pytest.mark.parametrize("lanes,cells,xdrop", [(1, 64, 7), (1, 32, 7), (2, 64, 7), (3, 64, 7), (2, 32, 3), (3, 32, 15), (4, 64, 7), (5, 64, 7),
+                                                (4, 32, 3), (5, 32, 15), (32, 1, 7), (32, 2, 15), (32, 4, 30), (16, 1, 3), (16, 2, 7), (16, 4, 15),
                                                 (8, 4, 7), (8, 8, 15), (0, 0, 7)])
 def test_device_source_matches_oracle(reads, lanes, cells, xdrop):
     inp, pairs = reads
@@ -83,7 +85,7 @@ def test_window_overflow_hands_over_to_the_wide_path(reads):
     rc, got, n_wide = emu_align(inp, *pairs, 7, 16, 1, 0.55, 0.1, 200)     # 16 slots: a quarter of the extensions outgrow them
     assert rc == 0 and n_wide > 20
     np.testing.assert_array_equal(got, want)
-    for lanes in (1, 3):                                                   # the thread-per-extension paths hand over the same way
+    for lanes in (1, 3, 5):                                                # the thread-per-extension paths hand over the same way
         rc, got, n_wide = emu_align(inp, *pairs, 7, lanes, 16, 0.55, 0.1, 200)
         assert rc == 0 and n_wide > 20
         np.testing.assert_array_equal(got, want)
@@ -95,7 +97,7 @@ def test_window_overflow_hands_over_to_the_wide_path(reads):
 def test_low_error_reads_and_seeds_at_the_read_ends():
     inp = fe.synthetic(60, 1500, coverage=15.0, err=0.02, seed=77, hi=40)       # extensions that run into the read ends
     pairs = candidate_pairs(inp, 200)
-    for lanes, cells in ((32, 1), (1, 64), (2, 64)):
+    for lanes, cells in ((32, 1), (1, 64), (2, 64), (4, 64)):
         rc, got, _ = emu_align(inp, *pairs, 7, lanes, cells)
         assert rc == 0
         np.testing.assert_array_equal(got, ol.oracle_align_post(inp, *pairs, 7))
@@ -105,7 +107,7 @@ def test_low_error_reads_and_seeds_at_the_read_ends():
     lens = inp.read_len
     pH = np.where(np.arange(n) % 2 == 0, 0, lens[r] - k).astype(np.uint16)      # empty prefix / empty suffix
     pV = np.where(np.arange(n) % 3 == 0, 0, lens[c] - k).astype(np.uint16)
-    for lanes, cells in ((1, 64), (3, 64), (32, 1), (16, 2), (0, 0)):
+    for lanes, cells in ((1, 64), (3, 64), (5, 64), (32, 1), (16, 2), (0, 0)):
         rc, got, _ = emu_align(inp, r, c, pH, pV, 7, lanes, cells)
         assert rc == 0
         np.testing.assert_array_equal(got, ol.oracle_align_post(inp, r, c, pH, pV, 7))
@@ -135,7 +137,7 @@ def test_bases_are_dna5_as_seqan_sees_them(reads):
     dirty.seqs = s
     want = ol.oracle_align_post(dirty, *pairs, 7)
     assert (want[:, :6] != ol.oracle_align(inp, *pairs, 7)).any()
-    for lanes, cells in ((1, 64), (2, 64), (32, 1), (0, 0)):
+    for lanes, cells in ((1, 64), (2, 64), (4, 64), (32, 1), (0, 0)):
         rc, got, _ = emu_align(dirty, *pairs, 7, lanes, cells)
         assert rc == 0
         np.testing.assert_array_equal(got, want)
@@ -212,7 +214,7 @@ def test_degenerate_reads_and_extreme_xdrop(xdrop):
     assert (want[:, 1] == ord("c")).sum() >= 10 and want[:, 0].max() >= 400
     if ol.have_ref():
         np.testing.assert_array_equal(want[:, :6], ol.ref_align(inp, *pairs, xdrop))
-    for lanes, cells in ((1, 64), (2, 64), (32, 1), (32, 4), (16, 2), (0, 0)):
+    for lanes, cells in ((1, 64), (2, 64), (4, 64), (32, 1), (32, 4), (16, 2), (0, 0)):
         rc_, got, _ = emu_align(inp, *pairs, xdrop, lanes, cells, 0.4, 0.1, -1)
         assert rc_ == 0
         np.testing.assert_array_equal(got, want)

@@ -11,4 +11,5 @@ timeout 90 python tools/xdrop_prof.py --logan 2>&1 | tail -20 | tee gpurun_out/f
 timeout 90 python tools/kmers_bench.py 20000 10000 gpurun_out/kmers_bench.json 2>&1 | tail -3
 timeout 60 ncu --set full --import-source on --clock-control none -k regex:k_xdrop_thread -c 1 -o gpurun_out/xdrop_thread64 python tools/xdrop_prof.py --prof 1 64 2>&1 | tail -2
 timeout 60 ncu --set full --import-source on --clock-control none -k regex:k_xdrop_thread_packed -c 1 -o gpurun_out/xdrop_packed64 python tools/xdrop_prof.py --prof 3 64 2>&1 | tail -2
+timeout 60 ncu --set full --import-source on --clock-control none -k regex:k_xdrop_thread_two -c 1 -o gpurun_out/xdrop_two64 python tools/xdrop_prof.py --prof 5 64 2>&1 | tail -2
 timeout 90 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/kmers_launches.csv python tools/kmers_bench.py 4000 10000 gpurun_out/kmers_ncu.json 2>&1 | tail -2
