@@ -107,3 +107,66 @@ def test_exchange_plan_is_consistent_across_ranks():
             np.testing.assert_array_equal(np.diff(segoff[s].numpy()), counts[s, lo:hi].numpy())
         assert recvbase.tolist() == [sum(ins[:s]) for s in range(world)]
         assert int(sendoff[-1]) == int(counts[r].sum()) and sendoff.numel() == n + 1
+
+
+# ---- row f1: the alignment step shards by pairs, no collective (bella_b200/distributed_xdrop.py) -----------------------
+
+class _EmulatedAligner:
+    """stands in for bella_b200.xdrop.XdropAligner on a CPU box: the same device source under the lane emulator"""
+
+    def set_reads(self, seqs, seq_off):
+        from bella_b200 import frontend as fe
+        self.inp = fe.OverlapInputs(n_reads=len(seq_off) - 1, n_kmers=0, nnz=0, A_colptr=None, A_rowids=None, A_values=None, A_strand=None,
+                                    B_colptr=None, B_rowids=None, B_values=None, B_strand=None, read_len=None, kmer_size=17, seqs=seqs, seq_off=seq_off)
+
+    def set_params(self, kmer_len, xdrop, ratiophi, delta, fixed):
+        self.inp.kmer_size = kmer_len
+        self.params = (xdrop, ratiophi, delta, fixed)
+
+    def align(self, rows, cols, posH, posV):
+        import test_xdrop_emu as emu
+        x, phi, delta, fixed = self.params
+        rc, out, _ = emu.emu_align(self.inp, rows, cols, posH, posV, x, 1, 64, phi, delta, fixed, warps=2)
+        assert rc == 0
+        return out
+
+
+def _xdrop_worker(rank, world, port, tmpdir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from bella_b200 import distributed_xdrop as dx, frontend as fe
+    import oracle_lib as ol
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    inp = fe.synthetic(100, 1000, coverage=12.0, seed=17)
+    c = ol.oracle_spgemm(inp, want_aux=False)
+    cols = np.repeat(np.arange(inp.n_reads, dtype=np.uint32), np.diff(c.colptrC.astype(np.int64)))
+    n = min(c.nnz, 240)
+    pairs = (c.rowids[:n], cols[:n], c.posH[:n], c.posV[:n])
+    a = dx.ShardedXdropAligner(rank, world, aligner_factory=_EmulatedAligner)
+    a.set_reads(inp.seqs, inp.seq_off)
+    a.set_params(inp.kmer_size, 7, 0.5, 0.1, -1)
+    lo, hi, out = a.align_my_share(*pairs)
+    # the slices tile the batch and the union is the oracle's answer (gathered on every rank)
+    parts = [None] * world
+    dist.all_gather_object(parts, (lo, hi, out))
+    parts.sort(key=lambda t: t[0])
+    assert parts[0][0] == 0 and parts[-1][1] == n and all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+    got = np.concatenate([p[2] for p in parts])
+    np.testing.assert_array_equal(got, ol.oracle_align_post(inp, *pairs, 7, 0.5, 0.1, -1))
+    cost = dx.pair_costs(inp.seq_off, *pairs, inp.kmer_size)
+    share = [cost[p[0]:p[1]].sum() for p in parts]
+    assert max(share) <= 1.35 * (sum(share) / world)            # balanced on expected work, not on pair count
+    dist.destroy_process_group()
+    open(os.path.join(tmpdir, f"xok{rank}"), "w").close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_alignment_shards_by_pairs_without_a_collective(world, tmp_path):
+    port = _free_port()
+    mp.spawn(_xdrop_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"xok{r}") for r in range(world))
