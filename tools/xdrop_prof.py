@@ -32,27 +32,33 @@ t = time.time()
 want = ol.oracle_align(big, *pairs, 7)
 cpu_s = time.time() - t
 out = []
-plan = ((7, [(1, 64), (2, 64), (3, 64), (4, 64), (5, 64), (5, 32), (3, 32), (1, 32), (32, 1), (16, 2), (8, 4), (32, 2), (16, 4), (8, 8)]), (25, [(32, 2), (16, 4), (8, 8), (32, 4)]))
+plan = ((7, [(1, 64), (1, 32), (32, 1), (16, 2), (8, 4), (32, 2), (16, 4), (8, 8), (2, 64), (3, 64), (4, 64), (5, 64), (5, 32), (3, 32)]), (25, [(32, 2), (16, 4), (8, 8), (32, 4)]))
 if "--quick" in sys.argv:
     plan = ((7, [(1, 64), (1, 32), (32, 2)]),)
 for x, shapes in plan:
     w = want if x == 7 else ol.oracle_align(big, *pairs, x)
     for shape in shapes:
-        a = T.aligner(big, x, shape)
-        a.align(*pairs)
-        ms = []
-        for _ in range(3):
-            got = a.align(*pairs)
-            ms.append(a.stats()["kernel_ms"])
-        st = a.stats()
-        out.append({"xdrop": x, "shape": shape, "pairs": n, "kernel_ms": sorted(ms)[1], "wide": st["wide_extensions"],
-                    "parity": bool(np.array_equal(got[:, :6], w)), "cpu_oracle_s_x7": cpu_s})
+        try:
+            a = T.aligner(big, x, shape)
+            a.align(*pairs)
+            ms = []
+            for _ in range(3):
+                got = a.align(*pairs)
+                ms.append(a.stats()["kernel_ms"])
+            st = a.stats()
+            out.append({"xdrop": x, "shape": shape, "pairs": n, "kernel_ms": sorted(ms)[1], "wide": st["wide_extensions"],
+                        "parity": bool(np.array_equal(got[:, :6], w)), "cpu_oracle_s_x7": cpu_s})
+            a.close()
+        except Exception as e:  # noqa: BLE001 -- a faulting shape must not hide the numbers of the others
+            out.append({"xdrop": x, "shape": shape, "error": repr(e)[:200]})
         print(out[-1], flush=True)
-        a.close()
+        if "error" in out[-1]:
+            break                                                 # the CUDA context may be gone
+name = "xdrop_shapes_quick.json" if "--quick" in sys.argv else "xdrop_shapes.json"
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", name), "w"), indent=1)
 if "--logan" in sys.argv and ol.have_logan():                     # the bar of SURVEY.md 8f: the reference kernel on the same box
     got, sec = ol.logan_align(big, *pairs, 7)
     out.append({"xdrop": 7, "shape": "LOGAN (reference, recompiled sm_100a)", "pairs": n, "extendSeedL_s": sec,
                 "identical_to_oracle": float((got == want).all(axis=1).mean())})
     print(out[-1], flush=True)
-name = "xdrop_shapes_quick_r01.json" if "--quick" in sys.argv else "xdrop_shapes_r01.json"
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", name), "w"), indent=1)
