@@ -264,6 +264,8 @@ int run_batch(bella_xdrop* h, uint64_t n_pairs, const uint32_t* d_rows, const ui
 		else if ((G == 2 || G == 3) && T == 32) rc = launch_thread_packed<32, 128>(h, P, Q, res, G == 3);
 		else if ((G == 4 || G == 5) && T == 64) rc = launch_thread_two<64, 256>(h, P, Q, res, G == 5);
 		else if ((G == 4 || G == 5) && T == 32) rc = launch_thread_two<32, 256>(h, P, Q, res, G == 5);
+		else if ((G == 4 || G == 5) && T == 128) rc = launch_thread_two<128, 128>(h, P, Q, res, G == 5);
+		else if ((G == 4 || G == 5) && T == 256) rc = launch_thread_two<256, 64>(h, P, Q, res, G == 5);
 		else return fail(h, BELLA_XDROP_EINVAL, "unsupported shape (lanes, cells per lane)");
 		if (rc) return rc;
 		k_xdrop_wide<<<wide_grid, WARPS * 32, 0, h->stream>>>(P, (const int*)h->wide.p, ctr + 1, ctr + 2, res, (int*)h->scratch.p, cap, ctr + 3);
@@ -350,7 +352,8 @@ int bella_xdrop_set_shape(bella_xdrop* h, int lanes, int cells_per_lane)
 		|| (lanes == 32 && (cells_per_lane == 1 || cells_per_lane == 2 || cells_per_lane == 4))
 		|| (lanes == 16 && (cells_per_lane == 1 || cells_per_lane == 2 || cells_per_lane == 4))
 		|| (lanes == 8 && (cells_per_lane == 4 || cells_per_lane == 8))
-		|| (lanes >= 1 && lanes <= 5 && (cells_per_lane == 32 || cells_per_lane == 64));
+		|| (lanes >= 1 && lanes <= 5 && (cells_per_lane == 32 || cells_per_lane == 64))
+		|| ((lanes == 4 || lanes == 5) && (cells_per_lane == 128 || cells_per_lane == 256));
 	if (!ok) return fail(h, BELLA_XDROP_EINVAL, "unsupported shape (lanes, cells per lane)");
 	h->lanes = lanes; h->cells = cells_per_lane;
 	return 0;

@@ -50,7 +50,7 @@ int bella_xdrop_set_params(bella_xdrop* h, int kmer_len, int xdrop, double ratio
 /* Lanes per extension and cells (window slots) per lane: (32,1) (32,2) (32,4) (16,1) (16,2) (16,4) (8,4) (8,8) = the
  * register kernel; (1,32) (1,64) = one thread per extension with the window in shared memory; (2,32) (2,64) = the same
  * with one packed word per cell, (3,W) = packed + longest extension first, (4,W) = both anti-diagonals of a column in one
- * word (256 B per thread), (5,W) = that + longest first (2..5 are opt-in: checked under the CPU emulator, not measured yet);
+ * word (4 W bytes per thread; W up to 256 for larger x), (5,W) = that + longest first (2..5 are opt-in: checked under the CPU emulator, not measured yet);
  * (0,0) = everything through the wide path; (-1,-1) = chosen from xdrop (default). */
 int bella_xdrop_set_shape(bella_xdrop* h, int lanes, int cells_per_lane);
 

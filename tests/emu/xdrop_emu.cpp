@@ -253,7 +253,9 @@ extern "C" int xdrop_emu_align(int G, int T, uint64_t n_pairs, const uint32_t* r
 			}
 			const int* ord = (G == 3 || G == 5) ? order.data() : nullptr;
 			if (G >= 4) {                                                            // both anti-diagonals of a column in one word
-				if (T == 64) run_thread_two<64>(P, Q, res.data(), n_warps, ord);
+				if (T == 256) run_thread_two<256>(P, Q, res.data(), n_warps, ord);
+				else if (T == 128) run_thread_two<128>(P, Q, res.data(), n_warps, ord);
+				else if (T == 64) run_thread_two<64>(P, Q, res.data(), n_warps, ord);
 				else if (T == 32) run_thread_two<32>(P, Q, res.data(), n_warps, ord);
 				else if (T == 16) run_thread_two<16>(P, Q, res.data(), n_warps, ord);
 				else return -2;

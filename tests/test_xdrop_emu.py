@@ -67,7 +67,7 @@ def reads():
 # (2, W) / (3, W) = the packed-word form of the thread path / the same with the longest-first job order;
 # (4, W) / (5, W) = both anti-diagonals of a column in one word / the same with the longest-first job order
 @pytest.mark.parametrize("lanes,cells,xdrop", [(1, 64, 7), (1, 32, 7), (2, 64, 7), (3, 64, 7), (2, 32, 3), (3, 32, 15), (4, 64, 7), (5, 64, 7),
-                                                (4, 32, 3), (5, 32, 15), (32, 1, 7), (32, 2, 15), (32, 4, 30), (16, 1, 3), (16, 2, 7), (16, 4, 15),
+                                                (4, 32, 3), (5, 32, 15), (4, 128, 30), (5, 256, 60), (32, 1, 7), (32, 2, 15), (32, 4, 30), (16, 1, 3), (16, 2, 7), (16, 4, 15),
                                                 (8, 4, 7), (8, 8, 15), (0, 0, 7)])
 def test_device_source_matches_oracle(reads, lanes, cells, xdrop):
     inp, pairs = reads

@@ -20,7 +20,7 @@ def candidate_pairs(inp, limit, seed=0):
 
 
 # ---- f1: the packed-word thread kernels (2, W), (4, W) and the longest-first job order (3, W), (5, W) ------------------
-@pytest.mark.parametrize("lanes,cells,xdrop", [(2, 64, 7), (3, 64, 7), (2, 32, 7), (3, 32, 3), (4, 64, 7), (5, 64, 7), (4, 32, 7), (5, 32, 3)])
+@pytest.mark.parametrize("lanes,cells,xdrop", [(2, 64, 7), (3, 64, 7), (2, 32, 7), (3, 32, 3), (4, 64, 7), (5, 64, 7), (4, 32, 7), (5, 32, 3), (5, 128, 25), (4, 256, 60)])
 def test_xdrop_unmeasured_shapes_match_oracle(lanes, cells, xdrop):
     from bella_b200 import xdrop as xd
     inp = fe.synthetic(400, 3000, seed=101)

@@ -32,7 +32,7 @@ t = time.time()
 want = ol.oracle_align(big, *pairs, 7)
 cpu_s = time.time() - t
 out = []
-plan = ((7, [(1, 64), (1, 32), (32, 1), (16, 2), (8, 4), (32, 2), (16, 4), (8, 8), (2, 64), (3, 64), (4, 64), (5, 64), (5, 32), (3, 32)]), (25, [(32, 2), (16, 4), (8, 8), (32, 4)]))
+plan = ((7, [(1, 64), (1, 32), (32, 1), (16, 2), (8, 4), (32, 2), (16, 4), (8, 8), (2, 64), (3, 64), (4, 64), (5, 64), (5, 32), (3, 32)]), (25, [(32, 2), (16, 4), (8, 8), (32, 4), (5, 128), (5, 256)]))
 if "--quick" in sys.argv:
     plan = ((7, [(1, 64), (1, 32), (32, 2)]),)
 for x, shapes in plan:
