@@ -218,3 +218,33 @@ def test_degenerate_reads_and_extreme_xdrop(xdrop):
         rc_, got, _ = emu_align(inp, *pairs, xdrop, lanes, cells, 0.4, 0.1, -1)
         assert rc_ == 0
         np.testing.assert_array_equal(got, want)
+
+
+def test_device_source_is_clean_under_address_sanitizer(tmp_path):
+    """every execution shape once more with the emulator built with -fsanitize=address: the per-thread windows, the base
+    rings and the wide path's scratch are heap blocks there, so an out-of-bounds slot is reported instead of going unnoticed"""
+    import shutil
+    import sys
+    cxx = shutil.which("g++") or "g++"
+    asan = subprocess.run([cxx, "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    subprocess.run(["make", "-s", "-C", EMU_DIR, "asan"], check=True)
+    code = f"""
+import ctypes, sys
+sys.path[:0] = {[os.path.dirname(EMU_DIR), os.path.dirname(os.path.dirname(EMU_DIR))]!r}
+import numpy as np
+import test_xdrop_emu as E, oracle_lib as ol
+from bella_b200 import frontend as fe
+E._emu = ctypes.CDLL({os.path.join(EMU_DIR, "_build", "libxdrop_emu_asan.so")!r})
+inp = fe.synthetic(80, 1000, coverage=12.0, seed=31)
+pairs = E.candidate_pairs(inp, 120, seed=3)
+for G, T, x in [(1, 64, 7), (1, 16, 7), (2, 64, 7), (2, 16, 7), (4, 64, 7), (4, 16, 7), (5, 128, 30), (32, 1, 7), (32, 4, 30), (16, 2, 7), (8, 4, 7),
+                (16, 1, 3), (0, 0, 7)]:
+    rc, got, _ = E.emu_align(inp, *pairs, x, G, T, 0.55, 0.1, -1, warps=2)
+    assert rc == 0 and np.array_equal(got, ol.oracle_align_post(inp, *pairs, x, 0.55, 0.1, -1)), (G, T, x)
+print("clean")
+"""
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0 and "clean" in out.stdout, (out.stdout[-500:], out.stderr[-3000:])
