@@ -64,7 +64,22 @@ def test_kmers_device_feeds_the_matrix_construction_and_the_spgemm():
     assert t["n_kmers"] == inp.n_kmers
     want = ol.oracle_spgemm(inp, want_aux=False)
     g = spgemm.OverlapSpGEMM(0)
-    g.set_inputs_tuples(inp.n_kmers, inp.n_reads, t["t_kmer"], t["t_read"], t["t_pos"], t["t_strand"], inp.read_len, inp.kmer_size, inp.bin_size)
+    strand = np.concatenate([t["t_strand"], np.zeros(8, np.uint8)])
+    g.set_inputs_tuples(inp.n_kmers, inp.n_reads, t["t_kmer"], t["t_read"], t["t_pos"], strand, inp.read_len, inp.kmer_size, inp.bin_size)
     flops, flopC, colptrC = g.symbolic()
     np.testing.assert_array_equal(colptrC, want.colptrC)        # the pattern of C does not depend on the k-mer ids
     g.close()
+
+
+# ---- the whole chain: reads -> k-mers (f3) -> matrices (f2) -> SpGEMM -> alignment (f1) -> lines (f4) -------------------
+def test_reads_to_overlaps_equals_the_oracle_chain():
+    import pipeline_util as pu
+    from bella_b200 import pipeline
+    seqs, offs = fe.simulate_reads(400000, 800, 5000, 0.15, (0.10, 0.60, 0.30), 21)
+    want = pu.oracle_chain(seqs, offs, ratiophi=0.55)
+    got = pipeline.overlap_reads(seqs, offs, ratiophi=0.55)
+    np.testing.assert_array_equal(got["colptrC"], want["C"].colptrC)
+    for name, ref in (("rows", want["C"].rowids), ("count", want["C"].count), ("posH", want["C"].posH), ("posV", want["C"].posV)):
+        np.testing.assert_array_equal(got[name], ref, err_msg=name)
+    np.testing.assert_array_equal(got["out8"], want["out8"])
+    assert got["lines"] == want["lines"] and len(got["lines"]) > 1000
