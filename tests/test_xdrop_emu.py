@@ -248,3 +248,32 @@ print("clean")
     env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0 and "clean" in out.stdout, (out.stdout[-500:], out.stderr[-3000:])
+
+
+def test_maximum_read_length_and_scores_beyond_16_bits():
+    """two 65 535-base reads (BELLA's position type is unsigned short) overlapping end to end at 3 % error: coordinates up to
+    the u16 limit and a score near 60 000 -- beyond what the reference's CUDA port keeps in `short` -- through every
+    thread-kernel encoding (plain ints, score << 6 | bases, scores relative to the drop-off limit)"""
+    rng = np.random.default_rng(11)
+    base = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 65535)
+    other = base.copy()
+    idx = rng.choice(len(other), len(other) * 3 // 100, replace=False)
+    other[idx] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), len(idx))         # substitutions only: same length
+    # a clean seed in the middle and one at each end
+    for p in (0, 30000, 65535 - 17):
+        other[p:p + 17] = base[p:p + 17]
+    seqs = np.concatenate([base, other])
+    off = np.array([0, 65535, 131070], dtype=np.uint64)
+    inp = fe.OverlapInputs(n_reads=2, n_kmers=0, nnz=0, A_colptr=None, A_rowids=None, A_values=None, A_strand=None, B_colptr=None,
+                           B_rowids=None, B_values=None, B_strand=None, read_len=np.array([65535, 65535], dtype=np.uint32), kmer_size=17,
+                           seqs=seqs, seq_off=off)
+    rows = np.array([1, 1, 1], dtype=np.uint32); cols = np.array([0, 0, 0], dtype=np.uint32)
+    pos = np.array([0, 30000, 65535 - 17], dtype=np.uint16)
+    want = ol.oracle_align_post(inp, rows, cols, pos, pos, 50, 0.5, 0.1, -1)
+    assert want[:, 0].min() > 40000 and (want[:, 3] == 65535).all() and (want[:, 2] == 0).all()
+    if ol.have_ref():
+        np.testing.assert_array_equal(want[:, :6], ol.ref_align(inp, rows, cols, pos, pos, 50))
+    for lanes, cells in ((1, 64), (2, 64), (4, 64), (5, 128), (32, 4), (0, 0)):
+        rc, got, _ = emu_align(inp, rows, cols, pos, pos, 50, lanes, cells, 0.5, 0.1, -1, warps=1)
+        assert rc == 0
+        np.testing.assert_array_equal(got, want)

@@ -100,6 +100,28 @@ def test_bases_are_dna5_as_seqan_sees_them(reads):
         a.close()
 
 
+def test_maximum_read_length_and_scores_beyond_16_bits():
+    """two 65 535-base reads overlapping end to end at 3 % error: coordinates up to the u16 limit, scores near 60 000"""
+    rng = np.random.default_rng(11)
+    base = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 65535)
+    other = base.copy()
+    idx = rng.choice(len(other), len(other) * 3 // 100, replace=False)
+    other[idx] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), len(idx))
+    for p in (0, 30000, 65535 - 17):
+        other[p:p + 17] = base[p:p + 17]
+    inp = fe.OverlapInputs(n_reads=2, n_kmers=0, nnz=0, A_colptr=None, A_rowids=None, A_values=None, A_strand=None, B_colptr=None,
+                           B_rowids=None, B_values=None, B_strand=None, read_len=np.array([65535, 65535], dtype=np.uint32), kmer_size=17,
+                           seqs=np.concatenate([base, other]), seq_off=np.array([0, 65535, 131070], dtype=np.uint64))
+    rows = np.array([1, 1, 1], dtype=np.uint32); cols = np.array([0, 0, 0], dtype=np.uint32)
+    pos = np.array([0, 30000, 65535 - 17], dtype=np.uint16)
+    want = ol.oracle_align_post(inp, rows, cols, pos, pos, 50, 0.5, 0.1, -1)
+    assert want[:, 0].min() > 40000
+    for shape in ((-1, -1), (1, 64), (32, 4), (0, 0)):
+        a = aligner(inp, 50, shape, ratiophi=0.5)
+        np.testing.assert_array_equal(a.align(rows, cols, pos, pos), want)
+        a.close()
+
+
 def test_reference_golden_fixture():
     z = np.load(os.path.join(golden_util.GOLDEN, "xdrop.npz"))
     inp = fe.OverlapInputs(n_reads=int(z["n_reads"]), n_kmers=0, nnz=0, A_colptr=None, A_rowids=None, A_values=None, A_strand=None,
