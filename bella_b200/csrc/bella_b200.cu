@@ -931,6 +931,15 @@ int bella_b200_get_B(bella_b200_handle* h, uint32_t* nnz, uint32_t* colptr_host,
 	return BELLA_B200_OK;
 }
 
+#ifdef BELLA_PHASE_CLOCKS
+int bella_b200_debug_phases(unsigned long long* out32, int reset)
+{
+	if (out32) cudaMemcpyFromSymbol(out32, bk::g_phase, sizeof(unsigned long long) * 32);
+	if (reset) { unsigned long long z[32] = {}; cudaMemcpyToSymbol(bk::g_phase, z, sizeof z); }
+	return 0;
+}
+#endif
+
 /* route mode (bella_b200/distributed.py, mode "route"): k-mer-partitioned records instead of an all-gather of B */
 int bella_b200_mg_route(bella_b200_handle* h, uint32_t n_local, uint32_t read_base, const uint32_t* colptr_local_dev, const uint32_t* rowids_dev,
 		const uint16_t* values_dev, uint32_t kmers_per_rank, int world, uint32_t* send_dev, uint64_t* send_counts_host)

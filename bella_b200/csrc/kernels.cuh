@@ -84,6 +84,17 @@ struct Meta {
 	unsigned int n_refine;
 };
 
+// -DBELLA_PHASE_CLOCKS: per-phase SM cycles of the group + fold and bucket kernels, summed over CTAs (thread 0's clock
+// between barriers); read back through bella_b200_debug_phases.  Profiling builds only.
+#ifdef BELLA_PHASE_CLOCKS
+__device__ unsigned long long g_phase[32];
+#define PHASE_BEGIN() long long ph_t0_ = clock64()
+#define PHASE(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_phase[i], (unsigned long long)(t_ - ph_t0_)); ph_t0_ = t_; } } while (0)
+#else
+#define PHASE_BEGIN() do {} while (0)
+#define PHASE(i) do {} while (0)
+#endif
+
 __device__ __forceinline__ void set_err(int* err, int code) { atomicCAS(err, 0, code); }
 __device__ __forceinline__ uint32_t getbit(const uint8_t* __restrict__ bits, uint64_t i) { return (bits[i >> 3] >> (i & 7)) & 1u; }
 __device__ __forceinline__ uint32_t ent_row(uint64_t e) { return (uint32_t)e & 0x7FFFFFFFu; }
@@ -228,6 +239,7 @@ __global__ void __launch_bounds__(256) k_bucket(uint32_t klo, uint32_t m, uint32
 		const uint32_t o0 = boff[b], size = boff[b + 1] - o0;
 		const uint32_t kbase = b * W, kw = min(W, m - kbase);      // k-mer ids are klo + kbase + k; A's colptr is local to [klo, klo + m)
 		const uint4* src = part + (size_t)b * BUCKET_CAP;
+		PHASE_BEGIN();
 		for (uint32_t k = tid; k <= kw; k += nt) off[k] = 0;
 		__syncthreads();
 		for (uint32_t x = tid; x < size; x += nt) {
@@ -238,7 +250,9 @@ __global__ void __launch_bounds__(256) k_bucket(uint32_t klo, uint32_t m, uint32
 			E[x] = (uint64_t)r.z | ((uint64_t)r.w << 32);
 		}
 		__syncthreads();
+		PHASE(16);
 		block_excl_scan<uint32_t>(off, kw, s_tmp);
+		PHASE(17);
 		// permute in place through registers: every thread first reads its elements, then all write
 		uint64_t ev[BUCKET_CAP / 256];
 #pragma unroll
@@ -250,6 +264,7 @@ __global__ void __launch_bounds__(256) k_bucket(uint32_t klo, uint32_t m, uint32
 			if (x < size) { uint32_t t = tmp[x]; E[off[t & 0xFFFu] + (t >> 12)] = ev[q]; }
 		}
 		__syncthreads();
+		PHASE(18);
 		for (uint32_t k = tid; k < kw; k += nt) {
 			const uint32_t s = off[k], e = off[k + 1];
 			Acolptr[kbase + k] = o0 + s;
@@ -266,8 +281,10 @@ __global__ void __launch_bounds__(256) k_bucket(uint32_t klo, uint32_t m, uint32
 		}
 		if (b == nb - 1 && tid == 0) Acolptr[m] = o0 + size;
 		__syncthreads();
+		PHASE(19);
 		for (uint32_t x = tid; x < size; x += nt) Aent[o0 + x] = E[x];
 		__syncthreads();
+		PHASE(20);
 	}
 }
 
@@ -846,6 +863,7 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 
 	#pragma unroll 1
 	for (uint32_t it = blockIdx.x; it < count; it += gridDim.x) {
+		PHASE_BEGIN();
 		const uint32_t u = list[it];
 		const uint32_t li = P.ucol[u], i = P.lo + li;
 		const uint64_t base = P.uptr[u];
@@ -876,9 +894,11 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 		#pragma unroll 1
 		for (uint32_t s = tid; s < ((Fi + 3) >> 1); s += NT) ((uint32_t*)cnt)[s] = 0;
 		if (tid == 0) { s_nlong = 0; s_nhuge = 0; s_next = 0; s_wide = 0; }
+		PHASE(15);
 		mbar_wait(&s_bar, phase);
 		phase ^= 1;
 		__syncthreads();                                           // tables cleared by all threads before anyone sets a bit
+		PHASE(0);
 
 		// --- distinct rows (== estimateNNZ_Hash) and the pair index, rows ascending ---
 		uint32_t nwords = words;
@@ -901,7 +921,9 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 			atomicOr(&bits[word_of(rel)], 1u << (rel & 31));
 		}
 		__syncthreads();
+		PHASE(1);
 		const uint32_t Z = block_scan_chunked<uint16_t>(pre, nwords, [&](uint32_t w) { return (uint32_t)__popc(bits[w]); }, s_tmp);
+		PHASE(2);
 		#pragma unroll 1
 		for (uint32_t x = tid; x < Fi; x += NT) {
 			const uint64_t r = prodS[x];
@@ -913,14 +935,17 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 			prodS[x] = ((r >> 32) & 0xFFFFFFFFull) | ((uint64_t)((uint32_t)r >> 31) << 32) | ((uint64_t)p << 34) | ((uint64_t)a << 48);
 		}
 		__syncthreads();
+		PHASE(3);
 		block_scan_chunked<uint16_t>(cnt, Z, [&](uint32_t p) { return (uint32_t)cnt[p]; }, s_tmp);     // counts -> offsets, poff[Z] = Fi
 		const uint16_t* poff = cnt;
+		PHASE(4);
 		#pragma unroll 1
 		for (uint32_t x = tid; x < Fi; x += NT) {
 			const uint64_t t = prodS[x];
 			sorted[poff[(uint32_t)(t >> 34) & 0x3FFFu] + ((uint32_t)(t >> 48) & 0x3FFFu)] = t & 0x1FFFFFFFFull;
 		}
 		__syncthreads();
+		PHASE(5);
 
 		// --- fold.  Queue: first the pairs longer than SHORT_FOLD (one warp each), then tiles of 32 pairs whose
 		//     short members are multiplied, ordered (position in B's column) and folded by one thread each ---
@@ -932,6 +957,7 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 			if ((uint32_t)(poff[p + 1] - poff[p]) > SHORT_FOLD) longlist[atomicAdd(&s_nlong, 1u)] = (uint16_t)p;
 		__syncthreads();
 		const uint32_t nlong = s_nlong, nitems = nlong + ((Z + 31) >> 5);
+		PHASE(6);
 		const uint32_t Lcol = P.B_colptr[i + 1] - j0;
 		uint32_t* scr = wscr + wid * WSCR_WORDS;
 		bool wide = false;
@@ -940,6 +966,9 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 			if (lane == 0) q = atomicAdd(&s_next, 1u);
 			q = __shfl_sync(FULL, q, 0);
 			if (q >= nitems) break;
+#if BELLA_PHASE_CLOCKS > 1
+			const long long wq0_ = clock64();
+#endif
 			if (q < nlong) {
 				const uint32_t p = longlist[q], s0 = poff[p], len = poff[p + 1] - s0;
 				if (len > 1024) { if (lane == 0) hugelist[atomicAdd(&s_nhuge, 1u)] = (uint16_t)p; continue; }
@@ -947,6 +976,9 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 				wide |= warp_prepare_pair(P, sorted + s0, hvL + s0, ovL + s0, len, j0, Lcol, (int)P.read_len[row], lenV, scr, lane);
 				PairResult R = warp_fold_pair<EXACT>(hvL + s0, ovL + s0, sorted + s0, len, K, BIN, lane);
 				if (lane == 0) out[p] = pack_result(row, R);
+#if BELLA_PHASE_CLOCKS > 1
+				if (lane == 0) { atomicAdd(&g_phase[9], (unsigned long long)(clock64() - wq0_)); atomicAdd(&g_phase[11], (unsigned long long)len); atomicAdd(&g_phase[13], 1ull); }
+#endif
 			} else {
 				const uint32_t p = ((q - nlong) << 5) + lane;
 				if (p >= Z) continue;
@@ -965,10 +997,15 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 #pragma unroll
 				for (int k = 0; k < (int)SHORT_FOLD; ++k) { hv[k] = (uint32_t)key[k]; ov[k] = (uint16_t)(key[k] >> 32); }
 				out[p] = pack_result(row, fold_short<EXACT>(hv, ov, len, K, BIN));
+#if BELLA_PHASE_CLOCKS > 1
+				atomicAdd(&g_phase[12], (unsigned long long)len); atomicAdd(&g_phase[14], 1ull);
+				if (lane == (uint32_t)__ffs(__activemask()) - 1u) atomicAdd(&g_phase[10], (unsigned long long)(clock64() - wq0_));
+#endif
 			}
 		}
 		if (!EXACT && (wide || K > 16383u)) s_wide = 1;
 		__syncthreads();
+		PHASE(7);
 		const uint32_t nhuge = s_nhuge;                             // at most CAP/1024 pairs: the whole CTA takes each
 		#pragma unroll 1
 		for (uint32_t q = 0; q < nhuge; ++q) {
@@ -999,6 +1036,7 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 			if (!EXACT && s_wide) redo[atomicAdd(redo_count, 1u)] = u;
 		}
 		__syncthreads();
+		PHASE(8);
 	}
 }
 

@@ -139,21 +139,65 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(inp, ncols, nthreads=0):
-    """One run of the CPU reference arm on output columns [0, ncols). -> (Z_sample, seconds, kind, cores)"""
+def host_threads():
+    """All the host threads the CPU arm may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, so the count is
+    passed explicitly (oracle/ref_driver.cpp honours it) instead of being left to the OpenMP default."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_reference_run(inp, ncols, nthreads=None, want_result=False):
+    """One run of the CPU reference arm on output columns [0, ncols). -> (Z_sample, seconds, kind, cores[, Result])"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
+    nthreads = nthreads or host_threads()
     if ol.have_ref() and inp.seqs is not None:
         r = ol.ref_spgemm(inp, ncols=ncols, nthreads=nthreads, want_aux=False)
-        return r.nnz, float(sum(r.times)), "reference", ol.ref().bella_ref_max_threads()
-    r = ol.oracle_spgemm(inp, ncols=ncols, nthreads=nthreads, want_aux=False)
-    return r.nnz, float(sum(r.times)), "port", ol.oracle().oracle_max_threads()
+        out = (r.nnz, float(sum(r.times)), "reference", nthreads)
+    else:
+        r = ol.oracle_spgemm(inp, ncols=ncols, nthreads=nthreads, want_aux=False)
+        out = (r.nnz, float(sum(r.times)), "port", nthreads)
+    return out + (r,) if want_result else out
+
+
+def check_parity(colptrC, res, ref, ncols):
+    """The GPU tuples (col,row,count,posH,posV) of output columns [0, ncols) against the CPU reference run of the same
+    process ('CPU and GPU measured back-to-back ... tuples compared ... must be bit-identical').
+    Both sides keep the rows of a column ascending.  -> description; raises SystemExit on any difference."""
+    rows, cnt, pH, pV = res
+    if not np.array_equal(np.asarray(colptrC[:ncols + 1], dtype=np.uint32), ref.colptrC[:ncols + 1]):
+        raise SystemExit("bench.py: PARITY FAILURE: colptrC of the GPU differs from the CPU reference")
+    z = int(ref.colptrC[ncols])
+    for name, a, b in (("rowids", rows, ref.rowids), ("count", cnt, ref.count), ("posH", pH, ref.posH), ("posV", pV, ref.posV)):
+        if not np.array_equal(np.asarray(a[:z]), b[:z]):
+            bad = int(np.flatnonzero(np.asarray(a[:z]) != b[:z])[0])
+            raise SystemExit(f"bench.py: PARITY FAILURE: {name}[{bad}] of the GPU differs from the CPU reference")
+    return z
+
+
+def tuple_checksum(col_lo, colptrC, res):
+    """Order-independent 64-bit checksum of the tuples (col,row,count,posH,posV) of a column range: the sum modulo 2^64 of a
+    mixed 64-bit word per tuple, so that the per-rank checksums of a sharded run add up to the single-GPU one."""
+    rows, cnt, pH, pV = (np.asarray(a) for a in res)
+    cp = np.asarray(colptrC, dtype=np.int64)
+    z = int(cp[-1] - cp[0])
+    cols = np.repeat(np.arange(col_lo, col_lo + len(cp) - 1, dtype=np.uint64), np.diff(cp))
+    with np.errstate(over="ignore"):
+        w = (cols << np.uint64(32)) | rows[:z].astype(np.uint64)
+        v = (cnt[:z].astype(np.uint64) << np.uint64(32)) | (pH[:z].astype(np.uint64) << np.uint64(16)) | pV[:z].astype(np.uint64)
+        x = (w * np.uint64(0x9E3779B97F4A7C15)) ^ (v * np.uint64(0xC2B2AE3D27D4EB4F))
+        x ^= x >> np.uint64(29)
+        x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(32)
+        return int(x.sum(dtype=np.uint64)), z
 
 
 def pick_sample_cols(inp, budget_s):
     """Column-prefix sample sized to ~budget_s seconds of CPU work (calibrated on a small prefix)."""
     c0 = min(inp.n_reads, 1500)
-    z, t, _, _ = cpu_reference_run(inp, c0)
+    z, t, _, _ = cpu_reference_run(inp, c0)[:4]
     if c0 == inp.n_reads:
         return c0
     c = int(c0 * budget_s / max(t, 1e-3))
@@ -315,18 +359,27 @@ def run_b200_arm(args, w):
     roof["frac"] = roof["achieved"] / peak
 
     # ---- CPU baseline beside it (bounded sample) ----
-    cpu = None
+    cpu, parity = None, None
     if not args.no_cpu:
         ncols = pick_sample_cols(inp, 15.0)
-        zc, tc, kind, cores = cpu_reference_run(inp, ncols)
+        zc, tc, kind, cores, ref = cpu_reference_run(inp, ncols, want_result=True)
         cpu = {"value": zc / tc, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"output columns [0,{ncols}) of {inp.n_reads}: {zc} output nnz in {tc:.2f}s (estimateFLOP+estimateNNZ_Hash+LocalSpGEMM)"}
+        # the tuples the timed e2e step returned against the CPU run of this same process (aborts on any difference)
+        zchk = check_parity(colptrC, res, ref, ncols)
+        parity = (f"bit-exact, {zchk} tuples (col,row,count,posH,posV) of output columns [0,{ncols}) of {inp.n_reads} "
+                  f"against the {kind} CPU run of this process")
+        log("[bench] parity: " + parity)
+    csum, _ = tuple_checksum(0, colptrC, res)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u16/u32",
             "data": "synthetic",
-            "config": {"workload": workload_name(w), "n_kmers": inp.n_kmers, "nnz_A": inp.nnz, "products": int(flops),
-                       "output_nnz": int(Z), "l2": "inputs (%.0f MB) larger than L2, no flush" % (in_bytes / 1e6)},
+            "config": {"workload": workload_name(w)},
+            "workload_stats": {"n_kmers": inp.n_kmers, "nnz_A": inp.nnz, "products": int(flops), "output_nnz": int(Z),
+                               "l2": "inputs (%.0f MB) larger than L2, no flush" % (in_bytes / 1e6),
+                               "step": "device Transpose() of B + symbolic + numeric (the reference arm times symbolic + numeric only)"},
+            "parity": parity, "checksum": f"{csum:016x}",
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     g.close()

@@ -73,8 +73,6 @@ def test_reference_arm_writes_what_the_oracle_computes(case, tmp_path, paf):
 
 @needs_lib
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU time was spent: never run on a B200 yet (the aligner behind it is "
-                                        "validated by test_xdrop_gpu.py); an XPASS in the log means it works")
 @pytest.mark.parametrize("paf,fixed", [(0, -1), (1, -1), (0, 400)])
 def test_b200_binding_writes_the_reference_output_file(case, tmp_path, paf, fixed):
     inp, c = case
