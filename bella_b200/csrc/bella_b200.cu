@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -48,7 +49,7 @@ struct DevBuf {
 } // namespace
 
 struct bella_b200_handle {
-	int device = 0;
+	int device = 0, sms = 148;
 	cudaStream_t stream = nullptr;
 	bool own_stream = true;
 	std::string err;
@@ -56,6 +57,7 @@ struct bella_b200_handle {
 	uint32_t n = 0, m = 0, lo = 0, hi = 0;
 	uint64_t nnzB = 0;
 	uint16_t K = 17, BIN = 500;
+	uint32_t ep_max = 16;                      // tuning knob (BELLA_B200_EP_MAX), see Params::ep_max
 	bool have_inputs = false, symbolic_done = false, numeric_done = false;
 	// input device pointers (borrowed or pointing into the owned buffers below)
 	const uint32_t *dB_colptr = nullptr, *dB_rowids = nullptr, *d_len = nullptr;
@@ -80,13 +82,15 @@ struct bella_b200_handle {
 	// matrix construction from tuples (bella_b200_set_inputs_tuples)
 	DevBuf tp_kmer, tp_read, tp_pos, tp_strand, tp_rs, tp_re, tp_nruns, tp_cnt, tp_cp, tp_merged, tp_tmpK, tp_tmpV, tp_slab;
 	float t_build_ms = 0;
-	DevBuf boff, bcur, part, Aent, Acolptr, flop32;
+	DevBuf boff, bcur, bsize, part, partK, Aent, Ainfo, Acolptr, flop32;
+	DevBuf rp_cur, rp_tiles, rp_E, rp_K;       // level 1 of the two-level partition: cursors, tile starts, coarse buckets
+	double cap_scale = 1.25;                   // head room of the coarse buckets over the average
 	// plan
 	uint32_t ucap = 0, U = 0, round = 0;
-	DevBuf nunits, ubase, shv, refine, colinfo, ucol, ucount, uptr, ucur, lists, redo, unnz, uoff;
+	DevBuf nunits, ubase, shv, refine, colinfo, ucol, ucount, uptr, ucur, ccur, lists, redo, unnz, uoff;
 	// products and results
 	DevBuf raw, out, colptrC, rowsC, countC, posH, posV, aux;
-	DevBuf meta, errflag, cubtmp;
+	DevBuf meta, errflag, cubtmp, unpinned;
 	Meta hmeta{};
 	uint64_t flops = 0, Z = 0;
 	cudaEvent_t ev[12]{};
@@ -159,48 +163,96 @@ int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32
 	const uint32_t ncols = cnt_hi - cnt_lo;
 	ENSURE(h->Acolptr, sizeof(uint32_t) * ((size_t)ml + 2));
 	ENSURE(h->Aent, sizeof(uint64_t) * (nnz + 2));
+	ENSURE(h->Ainfo, nnz + 16);
 	CK(cudaMemsetAsync(flop_out, 0, sizeof(uint32_t) * (size_t)ncols, h->stream));
 	if (!nnz || !ml || !ncols) {
 		CK(cudaMemsetAsync(h->Acolptr.p, 0, sizeof(uint32_t) * ((size_t)ml + 2), h->stream));
+		ENSURE(h->boff, sizeof(uint32_t) * 2);
+		CK(cudaMemsetAsync(h->boff.p, 0, sizeof(uint32_t) * 2, h->stream));   // boff[NB] is the number of entries of A: none
+		h->NB = 0;
 		return 0;
 	}
 	if (!h->W) {
+		// buckets of 2^wshift k-mers, about 0.7 * BUCKET_CAP entries each on average
 		double avg = rec ? (double)nnz / (double)ml : (double)nnz / (double)h->m;
-		double w = 0.6 * BUCKET_CAP / (avg > 0.25 ? avg : 0.25);
-		h->W = (uint32_t)(w < 1 ? 1 : w > BUCKET_WMAX ? BUCKET_WMAX : w);
+		double w = 0.7 * BUCKET_CAP / (avg > 0.25 ? avg : 0.25);
+		uint32_t W = 1;
+		while (W * 2 <= BUCKET_WMAX && (double)(W * 2) <= w) W *= 2;
+		h->W = W;
 	}
 	const uint32_t W = h->W;
+	uint32_t wshift = 0;
+	while ((1u << wshift) < W) ++wshift;
 	const uint32_t NB = (uint32_t)(((uint64_t)ml + W - 1) / W);
 	h->NB = NB;
-	ENSURE(h->bcur, sizeof(uint32_t) * ((size_t)NB + 2));
+	ENSURE(h->bcur, sizeof(uint32_t) * ((size_t)NB + 2) * BCNT_STRIDE);
+	ENSURE(h->bsize, sizeof(uint32_t) * ((size_t)NB + 2));
 	ENSURE(h->boff, sizeof(uint32_t) * ((size_t)NB + 2));
-	ENSURE(h->part, sizeof(uint4) * (size_t)NB * BUCKET_CAP);
-	CK(cudaMemsetAsync(h->bcur.p, 0, sizeof(uint32_t) * ((size_t)NB + 2), h->stream));
-	CK(cudaEventRecord(h->ev[8], h->stream));
+	ENSURE(h->part, sizeof(uint64_t) * (size_t)NB * BUCKET_CAP + 64);
+	ENSURE(h->partK, sizeof(uint16_t) * (size_t)NB * BUCKET_CAP + 64);
+	CK(cudaMemsetAsync(h->bcur.p, 0, sizeof(uint32_t) * ((size_t)NB + 2) * BCNT_STRIDE, h->stream));
+	uint32_t* bcnt = h->bcur.as<uint32_t>();
+	uint64_t* partE = h->part.as<uint64_t>();
+	uint16_t* partK = h->partK.as<uint16_t>();
 	if (rec) {
-		k_partition_rec<<<grid_for(nrec, 256), 256, 0, h->stream>>>(nrec, rec, h->klo, h->khi, W, h->bcur.as<uint32_t>(), h->part.as<uint4>(),
-			h->errflag.as<int>());
+		CK(cudaEventRecord(h->ev[8], h->stream));
+		k_partition_rec<<<grid_for(nrec, 256), 256, 0, h->stream>>>(nrec, rec, h->klo, h->khi, wshift, bcnt, partE, partK, h->errflag.as<int>());
 		LAUNCHED();
-	} else if (h->n_chunks > 0) {
-		// host inputs are still arriving chunk by chunk: partition each range of reads as soon as it is on the device
-		for (int c = 0; c < h->n_chunks; ++c) {
-			const uint32_t c0 = h->chunk_lo[c] > row_lo ? h->chunk_lo[c] : row_lo, c1 = h->chunk_lo[c + 1];
-			CK(cudaStreamWaitEvent(h->stream, h->chunk_ev[c], 0));
-			if (c0 >= c1) continue;
-			k_partition<<<grid_for((uint64_t)(c1 - c0) * 32, 256), 256, 0, h->stream>>>(c1, c0, h->klo, h->khi, h->dB_colptr, h->dB_rowids,
-				h->dB_values, h->dB_strand, W, h->bcur.as<uint32_t>(), h->part.as<uint4>(), h->errflag.as<int>());
+	} else {
+		// two levels: the fine-bucket bits are split between a coarse level (nb1 buckets of 2^shift1 k-mers) and the fine
+		// buckets inside one coarse bucket, at most RP_NBMAX each
+		uint32_t bits = 0;
+		while ((1ull << bits) < NB) ++bits;
+		uint32_t l2 = bits / 2, l1 = bits - l2;
+		if (l1 > 10) { l1 = 10; l2 = bits - l1; }
+		if (l2 > 10) return fail(h, BELLA_B200_ERR_RANGE, "%u transpose buckets are more than the two-level partition addresses", NB);
+		const uint32_t shift1 = wshift + l2;
+		const uint32_t nb1 = (uint32_t)(((uint64_t)ml + (1ull << shift1) - 1) >> shift1);
+		const double share = (double)ml / (double)(h->m ? h->m : 1);           // multi-GPU: only the k-mers [klo, khi) are this handle's
+		const uint64_t cap64 = (uint64_t)((double)nnz * share / nb1 * h->cap_scale) + 2 * RP_TILE;
+		if (cap64 > 0x7FFFFFFFull) return fail(h, BELLA_B200_ERR_RANGE, "coarse transpose bucket too large");
+		const uint32_t cap1 = (uint32_t)((cap64 + 15) & ~15ull);
+		ENSURE(h->rp_cur, sizeof(uint32_t) * ((size_t)nb1 + 2) * BCNT_STRIDE);
+		ENSURE(h->rp_tiles, sizeof(uint32_t) * ((size_t)nb1 + 2));
+		ENSURE(h->rp_E, sizeof(uint64_t) * (size_t)nb1 * cap1 + 64);
+		ENSURE(h->rp_K, sizeof(uint32_t) * (size_t)nb1 * cap1 + 64);
+		CK(cudaMemsetAsync(h->rp_cur.p, 0, sizeof(uint32_t) * ((size_t)nb1 + 2) * BCNT_STRIDE, h->stream));
+		CK(cudaFuncSetAttribute(k_rp1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RP_SMEM));
+		CK(cudaFuncSetAttribute(k_rp2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RP_SMEM));
+		CK(cudaEventRecord(h->ev[8], h->stream));
+		const uint32_t warps_per_cta = RP_THREADS / 32;
+		auto rp1 = [&](uint32_t r0, uint32_t r1) {
+			uint32_t g = (r1 - r0 + warps_per_cta - 1) / warps_per_cta;
+			if (g > (uint32_t)h->sms * 2) g = (uint32_t)h->sms * 2;
+			k_rp1<<<g, RP_THREADS, RP_SMEM, h->stream>>>(r1, r0, h->klo, h->khi, h->dB_colptr, h->dB_rowids, h->dB_values, h->dB_strand,
+				shift1, nb1, cap1, h->rp_cur.as<uint32_t>(), h->rp_E.as<uint64_t>(), h->rp_K.as<uint32_t>(), h->errflag.as<int>());
+		};
+		if (h->n_chunks > 0) {
+			// host inputs are still arriving chunk by chunk: partition each range of reads as soon as it is on the device
+			for (int c = 0; c < h->n_chunks; ++c) {
+				const uint32_t c0 = h->chunk_lo[c] > row_lo ? h->chunk_lo[c] : row_lo, c1 = h->chunk_lo[c + 1];
+				CK(cudaStreamWaitEvent(h->stream, h->chunk_ev[c], 0));
+				if (c0 >= c1) continue;
+				rp1(c0, c1);
+				LAUNCHED();
+			}
+		} else if (n > row_lo) {
+			rp1(row_lo, n);
 			LAUNCHED();
 		}
-	} else {
-		k_partition<<<grid_for((uint64_t)(n - row_lo) * 32, 256), 256, 0, h->stream>>>(n, row_lo, h->klo, h->khi, h->dB_colptr, h->dB_rowids,
-			h->dB_values, h->dB_strand, W, h->bcur.as<uint32_t>(), h->part.as<uint4>(), h->errflag.as<int>());
+		k_rp_tiles<<<1, 1024, 0, h->stream>>>(nb1, cap1, h->rp_cur.as<uint32_t>(), h->rp_tiles.as<uint32_t>());
+		LAUNCHED();
+		k_rp2<<<h->sms * 2, RP_THREADS, RP_SMEM, h->stream>>>(shift1, wshift, nb1, cap1, h->rp_cur.as<uint32_t>(), h->rp_tiles.as<uint32_t>(),
+			h->rp_E.as<uint64_t>(), h->rp_K.as<uint32_t>(), bcnt, partE, partK, h->errflag.as<int>());
 		LAUNCHED();
 	}
 	CK(cudaEventRecord(h->ev[9], h->stream));
-	if (int rc = exclusive_scan(h, h->bcur.as<uint32_t>(), h->boff.as<uint32_t>(), NB + 1)) return rc;
+	k_bucket_sizes<<<grid_for(NB + 1, 256), 256, 0, h->stream>>>(NB, bcnt, h->bsize.as<uint32_t>());
+	LAUNCHED();
+	if (int rc = exclusive_scan(h, h->bsize.as<uint32_t>(), h->boff.as<uint32_t>(), NB + 1)) return rc;
 	CK(cudaFuncSetAttribute(k_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BUCKET_SMEM));
-	k_bucket<<<NB < 148u * 12 ? NB : 148u * 12, 256, BUCKET_SMEM, h->stream>>>(h->klo, ml, cnt_lo, cnt_hi, W, NB, h->boff.as<uint32_t>(),
-		h->part.as<uint4>(), h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), flop_out, h->errflag.as<int>());
+	k_bucket<<<NB < 148u * 16 ? NB : 148u * 16, 256, BUCKET_SMEM, h->stream>>>(h->klo, ml, cnt_lo, cnt_hi, wshift, NB, h->boff.as<uint32_t>(),
+		partE, partK, h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), h->Ainfo.as<uint8_t>(), flop_out, h->errflag.as<int>());
 	LAUNCHED();
 	return 0;
 }
@@ -220,6 +272,7 @@ int run_plan(bella_b200_handle* h)
 	ENSURE(h->ucount, sizeof(uint32_t) * ((size_t)ucap + 2));
 	ENSURE(h->uptr, sizeof(uint64_t) * ((size_t)ucap + 2));
 	ENSURE(h->ucur, sizeof(uint64_t) * ((size_t)ucap + 2));
+	ENSURE(h->ccur, sizeof(uint64_t) * ((size_t)ncols + 1) * CCUR_STRIDE);
 	ENSURE(h->unnz, sizeof(uint32_t) * ((size_t)ucap + 2));
 	ENSURE(h->uoff, sizeof(uint32_t) * ((size_t)ucap + 2));
 	ENSURE(h->lists, sizeof(uint32_t) * (size_t)(NCLASS + 1) * ((size_t)ucap + 1));
@@ -249,7 +302,7 @@ int run_plan(bella_b200_handle* h)
 		if (int rc = exclusive_scan(h, padded, h->uptr.as<unsigned long long>(), ucap + 1)) return rc;
 	}
 	k_classify_units<<<grid_for(ucap, 256), 256, 0, h->stream>>>(ucap, h->ucol.as<uint32_t>(), h->ucount.as<uint32_t>(), h->colinfo.as<ColInfo>(),
-		h->uptr.as<uint64_t>(), h->ucur.as<unsigned long long>(), h->lists.as<uint32_t>(), h->refine.as<uint8_t>(), h->round,
+		h->uptr.as<uint64_t>(), h->ucur.as<unsigned long long>(), h->ccur.as<unsigned long long>(), h->lists.as<uint32_t>(), h->refine.as<uint8_t>(), h->round,
 		h->meta.as<Meta>(), h->errflag.as<int>());
 	LAUNCHED();
 	return 0;
@@ -259,6 +312,7 @@ Params make_params(bella_b200_handle* h)
 {
 	Params P{};
 	P.n = h->n; P.m = h->m; P.lo = h->lo; P.hi = h->hi; P.K = h->K; P.BIN = h->BIN;
+	P.ep_max = h->ep_max;
 	P.B_colptr = h->dB_colptr; P.B_rowids = h->dB_rowids; P.B_values = h->dB_values; P.B_strand = h->dB_strand; P.read_len = h->d_len;
 	P.A_colptr = h->Acolptr.as<uint32_t>(); P.Aent = h->Aent.as<uint64_t>();
 	P.colinfo = h->colinfo.as<ColInfo>(); P.ucol = h->ucol.as<uint32_t>(); P.ucount = h->ucount.as<uint32_t>();
@@ -312,6 +366,7 @@ int plan_loop(bella_b200_handle* h, bool own_transpose)
 		if (e == ERR_BUCKET && own_transpose) {
 			if (h->W <= 1) return fail(h, BELLA_B200_ERR_RANGE, "a k-mer occurs in more than %u reads", BUCKET_CAP);
 			h->W = h->W / 2;
+			h->cap_scale *= 1.5;
 			need_transpose = true;
 			CK(cudaMemsetAsync(h->errflag.p, 0, sizeof(int), h->stream));
 			continue;
@@ -392,7 +447,8 @@ int run_symbolic(bella_b200_handle* h)
 	Params P = make_params(h);
 	CK(cudaEventRecord(h->ev[2], h->stream));
 	if (h->flops) {
-		k_scatter<<<grid_for(h->m, 256), 256, 0, h->stream>>>(h->m, h->lo, h->hi, P.A_colptr, P.Aent, P.colinfo, P.ucur, P.raw);
+		k_scatter<<<grid_for((h->nnzB + 3) / 4, 256, 148 * 32), 256, 0, h->stream>>>(h->boff.as<uint32_t>() + h->NB, h->m, h->lo, h->hi, P.A_colptr, P.Aent, h->Ainfo.as<uint8_t>(),
+			h->ccur.as<unsigned long long>(), P.colinfo, P.ucur, P.raw);
 		LAUNCHED();
 	}
 	if (int rc = group_and_output(h)) return rc;
@@ -414,9 +470,12 @@ int run_numeric(bella_b200_handle* h)
 	ENSURE(h->posH, sizeof(uint16_t) * (Z + 1));
 	ENSURE(h->posV, sizeof(uint16_t) * (Z + 1));
 	ENSURE(h->aux, sizeof(uint16_t) * 3 * (Z + 1));
+	ENSURE(h->unpinned, sizeof(unsigned long long));
+	CK(cudaMemsetAsync(h->unpinned.p, 0, sizeof(unsigned long long), h->stream));
 	if (Z && h->U) {
 		k_compact<<<grid_for((uint64_t)h->U * 32, 256), 256, 0, h->stream>>>(h->U, h->uptr.as<uint64_t>(), h->uoff.as<uint32_t>(), h->out.as<uint4>(),
-			h->rowsC.as<uint32_t>(), h->countC.as<uint16_t>(), h->posH.as<uint16_t>(), h->posV.as<uint16_t>(), h->aux.as<uint16_t>());
+			h->rowsC.as<uint32_t>(), h->countC.as<uint16_t>(), h->posH.as<uint16_t>(), h->posV.as<uint16_t>(), h->aux.as<uint16_t>(),
+			h->unpinned.as<unsigned long long>());
 		LAUNCHED();
 	}
 	h->numeric_done = true;
@@ -441,7 +500,7 @@ void reset_problem(bella_b200_handle* h, const bella_csc_view* B, uint16_t K, ui
 {
 	h->n = B->cols; h->m = B->rows; h->nnzB = B->nnz;
 	h->lo = 0; h->hi = h->n; h->K = K; h->BIN = BIN;
-	h->W = 0;
+	h->W = 0; h->cap_scale = 1.25;
 	h->klo = 0; h->khi = h->m;
 	h->mg_recv = nullptr;
 	h->have_inputs = true; h->symbolic_done = h->numeric_done = false;
@@ -465,6 +524,8 @@ int bella_b200_create(bella_b200_handle** out, int device)
 	if (cudaSetDevice(device) != cudaSuccess) return BELLA_B200_ERR_CUDA;
 	bella_b200_handle* h = new bella_b200_handle();
 	h->device = device;
+	h->sms = prop.multiProcessorCount;
+	if (const char* e = getenv("BELLA_B200_EP_MAX")) { int v = atoi(e); if (v >= 1 && v <= (int)EP_LIMIT) h->ep_max = (uint32_t)v; }
 	if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return BELLA_B200_ERR_CUDA; }
 	for (auto& e : h->ev) cudaEventCreate(&e);
 	cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
@@ -481,10 +542,10 @@ int bella_b200_destroy(bella_b200_handle* h)
 	if (!h) return BELLA_B200_ERR_ARG;
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->stream);
-	DevBuf* bufs[] = {&h->oB_colptr, &h->oB_rowids, &h->oB_values, &h->oB_strand, &h->o_len, &h->boff, &h->bcur, &h->part,
+	DevBuf* bufs[] = {&h->oB_colptr, &h->oB_rowids, &h->oB_values, &h->oB_strand, &h->o_len, &h->boff, &h->bcur, &h->bsize, &h->part, &h->partK, &h->Ainfo, &h->ccur, &h->rp_cur, &h->rp_tiles, &h->rp_E, &h->rp_K,
 		&h->Aent, &h->Acolptr, &h->flop32, &h->nunits, &h->ubase, &h->shv, &h->refine, &h->colinfo, &h->ucol, &h->ucount,
 		&h->uptr, &h->ucur, &h->lists, &h->redo, &h->unnz, &h->uoff, &h->raw, &h->out, &h->colptrC, &h->rowsC, &h->countC, &h->posH, &h->posV,
-		&h->aux, &h->meta, &h->errflag, &h->cubtmp, &h->mg_colinfo, &h->mg_ucur, &h->tp_kmer, &h->tp_read, &h->tp_pos, &h->tp_strand,
+		&h->aux, &h->meta, &h->errflag, &h->cubtmp, &h->unpinned, &h->mg_colinfo, &h->mg_ucur, &h->tp_kmer, &h->tp_read, &h->tp_pos, &h->tp_strand,
 		&h->tp_rs, &h->tp_re, &h->tp_nruns, &h->tp_cnt, &h->tp_cp, &h->tp_merged, &h->tp_tmpK, &h->tp_tmpV, &h->tp_slab};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -550,6 +611,16 @@ int bella_b200_set_inputs(bella_b200_handle* h, const bella_csc_view* A, const b
 	CK(cudaEventRecord(h->copy_end, cs));
 	h->n_chunks = nc;
 	return BELLA_B200_OK;
+}
+
+int bella_b200_set_inputs_csr(bella_b200_handle* h, const bella_csr_view* A_csr, const uint32_t* read_len,
+		const uint8_t* strand, uint16_t kmer_size, uint16_t bin_size)
+{
+	if (!h) return BELLA_B200_ERR_ARG;
+	bella_csc_view B;
+	if (!A_csr) return fail(h, BELLA_B200_ERR_ARG, "A_csr is required");
+	if (bella_csr_as_transposed_csc(A_csr, &B)) return fail(h, BELLA_B200_ERR_ARG, "one-based CSR views (CSR::ConvertOneBased) are not accepted");
+	return bella_b200_set_inputs(h, nullptr, &B, read_len, nullptr, strand, kmer_size, bin_size);
 }
 
 int bella_b200_set_inputs_device(bella_b200_handle* h, const bella_csc_view* A, const bella_csc_view* B,
@@ -670,6 +741,16 @@ int bella_b200_numeric_aux(bella_b200_handle* h, uint32_t col_begin, uint32_t co
 	return BELLA_B200_OK;
 }
 
+int bella_b200_n_unpinned(bella_b200_handle* h, uint64_t* n_unpinned)
+{
+	if (!h || !h->numeric_done || !n_unpinned) return fail(h, BELLA_B200_ERR_ARG, "numeric phase has not run");
+	unsigned long long v = 0;
+	CK(cudaMemcpyAsync(&v, h->unpinned.p, sizeof v, cudaMemcpyDeviceToHost, h->stream));
+	CK(cudaStreamSynchronize(h->stream));
+	*n_unpinned = v;
+	return BELLA_B200_OK;
+}
+
 int bella_b200_result_device(bella_b200_handle* h, const uint32_t** colptrC, const uint32_t** rowidsC,
 		const uint16_t** count, const uint16_t** posH, const uint16_t** posV, uint64_t* nnzC)
 {
@@ -738,6 +819,7 @@ int bella_b200_mg_transpose(bella_b200_handle* h, uint32_t kmer_lo, uint32_t kme
 		if (e == ERR_BUCKET) {
 			if (h->W <= 1) return fail(h, BELLA_B200_ERR_RANGE, "a k-mer occurs in more than %u reads", BUCKET_CAP);
 			h->W = h->W / 2;
+			h->cap_scale *= 1.5;
 			continue;
 		}
 		if (e) return report_device_error(h, e);
@@ -752,14 +834,14 @@ int bella_b200_mg_scatter(bella_b200_handle* h, const uint64_t* sendoff_dev, uin
 	if (!h || !h->have_inputs || !sendoff_dev) return fail(h, BELLA_B200_ERR_ARG, "bella_b200_mg_transpose first");
 	CK(cudaSetDevice(h->device));
 	const uint32_t n = h->n, ml = h->khi - h->klo;
-	ENSURE(h->mg_colinfo, sizeof(ColInfo) * ((size_t)n + 1));
-	ENSURE(h->mg_ucur, sizeof(uint64_t) * ((size_t)n + 1));
+	ENSURE(h->mg_ucur, sizeof(uint64_t) * ((size_t)n + 1) * CCUR_STRIDE);
 	CK(cudaEventRecord(h->ev[10], h->stream));
 	if (n && ml) {
-		k_mg_colinfo<<<grid_for(n, 256), 256, 0, h->stream>>>(n, sendoff_dev, h->mg_colinfo.as<ColInfo>(), h->mg_ucur.as<unsigned long long>());
+		// every output column is "light" here: its cursor is its place in the send buffer
+		k_mg_colinfo<<<grid_for(n, 256), 256, 0, h->stream>>>(n, sendoff_dev, h->mg_ucur.as<unsigned long long>());
 		LAUNCHED();
-		k_scatter<<<grid_for(ml, 256), 256, 0, h->stream>>>(ml, 0, n, h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), h->mg_colinfo.as<ColInfo>(),
-			h->mg_ucur.as<unsigned long long>(), sendbuf_dev);
+		k_scatter<<<grid_for((h->nnzB + 3) / 4, 256, 148 * 32), 256, 0, h->stream>>>(h->boff.as<uint32_t>() + h->NB, ml, 0, n, h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(),
+			h->Ainfo.as<uint8_t>(), h->mg_ucur.as<unsigned long long>(), nullptr, nullptr, sendbuf_dev);
 		LAUNCHED();
 	}
 	CK(cudaEventRecord(h->ev[2], h->stream));
@@ -997,6 +1079,7 @@ int bella_b200_mg_transpose_records(bella_b200_handle* h, const uint32_t* rec_de
 		if (e == ERR_BUCKET) {
 			if (h->W <= 1) return fail(h, BELLA_B200_ERR_RANGE, "a k-mer occurs in more than %u reads", BUCKET_CAP);
 			h->W = h->W / 2;
+			h->cap_scale *= 1.5;
 			continue;
 		}
 		if (e) return report_device_error(h, e);

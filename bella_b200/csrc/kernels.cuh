@@ -40,11 +40,9 @@ constexpr int NCLASS = 3;
 constexpr uint32_t CLASS_CAP[NCLASS] = {2048, 4096, 8192};
 constexpr uint32_t UNIT_CAP = 8192;        // products per unit (largest shared-memory class)
 constexpr uint32_t BUCKET_CAP = 4096;      // entries per transpose bucket
-constexpr uint32_t BUCKET_WMAX = 2048;     // k-mers per transpose bucket
+constexpr uint32_t BUCKET_WMAX = 1024;     // k-mers per transpose bucket (a power of two)
 constexpr uint32_t MAX_SPAN_SHIFT = 22;    // a unit covers at most 2^22 rows (two-level bitmap: 4097 words)
-constexpr uint32_t SHORT_FOLD = 8;         // pairs up to this many products are folded by one thread
 constexpr int GF_THREADS = 256;
-constexpr size_t BUCKET_SMEM = (size_t)BUCKET_CAP * 12 + ((size_t)BUCKET_WMAX + 2) * 4;
 
 // Packed formats (64-bit)
 //   Aent : row(31) | strand<<31 | pos(16)<<32 | jrank(16)<<48     A's columns, rows ascending;
@@ -58,6 +56,7 @@ struct ColInfo { uint32_t ubase; uint32_t sh; };
 
 struct Params {
 	uint32_t n, m, lo, hi, K, BIN;
+	uint32_t ep_max;              // pairs up to this many products are ranked and folded one thread per product, longer ones one warp per pair
 	const uint32_t* B_colptr;
 	const uint32_t* B_rowids;
 	const uint16_t* B_values;
@@ -182,109 +181,246 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 // ================================ transpose =================================================
 
-// One warp per read (column of B): its nonzeros go to their k-mer bucket (W consecutive k-mer ids,
-// a fixed-capacity region of BUCKET_CAP 16-byte records {k-mer id, -, entry}).  The write frontier is
-// one open sector per bucket, so the small stores merge in L2.  Rows below lo never matter.
-__global__ void __launch_bounds__(256) k_partition(uint32_t n, uint32_t lo, uint32_t klo, uint32_t khi, const uint32_t* __restrict__ Bcolptr,   // reads [lo, n)
-		const uint32_t* __restrict__ Brow, const uint16_t* __restrict__ Bval, const uint8_t* __restrict__ Bstrand,
-		uint32_t W, uint32_t* __restrict__ bcnt, uint4* __restrict__ part, int* err)
+// B's nonzeros (read-major) -> buckets of 2^wshift consecutive k-mer ids (a fixed-capacity region of BUCKET_CAP records
+// per bucket: the packed entry in partE, the k-mer id inside the bucket in partK), as a two-level radix partition.  A
+// direct partition costs one cursor atomic with return and one scattered store per nonzero, and the chip sustains only
+// about 83 G such scattered transactions per second (profiles/README.md); here a CTA stages a tile of nonzeros in shared
+// memory, ordered by bucket, so that global memory sees one cursor atomic per (tile, bucket) and coalesced runs:
+//   k_rp1   level 1: reads -> nb1 coarse buckets of 2^shift1 k-mers (records: entry 8 B + k-mer id 4 B)
+//   k_rp2   level 2: one coarse bucket at a time -> its 2^(shift1 - wshift) fine buckets (entry 8 B + id inside the bucket 2 B)
+// Every global cursor has its own 32-byte sector (BCNT_STRIDE words).
+constexpr uint32_t BCNT_STRIDE = 8;
+constexpr uint32_t CCUR_STRIDE = 4;        // the scatter's per-column cursors: 8-byte words, one per 32-byte sector
+constexpr unsigned long long CCUR_HEAVY = 1ull << 63;
+constexpr uint32_t AINFO_ESC = 255;        // Ainfo: entries behind this one in its column of A; 255 = that many or more (the count then comes from A's colptr)
+constexpr int RP_THREADS = 512;
+constexpr int RP_ITEMS = 8;                // nonzeros per thread and tile
+constexpr int RP_TILE = RP_THREADS * RP_ITEMS;
+constexpr uint32_t RP_NBMAX = 1024;        // buckets of one level
+constexpr size_t RP_SMEM = (size_t)RP_TILE * 12 + ((size_t)RP_NBMAX + 2) * 8;
+
+// scan of the tile's histogram (in place: counts -> starts, total at [nb]) + one global cursor atomic per non-empty bucket.
+// Ends with a barrier.  gstride: distance of the global cursors in words.
+__device__ __forceinline__ void rp_reserve(uint32_t* hist, uint32_t* gbase, uint32_t nb, uint32_t* gcur, uint32_t gstride, uint32_t cap,
+		uint32_t* s_tmp, int* err)
 {
-	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-	for (uint32_t i = lo + warp; i < n; i += nwarps) {
-		const uint32_t j0 = Bcolptr[i], j1 = Bcolptr[i + 1];
-		if (j1 - j0 > 65536u) { if (lane == 0) set_err(err, -4); continue; }
-		for (uint32_t jb = j0; jb < j1; jb += 128) {
-			uint32_t c[4], b[4], q[4];
-			bool mine[4];                                      // k-mers outside [klo, khi) belong to another GPU's transpose
+	block_excl_scan<uint32_t>(hist, nb, s_tmp);
+	for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
+		const uint32_t c = hist[b + 1] - hist[b];
+		if (c) {
+			const uint32_t g = atomicAdd(&gcur[(size_t)b * gstride], c);
+			if (g + c > cap) set_err(err, -6);
+			gbase[b] = g;
+		}
+	}
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(RP_THREADS) k_rp1(uint32_t n, uint32_t lo, uint32_t klo, uint32_t khi, const uint32_t* __restrict__ Bcolptr,   // reads [lo, n)
+		const uint32_t* __restrict__ Brow, const uint16_t* __restrict__ Bval, const uint8_t* __restrict__ Bstrand,
+		uint32_t shift1, uint32_t nb1, uint32_t cap1, uint32_t* __restrict__ gcur1, uint64_t* __restrict__ E1, uint32_t* __restrict__ K1, int* err)
+{
+	extern __shared__ __align__(16) unsigned char rsm[];
+	uint64_t* SE = (uint64_t*)rsm;                             // [RP_TILE]
+	uint32_t* SK = (uint32_t*)(SE + RP_TILE);                  // [RP_TILE]
+	uint32_t* hist = SK + RP_TILE;                             // [RP_NBMAX + 2]
+	uint32_t* gbase = hist + RP_NBMAX + 2;                     // [RP_NBMAX + 2]
+	__shared__ uint32_t s_tmp[34];
+	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwc = RP_THREADS / 32;
+	const uint32_t wstride = gridDim.x * nwc;
+	for (uint32_t b = tid; b <= nb1; b += RP_THREADS) hist[b] = 0;
+	__syncthreads();
+	uint32_t i = lo + blockIdx.x * nwc + wid;                  // this warp's current read
+	uint32_t j0 = 0, j1 = 0, jb = 0;
+	if (i < n) { j0 = Bcolptr[i]; j1 = Bcolptr[i + 1]; jb = j0; if (j1 - j0 > 65536u) { if (lane == 0) set_err(err, -4); jb = j1; } }
+	for (;;) {
+		// a warp that has finished its read moves to the next one (reads without k-mers are skipped)
+		while (i < n && jb >= j1) {
+			i += wstride;
+			if (i < n) { j0 = Bcolptr[i]; j1 = Bcolptr[i + 1]; jb = j0; if (j1 - j0 > 65536u) { if (lane == 0) set_err(err, -4); jb = j1; } }
+		}
+		if (!__syncthreads_or(i < n)) break;
+		uint64_t ev[RP_ITEMS];
+		uint32_t kv[RP_ITEMS], sl[RP_ITEMS];
 #pragma unroll
-			for (int u = 0; u < 4; ++u) {
-				uint32_t j = jb + u * 32 + lane;
-				mine[u] = false;
-				if (j < j1) {
-					c[u] = Brow[j];
-					const uint32_t kid = Bstrand ? c[u] : c[u] & 0x7FFFFFFFu;
-					mine[u] = kid >= klo && kid < khi;
-					if (mine[u]) { b[u] = (kid - klo) / W; q[u] = atomicAdd(&bcnt[b[u]], 1u); }
-				}
-			}
-#pragma unroll
-			for (int u = 0; u < 4; ++u) {
-				uint32_t j = jb + u * 32 + lane;
-				if (mine[u]) {
-					if (q[u] >= BUCKET_CAP) { set_err(err, -6); continue; }
-					const uint32_t st = Bstrand ? getbit(Bstrand, j) : c[u] >> 31;
-					const uint64_t e = (uint64_t)i | ((uint64_t)st << 31) | ((uint64_t)Bval[j] << 32) | ((uint64_t)(j - j0) << 48);
-					part[(size_t)b[u] * BUCKET_CAP + q[u]] = make_uint4(Bstrand ? c[u] : c[u] & 0x7FFFFFFFu, 0u, (uint32_t)e, (uint32_t)(e >> 32));
+		for (int u = 0; u < RP_ITEMS; ++u) {
+			const uint32_t j = jb + u * 32 + lane;
+			sl[u] = 0xFFFFFFFFu;
+			if (i < n && j < j1) {
+				const uint32_t c = Brow[j];
+				const uint32_t kid = Bstrand ? c : c & 0x7FFFFFFFu;
+				if (kid >= klo && kid < khi) {                        // k-mers outside [klo, khi) belong to another GPU's transpose
+					const uint32_t st = Bstrand ? getbit(Bstrand, j) : c >> 31;
+					kv[u] = kid - klo;
+					ev[u] = (uint64_t)i | ((uint64_t)st << 31) | ((uint64_t)Bval[j] << 32) | ((uint64_t)(j - j0) << 48);
+					sl[u] = atomicAdd(&hist[kv[u] >> shift1], 1u);
 				}
 			}
 		}
+		if (i < n) jb += 32 * RP_ITEMS;
+		__syncthreads();
+		rp_reserve(hist, gbase, nb1, gcur1, BCNT_STRIDE, cap1, s_tmp, err);
+#pragma unroll
+		for (int u = 0; u < RP_ITEMS; ++u)
+			if (sl[u] != 0xFFFFFFFFu) { const uint32_t at = hist[kv[u] >> shift1] + sl[u]; SE[at] = ev[u]; SK[at] = kv[u]; }
+		__syncthreads();
+		const uint32_t total = hist[nb1];
+		for (uint32_t t = tid; t < total; t += RP_THREADS) {
+			const uint32_t k = SK[t], b = k >> shift1;
+			const uint32_t g = gbase[b] + (t - hist[b]);
+			if (g < cap1) { const size_t at = (size_t)b * cap1 + g; E1[at] = SE[t]; K1[at] = k; }
+		}
+		__syncthreads();
+		for (uint32_t b = tid; b <= nb1; b += RP_THREADS) hist[b] = 0;
+		__syncthreads();
 	}
 }
 
-// One CTA per bucket: counting sort by k-mer in shared memory, each column sorted by read id,
-// coalesced write of Aent and A's colptr, product counts per output column.
-__global__ void __launch_bounds__(256) k_bucket(uint32_t klo, uint32_t m, uint32_t lo, uint32_t hi, uint32_t W, uint32_t nb,
-		const uint32_t* __restrict__ boff, const uint4* __restrict__ part,
-		uint32_t* __restrict__ Acolptr, uint64_t* __restrict__ Aent, uint32_t* __restrict__ flop32, const int* err)
+// tiles of the coarse buckets for level 2: tstart[c] = first tile of coarse bucket c, tstart[nb1] = number of tiles
+__global__ void __launch_bounds__(1024) k_rp_tiles(uint32_t nb1, uint32_t cap1, const uint32_t* __restrict__ gcur1, uint32_t* __restrict__ tstart)
 {
-	extern __shared__ __align__(16) unsigned char bsm[];
-	uint64_t* E = (uint64_t*)bsm;                              // [BUCKET_CAP]
-	uint32_t* tmp = (uint32_t*)(E + BUCKET_CAP);               // [BUCKET_CAP]
-	uint32_t* off = tmp + BUCKET_CAP;                          // [BUCKET_WMAX + 2]
+	__shared__ uint32_t t[RP_NBMAX + 2];
 	__shared__ uint32_t s_tmp[34];
+	for (uint32_t c = threadIdx.x; c < nb1; c += blockDim.x) t[c] = (min(gcur1[(size_t)c * BCNT_STRIDE], cap1) + RP_TILE - 1) / RP_TILE;
+	__syncthreads();
+	block_excl_scan<uint32_t>(t, nb1, s_tmp);
+	for (uint32_t c = threadIdx.x; c <= nb1; c += blockDim.x) tstart[c] = t[c];
+}
+
+__global__ void __launch_bounds__(RP_THREADS) k_rp2(uint32_t shift1, uint32_t wshift, uint32_t nb1, uint32_t cap1, const uint32_t* __restrict__ gcur1,
+		const uint32_t* __restrict__ tstart, const uint64_t* __restrict__ E1, const uint32_t* __restrict__ K1,
+		uint32_t* __restrict__ bcnt, uint64_t* __restrict__ partE, uint16_t* __restrict__ partK, int* err)
+{
+	extern __shared__ __align__(16) unsigned char rsm[];
+	uint64_t* SE = (uint64_t*)rsm;
+	uint32_t* SK = (uint32_t*)(SE + RP_TILE);
+	uint32_t* hist = SK + RP_TILE;
+	uint32_t* gbase = hist + RP_NBMAX + 2;
+	__shared__ uint32_t s_tmp[34];
+	__shared__ uint32_t s_c;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t nb2 = 1u << (shift1 - wshift), wmask = (1u << wshift) - 1u;
+	const uint32_t ntiles = tstart[nb1];
+	for (uint32_t b = tid; b <= nb2; b += RP_THREADS) hist[b] = 0;
+	for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		if (tid == 0) {
+			uint32_t a = 0, b = nb1;                                // last coarse bucket c with tstart[c] <= tile
+			while (b - a > 1) { const uint32_t c = (a + b) >> 1; if (tstart[c] <= tile) a = c; else b = c; }
+			s_c = a;
+		}
+		__syncthreads();
+		const uint32_t c = s_c;
+		const uint32_t cnt = min(gcur1[(size_t)c * BCNT_STRIDE], cap1), first = (tile - tstart[c]) * RP_TILE;
+		const uint32_t len = min((uint32_t)RP_TILE, cnt - first);
+		const uint64_t* e1 = E1 + (size_t)c * cap1 + first;
+		const uint32_t* k1 = K1 + (size_t)c * cap1 + first;
+		const uint32_t fbase = c << (shift1 - wshift);              // first fine bucket of this coarse bucket
+		uint64_t ev[RP_ITEMS];
+		uint32_t kv[RP_ITEMS], sl[RP_ITEMS];
+#pragma unroll
+		for (int u = 0; u < RP_ITEMS; ++u) {
+			const uint32_t x = u * RP_THREADS + tid;
+			sl[u] = 0xFFFFFFFFu;
+			if (x < len) { ev[u] = e1[x]; kv[u] = k1[x]; sl[u] = atomicAdd(&hist[(kv[u] >> wshift) - fbase], 1u); }
+		}
+		__syncthreads();
+		rp_reserve(hist, gbase, nb2, bcnt + (size_t)fbase * BCNT_STRIDE, BCNT_STRIDE, BUCKET_CAP, s_tmp, err);
+#pragma unroll
+		for (int u = 0; u < RP_ITEMS; ++u)
+			if (sl[u] != 0xFFFFFFFFu) { const uint32_t at = hist[(kv[u] >> wshift) - fbase] + sl[u]; SE[at] = ev[u]; SK[at] = kv[u]; }
+		__syncthreads();
+		for (uint32_t t = tid; t < len; t += RP_THREADS) {
+			const uint32_t k = SK[t], f = k >> wshift, b = f - fbase;
+			const uint32_t g = gbase[b] + (t - hist[b]);
+			if (g < BUCKET_CAP) { const size_t at = (size_t)f * BUCKET_CAP + g; partE[at] = SE[t]; partK[at] = (uint16_t)(k & wmask); }
+		}
+		__syncthreads();
+		for (uint32_t b = tid; b <= nb2; b += RP_THREADS) hist[b] = 0;
+		__syncthreads();
+	}
+}
+
+// bucket sizes (one per 32-byte sector) -> dense array for the scan
+__global__ void k_bucket_sizes(uint32_t nb, const uint32_t* __restrict__ bcnt, uint32_t* __restrict__ bsize)
+{
+	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b <= nb; b += gridDim.x * blockDim.x) bsize[b] = b < nb ? min(bcnt[(size_t)b * BCNT_STRIDE], BUCKET_CAP) : 0;
+}
+
+// One CTA per bucket: the bucket arrives in shared memory as two bulk async copies (TMA 1-D); counting sort by k-mer;
+// every entry then finds its place among the 2..8 entries of its column by read id and goes out to Aent (A's columns:
+// rows ascending) with the per-column product counts (== estimateFLOP, overlap.hpp:157-202) and A's colptr.
+constexpr size_t BUCKET_SMEM = (size_t)BUCKET_CAP * (8 + 2 + 2) + ((size_t)BUCKET_WMAX + 2) * 4;
+__global__ void __launch_bounds__(256, 4) k_bucket(uint32_t klo, uint32_t m, uint32_t lo, uint32_t hi, uint32_t wshift, uint32_t nb,
+		const uint32_t* __restrict__ boff, const uint64_t* __restrict__ partE, const uint16_t* __restrict__ partK,
+		uint32_t* __restrict__ Acolptr, uint64_t* __restrict__ Aent, uint8_t* __restrict__ Ainfo, uint32_t* __restrict__ flop32, const int* err)
+{
+	extern __shared__ __align__(128) unsigned char bsm[];
+	uint64_t* E = (uint64_t*)bsm;                              // [BUCKET_CAP]
+	uint16_t* KR = (uint16_t*)(E + BUCKET_CAP);                // [BUCKET_CAP] k-mer of the entry (arrival order, later grouped order)
+	uint16_t* SL = KR + BUCKET_CAP;                            // [BUCKET_CAP] arrival slot inside its column
+	uint32_t* off = (uint32_t*)(SL + BUCKET_CAP);              // [BUCKET_WMAX + 2]
+	__shared__ uint32_t s_tmp[34];
+	__shared__ __align__(8) uint64_t s_bar;
 	const uint32_t tid = threadIdx.x, nt = blockDim.x;
+	const uint32_t W = 1u << wshift;
 	if (*err != 0) return;                                     // a bucket overflowed: the host retries with narrower buckets
+	if (tid == 0) mbar_init(&s_bar, 1);
+	__syncthreads();
+	uint32_t phase = 0;
 	for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
 		const uint32_t o0 = boff[b], size = boff[b + 1] - o0;
 		const uint32_t kbase = b * W, kw = min(W, m - kbase);      // k-mer ids are klo + kbase + k; A's colptr is local to [klo, klo + m)
-		const uint4* src = part + (size_t)b * BUCKET_CAP;
 		PHASE_BEGIN();
-		for (uint32_t k = tid; k <= kw; k += nt) off[k] = 0;
-		__syncthreads();
-		for (uint32_t x = tid; x < size; x += nt) {
-			const uint4 r = src[x];
-			const uint32_t k = r.x - klo - kbase;
-			const uint32_t arr = atomicAdd(&off[k], 1u);
-			tmp[x] = k | (arr << 12);
-			E[x] = (uint64_t)r.z | ((uint64_t)r.w << 32);
+		if (tid == 0 && size) {
+			fence_proxy_async();
+			const uint32_t be = (size * 8u + 15u) & ~15u, bk2 = (size * 2u + 15u) & ~15u;
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(be + bk2) : "memory");
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				::"r"(smem_u32(E)), "l"(partE + (size_t)b * BUCKET_CAP), "r"(be), "r"(smem_u32(&s_bar)) : "memory");
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				::"r"(smem_u32(KR)), "l"(partK + (size_t)b * BUCKET_CAP), "r"(bk2), "r"(smem_u32(&s_bar)) : "memory");
 		}
+		for (uint32_t k = tid; k <= kw; k += nt) off[k] = 0;
+		if (size) { mbar_wait(&s_bar, phase); phase ^= 1; }
+		__syncthreads();
+		for (uint32_t x = tid; x < size; x += nt) SL[x] = (uint16_t)atomicAdd(&off[KR[x]], 1u);
 		__syncthreads();
 		PHASE(16);
 		block_excl_scan<uint32_t>(off, kw, s_tmp);
 		PHASE(17);
-		// permute in place through registers: every thread first reads its elements, then all write
+		// group by k-mer in place through registers: every thread first reads its elements, then all write
 		uint64_t ev[BUCKET_CAP / 256];
+		uint32_t pk[BUCKET_CAP / 256];
 #pragma unroll
-		for (int q = 0; q < (int)(BUCKET_CAP / 256); ++q) { uint32_t x = tid + q * 256; ev[q] = x < size ? E[x] : 0; }
+		for (int q = 0; q < (int)(BUCKET_CAP / 256); ++q) {
+			const uint32_t x = tid + q * 256;
+			if (x < size) { const uint32_t k = KR[x]; ev[q] = E[x]; pk[q] = (off[k] + SL[x]) | (k << 16); }
+		}
 		__syncthreads();
 #pragma unroll
 		for (int q = 0; q < (int)(BUCKET_CAP / 256); ++q) {
-			uint32_t x = tid + q * 256;
-			if (x < size) { uint32_t t = tmp[x]; E[off[t & 0xFFFu] + (t >> 12)] = ev[q]; }
+			const uint32_t x = tid + q * 256;
+			if (x < size) { E[pk[q] & 0xFFFFu] = ev[q]; KR[pk[q] & 0xFFFFu] = (uint16_t)(pk[q] >> 16); }
 		}
 		__syncthreads();
 		PHASE(18);
-		for (uint32_t k = tid; k < kw; k += nt) {
-			const uint32_t s = off[k], e = off[k + 1];
-			Acolptr[kbase + k] = o0 + s;
-			for (uint32_t a = s + 1; a < e; ++a) {          // insertion sort by read id (columns are 2..8 long)
-				uint64_t x = E[a];
-				uint32_t p = a;
-				while (p > s && ent_row(E[p - 1]) > ent_row(x)) { E[p] = E[p - 1]; --p; }
-				E[p] = x;
-			}
-			for (uint32_t a = s; a + 1 < e; ++a) {
-				uint32_t r = ent_row(E[a]);
-				if (r >= lo && r < hi) atomicAdd(&flop32[r - lo], e - 1 - a);
-			}
+		// every entry: rank by read id among its column, straight to its final place (the stores of a column's entries fall
+		// into the same one or two sectors, so the warp's store is as coalesced as an ordered one)
+		for (uint32_t y = tid; y < size; y += nt) {
+			const uint32_t k = KR[y], s = off[k], e = off[k + 1];
+			const uint64_t x = E[y];
+			const uint32_t r = ent_row(x);
+			uint32_t rho = 0;
+			for (uint32_t z = s; z < e; ++z) rho += ent_row(E[z]) < r;
+			Aent[o0 + s + rho] = x;
+			const uint32_t after = e - s - 1 - rho;                 // products this entry's read collects as the column read
+			Ainfo[o0 + s + rho] = (uint8_t)min(after, AINFO_ESC);
+			if (after && r >= lo && r < hi) atomicAdd(&flop32[r - lo], after);
 		}
+		for (uint32_t k = tid; k < kw; k += nt) Acolptr[kbase + k] = o0 + off[k];
 		if (b == nb - 1 && tid == 0) Acolptr[m] = o0 + size;
 		__syncthreads();
 		PHASE(19);
-		for (uint32_t x = tid; x < size; x += nt) Aent[o0 + x] = E[x];
-		__syncthreads();
-		PHASE(20);
 	}
 }
 
@@ -363,13 +499,17 @@ __global__ void __launch_bounds__(256) k_count_units(uint32_t m, uint32_t lo, ui
 // they already are a single row (sh == 0): those go to the huge-pair list (class NCLASS).
 __global__ void k_classify_units(uint32_t ucap, const uint32_t* __restrict__ ucol, const uint32_t* __restrict__ ucount,
 		const ColInfo* __restrict__ colinfo, const uint64_t* __restrict__ uptr, unsigned long long* __restrict__ ucur,
-		uint32_t* __restrict__ lists, uint8_t* __restrict__ refine, uint32_t round, Meta* meta, const int* err)
+		unsigned long long* __restrict__ ccur, uint32_t* __restrict__ lists, uint8_t* __restrict__ refine, uint32_t round, Meta* meta, const int* err)
 {
 	if (*err != 0) return;
 	const uint32_t U = meta->n_units;
 	for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += gridDim.x * blockDim.x) {
 		const uint32_t f = ucount[u];
 		ucur[u] = uptr[u];
+		{
+			const uint32_t li = ucol[u];                             // the scatter's per-column cursor: the region of a light column, or the heavy mark
+			ccur[(size_t)li * CCUR_STRIDE] = colinfo[li].sh == 31 ? (unsigned long long)uptr[u] : CCUR_HEAVY;
+		}
 		if (!f) continue;
 		int c = f <= CLASS_CAP[0] ? 0 : f <= CLASS_CAP[1] ? 1 : f <= CLASS_CAP[2] ? 2 : 3;
 		if (c == 3) {
@@ -382,73 +522,62 @@ __global__ void k_classify_units(uint32_t ucap, const uint32_t* __restrict__ uco
 }
 
 // ================================ scatter ===================================================
-// Thread per k-mer column (r_0 < r_1 < ...): entry a owns the run of products (col r_a, row r_b), b > a.
-// A light column's run is written contiguously into the column's region after one cursor atomic.
-__global__ void __launch_bounds__(256) k_scatter(uint32_t m, uint32_t lo, uint32_t hi, const uint32_t* __restrict__ Acolptr,
-		const uint64_t* __restrict__ Aent, const ColInfo* __restrict__ colinfo, unsigned long long* __restrict__ ucur,
-		uint64_t* __restrict__ raw)
+// One thread per entry of A.  In its k-mer column (r_0 < r_1 < ...) entry a owns the run of products (col r_a, row r_b),
+// b > a: `Ainfo` (written by k_bucket) says how many entries follow it in the column, so the thread needs nothing but its
+// own entry, one cursor atomic on its output column and the entries behind it.  ccur: one cursor per output column in its
+// own 32-byte sector (CCUR_STRIDE words of 8 bytes); bit 63 marks a heavy column, whose products go to row-range units
+// one by one through `ucur`.
+
+__device__ __forceinline__ uint32_t entries_after(uint32_t x, uint32_t info, const uint32_t* __restrict__ Acolptr, uint32_t m)
 {
-	constexpr int D = 8;
+	if (info < AINFO_ESC) return info;
+	uint32_t a = 0, b = m;                                     // last column c with Acolptr[c] <= x
+	while (b - a > 1) { const uint32_t c = (a + b) >> 1; if (Acolptr[c] <= x) a = c; else b = c; }
+	return Acolptr[a + 1] - 1 - x;
+}
+
+__global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ nnzA_ptr, uint32_t m, uint32_t lo, uint32_t hi, const uint32_t* __restrict__ Acolptr,
+		const uint64_t* __restrict__ Aent, const uint8_t* __restrict__ Ainfo, unsigned long long* __restrict__ ccur,
+		const ColInfo* __restrict__ colinfo, unsigned long long* __restrict__ ucur, uint64_t* __restrict__ raw)
+{
+	constexpr int ILP = 4;
 	constexpr uint64_t LOW48 = 0x0000FFFFFFFFFFFFull;
-	for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < m; c += gridDim.x * blockDim.x) {
-		const uint32_t s = Acolptr[c], e = Acolptr[c + 1], d = e - s;
-		if (d < 2) continue;
-		if (d <= D) {
-			uint64_t ent[D];
-			unsigned long long q[D];
-			uint32_t heavy = 0;
+	const uint32_t stride = gridDim.x * blockDim.x;
+	const uint32_t nnzA = *nnzA_ptr;                           // entries of A on this device (the end of the last transpose bucket)
+	for (uint32_t x0 = blockIdx.x * blockDim.x + threadIdx.x; x0 < nnzA; x0 += stride * ILP) {
+		uint32_t after[ILP];
+		uint64_t ea[ILP];
+		unsigned long long q[ILP];
 #pragma unroll
-			for (int a = 0; a < D; ++a) ent[a] = a < (int)d ? Aent[s + a] : 0;
+		for (int u = 0; u < ILP; ++u) {
+			const uint32_t x = x0 + u * stride;
+			after[u] = 0;
+			if (x < nnzA) { after[u] = Ainfo[x]; ea[u] = Aent[x]; }
+		}
 #pragma unroll
-			for (int a = 0; a < D - 1; ++a) {
-				q[a] = ~0ull;
-				if (a + 1 < (int)d) {
-					const uint32_t ra = ent_row(ent[a]);
-					if (ra >= lo && ra < hi) {
-						const ColInfo ci = colinfo[ra - lo];
-						if (ci.sh == 31) q[a] = atomicAdd(&ucur[ci.ubase], (unsigned long long)(d - 1 - a));
-						else heavy |= 1u << a;
-					}
-				}
-			}
+		for (int u = 0; u < ILP; ++u) {
+			if (!after[u]) continue;
+			const uint32_t ra = ent_row(ea[u]);
+			if (ra < lo || ra >= hi) { after[u] = 0; continue; }
+			if (after[u] == AINFO_ESC) after[u] = entries_after(x0 + u * stride, AINFO_ESC, Acolptr, m);
+			q[u] = atomicAdd(&ccur[(size_t)(ra - lo) * CCUR_STRIDE], (unsigned long long)after[u]);
+		}
 #pragma unroll
-			for (int a = 0; a < D - 1; ++a) {
-				if (q[a] != ~0ull) {
-					const uint64_t top = ent[a] & ~LOW48;
-					unsigned long long p = q[a];
-#pragma unroll
-					for (int b = a + 1; b < D; ++b)
-						if (b < (int)d) raw[p++] = (ent[b] & LOW48) | top;
-				}
-			}
-			if (heavy) {
-#pragma unroll
-				for (int a = 0; a < D - 1; ++a) {
-					if (heavy >> a & 1u) {
-						const uint32_t ra = ent_row(ent[a]);
-						const ColInfo ci = colinfo[ra - lo];
-						const uint64_t top = ent[a] & ~LOW48;
-#pragma unroll
-						for (int b = a + 1; b < D; ++b)
-							if (b < (int)d) raw[atomicAdd(&ucur[unit_of(ci, ra, ent_row(ent[b]))], 1ull)] = (ent[b] & LOW48) | top;
-					}
-				}
-			}
-		} else {
-			for (uint32_t a = s; a + 1 < e; ++a) {
-				const uint64_t ea = Aent[a];
-				const uint32_t ra = ent_row(ea);
-				if (ra < lo || ra >= hi) continue;
+		for (int u = 0; u < ILP; ++u) {
+			if (!after[u]) continue;
+			const uint64_t* nxt = Aent + (x0 + u * stride) + 1;
+			const uint64_t top = ea[u] & ~LOW48;
+			if (!(q[u] & CCUR_HEAVY)) {
+				uint64_t* dst = raw + q[u];
+				#pragma unroll 1
+				for (uint32_t b = 0; b < after[u]; ++b) dst[b] = (nxt[b] & LOW48) | top;
+			} else {
+				const uint32_t ra = ent_row(ea[u]);
 				const ColInfo ci = colinfo[ra - lo];
-				const uint64_t top = ea & ~LOW48;
-				if (ci.sh == 31) {
-					unsigned long long p = atomicAdd(&ucur[ci.ubase], (unsigned long long)(e - 1 - a));
-					for (uint32_t b = a + 1; b < e; ++b) raw[p++] = (Aent[b] & LOW48) | top;
-				} else {
-					for (uint32_t b = a + 1; b < e; ++b) {
-						const uint64_t eb = Aent[b];
-						raw[atomicAdd(&ucur[unit_of(ci, ra, ent_row(eb))], 1ull)] = (eb & LOW48) | top;
-					}
+				#pragma unroll 1
+				for (uint32_t b = 0; b < after[u]; ++b) {
+					const uint64_t eb = nxt[b];
+					raw[atomicAdd(&ucur[unit_of(ci, ra, ent_row(eb))], 1ull)] = (eb & LOW48) | top;
 				}
 			}
 		}
@@ -504,76 +633,6 @@ struct PairResult { uint32_t count, hv, nbins, sup, ov; };
 __device__ __forceinline__ uint4 pack_result(uint32_t row, const PairResult& r)
 {
 	return make_uint4(row, (r.count & 0xFFFFu) | (r.nbins << 16), r.hv, (r.sup & 0xFFFFu) | (r.ov << 16));
-}
-
-// the rare case of fold_short: consecutive overlap estimates further apart than binSize (several bins).
-// Out of line and rolled: it keeps the hot kernel's instruction footprint small.
-template <bool EXACT>
-__device__ __noinline__ PairResult fold_short_forest(const uint32_t (&hvr)[SHORT_FOLD], const uint16_t (&ovr)[SHORT_FOLD], uint32_t np, uint32_t K, int BIN)
-{
-	constexpr int CAP = SHORT_FOLD;
-	const uint32_t lim = far_limit<EXACT>(K);
-	uint32_t hv[CAP];
-	uint16_t ov[CAP];
-	uint8_t par[CAP], sup[CAP];
-#pragma unroll
-	for (int a = 0; a < CAP; ++a) { hv[a] = hvr[a]; ov[a] = ovr[a]; }
-#pragma unroll 1
-	for (uint32_t b = 0; b < np; ++b) {
-		uint32_t t = b + 1;
-		while (t < np && abs((int)ov[t] - (int)ov[b]) >= BIN) ++t;
-		par[b] = t < np ? (uint8_t)t : (uint8_t)0xFF;
-		sup[b] = 0;
-	}
-	uint32_t csum = 0;
-#pragma unroll 1
-	for (uint32_t s = 0; s < np; ++s) {
-		const FarKey key = far_key<EXACT>(hv[s], K);
-		uint32_t a = par[s], last = s;
-		while (a != 0xFF && is_far<EXACT>(hv[a], key, lim)) { ++csum; last = a; a = par[a]; }
-		if (a == 0xFF) ++sup[last];
-	}
-	uint32_t best = 0, bt = 0, nb = 0;
-#pragma unroll 1
-	for (uint32_t t = 0; t < np; ++t)
-		if (par[t] == 0xFF) { ++nb; if (sup[t] >= best) { best = sup[t]; bt = t; } }
-	PairResult R;
-	R.count = (np + csum) & 0xFFFFu; R.hv = hv[bt]; R.nbins = nb; R.sup = best; R.ov = ov[bt];
-	return R;
-}
-
-// one thread, P <= SHORT_FOLD, products in fold order (hv = h | v<<16, ov = overlap estimate)
-template <bool EXACT>
-__device__ __forceinline__ PairResult fold_short(const uint32_t (&hv)[SHORT_FOLD], const uint16_t (&ov)[SHORT_FOLD], uint32_t np, uint32_t K, int BIN)
-{
-	constexpr int CAP = SHORT_FOLD;
-	const uint32_t lim = far_limit<EXACT>(K);
-	bool linear = true;
-#pragma unroll
-	for (int a = 1; a < CAP; ++a)
-		if (a < (int)np) linear &= abs((int)ov[a] - (int)ov[a - 1]) < BIN;
-	PairResult R;
-	uint32_t csum = 0;
-	if (np == 1) { R.count = 1; R.hv = hv[0]; R.nbins = 1; R.sup = 1; R.ov = ov[0]; return R; }
-	if (linear) {
-		uint32_t surv = 0, last_hv = 0, last_ov = 0;
-#pragma unroll
-		for (int s = 0; s < CAP; ++s) {
-			if (s < (int)np) {
-				const FarKey key = far_key<EXACT>(hv[s], K);
-				bool alive = true;
-#pragma unroll
-				for (int t = s + 1; t < CAP; ++t) {
-					if (t < (int)np) { alive = alive && is_far<EXACT>(hv[t], key, lim); csum += alive; }
-				}
-				surv += alive;
-				last_hv = hv[s]; last_ov = ov[s];
-			}
-		}
-		R.count = (np + csum) & 0xFFFFu; R.hv = last_hv; R.nbins = 1; R.sup = surv; R.ov = last_ov;
-		return R;
-	}
-	return fold_short_forest<EXACT>(hv, ov, np, K, BIN);
 }
 
 // The forest part shared by the cooperative folds: parents, ancestor walks, best root.
@@ -677,7 +736,7 @@ __device__ __noinline__ PairResult fold_cta(const uint32_t* hv, const uint16_t* 
 constexpr uint32_t WSCR_WORDS = 192;       // per-warp scratch: position bitmap [128] + its prefix u16[128]
 constexpr uint32_t JR_BITMAP_MAX = 4096;   // columns of B up to this length rank through the bitmap
 
-// One warp folds a pair of P > SHORT_FOLD products (hv/ov in fold order; hv + P0 is the pair's slice of a
+// One warp folds a pair of P products (hv/ov in fold order; hv + P0 is the pair's slice of a
 // 16-byte aligned array, see fold_linear_rounds).  `own` is the pair's own 8*P-byte scratch.
 template <bool EXACT>
 __device__ __forceinline__ PairResult warp_fold_pair(const uint32_t* hv, const uint16_t* ov, uint64_t* own, uint32_t P, uint32_t K, int BIN,
@@ -739,49 +798,22 @@ __device__ __forceinline__ uint32_t block_scan_chunked(T* out, uint32_t n, F val
 	return total;
 }
 
-// sorting network for 8 keys (19 compare-exchanges)
-__device__ __forceinline__ void cex(uint64_t& a, uint64_t& b) { const uint64_t lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
-__device__ __forceinline__ void sort8(uint64_t (&k)[8])
-{
-	cex(k[0], k[1]); cex(k[2], k[3]); cex(k[4], k[5]); cex(k[6], k[7]);
-	cex(k[0], k[2]); cex(k[1], k[3]); cex(k[4], k[6]); cex(k[5], k[7]);
-	cex(k[1], k[2]); cex(k[5], k[6]); cex(k[0], k[4]); cex(k[3], k[7]);
-	cex(k[1], k[5]); cex(k[2], k[6]);
-	cex(k[1], k[4]); cex(k[3], k[6]);
-	cex(k[2], k[4]); cex(k[3], k[5]);
-	cex(k[3], k[4]);
-}
-
 template <int CAP>
 struct GF {
-	static constexpr size_t PROD = 0;                                  // u64[CAP]  raw -> packed (h, jr, pair, slot); later hv u32[CAP] + ov u16[CAP] of the long pairs
+	static constexpr size_t PROD = 0;                                  // u64[CAP]  raw -> packed (h, jr, pair, slot); later hv u32[CAP] + ov u16[CAP] in fold order + acc u32[CAP/2]
 	static constexpr size_t REC = PROD + 8 * (size_t)CAP;              // u64[CAP]  bits u32[CAP] + pre u16[CAP+2], then the products sorted by pair
 	static constexpr size_t CNT = REC + 8 * (size_t)CAP + 16;          // u16[CAP+2] per pair count -> offsets
 	static constexpr size_t ROW = CNT + 2 * (size_t)CAP + 16;          // u32[CAP]  row id of the pair
-	static constexpr size_t LST = ROW + 4 * (size_t)CAP;               // u16[CAP/8] pairs longer than SHORT_FOLD
-	static constexpr size_t L1 = LST + 2 * ((size_t)CAP / 8);          // u32[l1cap+1] level-1 bitmap + u32[l1cap+2] prefix (two-level units only)
+	static constexpr size_t LST = ROW + 4 * (size_t)CAP;               // u16[CAP/2] pairs for the warp path: longer than EP_MAX, or several bins
+	static constexpr size_t HEAD = LST + 2 * ((size_t)CAP / 2);        // u32[CAP/32+2] bit y set <=> a pair starts at sorted position y (+ sentinel at Fi)
+	static constexpr size_t L1 = HEAD + 4 * ((size_t)CAP / 32 + 2);    // u32[l1cap+1] level-1 bitmap + u32[l1cap+2] prefix (two-level units only)
 	static size_t bytes(uint32_t l1cap) { return L1 + 8 * ((size_t)l1cap + 2); }
 };
 
-// multiply of one product (overlapop) -> key ordered by the position in B's column:
-// jrank(16)<<48 | overlap(16)<<32 | v(16)<<16 | h(16)
-__device__ __forceinline__ uint64_t product_key(const Params& P, uint64_t rec, uint32_t j0, int lenH, int lenV, bool& wide)
+// One warp: the products of a long pair (keys, arrival order) -> hv/ov in fold order (position in B's
+// column).  The positions of one pair are distinct, so a bitmap over them ranks in O(len + L/32).
+__device__ __forceinline__ void warp_rank_pair(const uint64_t* key, uint32_t* hv, uint16_t* ov, uint32_t len, uint32_t L, uint32_t* scr, uint32_t lane)
 {
-	const uint32_t h = (uint32_t)rec & 0xFFFFu, jr = ((uint32_t)rec >> 16), sH = (uint32_t)(rec >> 32) & 1u;
-	const uint32_t jg = j0 + jr;
-	const uint32_t v = P.B_values[jg], sV = strand_of(P.B_strand, P.B_rowids, jg);
-	const uint32_t ov = overlap_estimate(lenH, lenV, h, v, sH == sV, P.K);
-	wide |= max(h, v) > 65535u - P.K;                              // positions this large need the 32-bit far test
-	return ((uint64_t)jr << 48) | ((uint64_t)ov << 32) | (uint64_t)(h | (v << 16));
-}
-
-// One warp: multiply the products of a long pair (rec, arrival order) and store them in fold order
-// (position in B's column) as hv/ov.  The positions of one pair are distinct, so a bitmap over
-// them ranks in O(len + L/32).  Returns (warp-uniform) whether a position needs the exact far test.
-__device__ __forceinline__ bool warp_prepare_pair(const Params& P, const uint64_t* rec, uint32_t* hv, uint16_t* ov, uint32_t len, uint32_t j0,
-		uint32_t L, int lenH, int lenV, uint32_t* scr, uint32_t lane)
-{
-	bool wide = false;
 	if (L <= JR_BITMAP_MAX) {
 		const uint32_t Lw = (L + 31) >> 5;
 		uint16_t* jpre = (uint16_t*)(scr + 128);
@@ -790,7 +822,7 @@ __device__ __forceinline__ bool warp_prepare_pair(const Params& P, const uint64_
 		__syncwarp();
 		#pragma unroll 1
 		for (uint32_t y = lane; y < len; y += 32) {
-			const uint32_t jr = ((uint32_t)rec[y] >> 16);
+			const uint32_t jr = (uint32_t)(key[y] >> 48);
 			atomicOr(&scr[jr >> 5], 1u << (jr & 31));
 		}
 		__syncwarp();
@@ -808,7 +840,7 @@ __device__ __forceinline__ bool warp_prepare_pair(const Params& P, const uint64_
 		__syncwarp();
 		#pragma unroll 1
 		for (uint32_t y = lane; y < len; y += 32) {
-			const uint64_t k = product_key(P, rec[y], j0, lenH, lenV, wide);
+			const uint64_t k = key[y];
 			const uint32_t jr = (uint32_t)(k >> 48);
 			const uint32_t rank = jpre[jr >> 5] + __popc(scr[jr >> 5] & ((1u << (jr & 31)) - 1u));
 			hv[rank] = (uint32_t)k; ov[rank] = (uint16_t)(k >> 32);
@@ -816,17 +848,18 @@ __device__ __forceinline__ bool warp_prepare_pair(const Params& P, const uint64_
 	} else {
 		#pragma unroll 1
 		for (uint32_t y = lane; y < len; y += 32) {
-			const uint64_t k = product_key(P, rec[y], j0, lenH, lenV, wide);
+			const uint64_t k = key[y];
 			const uint32_t jr = (uint32_t)(k >> 48);
 			uint32_t rank = 0;
 			#pragma unroll 1
-			for (uint32_t z = 0; z < len; ++z) rank += (((uint32_t)rec[z] >> 16) < jr);
+			for (uint32_t z = 0; z < len; ++z) rank += ((uint32_t)(key[z] >> 48) < jr);
 			hv[rank] = (uint32_t)k; ov[rank] = (uint16_t)(k >> 32);
 		}
 	}
 	__syncwarp();
-	return __any_sync(FULL, wide);
 }
+
+constexpr uint32_t EP_LIMIT = 128;         // upper bound of Params::ep_max (the per-pair accumulator packs counts for pairs up to this size)
 
 // EXACT = false is the fast kernel (packed 16-bit far test); a unit in which a position is too large for
 // it is appended to `redo` and done again by the EXACT = true instance (launched with redo as its list).
@@ -850,11 +883,13 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 	uint16_t* pre = (uint16_t*)(smem + GF<CAP>::REC + 4 * (size_t)CAP);
 	uint16_t* cnt = (uint16_t*)(smem + GF<CAP>::CNT);
 	uint32_t* rowS = (uint32_t*)(smem + GF<CAP>::ROW);
-	uint16_t* longlist = (uint16_t*)(smem + GF<CAP>::LST);
+	uint16_t* todo = (uint16_t*)(smem + GF<CAP>::LST);
+	uint32_t* head = (uint32_t*)(smem + GF<CAP>::HEAD);
+	uint32_t* acc = (uint32_t*)(smem + GF<CAP>::PROD + 6 * (size_t)CAP);       // u32[CAP/2], indexed by (pair start) / 2
 	uint32_t* l1 = (uint32_t*)(smem + GF<CAP>::L1);
 	uint32_t* l1pre = l1 + l1cap + 1;
 	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	const uint32_t K = P.K;
+	const uint32_t K = P.K, EP_MAX = P.ep_max;
 	const int BIN = (int)P.BIN;
 
 	if (tid == 0) mbar_init(&s_bar, 1);
@@ -893,7 +928,12 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 		for (uint32_t s = tid; s < nclear; s += NT) bits[s] = 0;
 		#pragma unroll 1
 		for (uint32_t s = tid; s < ((Fi + 3) >> 1); s += NT) ((uint32_t*)cnt)[s] = 0;
+		#pragma unroll 1
+		for (uint32_t s = tid; s < (Fi >> 5) + 2; s += NT) head[s] = 0;
 		if (tid == 0) { s_nlong = 0; s_nhuge = 0; s_next = 0; s_wide = 0; }
+		// what the multiply needs of the column read: where its k-mers start in B, and its length
+		const uint32_t j0 = P.B_colptr[i];
+		const int lenV = (int)P.read_len[i];
 		PHASE(15);
 		mbar_wait(&s_bar, phase);
 		phase ^= 1;
@@ -939,88 +979,120 @@ __global__ void __launch_bounds__(NT) k_group_fold(Params P, const uint32_t* __r
 		block_scan_chunked<uint16_t>(cnt, Z, [&](uint32_t p) { return (uint32_t)cnt[p]; }, s_tmp);     // counts -> offsets, poff[Z] = Fi
 		const uint16_t* poff = cnt;
 		PHASE(4);
+		// --- placement by pair, fused with the multiply (overlapop): key = jrank<<48 | overlap<<32 | v<<16 | h ---
+		bool wide = false;
 		#pragma unroll 1
 		for (uint32_t x = tid; x < Fi; x += NT) {
 			const uint64_t t = prodS[x];
-			sorted[poff[(uint32_t)(t >> 34) & 0x3FFFu] + ((uint32_t)(t >> 48) & 0x3FFFu)] = t & 0x1FFFFFFFFull;
+			const uint32_t p = (uint32_t)(t >> 34) & 0x3FFFu;
+			const uint32_t h = (uint32_t)t & 0xFFFFu, jr = (uint32_t)t >> 16, sH = (uint32_t)(t >> 32) & 1u;
+			const uint32_t jg = j0 + jr;
+			const uint32_t v = P.B_values[jg], sV = strand_of(P.B_strand, P.B_rowids, jg);
+			const uint32_t ov = overlap_estimate((int)P.read_len[rowS[p]], lenV, h, v, sH == sV, K);
+			wide |= max(h, v) > 65535u - K;                          // positions this large need the 32-bit far test
+			sorted[poff[p] + ((uint32_t)(t >> 48) & 0x3FFFu)] = ((uint64_t)jr << 48) | ((uint64_t)ov << 32) | (uint64_t)(h | (v << 16));
 		}
+		#pragma unroll 1
+		for (uint32_t p = tid; p <= Z; p += NT) { const uint32_t y = poff[p]; atomicOr(&head[y >> 5], 1u << (y & 31)); }   // p == Z: sentinel at Fi
+		if (!EXACT && (wide || K > 16383u)) s_wide = 1;
 		__syncthreads();
 		PHASE(5);
 
-		// --- fold.  Queue: first the pairs longer than SHORT_FOLD (one warp each), then tiles of 32 pairs whose
-		//     short members are multiplied, ordered (position in B's column) and folded by one thread each ---
-		const uint32_t j0 = P.B_colptr[i];
-		const int lenV = (int)P.read_len[i];
+		// --- fold order = position in B's column.  One thread per product: its pair is [start, end) between two head
+		//     bits; its rank is the number of smaller positions in the pair (pairs up to EP_MAX products) ---
 		uint4* out = P.out + base;
-		#pragma unroll 1
-		for (uint32_t p = tid; p < Z; p += NT)
-			if ((uint32_t)(poff[p + 1] - poff[p]) > SHORT_FOLD) longlist[atomicAdd(&s_nlong, 1u)] = (uint16_t)p;
-		__syncthreads();
-		const uint32_t nlong = s_nlong, nitems = nlong + ((Z + 31) >> 5);
-		PHASE(6);
 		const uint32_t Lcol = P.B_colptr[i + 1] - j0;
+		#pragma unroll 1
+		for (uint32_t s = tid; s < ((Fi + 1) >> 1); s += NT) acc[s] = 0;
+		auto pair_of = [&](uint32_t y, uint32_t& start, uint32_t& end) {
+			uint32_t w = y >> 5;
+			const uint32_t below = (2u << (y & 31)) - 1u;               // bits <= y
+			uint32_t m = head[w] & below;
+			while (!m) m = head[--w];                                  // bit 0 of word 0 is always set
+			start = (w << 5) + 31u - (uint32_t)__clz(m);
+			w = y >> 5;
+			m = head[w] & ~below;
+			while (!m) m = head[++w];                                  // the sentinel at Fi ends the search
+			end = (w << 5) + (uint32_t)__ffs(m) - 1u;
+		};
+		#pragma unroll 1
+		for (uint32_t y = tid; y < Fi; y += NT) {
+			uint32_t start, end;
+			pair_of(y, start, end);
+			const uint32_t len = end - start;
+			if (len > EP_MAX) continue;
+			const uint64_t k = sorted[y];
+			const uint32_t jr = (uint32_t)(k >> 48);
+			uint32_t rank = 0;
+			const uint32_t* hi = (const uint32_t*)sorted + 1;
+			#pragma unroll 1
+			for (uint32_t z = start; z < end; ++z) rank += (hi[2 * z] >> 16) < jr;
+			hvL[start + rank] = (uint32_t)k; ovL[start + rank] = (uint16_t)(k >> 32);
+		}
+		__syncthreads();
+		PHASE(6);
+
+		// --- fold (chain.hpp:100-150), the one-bin case: product s is dropped at the first later product that is near it ---
+		{
+			const uint32_t lim = far_limit<EXACT>(K);
+			#pragma unroll 1
+			for (uint32_t sx = tid; sx < Fi; sx += NT) {
+				uint32_t start, end;
+				pair_of(sx, start, end);
+				const uint32_t len = end - start;
+				if (len < 2 || len > EP_MAX) continue;
+				if (sx > start && abs((int)ovL[sx] - (int)ovL[sx - 1]) >= BIN) atomicOr(&acc[start >> 1], 0x80000000u);   // several bins
+				const FarKey key = far_key<EXACT>(hvL[sx], K);
+				uint32_t t = sx + 1;
+				#pragma unroll 1
+				for (; t < end; ++t) if (!is_far<EXACT>(hvL[t], key, lim)) break;
+				atomicAdd(&acc[start >> 1], (t - sx - 1) + ((uint32_t)(t == end) << 20));
+			}
+		}
+		__syncthreads();
+		// --- one thread per pair: result of the one-bin pairs; the others go to the warp path ---
+		#pragma unroll 1
+		for (uint32_t p = tid; p < Z; p += NT) {
+			const uint32_t start = poff[p], len = poff[p + 1] - start;
+			PairResult R;
+			if (len == 1) { R.count = 1; R.hv = hvL[start]; R.nbins = 1; R.sup = 1; R.ov = ovL[start]; }
+			else {
+				const uint32_t a = len <= EP_MAX ? acc[start >> 1] : 0x80000000u;
+				if (a >> 31) { todo[atomicAdd(&s_nlong, 1u)] = (uint16_t)p; continue; }
+				R.count = (len + (a & 0xFFFFFu)) & 0xFFFFu; R.hv = hvL[start + len - 1]; R.nbins = 1; R.sup = (a >> 20) & 0x7FFu; R.ov = ovL[start + len - 1];
+			}
+			out[p] = pack_result(rowS[p], R);
+		}
+		__syncthreads();
+		PHASE(7);
+		// --- warp path: one warp per remaining pair (longer than EP_MAX: ranked through a position bitmap; several bins: the forest) ---
+		const uint32_t nlong = s_nlong;
 		uint32_t* scr = wscr + wid * WSCR_WORDS;
-		bool wide = false;
 		for (;;) {
 			uint32_t q = 0;
 			if (lane == 0) q = atomicAdd(&s_next, 1u);
 			q = __shfl_sync(FULL, q, 0);
-			if (q >= nitems) break;
-#if BELLA_PHASE_CLOCKS > 1
-			const long long wq0_ = clock64();
-#endif
-			if (q < nlong) {
-				const uint32_t p = longlist[q], s0 = poff[p], len = poff[p + 1] - s0;
-				if (len > 1024) { if (lane == 0) hugelist[atomicAdd(&s_nhuge, 1u)] = (uint16_t)p; continue; }
-				const uint32_t row = rowS[p];
-				wide |= warp_prepare_pair(P, sorted + s0, hvL + s0, ovL + s0, len, j0, Lcol, (int)P.read_len[row], lenV, scr, lane);
-				PairResult R = warp_fold_pair<EXACT>(hvL + s0, ovL + s0, sorted + s0, len, K, BIN, lane);
-				if (lane == 0) out[p] = pack_result(row, R);
-#if BELLA_PHASE_CLOCKS > 1
-				if (lane == 0) { atomicAdd(&g_phase[9], (unsigned long long)(clock64() - wq0_)); atomicAdd(&g_phase[11], (unsigned long long)len); atomicAdd(&g_phase[13], 1ull); }
-#endif
-			} else {
-				const uint32_t p = ((q - nlong) << 5) + lane;
-				if (p >= Z) continue;
-				const uint32_t s0 = poff[p], len = poff[p + 1] - s0;
-				if (len > SHORT_FOLD) continue;
-				const uint32_t row = rowS[p];
-				const int lenH = (int)P.read_len[row];
-				uint64_t key[SHORT_FOLD];
-#pragma unroll 1
-				for (uint32_t k = 0; k < len; ++k) sorted[s0 + k] = product_key(P, sorted[s0 + k], j0, lenH, lenV, wide);   // in place (own slots)
-#pragma unroll
-				for (int k = 0; k < (int)SHORT_FOLD; ++k) key[k] = k < (int)len ? sorted[s0 + k] : ~0ull;
-				if (len > 1) sort8(key);
-				uint32_t hv[SHORT_FOLD];
-				uint16_t ov[SHORT_FOLD];
-#pragma unroll
-				for (int k = 0; k < (int)SHORT_FOLD; ++k) { hv[k] = (uint32_t)key[k]; ov[k] = (uint16_t)(key[k] >> 32); }
-				out[p] = pack_result(row, fold_short<EXACT>(hv, ov, len, K, BIN));
-#if BELLA_PHASE_CLOCKS > 1
-				atomicAdd(&g_phase[12], (unsigned long long)len); atomicAdd(&g_phase[14], 1ull);
-				if (lane == (uint32_t)__ffs(__activemask()) - 1u) atomicAdd(&g_phase[10], (unsigned long long)(clock64() - wq0_));
-#endif
-			}
+			if (q >= nlong) break;
+			const uint32_t p = todo[q], s0 = poff[p], len = poff[p + 1] - s0;
+			if (len > 1024) { if (lane == 0) hugelist[atomicAdd(&s_nhuge, 1u)] = (uint16_t)p; continue; }
+			if (len > EP_MAX) warp_rank_pair(sorted + s0, hvL + s0, ovL + s0, len, Lcol, scr, lane);
+			PairResult R = warp_fold_pair<EXACT>(hvL + s0, ovL + s0, sorted + s0, len, K, BIN, lane);
+			if (lane == 0) out[p] = pack_result(rowS[p], R);
 		}
-		if (!EXACT && (wide || K > 16383u)) s_wide = 1;
 		__syncthreads();
-		PHASE(7);
+		PHASE(8);
 		const uint32_t nhuge = s_nhuge;                             // at most CAP/1024 pairs: the whole CTA takes each
 		#pragma unroll 1
 		for (uint32_t q = 0; q < nhuge; ++q) {
 			const uint32_t p = hugelist[q], s0 = poff[p], len = poff[p + 1] - s0;
 			const uint32_t row = rowS[p];
-			const int lenH = (int)P.read_len[row];
 			#pragma unroll 1
 			for (uint32_t y = tid; y < len; y += NT) {
-				bool w2 = false;
-				const uint64_t k = product_key(P, sorted[s0 + y], j0, lenH, lenV, w2);
-				if (!EXACT && w2) s_wide = 1;
+				const uint64_t k = sorted[s0 + y];
 				const uint32_t jr = (uint32_t)(k >> 48);
 				uint32_t rank = 0;
 				#pragma unroll 1
-				for (uint32_t z = s0; z < s0 + len; ++z) rank += (((uint32_t)sorted[z] >> 16) < jr);
+				for (uint32_t z = s0; z < s0 + len; ++z) rank += ((uint32_t)(sorted[z] >> 48) < jr);
 				hvL[s0 + rank] = (uint32_t)k; ovL[s0 + rank] = (uint16_t)(k >> 32);
 			}
 			if (tid < 3) s_part[tid] = 0;
@@ -1098,12 +1170,9 @@ __global__ void __launch_bounds__(1024) k_huge_pair(Params P, const uint32_t* __
 // per source GPU.  k_regroup moves the segments into the unit regions the group kernel expects
 // (COUNT = true only counts the products per unit of the heavy columns, for the planner).
 
-__global__ void k_mg_colinfo(uint32_t n, const uint64_t* __restrict__ sendoff, ColInfo* __restrict__ colinfo, unsigned long long* __restrict__ ucur)
+__global__ void k_mg_colinfo(uint32_t n, const uint64_t* __restrict__ sendoff, unsigned long long* __restrict__ ccur)
 {
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		colinfo[i] = ColInfo{i, 31u};
-		ucur[i] = sendoff[i];
-	}
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) ccur[(size_t)i * CCUR_STRIDE] = sendoff[i];
 }
 
 __global__ void k_mg_sum_counts(uint32_t n, uint32_t lo, uint32_t ncols, uint32_t world, const uint32_t* __restrict__ counts_all,
@@ -1230,17 +1299,19 @@ __global__ void __launch_bounds__(256) k_route_fill(uint32_t n_local, uint32_t r
 }
 
 // received records -> k-mer buckets (the same fixed-capacity layout k_partition fills)
-__global__ void __launch_bounds__(256) k_partition_rec(uint64_t nrec, const uint32_t* __restrict__ rec, uint32_t klo, uint32_t khi, uint32_t W,
-		uint32_t* __restrict__ bcnt, uint4* __restrict__ part, int* err)
+__global__ void __launch_bounds__(256) k_partition_rec(uint64_t nrec, const uint32_t* __restrict__ rec, uint32_t klo, uint32_t khi, uint32_t wshift,
+		uint32_t* __restrict__ bcnt, uint64_t* __restrict__ partE, uint16_t* __restrict__ partK, int* err)
 {
+	const uint32_t wmask = (1u << wshift) - 1u;
 	for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < nrec; t += (uint64_t)gridDim.x * blockDim.x) {
 		const uint32_t c = rec[3 * t], kid = c & 0x7FFFFFFFu, rd = rec[3 * t + 1], pj = rec[3 * t + 2];
 		if (kid < klo || kid >= khi) { set_err(err, -5); continue; }
-		const uint32_t b = (kid - klo) / W;
-		const uint32_t q = atomicAdd(&bcnt[b], 1u);
+		const uint32_t b = (kid - klo) >> wshift;
+		const uint32_t q = atomicAdd(&bcnt[(size_t)b * BCNT_STRIDE], 1u);
 		if (q >= BUCKET_CAP) { set_err(err, -6); continue; }
-		const uint64_t e = (uint64_t)rd | ((uint64_t)(c >> 31) << 31) | ((uint64_t)(pj & 0xFFFFu) << 32) | ((uint64_t)(pj >> 16) << 48);
-		part[(size_t)b * BUCKET_CAP + q] = make_uint4(kid, 0u, (uint32_t)e, (uint32_t)(e >> 32));
+		const size_t at = (size_t)b * BUCKET_CAP + q;
+		partE[at] = (uint64_t)rd | ((uint64_t)(c >> 31) << 31) | ((uint64_t)(pj & 0xFFFFu) << 32) | ((uint64_t)(pj >> 16) << 48);
+		partK[at] = (uint16_t)((kid - klo) & wmask);
 	}
 }
 
@@ -1373,7 +1444,7 @@ __global__ void k_colptr(uint32_t ncols, const uint32_t* __restrict__ ubase, con
 // one warp per unit: per-unit pair records -> C (SoA), at the unit's final offset
 __global__ void __launch_bounds__(256) k_compact(uint32_t U, const uint64_t* __restrict__ uptr, const uint32_t* __restrict__ uoff,
 		const uint4* __restrict__ out, uint32_t* __restrict__ rowsC, uint16_t* __restrict__ countC, uint16_t* __restrict__ posH,
-		uint16_t* __restrict__ posV, uint16_t* __restrict__ aux)
+		uint16_t* __restrict__ posV, uint16_t* __restrict__ aux, unsigned long long* __restrict__ n_unpinned)
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -1382,6 +1453,8 @@ __global__ void __launch_bounds__(256) k_compact(uint32_t U, const uint64_t* __r
 		const uint4* src = out + uptr[u];
 		for (uint32_t p = lane; p < Z; p += 32) {
 			const uint4 r = src[p];
+			// choose() (common.h:162-170) runs std::sort over the bins: its tie order is pinned for up to 16 bins only
+			if ((r.y >> 16) > 16u) atomicAdd(n_unpinned, 1ull);
 			const size_t g = (size_t)g0 + p;
 			rowsC[g] = r.x;
 			countC[g] = (uint16_t)(r.y & 0xFFFFu);

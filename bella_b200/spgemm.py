@@ -17,6 +17,12 @@ ERRORS = {-1: "bad argument", -2: "CUDA error / no usable sm_100 device (there i
           -3: "device out of memory", -4: "count exceeds the reference's index types", -5: "internal device error"}
 
 
+class CsrView(ctypes.Structure):
+    """bella_csr_view: mirror of CSR<uint32_t, unsigned short> (reference include/common/CSR.h:15-67)"""
+    _fields_ = [("rows", ctypes.c_uint32), ("cols", ctypes.c_uint32), ("nnz", ctypes.c_uint32),
+                ("rowptr", ctypes.c_void_p), ("colids", ctypes.c_void_p), ("values", ctypes.c_void_p), ("zerobased", ctypes.c_int)]
+
+
 class CscView(ctypes.Structure):
     _fields_ = [("rows", ctypes.c_uint32), ("cols", ctypes.c_uint32), ("nnz", ctypes.c_uint32),
                 ("colptr", ctypes.c_void_p), ("rowids", ctypes.c_void_p), ("values", ctypes.c_void_p)]
@@ -36,11 +42,13 @@ def lib():
         L.bella_b200_last_error.restype = ctypes.c_char_p
         for f in ("bella_b200_set_inputs", "bella_b200_set_inputs_device"):
             getattr(L, f).argtypes = [H, ctypes.POINTER(CscView), ctypes.POINTER(CscView), vp, vp, vp, ctypes.c_uint16, ctypes.c_uint16]
+        L.bella_b200_set_inputs_csr.argtypes = [H, ctypes.POINTER(CsrView), vp, vp, ctypes.c_uint16, ctypes.c_uint16]
         L.bella_b200_set_column_range.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32]
         L.bella_b200_symbolic.argtypes = [H, ctypes.POINTER(ctypes.c_uint64), vp, vp]
         L.bella_b200_numeric.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp, vp]
         L.bella_b200_numeric_aux.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp]
         L.bella_b200_numeric_device.argtypes = [H]
+        L.bella_b200_n_unpinned.argtypes = [H, ctypes.POINTER(ctypes.c_uint64)]
         L.bella_b200_result_device.argtypes = [H] + [ctypes.POINTER(vp)] * 5 + [ctypes.POINTER(ctypes.c_uint64)]
         L.bella_b200_run_resident.argtypes = [H, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
         L.bella_b200_get_timings.argtypes = [H, ctypes.POINTER(ctypes.c_float)]
@@ -59,7 +67,7 @@ def lib():
     return _lib
 
 
-EXPORTS = ["bella_b200_create", "bella_b200_destroy", "bella_b200_last_error", "bella_b200_set_inputs",
+EXPORTS = ["bella_b200_set_inputs_csr", "bella_b200_n_unpinned", "bella_b200_create", "bella_b200_destroy", "bella_b200_last_error", "bella_b200_set_inputs",
            "bella_b200_set_inputs_device", "bella_b200_set_column_range", "bella_b200_symbolic",
            "bella_b200_numeric", "bella_b200_numeric_aux", "bella_b200_numeric_device",
            "bella_b200_result_device", "bella_b200_run_resident", "bella_b200_get_timings", "bella_b200_stream",
@@ -253,6 +261,20 @@ class OverlapSpGEMM:
         out = {k: (p.value or 0) for k, p in zip(("colptrC", "rowids", "count", "posH", "posV"), ptrs)}
         out["nnz"] = z.value
         return out
+
+    def n_unpinned(self):
+        """pairs with more than 16 bins (choose()'s tie order is unpinned there, common.h:162-170)"""
+        v = ctypes.c_uint64(0)
+        self._check(self._L.bella_b200_n_unpinned(self._h, ctypes.byref(v)), "bella_b200_n_unpinned")
+        return int(v.value)
+
+    def set_inputs_csr(self, inp):
+        """The CSR surface: A row-major == B's CSC arrays (include/bella_b200.h bella_csr_view)."""
+        v = CsrView(inp.n_reads, inp.n_kmers, inp.nnz, _ptr(inp.B_colptr), _ptr(inp.B_rowids), _ptr(inp.B_values), 1)
+        self._keep = inp
+        self._check(self._L.bella_b200_set_inputs_csr(self._h, ctypes.byref(v), _ptr(inp.read_len), _ptr(inp.B_strand), inp.kmer_size, inp.bin_size),
+                    "bella_b200_set_inputs_csr")
+        self.n, self.m, self.lo, self.hi = inp.n_reads, inp.n_kmers, 0, inp.n_reads
 
     def numeric_device(self):
         self._check(self._L.bella_b200_numeric_device(self._h), "bella_b200_numeric_device")

@@ -52,6 +52,31 @@ typedef struct bella_csc_view {
 	const uint16_t* values;   /* [nnz]    */
 } bella_csc_view;
 
+/* Mirror of the public members of CSR<uint32_t, unsigned short> (reference include/common/CSR.h:15-67; the CSC -> CSR
+ * conversion is src/CSR.cpp:59-91).  BELLA itself never instantiates CSR on this path, but a caller
+ * that holds its read x k-mer matrix row-major can hand it over as is: the CSR arrays of A ARE the CSC arrays of
+ * B = A^T (rowptr == B.colptr, colids == B.rowids), see bella_csr_as_transposed_csc below.  The order of the entries
+ * inside a row is then the fold order of the semiring (what B's column order is for the CSC surface): the reference's
+ * own conversion CSR(const CSC&) emits a row's entries by ascending column id, which is NOT the order MergeDuplicates
+ * left in `transpmat`, so results equal the reference's only if the rows keep transpmat's column order. */
+typedef struct bella_csr_view {
+	uint32_t rows, cols, nnz;
+	const uint32_t* rowptr;   /* [rows+1] */
+	const uint32_t* colids;   /* [nnz]    */
+	const uint16_t* values;   /* [nnz]    */
+	int zerobased;            /* CSR::zerobased; one-based views (after ConvertOneBased(), CSR.h:41-49) are refused */
+} bella_csr_view;
+
+/* Zero-copy reinterpretation: CSR of A (reads x k-mers) -> CSC of B = A^T (k-mers x reads).  Returns 0, or
+ * BELLA_B200_ERR_ARG for a one-based view. */
+static inline int bella_csr_as_transposed_csc(const bella_csr_view* A_csr, bella_csc_view* B_out)
+{
+	if (!A_csr || !B_out || !A_csr->zerobased) return -1;
+	B_out->rows = A_csr->cols; B_out->cols = A_csr->rows; B_out->nnz = A_csr->nnz;
+	B_out->colptr = A_csr->rowptr; B_out->rowids = A_csr->colids; B_out->values = A_csr->values;
+	return 0;
+}
+
 /* One handle per GPU.  device = CUDA ordinal. */
 int bella_b200_create(bella_b200_handle** out, int device);
 int bella_b200_destroy(bella_b200_handle* h);
@@ -73,6 +98,12 @@ const char* bella_b200_last_error(const bella_b200_handle* h);
 int bella_b200_set_inputs(bella_b200_handle* h, const bella_csc_view* A, const bella_csc_view* B,
 		const uint32_t* read_len, const uint8_t* strand_A, const uint8_t* strand_B,
 		uint16_t kmer_size, uint16_t bin_size);
+
+/* The CSR surface of the same call: A given row-major (reads x k-mers, HOST arrays).  Equivalent to
+ * bella_b200_set_inputs(h, NULL, B, ...) with B = bella_csr_as_transposed_csc(A_csr); strand bits are per nonzero in the
+ * CSR array order. */
+int bella_b200_set_inputs_csr(bella_b200_handle* h, const bella_csr_view* A_csr, const uint32_t* read_len,
+		const uint8_t* strand, uint16_t kmer_size, uint16_t bin_size);
 
 /* Same, but every pointer (including those inside the views) is a DEVICE pointer on the handle's
  * GPU; nothing is copied and the caller keeps the buffers alive until the next set_inputs/destroy.
@@ -111,6 +142,13 @@ int bella_b200_numeric(bella_b200_handle* h, uint32_t col_begin, uint32_t col_en
  *   overlap  overlap estimate of the chosen bin   (spmatType_::overlaplength(), common.h:152-159) */
 int bella_b200_numeric_aux(bella_b200_handle* h, uint32_t col_begin, uint32_t col_end,
 		uint16_t* nbins, uint16_t* support, uint16_t* overlap);
+
+/* Number of output nonzeros of the handle's column range whose final value has MORE THAN 16 bins.  For those the
+ * reference's choose() (include/common/common.h:162-170) depends on the tie order of libstdc++'s introsort, which is
+ * pinned (insertion sort, stable) only up to 16 elements: the device picks the best-supported bin with ties to the most
+ * recent one, exactly as for fewer bins, and reports here how many pairs that rule was not validated for (0 on every
+ * input seen so far; the CPU oracle counts the same thing).  Valid after the numeric phase. */
+int bella_b200_n_unpinned(bella_b200_handle* h, uint64_t* n_unpinned);
 
 /* Device-resident results of the whole column range after bella_b200_numeric_device():
  * runs the numeric phase without any device->host copy. */

@@ -181,3 +181,33 @@ def test_gpu_many_reads_two_level_row_bitmap():
     inp = fe.synthetic(70000, 1000, coverage=20.0, seed=41)
     assert inp.n_reads > 65536 + 2048
     ol.assert_same(gpu_result(inp), ol.oracle_spgemm(inp))
+
+
+def test_gpu_csr_surface_and_unpinned_count(small_inputs):
+    """a14: A handed over row-major (bella_csr_view; CSR.h:15-67) is B's CSC reinterpreted -- same results; and the count
+    of pairs with more than 16 bins (choose()'s unpinned tie order, common.h:162-170) equals the oracle's."""
+    from bella_b200 import spgemm
+    want = ol.oracle_spgemm(small_inputs)
+    g = spgemm.OverlapSpGEMM(0)
+    try:
+        g.set_inputs_csr(small_inputs)
+        flops, flopC, colptrC = g.symbolic()
+        rows, cnt, pH, pV, aux = g.numeric(aux=True)
+        got = ol.Result(flopC, colptrC, rows, cnt, pH, pV, aux)
+        ol.assert_same(got, want)
+        assert g.n_unpinned() == want.unpinned == int((want.aux[:, 0] > 16).sum())
+    finally:
+        g.close()
+
+
+def test_gpu_one_based_csr_is_refused(small_inputs):
+    import ctypes
+    from bella_b200 import spgemm
+    inp = small_inputs
+    g = spgemm.OverlapSpGEMM(0)
+    try:
+        v = spgemm.CsrView(inp.n_reads, inp.n_kmers, inp.nnz, inp.B_colptr.ctypes.data, inp.B_rowids.ctypes.data, inp.B_values.ctypes.data, 0)
+        rc = spgemm.lib().bella_b200_set_inputs_csr(g._h, ctypes.byref(v), inp.read_len.ctypes.data, inp.B_strand.ctypes.data, 17, 500)
+        assert rc == -1
+    finally:
+        g.close()
