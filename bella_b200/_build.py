@@ -1,4 +1,5 @@
-"""In-tree builds of the native libraries (no JIT cache: the built .so files travel with the repo).
+"""In-tree builds of the native libraries (no JIT cache: the built .so files are git-ignored but travel to the GPU box with the
+snapshot of the tree, each with a `.src` digest of the sources it was built from).
 
   libbella_b200.so      bella_b200/csrc/bella_b200.cu  -- CUDA kernels (sm_100a) + the C-ABI (include/bella_b200.h)
   libbella_xdrop.so     bella_b200/csrc/bella_xdrop.cu -- "next" row f1: X-drop seed-and-extend kernels + C-ABI (include/bella_xdrop.h)
@@ -23,11 +24,29 @@ NVCC_FLAGS = [
 ]
 
 
-def _stale(target, sources):
-    if not os.path.exists(target):
+def _digest(sources, flags=()):
+    import hashlib
+    h = hashlib.sha256(" ".join(flags).encode())
+    for s in sources:
+        with open(s, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stale(target, sources, flags=()):
+    """A library is current when the digest of its sources (written beside it when it was built) matches: file times do
+    not survive the copy to the GPU box, a digest does.  The bindings call build_*() on every load, so a parity test can
+    never run against a binary built from older kernels."""
+    side = target + ".src"
+    if not (os.path.exists(target) and os.path.exists(side)):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(s) > t for s in sources)
+    with open(side) as f:
+        return f.read().strip() != _digest(sources, flags)
+
+
+def _built(target, sources, flags=()):
+    with open(target + ".src", "w") as f:
+        f.write(_digest(sources, flags))
 
 
 def _nvcc():
@@ -46,6 +65,7 @@ def build_cuda(force=False, verbose=False):
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)
+    _built(LIB_CUDA, srcs)
     return LIB_CUDA
 
 
@@ -58,6 +78,7 @@ def build_xdrop(force=False, verbose=False):
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)
+    _built(LIB_XDROP, srcs)
     return LIB_XDROP
 
 
@@ -70,6 +91,7 @@ def build_kmers(force=False, verbose=False):
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)
+    _built(LIB_KMERS, srcs)
     return LIB_KMERS
 
 
@@ -79,6 +101,7 @@ def build_frontend(force=False):
         return LIB_FE
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     subprocess.run([cxx, "-O3", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-Wall", "-o", LIB_FE, src], check=True)
+    _built(LIB_FE, [src])
     return LIB_FE
 
 

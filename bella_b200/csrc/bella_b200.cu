@@ -66,8 +66,13 @@ struct bella_b200_handle {
 	DevBuf oB_colptr, oB_rowids, oB_values, oB_strand, o_len;
 	// chunked upload of host inputs, overlapped with the transpose (bella_b200_set_inputs)
 	static constexpr int MAX_CHUNKS = 8;
+	cudaStream_t sc_stream = nullptr;          // the scatter passes of the scatter | group pipeline
+	cudaEvent_t sc_t0 = nullptr, sc_t1 = nullptr;
+	uint32_t nrange = 1;                       // ranges of that pipeline in the current pass (1: multi-GPU finish)
 	cudaStream_t copy_stream = nullptr, aux_stream = nullptr;   // aux: the larger group classes run beside the 2048 class
 	cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+	static constexpr int PIPE = 4;             // ranges of the level-2 partition | bucket pipeline and of the scatter | group pipeline
+	cudaEvent_t pipe_ev[PIPE]{};
 	cudaEvent_t chunk_ev[MAX_CHUNKS]{}, copy_begin = nullptr, copy_end = nullptr;
 	uint32_t chunk_lo[MAX_CHUNKS + 1]{};
 	int n_chunks = 0;                          // > 0: reads [chunk_lo[c], chunk_lo[c+1]) are on the device once chunk_ev[c] has fired
@@ -125,6 +130,7 @@ inline int grid_for(uint64_t work, int threads, int cap = 148 * 16)
 	return (int)g;
 }
 
+struct Widen { __host__ __device__ unsigned long long operator()(uint32_t x) const { return x; } };
 struct PadEven { __host__ __device__ unsigned long long operator()(uint32_t x) const { return ((unsigned long long)x + 1ull) & ~1ull; } };
 
 template <class In, class Out>
@@ -148,9 +154,36 @@ int read_flags(bella_b200_handle* h, int* e)
 
 int report_device_error(bella_b200_handle* h, int e)
 {
+	if (e == -9) return fail(h, BELLA_B200_ERR_CAPACITY, "a multi-GPU exchange buffer is too small on some rank (the needed sizes are behind the push plan)");
+	if (e == ERR_BUCKET) return fail(h, BELLA_B200_ERR_CAPACITY, "a transpose bucket overflowed on some rank");
 	if (e == BELLA_B200_ERR_RANGE)
 		return fail(h, e, "a read has more than 65536 k-mers, or one read pair shares more than 65535 k-mers");
 	return fail(h, BELLA_B200_ERR_INTERNAL, "device-side error %d", e);
+}
+
+// Geometry of the two-level partition of `ml` k-mer ids holding about `nnz` nonzeros: fine buckets of W = 2^wshift k-mers
+// (about 0.7 * BUCKET_CAP entries on average), coarse buckets of 2^shift1 k-mers, at most RP_NBMAX of each per level.
+struct RpGeom { uint32_t W, wshift, NB, l2, shift1, nb1; };
+int rp_geometry(uint64_t ml, uint64_t nnz, uint32_t W_forced, RpGeom* g)
+{
+	uint32_t W = W_forced;
+	if (!W) {
+		double avg = (double)nnz / (double)(ml ? ml : 1);
+		double w = 0.7 * BUCKET_CAP / (avg > 0.25 ? avg : 0.25);
+		W = 1;
+		while (W * 2 <= BUCKET_WMAX && (double)(W * 2) <= w) W *= 2;
+	}
+	g->W = W; g->wshift = 0;
+	while ((1u << g->wshift) < W) ++g->wshift;
+	g->NB = (uint32_t)((ml + W - 1) / W);
+	uint32_t bits = 0;
+	while ((1ull << bits) < g->NB) ++bits;
+	uint32_t l2 = bits / 2, l1 = bits - l2;
+	if (l1 > 10) { l1 = 10; l2 = bits - l1; }
+	if (l2 > 10) return -1;
+	g->l2 = l2; g->shift1 = g->wshift + l2;
+	g->nb1 = (uint32_t)((ml + (1ull << g->shift1) - 1) >> g->shift1);
+	return 0;
 }
 
 // transpose: B (read-major) -> Aent (k-mer-major, columns sorted by read id) for the k-mers [klo, khi)
@@ -172,18 +205,11 @@ int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32
 		h->NB = 0;
 		return 0;
 	}
-	if (!h->W) {
-		// buckets of 2^wshift k-mers, about 0.7 * BUCKET_CAP entries each on average
-		double avg = rec ? (double)nnz / (double)ml : (double)nnz / (double)h->m;
-		double w = 0.7 * BUCKET_CAP / (avg > 0.25 ? avg : 0.25);
-		uint32_t W = 1;
-		while (W * 2 <= BUCKET_WMAX && (double)(W * 2) <= w) W *= 2;
-		h->W = W;
-	}
-	const uint32_t W = h->W;
-	uint32_t wshift = 0;
-	while ((1u << wshift) < W) ++wshift;
-	const uint32_t NB = (uint32_t)(((uint64_t)ml + W - 1) / W);
+	RpGeom geo;
+	if (rp_geometry(ml, rec ? nnz : (uint64_t)((double)nnz * ml / (h->m ? h->m : 1)), h->W, &geo))
+		return fail(h, BELLA_B200_ERR_RANGE, "%u k-mers are more than the two-level partition addresses", ml);
+	h->W = geo.W;
+	const uint32_t W = geo.W, wshift = geo.wshift, NB = geo.NB;
 	h->NB = NB;
 	ENSURE(h->bcur, sizeof(uint32_t) * ((size_t)NB + 2) * BCNT_STRIDE);
 	ENSURE(h->bsize, sizeof(uint32_t) * ((size_t)NB + 2));
@@ -199,24 +225,18 @@ int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32
 		k_partition_rec<<<grid_for(nrec, 256), 256, 0, h->stream>>>(nrec, rec, h->klo, h->khi, wshift, bcnt, partE, partK, h->errflag.as<int>());
 		LAUNCHED();
 	} else {
-		// two levels: the fine-bucket bits are split between a coarse level (nb1 buckets of 2^shift1 k-mers) and the fine
-		// buckets inside one coarse bucket, at most RP_NBMAX each
-		uint32_t bits = 0;
-		while ((1ull << bits) < NB) ++bits;
-		uint32_t l2 = bits / 2, l1 = bits - l2;
-		if (l1 > 10) { l1 = 10; l2 = bits - l1; }
-		if (l2 > 10) return fail(h, BELLA_B200_ERR_RANGE, "%u transpose buckets are more than the two-level partition addresses", NB);
-		const uint32_t shift1 = wshift + l2;
-		const uint32_t nb1 = (uint32_t)(((uint64_t)ml + (1ull << shift1) - 1) >> shift1);
+		const uint32_t l2 = geo.l2, shift1 = geo.shift1, nb1 = geo.nb1;
 		const double share = (double)ml / (double)(h->m ? h->m : 1);           // multi-GPU: only the k-mers [klo, khi) are this handle's
-		const uint64_t cap64 = (uint64_t)((double)nnz * share / nb1 * h->cap_scale) + 2 * RP_TILE;
+		const uint32_t groups = 1;                                             // one writer per coarse bucket on one GPU
+		const uint32_t nsb = nb1 * groups;
+		const uint64_t cap64 = (uint64_t)((double)nnz * share / nsb * h->cap_scale) + 2 * RP_TILE;
 		if (cap64 > 0x7FFFFFFFull) return fail(h, BELLA_B200_ERR_RANGE, "coarse transpose bucket too large");
 		const uint32_t cap1 = (uint32_t)((cap64 + 15) & ~15ull);
-		ENSURE(h->rp_cur, sizeof(uint32_t) * ((size_t)nb1 + 2) * BCNT_STRIDE);
-		ENSURE(h->rp_tiles, sizeof(uint32_t) * ((size_t)nb1 + 2));
-		ENSURE(h->rp_E, sizeof(uint64_t) * (size_t)nb1 * cap1 + 64);
-		ENSURE(h->rp_K, sizeof(uint32_t) * (size_t)nb1 * cap1 + 64);
-		CK(cudaMemsetAsync(h->rp_cur.p, 0, sizeof(uint32_t) * ((size_t)nb1 + 2) * BCNT_STRIDE, h->stream));
+		ENSURE(h->rp_cur, sizeof(uint32_t) * ((size_t)nsb + 2) * BCNT_STRIDE);
+		ENSURE(h->rp_tiles, sizeof(uint32_t) * ((size_t)nsb + 2));
+		ENSURE(h->rp_E, sizeof(uint64_t) * (size_t)nsb * cap1 + 64);
+		ENSURE(h->rp_K, sizeof(uint32_t) * (size_t)nsb * cap1 + 64);
+		CK(cudaMemsetAsync(h->rp_cur.p, 0, sizeof(uint32_t) * ((size_t)nsb + 2) * BCNT_STRIDE, h->stream));
 		CK(cudaFuncSetAttribute(k_rp1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RP_SMEM));
 		CK(cudaFuncSetAttribute(k_rp2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RP_SMEM));
 		CK(cudaEventRecord(h->ev[8], h->stream));
@@ -224,8 +244,11 @@ int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32
 		auto rp1 = [&](uint32_t r0, uint32_t r1) {
 			uint32_t g = (r1 - r0 + warps_per_cta - 1) / warps_per_cta;
 			if (g > (uint32_t)h->sms * 2) g = (uint32_t)h->sms * 2;
+			RpOut O{};
+			O.groups = 1; O.me = 0; O.nb1_loc = nb1; O.kpr = 0;
+			O.E[0] = h->rp_E.as<uint64_t>(); O.K[0] = h->rp_K.as<uint32_t>();
 			k_rp1<<<g, RP_THREADS, RP_SMEM, h->stream>>>(r1, r0, h->klo, h->khi, h->dB_colptr, h->dB_rowids, h->dB_values, h->dB_strand,
-				shift1, nb1, cap1, h->rp_cur.as<uint32_t>(), h->rp_E.as<uint64_t>(), h->rp_K.as<uint32_t>(), h->errflag.as<int>());
+				shift1, nb1, cap1, h->rp_cur.as<uint32_t>(), O, h->errflag.as<int>());
 		};
 		if (h->n_chunks > 0) {
 			// host inputs are still arriving chunk by chunk: partition each range of reads as soon as it is on the device
@@ -240,18 +263,42 @@ int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32
 			rp1(row_lo, n);
 			LAUNCHED();
 		}
-		k_rp_tiles<<<1, 1024, 0, h->stream>>>(nb1, cap1, h->rp_cur.as<uint32_t>(), h->rp_tiles.as<uint32_t>());
+		k_rp_tiles<<<1, 1024, 0, h->stream>>>(nsb, cap1, h->rp_cur.as<uint32_t>(), h->rp_tiles.as<uint32_t>());
 		LAUNCHED();
-		k_rp2<<<h->sms * 2, RP_THREADS, RP_SMEM, h->stream>>>(shift1, wshift, nb1, cap1, h->rp_cur.as<uint32_t>(), h->rp_tiles.as<uint32_t>(),
-			h->rp_E.as<uint64_t>(), h->rp_K.as<uint32_t>(), bcnt, partE, partK, h->errflag.as<int>());
-		LAUNCHED();
+		// Level 2 and the bucket kernel run as a pipeline over a few ranges of coarse buckets: the partition is bound by
+		// memory latency, the bucket kernel by instruction issue, so the bucket kernel of one range runs (on the second
+		// stream) beside the level-2 partition of the next.
+		const uint32_t G = (nb1 >= 8 && getenv("BELLA_B200_PIPE_BUCKET")) ? (uint32_t)bella_b200_handle::PIPE : 1u;   // measured: no gain (profiles/README.md), off
+		CK(cudaFuncSetAttribute(k_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BUCKET_SMEM));
+		for (uint32_t g = 0; g < G; ++g) {
+			const uint32_t c0 = (uint32_t)((uint64_t)nb1 * g / G), c1 = (uint32_t)((uint64_t)nb1 * (g + 1) / G);
+			uint64_t f0 = (uint64_t)c0 << l2, f1 = (uint64_t)c1 << l2;
+			if (f0 > NB) f0 = NB;
+			if (f1 > NB || g + 1 == G) f1 = NB;
+			k_rp2<<<h->sms * 2, RP_THREADS, RP_SMEM, h->stream>>>(shift1, wshift, nsb, groups, cap1, h->rp_cur.as<uint32_t>(), h->rp_tiles.as<uint32_t>(),
+				c0 * groups, c1 * groups, h->rp_E.as<uint64_t>(), h->rp_K.as<uint32_t>(), bcnt, partE, partK, h->errflag.as<int>());
+			LAUNCHED();
+			CK(cudaEventRecord(h->pipe_ev[g], h->stream));
+			CK(cudaStreamWaitEvent(h->aux_stream, h->pipe_ev[g], 0));
+			if (f1 > f0) {
+				const uint32_t nbk = (uint32_t)(f1 - f0);
+				k_bucket_offsets<<<1, 1024, 0, h->aux_stream>>>((uint32_t)f0, (uint32_t)f1, bcnt, h->boff.as<uint32_t>());
+				LAUNCHED();
+				k_bucket<<<nbk < 148u * 16 ? nbk : 148u * 16, 256, BUCKET_SMEM, h->aux_stream>>>(h->klo, ml, cnt_lo, cnt_hi, wshift, (uint32_t)f0, (uint32_t)f1, NB,
+					h->boff.as<uint32_t>(), partE, partK, h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), h->Ainfo.as<uint8_t>(), flop_out, h->errflag.as<int>());
+				LAUNCHED();
+			}
+		}
+		CK(cudaEventRecord(h->ev[9], h->stream));
+		CK(cudaEventRecord(h->aux_join, h->aux_stream));
+		CK(cudaStreamWaitEvent(h->stream, h->aux_join, 0));
+		return 0;
 	}
 	CK(cudaEventRecord(h->ev[9], h->stream));
-	k_bucket_sizes<<<grid_for(NB + 1, 256), 256, 0, h->stream>>>(NB, bcnt, h->bsize.as<uint32_t>());
+	k_bucket_offsets<<<1, 1024, 0, h->stream>>>(0u, NB, bcnt, h->boff.as<uint32_t>());
 	LAUNCHED();
-	if (int rc = exclusive_scan(h, h->bsize.as<uint32_t>(), h->boff.as<uint32_t>(), NB + 1)) return rc;
 	CK(cudaFuncSetAttribute(k_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BUCKET_SMEM));
-	k_bucket<<<NB < 148u * 16 ? NB : 148u * 16, 256, BUCKET_SMEM, h->stream>>>(h->klo, ml, cnt_lo, cnt_hi, wshift, NB, h->boff.as<uint32_t>(),
+	k_bucket<<<NB < 148u * 16 ? NB : 148u * 16, 256, BUCKET_SMEM, h->stream>>>(h->klo, ml, cnt_lo, cnt_hi, wshift, 0u, NB, NB, h->boff.as<uint32_t>(),
 		partE, partK, h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), h->Ainfo.as<uint8_t>(), flop_out, h->errflag.as<int>());
 	LAUNCHED();
 	return 0;
@@ -275,7 +322,7 @@ int run_plan(bella_b200_handle* h)
 	ENSURE(h->ccur, sizeof(uint64_t) * ((size_t)ncols + 1) * CCUR_STRIDE);
 	ENSURE(h->unnz, sizeof(uint32_t) * ((size_t)ucap + 2));
 	ENSURE(h->uoff, sizeof(uint32_t) * ((size_t)ucap + 2));
-	ENSURE(h->lists, sizeof(uint32_t) * (size_t)(NCLASS + 1) * ((size_t)ucap + 1));
+	ENSURE(h->lists, sizeof(uint32_t) * (size_t)NRANGE * (NCLASS + 1) * ((size_t)ucap + 1));
 	CK(cudaMemsetAsync(h->meta.p, 0, sizeof(Meta), h->stream));
 	CK(cudaMemsetAsync(h->nunits.p, 0, sizeof(uint32_t) * ((size_t)ncols + 1), h->stream));
 	CK(cudaMemsetAsync(h->ucount.p, 0, sizeof(uint32_t) * ((size_t)ucap + 2), h->stream));
@@ -303,7 +350,7 @@ int run_plan(bella_b200_handle* h)
 	}
 	k_classify_units<<<grid_for(ucap, 256), 256, 0, h->stream>>>(ucap, h->ucol.as<uint32_t>(), h->ucount.as<uint32_t>(), h->colinfo.as<ColInfo>(),
 		h->uptr.as<uint64_t>(), h->ucur.as<unsigned long long>(), h->ccur.as<unsigned long long>(), h->lists.as<uint32_t>(), h->refine.as<uint8_t>(), h->round,
-		h->meta.as<Meta>(), h->errflag.as<int>());
+		h->nrange, h->meta.as<Meta>(), h->errflag.as<int>());
 	LAUNCHED();
 	return 0;
 }
@@ -323,14 +370,14 @@ Params make_params(bella_b200_handle* h)
 }
 
 template <int CAP, int NT>
-int launch_group(bella_b200_handle* h, const Params& P, int cls, uint32_t count, uint32_t l1cap, int ctas_per_sm, cudaStream_t st)
+int launch_group(bella_b200_handle* h, const Params& P, int rg, int cls, uint32_t count, uint32_t l1cap, int ctas_per_sm, cudaStream_t st)
 {
-	// fast instance over the class list, then the exact instance over whatever the fast one handed back
+	// fast instance over the class list of the range, then the exact instance over whatever the fast one handed back
 	const uint32_t ucap = h->ucap;
-	const uint32_t* list = h->lists.as<uint32_t>() + (size_t)cls * ucap;
-	uint32_t* redo = h->redo.as<uint32_t>() + (size_t)cls * (ucap + 1);
+	const uint32_t* list = h->lists.as<uint32_t>() + ((size_t)rg * (NCLASS + 1) + cls) * ucap;
+	uint32_t* redo = h->redo.as<uint32_t>() + ((size_t)rg * NCLASS + cls) * (ucap + 1);
 	uint32_t* redo_count = redo + ucap;
-	const uint32_t* class_count = &h->meta.as<Meta>()->class_count[cls];
+	const uint32_t* class_count = &h->meta.as<Meta>()->class_count[rg][cls];
 	const size_t smem = GF<CAP>::bytes(l1cap);
 	CK(cudaFuncSetAttribute(k_group_fold<CAP, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	CK(cudaFuncSetAttribute(k_group_fold<CAP, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -388,32 +435,53 @@ int plan_loop(bella_b200_handle* h, bool own_transpose)
 	return 0;
 }
 
-// group + fold over the unit regions, then C's colptr; ends with the one host synchronisation that returns nnz(C)
-int group_and_output(bella_b200_handle* h)
+// scatter (unless the products are already in the unit regions: multi-GPU) + group + fold, then C's colptr; ends with the one
+// host synchronisation that returns nnz(C).  Single GPU: a pipeline over h->nrange ranges of output columns -- the scatter
+// is bound by scattered memory transactions and the group + fold kernels by instruction issue, so the scatter of one range
+// runs (on its own stream) beside the group + fold kernels of the range before.
+int group_and_output(bella_b200_handle* h, bool do_scatter)
 {
 	const uint32_t ncols = h->hi - h->lo;
 	const uint32_t U = h->U, ucap = h->ucap;
-	const uint32_t* cc = h->hmeta.class_count;
+	const int R = (int)h->nrange;
 	Params P = make_params(h);
 	CK(cudaEventRecord(h->ev[3], h->stream));
 	// level-1 bitmap words a unit can need: light columns span at most n rows, heavy units at most 2^MAX_SPAN_SHIFT
 	uint32_t span = h->n < (1u << MAX_SPAN_SHIFT) ? h->n : (1u << MAX_SPAN_SHIFT);
 	const uint32_t l1cap = (span + 1023 + 32) / 1024 + 1;
 	const uint32_t* lists = h->lists.as<uint32_t>();
-	ENSURE(h->redo, sizeof(uint32_t) * (size_t)NCLASS * ((size_t)ucap + 1));
-	for (int c = 0; c < NCLASS; ++c)
+	ENSURE(h->redo, sizeof(uint32_t) * (size_t)NRANGE * NCLASS * ((size_t)ucap + 1));
+	for (int c = 0; c < R * NCLASS; ++c)
 		CK(cudaMemsetAsync(h->redo.as<uint32_t>() + (size_t)c * (ucap + 1) + ucap, 0, sizeof(uint32_t), h->stream));
-	// the larger classes (few, long-running CTAs) start first on a second stream; the 2048 class fills the rest of the GPU
 	CK(cudaEventRecord(h->aux_fork, h->stream));
-	CK(cudaStreamWaitEvent(h->aux_stream, h->aux_fork, 0));
-	if (int rc = launch_group<8192, 1024>(h, P, 2, cc[2], l1cap, 1, h->aux_stream)) return rc;
-	if (int rc = launch_group<4096, 512>(h, P, 1, cc[1], l1cap, 2, h->aux_stream)) return rc;
-	if (cc[3]) {
-		k_huge_pair<<<cc[3] < 148u ? cc[3] : 148u, 1024, 0, h->aux_stream>>>(P, lists + (size_t)3 * ucap, cc[3]);
-		LAUNCHED();
+	if (do_scatter && h->flops) {
+		CK(cudaStreamWaitEvent(h->sc_stream, h->aux_fork, 0));
+		CK(cudaEventRecord(h->sc_t0, h->sc_stream));
+		for (int r = 0; r < R; ++r) {
+			k_scatter<<<grid_for((h->nnzB + 3) / 4, 256, 148 * 32), 256, 0, h->sc_stream>>>(h->boff.as<uint32_t>() + h->NB, h->m, h->lo, h->hi, P.A_colptr, P.Aent,
+				h->Ainfo.as<uint8_t>(), h->ccur.as<unsigned long long>(), P.colinfo, P.ucur, P.raw, h->meta.as<Meta>(), (uint32_t)r, (uint32_t)R, nullptr);
+			LAUNCHED();
+			CK(cudaEventRecord(h->pipe_ev[r], h->sc_stream));
+		}
+		CK(cudaEventRecord(h->sc_t1, h->sc_stream));
+	}
+	for (int r = 0; r < R; ++r) {
+		const uint32_t* cc = h->hmeta.class_count[r];
+		if (do_scatter && h->flops) {
+			CK(cudaStreamWaitEvent(h->stream, h->pipe_ev[r], 0));
+			CK(cudaEventRecord(h->aux_fork, h->stream));
+		}
+		// the larger classes (few, long-running CTAs) go to a second stream; the 2048 class fills the rest of the GPU
+		CK(cudaStreamWaitEvent(h->aux_stream, h->aux_fork, 0));
+		if (int rc = launch_group<8192, 1024>(h, P, r, 2, cc[2], l1cap, 1, h->aux_stream)) return rc;
+		if (int rc = launch_group<4096, 512>(h, P, r, 1, cc[1], l1cap, 2, h->aux_stream)) return rc;
+		if (cc[3]) {
+			k_huge_pair<<<cc[3] < 148u ? cc[3] : 148u, 1024, 0, h->aux_stream>>>(P, lists + ((size_t)r * (NCLASS + 1) + 3) * ucap, cc[3]);
+			LAUNCHED();
+		}
+		if (int rc = launch_group<2048, 256>(h, P, r, 0, cc[0], l1cap, 4, h->stream)) return rc;
 	}
 	CK(cudaEventRecord(h->aux_join, h->aux_stream));
-	if (int rc = launch_group<2048, 256>(h, P, 0, cc[0], l1cap, 4, h->stream)) return rc;
 	CK(cudaStreamWaitEvent(h->stream, h->aux_join, 0));
 	CK(cudaEventRecord(h->ev[4], h->stream));
 	if (int rc = exclusive_scan(h, h->unnz.as<uint32_t>(), h->uoff.as<uint32_t>(), U + 1)) return rc;
@@ -427,7 +495,9 @@ int group_and_output(bella_b200_handle* h)
 	CK(cudaStreamSynchronize(h->stream));
 	if (e) return report_device_error(h, e);
 	h->Z = z32;
-	CK(cudaEventElapsedTime(&h->t_ms[1], h->ev[3], h->ev[4]));    // group + fold
+	CK(cudaEventElapsedTime(&h->t_ms[1], h->ev[3], h->ev[4]));    // scatter | group + fold pipeline (the scatter passes run beside the group kernels)
+	h->t_ms[7] = 0;
+	if (do_scatter && h->flops) CK(cudaEventElapsedTime(&h->t_ms[7], h->sc_t0, h->sc_t1));   // the scatter passes alone, first to last
 	CK(cudaEventElapsedTime(&h->t_scans, h->ev[4], h->ev[5]));    // scans + colptr
 	h->symbolic_done = true;
 	h->numeric_done = false;
@@ -442,21 +512,17 @@ int run_symbolic(bella_b200_handle* h)
 	CK(cudaMemsetAsync(h->errflag.p, 0, sizeof(int), h->stream));
 	h->klo = 0; h->khi = h->m;
 	h->mg_recv = nullptr;
+	h->nrange = h->nnzB >= (1u << 22) ? 2u : 1u;                      // two ranges measured best (profiles/README.md); small inputs: one
+	if (const char* e = getenv("BELLA_B200_NRANGE")) { int v = atoi(e); if (v >= 1 && v <= NRANGE) h->nrange = (uint32_t)v; }
 	CK(cudaEventRecord(h->ev[0], h->stream));
 	if (int rc = plan_loop(h, true)) return rc;
 	Params P = make_params(h);
 	CK(cudaEventRecord(h->ev[2], h->stream));
-	if (h->flops) {
-		k_scatter<<<grid_for((h->nnzB + 3) / 4, 256, 148 * 32), 256, 0, h->stream>>>(h->boff.as<uint32_t>() + h->NB, h->m, h->lo, h->hi, P.A_colptr, P.Aent, h->Ainfo.as<uint8_t>(),
-			h->ccur.as<unsigned long long>(), P.colinfo, P.ucur, P.raw);
-		LAUNCHED();
-	}
-	if (int rc = group_and_output(h)) return rc;
+	if (int rc = group_and_output(h, true)) return rc;
 	if (h->nnzB && h->m && h->hi > h->lo) {
 		CK(cudaEventElapsedTime(&h->t_ms[0], h->ev[8], h->ev[9]));    // k_partition (includes waiting for the upload when it is still running)
 		CK(cudaEventElapsedTime(&h->t_ms[6], h->ev[9], h->ev[2]));    // k_bucket + plan
 	} else h->t_ms[0] = h->t_ms[6] = 0;
-	CK(cudaEventElapsedTime(&h->t_ms[7], h->ev[2], h->ev[3]));    // scatter
 	return 0;
 }
 
@@ -530,8 +596,11 @@ int bella_b200_create(bella_b200_handle** out, int device)
 	for (auto& e : h->ev) cudaEventCreate(&e);
 	cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
 	cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+	cudaStreamCreateWithFlags(&h->sc_stream, cudaStreamNonBlocking);
+	cudaEventCreate(&h->sc_t0); cudaEventCreate(&h->sc_t1);
 	cudaEventCreateWithFlags(&h->aux_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->aux_join, cudaEventDisableTiming);
 	for (auto& e : h->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+	for (auto& e : h->pipe_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
 	cudaEventCreate(&h->copy_begin); cudaEventCreate(&h->copy_end);
 	*out = h;
 	return BELLA_B200_OK;
@@ -550,10 +619,14 @@ int bella_b200_destroy(bella_b200_handle* h)
 	for (DevBuf* b : bufs) b->release();
 	for (auto& e : h->ev) if (e) cudaEventDestroy(e);
 	for (auto& e : h->chunk_ev) if (e) cudaEventDestroy(e);
+	for (auto& e : h->pipe_ev) if (e) cudaEventDestroy(e);
 	if (h->copy_begin) cudaEventDestroy(h->copy_begin);
 	if (h->copy_end) cudaEventDestroy(h->copy_end);
 	if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
 	if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
+	if (h->sc_stream) { cudaStreamSynchronize(h->sc_stream); cudaStreamDestroy(h->sc_stream); }
+	if (h->sc_t0) cudaEventDestroy(h->sc_t0);
+	if (h->sc_t1) cudaEventDestroy(h->sc_t1);
 	if (h->aux_fork) cudaEventDestroy(h->aux_fork);
 	if (h->aux_join) cudaEventDestroy(h->aux_join);
 	if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -741,6 +814,13 @@ int bella_b200_numeric_aux(bella_b200_handle* h, uint32_t col_begin, uint32_t co
 	return BELLA_B200_OK;
 }
 
+int bella_b200_get_flops(bella_b200_handle* h, uint64_t* flops)
+{
+	if (!h || !h->symbolic_done || !flops) return fail(h, BELLA_B200_ERR_ARG, "the symbolic phase has not run");
+	*flops = h->flops;
+	return BELLA_B200_OK;
+}
+
 int bella_b200_n_unpinned(bella_b200_handle* h, uint64_t* n_unpinned)
 {
 	if (!h || !h->numeric_done || !n_unpinned) return fail(h, BELLA_B200_ERR_ARG, "numeric phase has not run");
@@ -841,7 +921,7 @@ int bella_b200_mg_scatter(bella_b200_handle* h, const uint64_t* sendoff_dev, uin
 		k_mg_colinfo<<<grid_for(n, 256), 256, 0, h->stream>>>(n, sendoff_dev, h->mg_ucur.as<unsigned long long>());
 		LAUNCHED();
 		k_scatter<<<grid_for((h->nnzB + 3) / 4, 256, 148 * 32), 256, 0, h->stream>>>(h->boff.as<uint32_t>() + h->NB, ml, 0, n, h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(),
-			h->Ainfo.as<uint8_t>(), h->mg_ucur.as<unsigned long long>(), nullptr, nullptr, sendbuf_dev);
+			h->Ainfo.as<uint8_t>(), h->mg_ucur.as<unsigned long long>(), nullptr, nullptr, sendbuf_dev, nullptr, 0u, 1u, h->errflag.as<int>());
 		LAUNCHED();
 	}
 	CK(cudaEventRecord(h->ev[2], h->stream));
@@ -866,13 +946,14 @@ int bella_b200_mg_finish(bella_b200_handle* h, uint32_t col_lo, uint32_t col_hi,
 			h->errflag.as<int>());
 		LAUNCHED();
 	}
+	h->nrange = 1;
 	int rc = plan_loop(h, false);
 	if (!rc && h->flops) {
 		k_regroup<false><<<148 * 8, 256, 0, h->stream>>>(h->n, col_lo, ncols, (uint32_t)world, counts_all_dev, segoff_dev, recvbase_dev, h->mg_recv,
 			h->colinfo.as<ColInfo>(), nullptr, h->ucur.as<unsigned long long>(), h->raw.as<uint64_t>(), h->meta.as<Meta>(), h->errflag.as<int>());
 		++h->launches;
 	}
-	if (!rc) rc = group_and_output(h);
+	if (!rc) rc = group_and_output(h, false);
 	h->mg_recv = nullptr;
 	if (rc) return rc;
 	if (h->nnzB && h->khi > h->klo && h->n) {
@@ -888,6 +969,155 @@ int bella_b200_get_colptr(bella_b200_handle* h, uint32_t* colptrC_host)
 	if (!h || !h->symbolic_done || !colptrC_host) return fail(h, BELLA_B200_ERR_ARG, "the symbolic phase has not run");
 	CK(cudaMemcpyAsync(colptrC_host, h->colptrC.p, sizeof(uint32_t) * ((size_t)(h->hi - h->lo) + 1), cudaMemcpyDeviceToHost, h->stream));
 	CK(cudaStreamSynchronize(h->stream));
+	return BELLA_B200_OK;
+}
+
+/* ---- multi-GPU over NVLink peer memory: no collective on the data path (bella_b200/distributed.py, mode "nvlink") ---- */
+
+int bella_b200_mg_geometry(uint32_t n_kmers, uint64_t nnz_total, int world, uint32_t* out8)
+{
+	if (!out8 || world < 1 || world > MG_MAXW) return BELLA_B200_ERR_ARG;
+	RpGeom g;
+	if (rp_geometry(n_kmers, nnz_total, 0, &g)) return BELLA_B200_ERR_RANGE;
+	const uint32_t nb1_loc = (g.nb1 + (uint32_t)world - 1) / (uint32_t)world;
+	const uint64_t kpr = (uint64_t)nb1_loc << g.shift1;
+	if (kpr > 0xFFFFFFFFull) return BELLA_B200_ERR_RANGE;
+	// a sub-region holds what ONE rank contributes to ONE coarse bucket: 1/world of the bucket on average
+	const uint64_t cap1 = (((uint64_t)((double)nnz_total / ((double)g.nb1 * world) * 1.3) + 2 * RP_TILE) + 15) & ~15ull;
+	if (cap1 > 0x7FFFFFFFull) return BELLA_B200_ERR_RANGE;
+	out8[0] = g.wshift; out8[1] = g.shift1; out8[2] = g.nb1; out8[3] = nb1_loc; out8[4] = (uint32_t)kpr; out8[5] = (uint32_t)cap1;
+	out8[6] = g.NB; out8[7] = g.l2;
+	return BELLA_B200_OK;
+}
+
+int bella_b200_mg_route_push(bella_b200_handle* h, uint32_t read_lo, uint32_t read_hi, const uint32_t* colptr_global_dev, const uint32_t* rowids_dev,
+		const uint16_t* values_dev, uint32_t n_kmers, const uint32_t* geom8, int world, int me, void* const* peer_E, void* const* peer_K, void* const* peer_cnt)
+{
+	if (!h || !geom8 || world < 1 || world > MG_MAXW || me < 0 || me >= world || !peer_E || !peer_K || !peer_cnt)
+		return fail(h, BELLA_B200_ERR_ARG, "bad arguments to bella_b200_mg_route_push");
+	CK(cudaSetDevice(h->device));
+	h->launches = 0;
+	ENSURE(h->errflag, 4 * sizeof(int));
+	const uint32_t shift1 = geom8[1], nb1 = geom8[2], nb1_loc = geom8[3], kpr = geom8[4], cap1 = geom8[5];
+	ENSURE(h->rp_cur, sizeof(uint32_t) * ((size_t)nb1 + 2) * BCNT_STRIDE);
+	CK(cudaMemsetAsync(h->rp_cur.p, 0, sizeof(uint32_t) * ((size_t)nb1 + 2) * BCNT_STRIDE, h->stream));
+	CK(cudaMemsetAsync(h->errflag.p, 0, sizeof(int), h->stream));
+	CK(cudaFuncSetAttribute(k_rp1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RP_SMEM));
+	CK(cudaEventRecord(h->ev[8], h->stream));
+	RpOut O{};
+	O.groups = (uint32_t)world; O.me = (uint32_t)me; O.nb1_loc = nb1_loc; O.kpr = kpr;
+	RpPost P{};
+	for (int d = 0; d < world; ++d) { O.E[d] = (uint64_t*)peer_E[d]; O.K[d] = (uint32_t*)peer_K[d]; P.cnt[d] = (uint32_t*)peer_cnt[d]; }
+	if (read_hi > read_lo) {
+		const uint32_t wpc = RP_THREADS / 32;
+		uint32_t g = (read_hi - read_lo + wpc - 1) / wpc;
+		if (g > (uint32_t)h->sms * 2) g = (uint32_t)h->sms * 2;
+		// the strand bit rides in bit 31 of the row ids (panel format): Bstrand == NULL
+		k_rp1<<<g, RP_THREADS, RP_SMEM, h->stream>>>(read_hi, read_lo, 0u, n_kmers, colptr_global_dev, rowids_dev, values_dev, nullptr,
+			shift1, nb1, cap1, h->rp_cur.as<uint32_t>(), O, h->errflag.as<int>());
+		LAUNCHED();
+	}
+	k_rp_post<<<grid_for(nb1, 256), 256, 0, h->stream>>>(nb1, cap1, (uint32_t)world, (uint32_t)me, nb1_loc, h->rp_cur.as<uint32_t>(), P);
+	LAUNCHED();
+	CK(cudaEventRecord(h->ev[9], h->stream));
+	return BELLA_B200_OK;
+}
+
+int bella_b200_mg_transpose_coarse(bella_b200_handle* h, uint32_t kmer_lo, uint32_t kmer_hi, const uint32_t* geom8, int world,
+		const uint64_t* E_dev, const uint32_t* K_dev, const uint32_t* cnt_dev, uint64_t nnz_cap, uint32_t* cnt_local_dev)
+{
+	if (!h || !h->have_inputs) return fail(h, BELLA_B200_ERR_ARG, "set_inputs first");
+	if (kmer_lo > kmer_hi || kmer_hi > h->m || !geom8 || !cnt_local_dev || world < 1 || world > MG_MAXW)
+		return fail(h, BELLA_B200_ERR_ARG, "bad arguments to bella_b200_mg_transpose_coarse");
+	CK(cudaSetDevice(h->device));
+	ENSURE(h->meta, sizeof(Meta));
+	ENSURE(h->errflag, 4 * sizeof(int));
+	h->klo = kmer_lo; h->khi = kmer_hi;
+	h->mg_recv = nullptr;
+	h->symbolic_done = h->numeric_done = false;
+	const uint32_t n = h->n, ml = kmer_hi - kmer_lo;
+	const uint32_t wshift = geom8[0], shift1 = geom8[1], nb1_loc = geom8[3], cap1 = geom8[5], l2 = geom8[7];
+	const uint32_t W = 1u << wshift;
+	const uint32_t NB = (uint32_t)(((uint64_t)ml + W - 1) / W);
+	const uint32_t nb1_mine = (uint32_t)(((uint64_t)ml + (1ull << shift1) - 1) >> shift1);
+	if (nb1_mine > nb1_loc) return fail(h, BELLA_B200_ERR_ARG, "k-mer range wider than the rank's coarse buckets");
+	h->W = W; h->NB = NB;
+	ENSURE(h->Acolptr, sizeof(uint32_t) * ((size_t)ml + 2));
+	ENSURE(h->Aent, sizeof(uint64_t) * (nnz_cap + 2));
+	ENSURE(h->Ainfo, nnz_cap + 16);
+	ENSURE(h->boff, sizeof(uint32_t) * ((size_t)NB + 2));
+	CK(cudaMemsetAsync(cnt_local_dev, 0, sizeof(uint32_t) * (size_t)n, h->stream));
+	if (!ml || !n) {
+		CK(cudaMemsetAsync(h->Acolptr.p, 0, sizeof(uint32_t) * ((size_t)ml + 2), h->stream));
+		CK(cudaMemsetAsync(h->boff.p, 0, sizeof(uint32_t) * 2, h->stream));
+		h->NB = 0;
+		CK(cudaEventRecord(h->ev[1], h->stream));
+		return BELLA_B200_OK;
+	}
+	ENSURE(h->bcur, sizeof(uint32_t) * ((size_t)NB + 2) * BCNT_STRIDE);
+	ENSURE(h->part, sizeof(uint64_t) * (size_t)NB * BUCKET_CAP + 64);
+	ENSURE(h->partK, sizeof(uint16_t) * (size_t)NB * BUCKET_CAP + 64);
+	const uint32_t nsb = nb1_mine * (uint32_t)world;
+	ENSURE(h->rp_tiles, sizeof(uint32_t) * ((size_t)nsb + 2));
+	CK(cudaMemsetAsync(h->bcur.p, 0, sizeof(uint32_t) * ((size_t)NB + 2) * BCNT_STRIDE, h->stream));
+	CK(cudaFuncSetAttribute(k_rp2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RP_SMEM));
+	CK(cudaFuncSetAttribute(k_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BUCKET_SMEM));
+	(void)l2;
+	k_rp_tiles<<<1, 1024, 0, h->stream>>>(nsb, cap1, cnt_dev, h->rp_tiles.as<uint32_t>());
+	LAUNCHED();
+	k_rp2<<<h->sms * 2, RP_THREADS, RP_SMEM, h->stream>>>(shift1, wshift, nsb, (uint32_t)world, cap1, cnt_dev, h->rp_tiles.as<uint32_t>(), 0u, nsb,
+		E_dev, K_dev, h->bcur.as<uint32_t>(), h->part.as<uint64_t>(), h->partK.as<uint16_t>(), h->errflag.as<int>());
+	LAUNCHED();
+	k_bucket_offsets<<<1, 1024, 0, h->stream>>>(0u, NB, h->bcur.as<uint32_t>(), h->boff.as<uint32_t>());
+	LAUNCHED();
+	k_bucket<<<NB < 148u * 16 ? NB : 148u * 16, 256, BUCKET_SMEM, h->stream>>>(kmer_lo, ml, 0u, n, wshift, 0u, NB, NB, h->boff.as<uint32_t>(),
+		h->part.as<uint64_t>(), h->partK.as<uint16_t>(), h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), h->Ainfo.as<uint8_t>(), cnt_local_dev, h->errflag.as<int>());
+	LAUNCHED();
+	CK(cudaEventRecord(h->ev[1], h->stream));
+	return BELLA_B200_OK;
+}
+
+int bella_b200_mg_post(bella_b200_handle* h, uint64_t count, const uint32_t* src_dev, int world, uint64_t at, void* const* peer_dst)
+{
+	if (!h || world < 1 || world > MG_MAXW || !peer_dst || (count && !src_dev)) return fail(h, BELLA_B200_ERR_ARG, "bad arguments to bella_b200_mg_post");
+	CK(cudaSetDevice(h->device));
+	MgPeers P{};
+	for (int d = 0; d < world; ++d) P.p[d] = peer_dst[d];
+	if (count) { k_mg_post<<<grid_for(count, 256), 256, 0, h->stream>>>(count, src_dev, (uint32_t)world, at, P); LAUNCHED(); }
+	return BELLA_B200_OK;
+}
+
+int bella_b200_mg_exchange(bella_b200_handle* h, int world, int me, const uint32_t* cuts_dev, const uint32_t* cnt_local_dev, void* const* peer_counts_all,
+		int phase, const uint32_t* counts_all_dev, uint64_t* scan_dev, uint64_t cap_recv, uint64_t cap_send, uint64_t* sendoff_dev, uint64_t* segoff_dev,
+		uint64_t* recvbase_dev, uint64_t* push_dev, uint64_t* sendbuf_dev, void* const* peer_recv)
+{
+	// phase 0: post this rank's per-column counts to every rank      (then the caller's barrier)
+	// phase 1: plan on the device, expand the products into the send buffer, push the blocks to their owners   (then a barrier)
+	if (!h || !h->have_inputs || world < 1 || world > MG_MAXW || me < 0 || me >= world) return fail(h, BELLA_B200_ERR_ARG, "bad arguments to bella_b200_mg_exchange");
+	CK(cudaSetDevice(h->device));
+	const uint32_t n = h->n;
+	if (phase == 0) {
+		MgPeers P{};
+		for (int d = 0; d < world; ++d) P.p[d] = peer_counts_all[d];
+		if (n) { k_mg_post<<<grid_for(n, 256), 256, 0, h->stream>>>((uint64_t)n, cnt_local_dev, (uint32_t)world, (uint64_t)me * n, P); LAUNCHED(); }
+		// and this rank's error flag (a bucket that overflowed, ...): slot `me` behind the counts, 16 words in
+		k_mg_post<<<1, 32, 0, h->stream>>>(1ull, (const uint32_t*)h->errflag.p, (uint32_t)world, (uint64_t)world * n + 16 + me, P);
+		LAUNCHED();
+		return BELLA_B200_OK;
+	}
+	// flat exclusive scan of counts_all (world rows of n) -> scan_dev u64 [world * n + 1]
+	{
+		auto in = thrust::make_transform_iterator(counts_all_dev, Widen());
+		if (int rc = exclusive_scan(h, in, (unsigned long long*)scan_dev, (uint32_t)((size_t)world * n + 1))) return rc;
+	}
+	k_mg_plan<<<grid_for((uint64_t)n + 1, 256), 256, 0, h->stream>>>((uint32_t)world, (uint32_t)me, n, cuts_dev, (const unsigned long long*)scan_dev, cap_recv, cap_send,
+		(const int*)(counts_all_dev + (size_t)world * n + 16), (unsigned long long*)sendoff_dev, (unsigned long long*)segoff_dev, (unsigned long long*)recvbase_dev, (unsigned long long*)push_dev, h->errflag.as<int>());
+	LAUNCHED();
+	if (int rc = bella_b200_mg_scatter(h, sendoff_dev, sendbuf_dev)) return rc;
+	MgPeers R{};
+	for (int d = 0; d < world; ++d) R.p[d] = peer_recv[d];
+	k_mg_push<<<h->sms * 4, 256, 0, h->stream>>>((uint32_t)world, sendbuf_dev, (const unsigned long long*)push_dev, R, h->errflag.as<int>());
+	LAUNCHED();
 	return BELLA_B200_OK;
 }
 

@@ -37,6 +37,7 @@ namespace bk {
 constexpr uint32_t NONE16 = 0xFFFFu;
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 constexpr int NCLASS = 3;
+constexpr int NRANGE = 4;                  // column ranges of the scatter | group + fold pipeline
 constexpr uint32_t CLASS_CAP[NCLASS] = {2048, 4096, 8192};
 constexpr uint32_t UNIT_CAP = 8192;        // products per unit (largest shared-memory class)
 constexpr uint32_t BUCKET_CAP = 4096;      // entries per transpose bucket
@@ -77,7 +78,8 @@ struct Params {
 
 struct Meta {
 	unsigned long long flops;
-	unsigned int class_count[NCLASS + 1];   // + overflow
+	unsigned int class_count[NRANGE][NCLASS + 1];   // per column range (the scatter | group pipeline) and capacity class (+ overflow)
+	unsigned int range_col[NRANGE + 1];      // first local column of every range (ncols when the range is empty)
 	unsigned int n_heavy_cols;
 	unsigned int n_units;
 	unsigned int n_refine;
@@ -193,39 +195,69 @@ constexpr uint32_t BCNT_STRIDE = 8;
 constexpr uint32_t CCUR_STRIDE = 4;        // the scatter's per-column cursors: 8-byte words, one per 32-byte sector
 constexpr unsigned long long CCUR_HEAVY = 1ull << 63;
 constexpr uint32_t AINFO_ESC = 255;        // Ainfo: entries behind this one in its column of A; 255 = that many or more (the count then comes from A's colptr)
-constexpr int RP_THREADS = 512;
+#ifndef BELLA_RP_THREADS
+#define BELLA_RP_THREADS 512
+#endif
+constexpr int RP_THREADS = BELLA_RP_THREADS;
 constexpr int RP_ITEMS = 8;                // nonzeros per thread and tile
 constexpr int RP_TILE = RP_THREADS * RP_ITEMS;
 constexpr uint32_t RP_NBMAX = 1024;        // buckets of one level
-constexpr size_t RP_SMEM = (size_t)RP_TILE * 12 + ((size_t)RP_NBMAX + 2) * 8;
+constexpr size_t RP_SMEM = (size_t)RP_TILE * 12 + ((size_t)RP_NBMAX + 2) * 12;
 
-// scan of the tile's histogram (in place: counts -> starts, total at [nb]) + one global cursor atomic per non-empty bucket.
-// Ends with a barrier.  gstride: distance of the global cursors in words.
-__device__ __forceinline__ void rp_reserve(uint32_t* hist, uint32_t* gbase, uint32_t nb, uint32_t* gcur, uint32_t gstride, uint32_t cap,
-		uint32_t* s_tmp, int* err)
+// The tile's histogram -> bucket starts inside the tile (off[0..nb], by warp 0 alone: nb <= 1024 bins, 32 per lane) and, at the
+// same time, one global cursor atomic per non-empty bucket (every thread takes a bucket: the round trip of the atomic hides
+// behind the scan).  hist is left zeroed for the next tile.  One barrier, at the end.  gstride: distance of the global cursors in words.
+__device__ __forceinline__ void rp_reserve(uint32_t* hist, uint32_t* off, uint32_t* gbase, uint32_t nb, uint32_t* gcur, uint32_t gstride, uint32_t cap, int* err)
 {
-	block_excl_scan<uint32_t>(hist, nb, s_tmp);
-	for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
-		const uint32_t c = hist[b + 1] - hist[b];
-		if (c) {
-			const uint32_t g = atomicAdd(&gcur[(size_t)b * gstride], c);
-			if (g + c > cap) set_err(err, -6);
-			gbase[b] = g;
-		}
+	const uint32_t tid = threadIdx.x, lane = tid & 31;
+	uint32_t g[(RP_NBMAX + RP_THREADS - 1) / RP_THREADS], c[(RP_NBMAX + RP_THREADS - 1) / RP_THREADS];
+#pragma unroll
+	for (int q = 0; q < (int)((RP_NBMAX + RP_THREADS - 1) / RP_THREADS); ++q) {
+		const uint32_t b = tid + q * RP_THREADS;
+		c[q] = b < nb ? hist[b] : 0;
+		if (c[q]) g[q] = atomicAdd(&gcur[(size_t)b * gstride], c[q]);
+	}
+	if (tid < 32) {
+		const uint32_t per = (nb + 31) >> 5, b0 = lane * per, b1 = min(b0 + per, nb);
+		uint32_t sum = 0;
+		for (uint32_t b = b0; b < b1; ++b) sum += hist[b];
+		uint32_t incl = sum;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+		uint32_t run = incl - sum;
+		for (uint32_t b = b0; b < b1; ++b) { off[b] = run; run += hist[b]; }
+		if (lane == 31) off[nb] = incl;
+	}
+#pragma unroll
+	for (int q = 0; q < (int)((RP_NBMAX + RP_THREADS - 1) / RP_THREADS); ++q) {
+		const uint32_t b = tid + q * RP_THREADS;
+		if (c[q]) { if (g[q] + c[q] > cap) set_err(err, -6); gbase[b] = g[q]; }
 	}
 	__syncthreads();
+	for (uint32_t b = tid; b < nb; b += RP_THREADS) hist[b] = 0;   // the next tile's atomics come after at least one more barrier
 }
 
-__global__ void __launch_bounds__(RP_THREADS) k_rp1(uint32_t n, uint32_t lo, uint32_t klo, uint32_t khi, const uint32_t* __restrict__ Bcolptr,   // reads [lo, n)
+// Where level 1 writes.  A coarse bucket is a region of `groups` sub-regions of cap1 records, one per writer: on one GPU there
+// is one writer (groups == 1); on several, coarse bucket b belongs to the rank b / nb1_loc that transposes its k-mers, the
+// regions are in that rank's (peer-mapped, NVLink) memory and every rank fills its own sub-region `me`, so the remote
+// stores need no remote cursor -- the cursors stay local and are posted to the owners afterwards (k_rp_post).
+constexpr int MG_MAXW = 8;
+struct RpOut {
+	uint32_t groups, me, nb1_loc, kpr;     // kpr = k-mers per rank = nb1_loc << shift1
+	uint64_t* E[MG_MAXW];
+	uint32_t* K[MG_MAXW];
+};
+
+__global__ void __launch_bounds__(RP_THREADS, 2) k_rp1(uint32_t n, uint32_t lo, uint32_t klo, uint32_t khi, const uint32_t* __restrict__ Bcolptr,   // reads [lo, n)
 		const uint32_t* __restrict__ Brow, const uint16_t* __restrict__ Bval, const uint8_t* __restrict__ Bstrand,
-		uint32_t shift1, uint32_t nb1, uint32_t cap1, uint32_t* __restrict__ gcur1, uint64_t* __restrict__ E1, uint32_t* __restrict__ K1, int* err)
+		uint32_t shift1, uint32_t nb1, uint32_t cap1, uint32_t* __restrict__ gcur1, const RpOut O, int* err)
 {
 	extern __shared__ __align__(16) unsigned char rsm[];
 	uint64_t* SE = (uint64_t*)rsm;                             // [RP_TILE]
 	uint32_t* SK = (uint32_t*)(SE + RP_TILE);                  // [RP_TILE]
 	uint32_t* hist = SK + RP_TILE;                             // [RP_NBMAX + 2]
 	uint32_t* gbase = hist + RP_NBMAX + 2;                     // [RP_NBMAX + 2]
-	__shared__ uint32_t s_tmp[34];
+	uint32_t* off = gbase + RP_NBMAX + 2;                      // [RP_NBMAX + 2]
 	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwc = RP_THREADS / 32;
 	const uint32_t wstride = gridDim.x * nwc;
 	for (uint32_t b = tid; b <= nb1; b += RP_THREADS) hist[b] = 0;
@@ -242,53 +274,75 @@ __global__ void __launch_bounds__(RP_THREADS) k_rp1(uint32_t n, uint32_t lo, uin
 		if (!__syncthreads_or(i < n)) break;
 		uint64_t ev[RP_ITEMS];
 		uint32_t kv[RP_ITEMS], sl[RP_ITEMS];
+		// all the loads of the tile first (k-mer id, position, strand byte: three independent streams), then the arithmetic:
+		// the kernel is bound by memory latency, so every load this warp will need is in flight at once
+		uint32_t cw[RP_ITEMS];
+		uint16_t pw[RP_ITEMS];
+		uint8_t sw[RP_ITEMS];
+#pragma unroll
+		for (int u = 0; u < RP_ITEMS; ++u) {
+			const uint32_t j = jb + u * 32 + lane;
+			const bool have = i < n && j < j1;
+			cw[u] = have ? Brow[j] : 0xFFFFFFFFu;
+			pw[u] = have ? Bval[j] : (uint16_t)0;
+			sw[u] = have && Bstrand ? Bstrand[j >> 3] : (uint8_t)0;
+		}
 #pragma unroll
 		for (int u = 0; u < RP_ITEMS; ++u) {
 			const uint32_t j = jb + u * 32 + lane;
 			sl[u] = 0xFFFFFFFFu;
 			if (i < n && j < j1) {
-				const uint32_t c = Brow[j];
+				const uint32_t c = cw[u];
 				const uint32_t kid = Bstrand ? c : c & 0x7FFFFFFFu;
 				if (kid >= klo && kid < khi) {                        // k-mers outside [klo, khi) belong to another GPU's transpose
-					const uint32_t st = Bstrand ? getbit(Bstrand, j) : c >> 31;
+					const uint32_t st = Bstrand ? (sw[u] >> (j & 7)) & 1u : c >> 31;
 					kv[u] = kid - klo;
-					ev[u] = (uint64_t)i | ((uint64_t)st << 31) | ((uint64_t)Bval[j] << 32) | ((uint64_t)(j - j0) << 48);
+					ev[u] = (uint64_t)i | ((uint64_t)st << 31) | ((uint64_t)pw[u] << 32) | ((uint64_t)(j - j0) << 48);
 					sl[u] = atomicAdd(&hist[kv[u] >> shift1], 1u);
 				}
 			}
 		}
 		if (i < n) jb += 32 * RP_ITEMS;
 		__syncthreads();
-		rp_reserve(hist, gbase, nb1, gcur1, BCNT_STRIDE, cap1, s_tmp, err);
+		rp_reserve(hist, off, gbase, nb1, gcur1, BCNT_STRIDE, cap1, err);
 #pragma unroll
 		for (int u = 0; u < RP_ITEMS; ++u)
-			if (sl[u] != 0xFFFFFFFFu) { const uint32_t at = hist[kv[u] >> shift1] + sl[u]; SE[at] = ev[u]; SK[at] = kv[u]; }
+			if (sl[u] != 0xFFFFFFFFu) { const uint32_t at = off[kv[u] >> shift1] + sl[u]; SE[at] = ev[u]; SK[at] = kv[u]; }
 		__syncthreads();
-		const uint32_t total = hist[nb1];
+		const uint32_t total = off[nb1];
 		for (uint32_t t = tid; t < total; t += RP_THREADS) {
 			const uint32_t k = SK[t], b = k >> shift1;
-			const uint32_t g = gbase[b] + (t - hist[b]);
-			if (g < cap1) { const size_t at = (size_t)b * cap1 + g; E1[at] = SE[t]; K1[at] = k; }
+			const uint32_t g = gbase[b] + (t - off[b]);
+			if (g < cap1) {
+				const uint32_t d = O.groups > 1 ? b / O.nb1_loc : 0u, bl = b - d * O.nb1_loc;
+				const size_t at = ((size_t)bl * O.groups + O.me) * cap1 + g;
+				O.E[d][at] = SE[t]; O.K[d][at] = k - d * O.kpr;      // k-mer id relative to the owner's range
+			}
 		}
-		__syncthreads();
-		for (uint32_t b = tid; b <= nb1; b += RP_THREADS) hist[b] = 0;
-		__syncthreads();
 	}
 }
 
-// tiles of the coarse buckets for level 2: tstart[c] = first tile of coarse bucket c, tstart[nb1] = number of tiles
-__global__ void __launch_bounds__(1024) k_rp_tiles(uint32_t nb1, uint32_t cap1, const uint32_t* __restrict__ gcur1, uint32_t* __restrict__ tstart)
+// several GPUs: every rank tells the owner of a coarse bucket how many records it has put into its sub-region
+struct RpPost { uint32_t* cnt[MG_MAXW]; };
+__global__ void k_rp_post(uint32_t nb1, uint32_t cap1, uint32_t world, uint32_t me, uint32_t nb1_loc, const uint32_t* __restrict__ gcur1, const RpPost P)
 {
-	__shared__ uint32_t t[RP_NBMAX + 2];
-	__shared__ uint32_t s_tmp[34];
-	for (uint32_t c = threadIdx.x; c < nb1; c += blockDim.x) t[c] = (min(gcur1[(size_t)c * BCNT_STRIDE], cap1) + RP_TILE - 1) / RP_TILE;
-	__syncthreads();
-	block_excl_scan<uint32_t>(t, nb1, s_tmp);
-	for (uint32_t c = threadIdx.x; c <= nb1; c += blockDim.x) tstart[c] = t[c];
+	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb1; b += gridDim.x * blockDim.x) {
+		const uint32_t d = b / nb1_loc, bl = b - d * nb1_loc;
+		P.cnt[d][((size_t)bl * world + me) * BCNT_STRIDE] = min(gcur1[(size_t)b * BCNT_STRIDE], cap1);
+	}
 }
 
-__global__ void __launch_bounds__(RP_THREADS) k_rp2(uint32_t shift1, uint32_t wshift, uint32_t nb1, uint32_t cap1, const uint32_t* __restrict__ gcur1,
-		const uint32_t* __restrict__ tstart, const uint64_t* __restrict__ E1, const uint32_t* __restrict__ K1,
+// tiles of the coarse sub-buckets for level 2: tstart[sb] = first tile of sub-bucket sb = c * groups + g, tstart[nsb] = number of tiles
+__global__ void __launch_bounds__(1024) k_rp_tiles(uint32_t nsb, uint32_t cap1, const uint32_t* __restrict__ gcur1, uint32_t* __restrict__ tstart)
+{
+	__shared__ uint32_t s_tmp[34];
+	for (uint32_t c = threadIdx.x; c < nsb; c += blockDim.x) tstart[c] = (min(gcur1[(size_t)c * BCNT_STRIDE], cap1) + RP_TILE - 1) / RP_TILE;
+	__syncthreads();
+	block_excl_scan<uint32_t>(tstart, nsb, s_tmp);
+}
+
+__global__ void __launch_bounds__(RP_THREADS) k_rp2(uint32_t shift1, uint32_t wshift, uint32_t nsb, uint32_t groups, uint32_t cap1, const uint32_t* __restrict__ gcur1,
+		const uint32_t* __restrict__ tstart, uint32_t sb_lo, uint32_t sb_hi, const uint64_t* __restrict__ E1, const uint32_t* __restrict__ K1,
 		uint32_t* __restrict__ bcnt, uint64_t* __restrict__ partE, uint16_t* __restrict__ partK, int* err)
 {
 	extern __shared__ __align__(16) unsigned char rsm[];
@@ -296,61 +350,88 @@ __global__ void __launch_bounds__(RP_THREADS) k_rp2(uint32_t shift1, uint32_t ws
 	uint32_t* SK = (uint32_t*)(SE + RP_TILE);
 	uint32_t* hist = SK + RP_TILE;
 	uint32_t* gbase = hist + RP_NBMAX + 2;
-	__shared__ uint32_t s_tmp[34];
+	uint32_t* off = gbase + RP_NBMAX + 2;
 	__shared__ uint32_t s_c;
 	const uint32_t tid = threadIdx.x;
 	const uint32_t nb2 = 1u << (shift1 - wshift), wmask = (1u << wshift) - 1u;
-	const uint32_t ntiles = tstart[nb1];
+	const uint32_t ntiles = tstart[sb_hi];                         // this launch: the tiles of the sub-buckets [sb_lo, sb_hi)
 	for (uint32_t b = tid; b <= nb2; b += RP_THREADS) hist[b] = 0;
-	for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+	for (uint32_t tile = tstart[sb_lo] + blockIdx.x; tile < ntiles; tile += gridDim.x) {
 		if (tid == 0) {
-			uint32_t a = 0, b = nb1;                                // last coarse bucket c with tstart[c] <= tile
+			uint32_t a = 0, b = nsb;                                // last sub-bucket sb with tstart[sb] <= tile (empty ones have equal starts: take the last)
 			while (b - a > 1) { const uint32_t c = (a + b) >> 1; if (tstart[c] <= tile) a = c; else b = c; }
 			s_c = a;
 		}
 		__syncthreads();
-		const uint32_t c = s_c;
-		const uint32_t cnt = min(gcur1[(size_t)c * BCNT_STRIDE], cap1), first = (tile - tstart[c]) * RP_TILE;
+		const uint32_t sb = s_c, c = sb / groups;
+		const uint32_t cnt = min(gcur1[(size_t)sb * BCNT_STRIDE], cap1), first = (tile - tstart[sb]) * RP_TILE;
 		const uint32_t len = min((uint32_t)RP_TILE, cnt - first);
-		const uint64_t* e1 = E1 + (size_t)c * cap1 + first;
-		const uint32_t* k1 = K1 + (size_t)c * cap1 + first;
+		const uint64_t* e1 = E1 + (size_t)sb * cap1 + first;
+		const uint32_t* k1 = K1 + (size_t)sb * cap1 + first;
 		const uint32_t fbase = c << (shift1 - wshift);              // first fine bucket of this coarse bucket
 		uint64_t ev[RP_ITEMS];
 		uint32_t kv[RP_ITEMS], sl[RP_ITEMS];
 #pragma unroll
+		for (int u = 0; u < RP_ITEMS; ++u) {                      // every load of the tile in flight before anything waits
+			const uint32_t x = u * RP_THREADS + tid;
+			if (x < len) { ev[u] = e1[x]; kv[u] = k1[x]; }
+		}
+#pragma unroll
 		for (int u = 0; u < RP_ITEMS; ++u) {
 			const uint32_t x = u * RP_THREADS + tid;
 			sl[u] = 0xFFFFFFFFu;
-			if (x < len) { ev[u] = e1[x]; kv[u] = k1[x]; sl[u] = atomicAdd(&hist[(kv[u] >> wshift) - fbase], 1u); }
+			if (x < len) sl[u] = atomicAdd(&hist[(kv[u] >> wshift) - fbase], 1u);
 		}
 		__syncthreads();
-		rp_reserve(hist, gbase, nb2, bcnt + (size_t)fbase * BCNT_STRIDE, BCNT_STRIDE, BUCKET_CAP, s_tmp, err);
+		rp_reserve(hist, off, gbase, nb2, bcnt + (size_t)fbase * BCNT_STRIDE, BCNT_STRIDE, BUCKET_CAP, err);
 #pragma unroll
 		for (int u = 0; u < RP_ITEMS; ++u)
-			if (sl[u] != 0xFFFFFFFFu) { const uint32_t at = hist[(kv[u] >> wshift) - fbase] + sl[u]; SE[at] = ev[u]; SK[at] = kv[u]; }
+			if (sl[u] != 0xFFFFFFFFu) { const uint32_t at = off[(kv[u] >> wshift) - fbase] + sl[u]; SE[at] = ev[u]; SK[at] = kv[u]; }
 		__syncthreads();
 		for (uint32_t t = tid; t < len; t += RP_THREADS) {
 			const uint32_t k = SK[t], f = k >> wshift, b = f - fbase;
-			const uint32_t g = gbase[b] + (t - hist[b]);
+			const uint32_t g = gbase[b] + (t - off[b]);
 			if (g < BUCKET_CAP) { const size_t at = (size_t)f * BUCKET_CAP + g; partE[at] = SE[t]; partK[at] = (uint16_t)(k & wmask); }
 		}
-		__syncthreads();
-		for (uint32_t b = tid; b <= nb2; b += RP_THREADS) hist[b] = 0;
-		__syncthreads();
 	}
 }
 
-// bucket sizes (one per 32-byte sector) -> dense array for the scan
-__global__ void k_bucket_sizes(uint32_t nb, const uint32_t* __restrict__ bcnt, uint32_t* __restrict__ bsize)
+// Where the buckets [f_lo, f_hi) start in A: boff[f] = boff[f_lo] + sizes before f (boff[f_lo] was left by the launch for the
+// previous range; 0 for the first), boff[f_hi] = the end.  One CTA: the ranges are consumed one after the other, while the
+// level-2 partition of the next range is still running.
+__global__ void __launch_bounds__(1024) k_bucket_offsets(uint32_t f_lo, uint32_t f_hi, const uint32_t* __restrict__ bcnt, uint32_t* __restrict__ boff)
 {
-	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b <= nb; b += gridDim.x * blockDim.x) bsize[b] = b < nb ? min(bcnt[(size_t)b * BCNT_STRIDE], BUCKET_CAP) : 0;
+	__shared__ uint32_t s_w[33];
+	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	uint32_t carry = f_lo ? boff[f_lo] : 0;
+	if (tid == 0 && !f_lo) boff[0] = 0;
+	for (uint32_t base = f_lo; base < f_hi; base += 1024) {
+		const uint32_t f = base + tid;
+		const uint32_t x = f < f_hi ? min(bcnt[(size_t)f * BCNT_STRIDE], BUCKET_CAP) : 0;
+		uint32_t v = x;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, v, o); if (lane >= (uint32_t)o) v += y; }
+		if (lane == 31) s_w[wid] = v;
+		__syncthreads();
+		if (wid == 0) {
+			uint32_t w = s_w[lane], ws = w;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, ws, o); if (lane >= (uint32_t)o) ws += y; }
+			s_w[lane] = ws - w;
+			if (lane == 31) s_w[32] = ws;
+		}
+		__syncthreads();
+		if (f < f_hi) boff[f + 1] = carry + s_w[wid] + v;
+		carry += s_w[32];
+		__syncthreads();
+	}
 }
 
 // One CTA per bucket: the bucket arrives in shared memory as two bulk async copies (TMA 1-D); counting sort by k-mer;
 // every entry then finds its place among the 2..8 entries of its column by read id and goes out to Aent (A's columns:
 // rows ascending) with the per-column product counts (== estimateFLOP, overlap.hpp:157-202) and A's colptr.
 constexpr size_t BUCKET_SMEM = (size_t)BUCKET_CAP * (8 + 2 + 2) + ((size_t)BUCKET_WMAX + 2) * 4;
-__global__ void __launch_bounds__(256, 4) k_bucket(uint32_t klo, uint32_t m, uint32_t lo, uint32_t hi, uint32_t wshift, uint32_t nb,
+__global__ void __launch_bounds__(256, 4) k_bucket(uint32_t klo, uint32_t m, uint32_t lo, uint32_t hi, uint32_t wshift, uint32_t b_lo, uint32_t b_hi, uint32_t nb,
 		const uint32_t* __restrict__ boff, const uint64_t* __restrict__ partE, const uint16_t* __restrict__ partK,
 		uint32_t* __restrict__ Acolptr, uint64_t* __restrict__ Aent, uint8_t* __restrict__ Ainfo, uint32_t* __restrict__ flop32, const int* err)
 {
@@ -367,7 +448,7 @@ __global__ void __launch_bounds__(256, 4) k_bucket(uint32_t klo, uint32_t m, uin
 	if (tid == 0) mbar_init(&s_bar, 1);
 	__syncthreads();
 	uint32_t phase = 0;
-	for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
+	for (uint32_t b = b_lo + blockIdx.x; b < b_hi; b += gridDim.x) {     // this launch: the buckets [b_lo, b_hi) of nb
 		const uint32_t o0 = boff[b], size = boff[b + 1] - o0;
 		const uint32_t kbase = b * W, kw = min(W, m - kbase);      // k-mer ids are klo + kbase + k; A's colptr is local to [klo, klo + m)
 		PHASE_BEGIN();
@@ -462,7 +543,10 @@ __global__ void k_units_init(uint32_t ncols, uint32_t ucap, const uint32_t* __re
 		Meta* meta, int* err)
 {
 	const uint32_t U = ubase[ncols];
-	if (blockIdx.x == 0 && threadIdx.x == 0) meta->n_units = U;
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		meta->n_units = U;
+		for (int r = 0; r <= NRANGE; ++r) meta->range_col[r] = ncols;
+	}
 	if (U > ucap) { if (blockIdx.x == 0 && threadIdx.x == 0) set_err(err, -7); return; }
 	for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < ncols; li += gridDim.x * blockDim.x) {
 		const uint32_t u0 = ubase[li], u1 = ubase[li + 1];
@@ -499,16 +583,20 @@ __global__ void __launch_bounds__(256) k_count_units(uint32_t m, uint32_t lo, ui
 // they already are a single row (sh == 0): those go to the huge-pair list (class NCLASS).
 __global__ void k_classify_units(uint32_t ucap, const uint32_t* __restrict__ ucol, const uint32_t* __restrict__ ucount,
 		const ColInfo* __restrict__ colinfo, const uint64_t* __restrict__ uptr, unsigned long long* __restrict__ ucur,
-		unsigned long long* __restrict__ ccur, uint32_t* __restrict__ lists, uint8_t* __restrict__ refine, uint32_t round, Meta* meta, const int* err)
+		unsigned long long* __restrict__ ccur, uint32_t* __restrict__ lists, uint8_t* __restrict__ refine, uint32_t round, uint32_t nrange, Meta* meta, const int* err)
 {
 	if (*err != 0) return;
 	const uint32_t U = meta->n_units;
+	const unsigned long long total = max((unsigned long long)uptr[U], 1ull);
 	for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += gridDim.x * blockDim.x) {
 		const uint32_t f = ucount[u];
 		ucur[u] = uptr[u];
+		// column ranges of about equal product counts (units are ordered by column, so a range is an interval of columns)
+		const uint32_t rg = nrange > 1 ? min(nrange - 1, (uint32_t)((unsigned long long)uptr[u] * nrange / total)) : 0u;
 		{
 			const uint32_t li = ucol[u];                             // the scatter's per-column cursor: the region of a light column, or the heavy mark
 			ccur[(size_t)li * CCUR_STRIDE] = colinfo[li].sh == 31 ? (unsigned long long)uptr[u] : CCUR_HEAVY;
+			atomicMin(&meta->range_col[rg], li);
 		}
 		if (!f) continue;
 		int c = f <= CLASS_CAP[0] ? 0 : f <= CLASS_CAP[1] ? 1 : f <= CLASS_CAP[2] ? 2 : 3;
@@ -516,8 +604,8 @@ __global__ void k_classify_units(uint32_t ucap, const uint32_t* __restrict__ uco
 			const uint32_t li = ucol[u];
 			if (colinfo[li].sh != 0) { refine[li] = (uint8_t)(round + 1); atomicAdd(&meta->n_refine, 1u); continue; }
 		}
-		uint32_t idx = atomicAdd(&meta->class_count[c], 1u);
-		lists[(size_t)c * ucap + idx] = u;
+		uint32_t idx = atomicAdd(&meta->class_count[rg][c], 1u);
+		lists[((size_t)rg * (NCLASS + 1) + c) * ucap + idx] = u;
 	}
 }
 
@@ -538,11 +626,20 @@ __device__ __forceinline__ uint32_t entries_after(uint32_t x, uint32_t info, con
 
 __global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ nnzA_ptr, uint32_t m, uint32_t lo, uint32_t hi, const uint32_t* __restrict__ Acolptr,
 		const uint64_t* __restrict__ Aent, const uint8_t* __restrict__ Ainfo, unsigned long long* __restrict__ ccur,
-		const ColInfo* __restrict__ colinfo, unsigned long long* __restrict__ ucur, uint64_t* __restrict__ raw)
+		const ColInfo* __restrict__ colinfo, unsigned long long* __restrict__ ucur, uint64_t* __restrict__ raw,
+		const Meta* __restrict__ meta, uint32_t range, uint32_t nrange, const int* __restrict__ stop)
 {
+	if (stop && *stop) return;                                  // multi-GPU: the exchange plan found a buffer too small
 	constexpr int ILP = 4;
 	constexpr uint64_t LOW48 = 0x0000FFFFFFFFFFFFull;
 	const uint32_t stride = gridDim.x * blockDim.x;
+	const uint32_t base = lo;                                  // the cursors are indexed by the local column
+	if (nrange > 1) {                                          // this launch: the output columns of one range of the pipeline
+		uint32_t c0 = meta->range_col[range], c1 = meta->range_col[nrange];
+		for (uint32_t r = range + 1; r < nrange; ++r) c1 = min(c1, meta->range_col[r]);
+		if (c0 >= c1) return;
+		hi = lo + c1; lo = lo + c0;
+	}
 	const uint32_t nnzA = *nnzA_ptr;                           // entries of A on this device (the end of the last transpose bucket)
 	for (uint32_t x0 = blockIdx.x * blockDim.x + threadIdx.x; x0 < nnzA; x0 += stride * ILP) {
 		uint32_t after[ILP];
@@ -560,7 +657,7 @@ __global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ nn
 			const uint32_t ra = ent_row(ea[u]);
 			if (ra < lo || ra >= hi) { after[u] = 0; continue; }
 			if (after[u] == AINFO_ESC) after[u] = entries_after(x0 + u * stride, AINFO_ESC, Acolptr, m);
-			q[u] = atomicAdd(&ccur[(size_t)(ra - lo) * CCUR_STRIDE], (unsigned long long)after[u]);
+			q[u] = atomicAdd(&ccur[(size_t)(ra - base) * CCUR_STRIDE], (unsigned long long)after[u]);
 		}
 #pragma unroll
 		for (int u = 0; u < ILP; ++u) {
@@ -573,7 +670,7 @@ __global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ nn
 				for (uint32_t b = 0; b < after[u]; ++b) dst[b] = (nxt[b] & LOW48) | top;
 			} else {
 				const uint32_t ra = ent_row(ea[u]);
-				const ColInfo ci = colinfo[ra - lo];
+				const ColInfo ci = colinfo[ra - base];
 				#pragma unroll 1
 				for (uint32_t b = 0; b < after[u]; ++b) {
 					const uint64_t eb = nxt[b];
@@ -1217,6 +1314,84 @@ __global__ void __launch_bounds__(256) k_regroup(uint32_t n, uint32_t lo, uint32
 				if (COUNT) atomicAdd(&ucount[u], 1u);
 				else raw[atomicAdd(&ucur[u], 1ull)] = r;
 			}
+		}
+	}
+}
+
+// ---- multi-GPU over NVLink peer memory (mode "nvlink" of bella_b200/distributed.py) ----
+// A 32-bit array of this rank to the same place on every rank (its per-column product counts: row `me` of counts_all;
+// the lengths of its reads): coalesced remote stores.
+struct MgPeers { void* p[MG_MAXW]; };
+__global__ void k_mg_post(uint64_t count, const uint32_t* __restrict__ src, uint32_t world, uint64_t at, const MgPeers dst)
+{
+	for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < count; c += (uint64_t)gridDim.x * blockDim.x) {
+		const uint32_t v = src[c];
+		for (uint32_t d = 0; d < world; ++d) ((uint32_t*)dst.p[d])[at + c] = v;
+	}
+}
+
+// The exchange plan, on the device, from the flat exclusive scan S of counts_all (u64 [world * n + 1]):
+//   sendoff[c]        where this rank's products for column c start in its send buffer (its own row's prefix)
+//   segoff[s][li]     per source rank s, the prefix of its counts over the columns this rank owns
+//   recvbase[s]       where source s's block starts in this rank's receive buffer
+//   push[d] = {first element of the send buffer that goes to rank d, count, offset in d's receive buffer}
+// cuts[world+1]: the column ranges the ranks own.  One launch, grid-stride; no host involvement.
+__global__ void k_mg_plan(uint32_t world, uint32_t me, uint32_t n, const uint32_t* __restrict__ cuts, const unsigned long long* __restrict__ S,
+		unsigned long long cap_recv, unsigned long long cap_send, const int* __restrict__ errs_all, unsigned long long* __restrict__ sendoff,
+		unsigned long long* __restrict__ segoff, unsigned long long* __restrict__ recvbase, unsigned long long* __restrict__ push, int* err)
+{
+	// Every rank sees the same counts, so every rank reaches the same verdict: an error any rank has posted (errs_all[s]), or a
+	// send / receive buffer that is too small on ANY rank (needs in push[3 * world + 0 / 1]), stops the step everywhere.
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		unsigned long long need_recv = 0, need_send = 0;
+		for (uint32_t d = 0; d < world; ++d) {
+			unsigned long long r = 0;
+			for (uint32_t s = 0; s < world; ++s) r += S[(size_t)s * n + cuts[d + 1]] - S[(size_t)s * n + cuts[d]];
+			need_recv = max(need_recv, r);
+			need_send = max(need_send, (unsigned long long)(S[(size_t)(d + 1) * n] - S[(size_t)d * n]));
+		}
+		push[3 * world + 0] = need_recv; push[3 * world + 1] = need_send;
+		for (uint32_t s = 0; s < world; ++s) if (errs_all[s]) set_err(err, errs_all[s]);
+		if (need_recv > cap_recv || need_send > cap_send) set_err(err, -9);
+	}
+	const uint32_t lo = cuts[me], hi = cuts[me + 1], ncols = hi - lo;
+	const uint64_t t0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, nt = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t c = t0; c <= n; c += nt) sendoff[c] = S[(size_t)me * n + c] - S[(size_t)me * n];
+	for (uint64_t x = t0; x < (uint64_t)world * (ncols + 1); x += nt) {
+		const uint32_t s = (uint32_t)(x / (ncols + 1)), li = (uint32_t)(x % (ncols + 1));
+		segoff[x] = S[(size_t)s * n + lo + li] - S[(size_t)s * n + lo];
+	}
+	if (t0 < world) {
+		const uint32_t d = (uint32_t)t0;                          // as a sender to d: what is in front of me in d's buffer
+		unsigned long long before = 0;
+		for (uint32_t s = 0; s < me; ++s) before += S[(size_t)s * n + cuts[d + 1]] - S[(size_t)s * n + cuts[d]];
+		push[3 * d + 0] = S[(size_t)me * n + cuts[d]] - S[(size_t)me * n];
+		push[3 * d + 1] = S[(size_t)me * n + cuts[d + 1]] - S[(size_t)me * n + cuts[d]];
+		push[3 * d + 2] = before;
+		unsigned long long mine = 0;                              // as the owner: source d's block
+		for (uint32_t s = 0; s < d; ++s) mine += S[(size_t)s * n + hi] - S[(size_t)s * n + lo];
+		recvbase[d] = mine;
+	}
+}
+
+// send buffer -> the owners' receive buffers (peer memory): one contiguous block per destination, 16-byte stores
+__global__ void __launch_bounds__(256) k_mg_push(uint32_t world, const uint64_t* __restrict__ send, const unsigned long long* __restrict__ push, const MgPeers recv,
+		const int* __restrict__ stop)
+{
+	if (*stop) return;
+	for (uint32_t d = 0; d < world; ++d) {
+		const unsigned long long first = push[3 * d], cnt = push[3 * d + 1], at = push[3 * d + 2];
+		const uint64_t* src = send + first;
+		uint64_t* dst = (uint64_t*)recv.p[d] + at;
+		const uint64_t t0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, nt = (uint64_t)gridDim.x * blockDim.x;
+		// src and dst may differ in their alignment to 16 bytes: scalar 8-byte stores then (still full 32-byte sectors per warp)
+		if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+			const ulonglong2* s2 = (const ulonglong2*)src;
+			ulonglong2* d2 = (ulonglong2*)dst;
+			for (uint64_t x = t0; x < cnt / 2; x += nt) d2[x] = s2[x];
+			if (t0 == 0 && (cnt & 1)) dst[cnt - 1] = src[cnt - 1];
+		} else {
+			for (uint64_t x = t0; x < cnt; x += nt) dst[x] = src[x];
 		}
 	}
 }

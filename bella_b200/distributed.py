@@ -13,6 +13,11 @@ Layout (the reference has no distributed code, so there is no call
     all-to-all moves every product (8 bytes) to the owner of its column;
   * the owner regroups what it received and runs the group + fold kernels on its columns
     (bella_b200_mg_finish).  Outputs are disjoint column ranges: no reduction, the caller concatenates.
+`mode="nvlink"` (the default of bench.py) takes NCCL off the data path altogether: a rank owns the output columns of its own
+reads, every rank maps the others' exchange buffers (torch symmetric memory = CUDA peer memory over NVLink / NVSwitch), level
+1 of the transpose stores each nonzero straight into the coarse k-mer bucket on the rank that transposes that k-mer range,
+the per-column counts and the products' blocks are pushed the same way, the exchange is planned by one scan and one kernel
+on the device, and the only thing between the phases is a device-side barrier (three per step) -- see _step_nvlink.
 (`mode="replicate"` keeps the first version: after the all-gather every rank transposes all reads at or
 above its first column itself and no products are exchanged.)
 
@@ -232,7 +237,7 @@ class ShardedOverlapSpGEMM:
 
     def load_shard(self, inp, pinned=False):
         """Take this rank's reads of `inp`, pack the panel and make it device resident."""
-        if self.mode == "route":
+        if self.mode in ("route", "nvlink"):
             # a rank owns the output columns of its own reads: shards balanced on the estimated products + the per-column
             # overhead of the group + fold stage (the same weights the exchange mode balances exactly, but up front)
             lens = np.diff(inp.B_colptr.astype(np.int64)).astype(np.float64)
@@ -256,7 +261,9 @@ class ShardedOverlapSpGEMM:
         if pinned:
             self.host_panel = self.host_panel.pin_memory()
         self.panel = self.host_panel.to(self.dev)
-        if self.mode == "route":
+        if self.mode == "nvlink":
+            self._setup_nvlink(inp.n_reads, inp.nnz, n_r, nnz_r)
+        if self.mode in ("route", "nvlink"):
             off, _ = panel_layout(n_r, nnz_r)
             p = self.panel
             self.loc = {"rowids": p[off["rowids"]:off["rowids"] + 4 * nnz_r].view(torch.int32),
@@ -266,12 +273,132 @@ class ShardedOverlapSpGEMM:
             self.nnz_local = nnz_r
         return r0, r1
 
+    def _setup_nvlink(self, n, nnz_total, n_r, nnz_r):
+        self._nnz_total = nnz_total
+        """Exchange buffers of the NVLink mode, allocated ONCE per sharding as one block of symmetric memory (every rank maps
+        every other rank's block); the layout is the same on all ranks."""
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        from . import spgemm
+        world, dev = self.world, self.dev
+        geom = np.zeros(8, dtype=np.uint32)
+        rc = spgemm.lib().bella_b200_mg_geometry(self.n_kmers, nnz_total, world, geom.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"bella_b200_mg_geometry failed: {rc}")
+        # a sub-region holds what ONE rank sends to ONE coarse bucket: sized for the rank with the most nonzeros (the shards
+        # are balanced on products, not on nonzeros)
+        max_nnz = max(b for _, b in self.shapes)
+        geom[5] = (int(1.3 * max_nnz / max(int(geom[2]), 1)) + 2 * 4096 + 15) // 16 * 16
+        self.geom = geom
+        wshift, shift1, nb1, nb1_loc, kpr, cap1 = (int(x) for x in geom[:6])
+        nsb = nb1_loc * world
+        if not hasattr(self, "cap_recv"):
+            # products a rank receives / sends (about flops / world; flops is about nnz for [l,u] = [2,8]); a step that finds them
+            # too small says so on every rank (BELLA_B200_ERR_CAPACITY) and _step_nvlink grows them
+            self.cap_recv = int(1.6 * nnz_total / world) + (1 << 20)
+            self.cap_send = self.cap_recv
+        lay, o = {}, 0
+        for name, nbytes in (("E", nsb * cap1 * 8), ("K", nsb * cap1 * 4), ("CNT", (nsb + 2) * 8 * 4), ("CALL", (world * n + 48) * 4),
+                             ("LEN0", (n + 16) * 4), ("LEN1", (n + 16) * 4), ("PROD", self.cap_recv * 8)):
+            lay[name] = int(o)
+            o = _up(int(o) + int(nbytes), 256)
+        o = int(o)
+        self.sym_layout, self.sym_bytes = lay, o
+        self.sym = symm.empty(o, dtype=torch.uint8, device=dev)
+        self.sym.zero_()
+        self.sym_hdl = symm.rendezvous(self.sym, dist.group.WORLD)
+        base = [int(p) for p in self.sym_hdl.buffer_ptrs]
+        self.peer = {k: [b + off for b in base] for k, off in lay.items()}
+        self.kr_lo = min(self.rank * kpr, self.n_kmers)
+        self.kr_hi = min((self.rank + 1) * kpr, self.n_kmers)
+        self.nnz_cap = nsb * cap1
+        self.loc_i32 = lambda name, count: self.sym[lay[name]:lay[name] + 4 * count].view(torch.int32)
+        # local work arrays (not symmetric)
+        ncols = self.cuts[self.rank + 1] - self.cuts[self.rank]
+        self.w_cnt = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+        self.w_scan = torch.zeros(world * n + 2, dtype=torch.int64, device=dev)
+        self.w_sendoff = torch.zeros(n + 2, dtype=torch.int64, device=dev)
+        self.w_segoff = torch.zeros(world * (ncols + 1) + 1, dtype=torch.int64, device=dev)
+        self.w_recvbase = torch.zeros(world + 1, dtype=torch.int64, device=dev)
+        self.w_push = torch.zeros(3 * world + 2, dtype=torch.int64, device=dev)
+        self.w_send = torch.empty(self.cap_send + 2, dtype=torch.int64, device=dev)
+        self.w_cuts = torch.tensor(self.cuts, dtype=torch.int32, device=dev)
+
+    def _step_nvlink(self, fetch):
+        """One batch without a collective on the data path (module docstring); every phase is one or two kernels of
+        libbella_b200.so, the barriers are torch symmetric-memory barriers on the same stream.  The send / receive buffers
+        are sized once; a batch that needs more is refused by every rank alike, the buffers grow and the batch runs again."""
+        from .spgemm import BellaB200Error
+        for _ in range(4):
+            try:
+                return self._step_nvlink_once(fetch)
+            except BellaB200Error as e:
+                if getattr(e, "code", 0) != -6:
+                    raise
+                need = [int(x) for x in self.w_push[3 * self.world:3 * self.world + 2].tolist()]
+                if need[0] <= self.cap_recv and need[1] <= self.cap_send:
+                    raise
+                self.cap_recv = max(self.cap_recv, int(1.25 * need[0]) + 4096)
+                self.cap_send = max(self.cap_send, int(1.25 * need[1]) + 4096)
+                torch.cuda.synchronize(self.dev)
+                self._setup_nvlink(self.cuts[-1], self._nnz_total, self.r1 - self.r0, self.nnz_local)
+        raise RuntimeError("the exchange buffers did not converge")
+
+    def _step_nvlink_once(self, fetch):
+        if self._profile:
+            import time
+            torch.cuda.synchronize(self.dev)
+            self._t0 = time.perf_counter()
+        g, world, rank = self.g, self.world, self.rank
+        r0, r1, n_r = self.r0, self.r1, self.r1 - self.r0
+        n = self.cuts[-1]
+        lay = self.sym_layout
+        if not hasattr(self, "colptr_local"):
+            # static per shard: the local colptr (the reads' k-mer counts travel with the panel)
+            cp = torch.zeros(n_r + 1, dtype=torch.int64, device=self.dev)
+            torch.cumsum(self.loc["counts"].to(torch.int64), 0, out=cp[1:])
+            self.colptr_local = cp.to(torch.int32)
+        colptr_global = self.colptr_local.data_ptr() - 4 * r0          # indexed by the GLOBAL read id
+        # (two copies of the lengths, alternating: a fast rank posts the next batch's while a slow one still folds this batch's)
+        self._flip = 1 - getattr(self, "_flip", 1)
+        LEN = "LEN%d" % self._flip
+        read_len = self.loc_i32(LEN, n)
+        g.set_inputs_device(n, self.n_kmers, self.nnz_local, (colptr_global, self.loc["rowids"], self.loc["values"]), read_len, None,
+                            self.kmer_size, self.bin_size)
+        # read lengths of this rank's reads -> every rank (4 bytes per read), then level 1 of the transpose into the owners' buckets
+        g.mg_post(n_r, self.loc["read_len"], world, r0, self.peer[LEN])
+        g.mg_route_push(r0, r1, colptr_global, self.loc["rowids"], self.loc["values"], self.n_kmers, self.geom, world, rank,
+                        self.peer["E"], self.peer["K"], self.peer["CNT"])
+        self.sym_hdl.barrier(channel=0)
+        self._tick("route_push + barrier")
+        g.mg_transpose_coarse(self.kr_lo, self.kr_hi, self.geom, world, self.sym.data_ptr() + lay["E"], self.sym.data_ptr() + lay["K"],
+                              self.sym.data_ptr() + lay["CNT"], self.nnz_cap, self.w_cnt)
+        self._tick("transpose (level 2 + buckets)")
+        g.mg_exchange(world, rank, self.w_cuts, self.w_cnt, self.peer["CALL"], 0)
+        self.sym_hdl.barrier(channel=0)
+        self._tick("counts + barrier")
+        g.mg_exchange(world, rank, self.w_cuts, self.w_cnt, self.peer["CALL"], 1, counts_all=self.sym.data_ptr() + lay["CALL"], scan=self.w_scan,
+                      cap_recv=self.cap_recv, cap_send=self.cap_send, sendoff=self.w_sendoff, segoff=self.w_segoff, recvbase=self.w_recvbase, push=self.w_push,
+                      sendbuf=self.w_send, peer_recv=self.peer["PROD"])
+        self.sym_hdl.barrier(channel=0)
+        self._tick("plan + expand + push + barrier")
+        g.mg_finish(r0, r1, world, self.sym.data_ptr() + lay["CALL"], self.w_segoff, self.w_recvbase, self.sym.data_ptr() + lay["PROD"])
+        self._tick("mg_finish")
+        if fetch:
+            colptrC = g.get_colptr(pinned=True)
+            res = g.numeric(pinned=True)
+            return int(colptrC[r1 - r0]), g.result_flops(), (r0, r1), (colptrC[:r1 - r0 + 1],) + res
+        g.numeric_device()
+        return int(g.result_nnz()), g.result_flops(), (r0, r1)
+
     def upload(self):
         """e2e leg: host panel -> device inside the timed region."""
         self.panel.copy_(self.host_panel, non_blocking=True)
 
     def step(self, fetch=False):
         """-> (Z of this rank's columns, products, (col_lo, col_hi)[, host results when fetch=True])"""
+        if self.mode == "nvlink":
+            return self._step_nvlink(fetch)
         if self.mode == "route":
             return self._step_route(fetch)
         if self._profile:

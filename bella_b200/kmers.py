@@ -22,8 +22,7 @@ def lib():
     global _lib
     if _lib is None:
         path = _build.LIB_KMERS
-        if not os.path.exists(path):
-            path = _build.build_kmers()
+        path = _build.build_kmers()                        # returns at once when the .so matches its sources
         L = ctypes.CDLL(path)
         vp, H = ctypes.c_void_p, ctypes.c_void_p
         L.bella_kmers_create.argtypes = [ctypes.c_int]

@@ -13,7 +13,7 @@ from . import _build
 
 _lib = None
 
-ERRORS = {-1: "bad argument", -2: "CUDA error / no usable sm_100 device (there is no CPU fallback)",
+ERRORS = {-6: "multi-GPU exchange buffer too small", -1: "bad argument", -2: "CUDA error / no usable sm_100 device (there is no CPU fallback)",
           -3: "device out of memory", -4: "count exceeds the reference's index types", -5: "internal device error"}
 
 
@@ -31,9 +31,9 @@ class CscView(ctypes.Structure):
 def lib():
     global _lib
     if _lib is None:
-        path = _build.LIB_CUDA
-        if not os.path.exists(path):
-            path = _build.build_cuda()
+        path = os.environ.get("BELLA_B200_LIB")          # A/B runs of two builds of the same library (profiling only)
+        if not path:
+            path = _build.build_cuda()                    # returns at once when the in-tree .so is newer than its sources
         L = ctypes.CDLL(path)
         vp, H = ctypes.c_void_p, ctypes.c_void_p
         L.bella_b200_create.argtypes = [ctypes.POINTER(H), ctypes.c_int]
@@ -49,6 +49,7 @@ def lib():
         L.bella_b200_numeric_aux.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp]
         L.bella_b200_numeric_device.argtypes = [H]
         L.bella_b200_n_unpinned.argtypes = [H, ctypes.POINTER(ctypes.c_uint64)]
+        L.bella_b200_get_flops.argtypes = [H, ctypes.POINTER(ctypes.c_uint64)]
         L.bella_b200_result_device.argtypes = [H] + [ctypes.POINTER(vp)] * 5 + [ctypes.POINTER(ctypes.c_uint64)]
         L.bella_b200_run_resident.argtypes = [H, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
         L.bella_b200_get_timings.argtypes = [H, ctypes.POINTER(ctypes.c_float)]
@@ -61,13 +62,20 @@ def lib():
         L.bella_b200_get_colptr.argtypes = [H, vp]
         L.bella_b200_mg_route.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp, ctypes.c_uint32, ctypes.c_int, vp, ctypes.POINTER(ctypes.c_uint64)]
         L.bella_b200_mg_transpose_records.argtypes = [H, vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, vp]
+        pp = ctypes.POINTER(vp)
+        L.bella_b200_mg_geometry.argtypes = [ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int, vp]
+        L.bella_b200_mg_route_push.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp, ctypes.c_uint32, vp, ctypes.c_int, ctypes.c_int, pp, pp, pp]
+        L.bella_b200_mg_transpose_coarse.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, vp, ctypes.c_int, vp, vp, vp, ctypes.c_uint64, vp]
+        L.bella_b200_mg_post.argtypes = [H, ctypes.c_uint64, vp, ctypes.c_int, ctypes.c_uint64, pp]
+        L.bella_b200_mg_exchange.argtypes = [H, ctypes.c_int, ctypes.c_int, vp, vp, pp, ctypes.c_int, vp, vp, ctypes.c_uint64, ctypes.c_uint64, vp, vp, vp, vp, vp, pp]
         L.bella_b200_set_inputs_tuples.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, vp, vp, vp, vp, vp, ctypes.c_uint16, ctypes.c_uint16]
         L.bella_b200_get_B.argtypes = [H, ctypes.POINTER(ctypes.c_uint32), vp, vp, vp, vp, ctypes.POINTER(ctypes.c_float)]
         _lib = L
     return _lib
 
 
-EXPORTS = ["bella_b200_set_inputs_csr", "bella_b200_n_unpinned", "bella_b200_create", "bella_b200_destroy", "bella_b200_last_error", "bella_b200_set_inputs",
+EXPORTS = ["bella_b200_get_flops", "bella_b200_mg_geometry", "bella_b200_mg_route_push", "bella_b200_mg_transpose_coarse", "bella_b200_mg_post", "bella_b200_mg_exchange",
+           "bella_b200_set_inputs_csr", "bella_b200_n_unpinned", "bella_b200_create", "bella_b200_destroy", "bella_b200_last_error", "bella_b200_set_inputs",
            "bella_b200_set_inputs_device", "bella_b200_set_column_range", "bella_b200_symbolic",
            "bella_b200_numeric", "bella_b200_numeric_aux", "bella_b200_numeric_device",
            "bella_b200_result_device", "bella_b200_run_resident", "bella_b200_get_timings", "bella_b200_stream",
@@ -124,7 +132,9 @@ class OverlapSpGEMM:
     def _check(self, rc, what):
         if rc != 0:
             msg = self._L.bella_b200_last_error(self._h)
-            raise BellaB200Error(f"{what}: {ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+            e = BellaB200Error(f"{what}: {ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+            e.code = rc
+            raise e
 
     def close(self):
         if self._h:
@@ -233,6 +243,27 @@ class OverlapSpGEMM:
         self._check(self._L.bella_b200_mg_transpose_records(self._h, _ptr(rec), nrec, kmer_lo, kmer_hi, _ptr(cnt_local)),
                     "bella_b200_mg_transpose_records")
 
+    @staticmethod
+    def _pp(ptrs):
+        return (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(int(p)) for p in ptrs])
+
+    def mg_route_push(self, read_lo, read_hi, colptr_global_ptr, rowids, values, n_kmers, geom, world, me, peer_E, peer_K, peer_cnt):
+        self._check(self._L.bella_b200_mg_route_push(self._h, read_lo, read_hi, _ptr(colptr_global_ptr), _ptr(rowids), _ptr(values), n_kmers, _ptr(geom),
+                                                     world, me, self._pp(peer_E), self._pp(peer_K), self._pp(peer_cnt)), "bella_b200_mg_route_push")
+
+    def mg_transpose_coarse(self, kmer_lo, kmer_hi, geom, world, E, K, cnt, nnz_cap, cnt_local):
+        self._check(self._L.bella_b200_mg_transpose_coarse(self._h, kmer_lo, kmer_hi, _ptr(geom), world, _ptr(E), _ptr(K), _ptr(cnt), nnz_cap, _ptr(cnt_local)),
+                    "bella_b200_mg_transpose_coarse")
+
+    def mg_post(self, count, src, world, at, peer_dst):
+        self._check(self._L.bella_b200_mg_post(self._h, count, _ptr(src), world, at, self._pp(peer_dst)), "bella_b200_mg_post")
+
+    def mg_exchange(self, world, me, cuts, cnt_local, peer_counts_all, phase, counts_all=None, scan=None, cap_recv=0, cap_send=0, sendoff=None, segoff=None,
+                    recvbase=None, push=None, sendbuf=None, peer_recv=None):
+        self._check(self._L.bella_b200_mg_exchange(self._h, world, me, _ptr(cuts), _ptr(cnt_local), self._pp(peer_counts_all), phase, _ptr(counts_all),
+                                                   _ptr(scan), cap_recv, cap_send, _ptr(sendoff), _ptr(segoff), _ptr(recvbase), _ptr(push), _ptr(sendbuf),
+                                                   self._pp(peer_recv if peer_recv is not None else peer_counts_all)), "bella_b200_mg_exchange")
+
     def mg_scatter(self, sendoff, sendbuf):
         self._check(self._L.bella_b200_mg_scatter(self._h, _ptr(sendoff), _ptr(sendbuf)), "bella_b200_mg_scatter")
 
@@ -246,6 +277,11 @@ class OverlapSpGEMM:
         self._check(self._L.bella_b200_get_colptr(self._h, _ptr(colptrC)), "bella_b200_get_colptr")
         self.colptrC = colptrC
         return colptrC
+
+    def result_flops(self):
+        v = ctypes.c_uint64(0)
+        self._check(self._L.bella_b200_get_flops(self._h, ctypes.byref(v)), "bella_b200_get_flops")
+        return int(v.value)
 
     def result_nnz(self):
         z = ctypes.c_uint64(0)

@@ -25,8 +25,7 @@ def lib():
     global _lib
     if _lib is None:
         path = _build.LIB_XDROP
-        if not os.path.exists(path):
-            path = _build.build_xdrop()
+        path = _build.build_xdrop()                        # returns at once when the .so matches its sources
         L = ctypes.CDLL(path)
         vp, H = ctypes.c_void_p, ctypes.c_void_p
         L.bella_xdrop_create.argtypes = [ctypes.c_int]

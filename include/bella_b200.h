@@ -41,6 +41,7 @@ extern "C" {
 #define BELLA_B200_ERR_OOM      -3   /* device allocation failed                                     */
 #define BELLA_B200_ERR_RANGE    -4   /* a count does not fit the reference's index types (u32 / u15) */
 #define BELLA_B200_ERR_INTERNAL -5   /* inconsistency detected on the device                         */
+#define BELLA_B200_ERR_CAPACITY -6   /* multi-GPU only: an exchange buffer sized by the caller is too small (every rank reports it) */
 
 typedef struct bella_b200_handle bella_b200_handle;
 
@@ -143,6 +144,10 @@ int bella_b200_numeric(bella_b200_handle* h, uint32_t col_begin, uint32_t col_en
 int bella_b200_numeric_aux(bella_b200_handle* h, uint32_t col_begin, uint32_t col_end,
 		uint16_t* nbins, uint16_t* support, uint16_t* overlap);
 
+/* Kept products of the handle's column range (== sum of estimateFLOP's array over the range), after the symbolic phase
+ * or bella_b200_mg_finish. */
+int bella_b200_get_flops(bella_b200_handle* h, uint64_t* flops);
+
 /* Number of output nonzeros of the handle's column range whose final value has MORE THAN 16 bins.  For those the
  * reference's choose() (include/common/common.h:162-170) depends on the tie order of libstdc++'s introsort, which is
  * pinned (insertion sort, stable) only up to 16 elements: the device picks the best-supported bin with ties to the most
@@ -199,6 +204,33 @@ int bella_b200_mg_route(bella_b200_handle* h, uint32_t n_local, uint32_t read_ba
 		const uint16_t* values_dev, uint32_t kmers_per_rank, int world, uint32_t* send_dev, uint64_t* send_counts_host);
 int bella_b200_mg_transpose_records(bella_b200_handle* h, const uint32_t* rec_dev, uint64_t nrec, uint32_t kmer_lo, uint32_t kmer_hi,
 		uint32_t* cnt_local_dev);
+/* NVLink mode (bella_b200/distributed.py mode "nvlink"): no collective on the data path.  Every rank maps the others'
+ * exchange buffers (CUDA peer memory over NVLink / NVSwitch; the Python side allocates them as torch symmetric memory)
+ * and the kernels store straight into the owner's memory; between the phases the caller only runs a barrier.
+ *   mg_geometry         the two-level partition all ranks agree on: out8 = {wshift, shift1, nb1 (coarse buckets), nb1_loc
+ *                       (coarse buckets per rank), k-mers per rank, cap1 (records per sub-region), fine buckets, l2}
+ *   mg_route_push       level 1 of the transpose of this rank's reads [read_lo, read_hi) (colptr indexed by the GLOBAL read
+ *                       id, strand bit in bit 31 of the row ids): every nonzero goes into the coarse bucket of its k-mer on
+ *                       the rank that transposes that k-mer range -- sub-region `me` of the bucket, in peer_E/peer_K[rank] --
+ *                       and the record counts into peer_cnt[rank]                       -- barrier --
+ *   mg_transpose_coarse level 2 + bucket kernel over the received coarse buckets; cnt_local_dev u32[n] as mg_transpose
+ *   mg_post             a 32-bit array of this rank to the same offset `at` on every rank (remote stores)
+ *   mg_exchange         phase 0: this rank's per-column counts -> row `me` of counts_all on every rank   -- barrier --
+ *                       (counts_all is u32 [world * n] + 16 words + one error word per rank; push_dev is u64 [3 * world + 2]: the last
+ *                       two words receive the largest receive / send block any rank needs)
+ *                       phase 1: exchange plan on the device (flat scan of counts_all + one kernel: send offsets, per-source
+ *                       segment offsets, receive bases, push blocks), expansion of this rank's products into its send
+ *                       buffer (mg_scatter), push of each destination's block into its receive buffer   -- barrier --
+ *   then mg_finish on the receive buffer. */
+int bella_b200_mg_geometry(uint32_t n_kmers, uint64_t nnz_total, int world, uint32_t* out8);
+int bella_b200_mg_route_push(bella_b200_handle* h, uint32_t read_lo, uint32_t read_hi, const uint32_t* colptr_global_dev, const uint32_t* rowids_dev,
+		const uint16_t* values_dev, uint32_t n_kmers, const uint32_t* geom8, int world, int me, void* const* peer_E, void* const* peer_K, void* const* peer_cnt);
+int bella_b200_mg_transpose_coarse(bella_b200_handle* h, uint32_t kmer_lo, uint32_t kmer_hi, const uint32_t* geom8, int world,
+		const uint64_t* E_dev, const uint32_t* K_dev, const uint32_t* cnt_dev, uint64_t nnz_cap, uint32_t* cnt_local_dev);
+int bella_b200_mg_post(bella_b200_handle* h, uint64_t count, const uint32_t* src_dev, int world, uint64_t at, void* const* peer_dst);
+int bella_b200_mg_exchange(bella_b200_handle* h, int world, int me, const uint32_t* cuts_dev, const uint32_t* cnt_local_dev, void* const* peer_counts_all,
+		int phase, const uint32_t* counts_all_dev, uint64_t* scan_dev, uint64_t cap_recv, uint64_t cap_send, uint64_t* sendoff_dev, uint64_t* segoff_dev,
+		uint64_t* recvbase_dev, uint64_t* push_dev, uint64_t* sendbuf_dev, void* const* peer_recv);
 /* colptrC of the handle's column range to HOST memory ([col_hi-col_lo+1]) once the symbolic phase has run. */
 int bella_b200_get_colptr(bella_b200_handle* h, uint32_t* colptrC_host);
 
