@@ -83,7 +83,7 @@ struct bella_b200_handle {
 	const uint64_t *mg_recv = nullptr, *mg_segoff = nullptr, *mg_recvbase = nullptr;
 	const uint32_t* mg_counts = nullptr;
 	int mg_world = 0;
-	DevBuf mg_colinfo, mg_ucur;
+	DevBuf mg_colinfo, mg_ucur, mg_rcur, mg_rtiles;
 	// matrix construction from tuples (bella_b200_set_inputs_tuples)
 	DevBuf tp_kmer, tp_read, tp_pos, tp_strand, tp_rs, tp_re, tp_nruns, tp_cnt, tp_cp, tp_merged, tp_tmpK, tp_tmpV, tp_slab;
 	float t_build_ms = 0;
@@ -614,7 +614,7 @@ int bella_b200_destroy(bella_b200_handle* h)
 	DevBuf* bufs[] = {&h->oB_colptr, &h->oB_rowids, &h->oB_values, &h->oB_strand, &h->o_len, &h->boff, &h->bcur, &h->bsize, &h->part, &h->partK, &h->Ainfo, &h->ccur, &h->rp_cur, &h->rp_tiles, &h->rp_E, &h->rp_K,
 		&h->Aent, &h->Acolptr, &h->flop32, &h->nunits, &h->ubase, &h->shv, &h->refine, &h->colinfo, &h->ucol, &h->ucount,
 		&h->uptr, &h->ucur, &h->lists, &h->redo, &h->unnz, &h->uoff, &h->raw, &h->out, &h->colptrC, &h->rowsC, &h->countC, &h->posH, &h->posV,
-		&h->aux, &h->meta, &h->errflag, &h->cubtmp, &h->unpinned, &h->mg_colinfo, &h->mg_ucur, &h->tp_kmer, &h->tp_read, &h->tp_pos, &h->tp_strand,
+		&h->aux, &h->meta, &h->errflag, &h->cubtmp, &h->unpinned, &h->mg_colinfo, &h->mg_ucur, &h->mg_rcur, &h->mg_rtiles, &h->tp_kmer, &h->tp_read, &h->tp_pos, &h->tp_strand,
 		&h->tp_rs, &h->tp_re, &h->tp_nruns, &h->tp_cnt, &h->tp_cp, &h->tp_merged, &h->tp_tmpK, &h->tp_tmpV, &h->tp_slab};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -982,8 +982,8 @@ int bella_b200_mg_geometry(uint32_t n_kmers, uint64_t nnz_total, int world, uint
 	const uint32_t nb1_loc = (g.nb1 + (uint32_t)world - 1) / (uint32_t)world;
 	const uint64_t kpr = (uint64_t)nb1_loc << g.shift1;
 	if (kpr > 0xFFFFFFFFull) return BELLA_B200_ERR_RANGE;
-	// a sub-region holds what ONE rank contributes to ONE coarse bucket: 1/world of the bucket on average
-	const uint64_t cap1 = (((uint64_t)((double)nnz_total / ((double)g.nb1 * world) * 1.3) + 2 * RP_TILE) + 15) & ~15ull;
+	// a slot holds what ONE rank sends to ONE rank: 1/world^2 of the nonzeros on average (the caller may raise it)
+	const uint64_t cap1 = (((uint64_t)((double)nnz_total / ((double)world * world) * 1.3) + 2 * RP_TILE) + 15) & ~15ull;
 	if (cap1 > 0x7FFFFFFFull) return BELLA_B200_ERR_RANGE;
 	out8[0] = g.wshift; out8[1] = g.shift1; out8[2] = g.nb1; out8[3] = nb1_loc; out8[4] = (uint32_t)kpr; out8[5] = (uint32_t)cap1;
 	out8[6] = g.NB; out8[7] = g.l2;
@@ -998,14 +998,15 @@ int bella_b200_mg_route_push(bella_b200_handle* h, uint32_t read_lo, uint32_t re
 	CK(cudaSetDevice(h->device));
 	h->launches = 0;
 	ENSURE(h->errflag, 4 * sizeof(int));
-	const uint32_t shift1 = geom8[1], nb1 = geom8[2], nb1_loc = geom8[3], kpr = geom8[4], cap1 = geom8[5];
-	ENSURE(h->rp_cur, sizeof(uint32_t) * ((size_t)nb1 + 2) * BCNT_STRIDE);
-	CK(cudaMemsetAsync(h->rp_cur.p, 0, sizeof(uint32_t) * ((size_t)nb1 + 2) * BCNT_STRIDE, h->stream));
+	// one bucket per destination rank: geom8[5] = records one rank may send to one rank
+	const uint32_t shift1 = geom8[1], nb1 = (uint32_t)world, nb1_loc = 1, kpr = geom8[4], cap1 = geom8[5];
+	ENSURE(h->mg_rcur, sizeof(uint32_t) * ((size_t)nb1 + 2) * BCNT_STRIDE);
+	CK(cudaMemsetAsync(h->mg_rcur.p, 0, sizeof(uint32_t) * ((size_t)nb1 + 2) * BCNT_STRIDE, h->stream));
 	CK(cudaMemsetAsync(h->errflag.p, 0, sizeof(int), h->stream));
 	CK(cudaFuncSetAttribute(k_rp1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RP_SMEM));
 	CK(cudaEventRecord(h->ev[8], h->stream));
 	RpOut O{};
-	O.groups = (uint32_t)world; O.me = (uint32_t)me; O.nb1_loc = nb1_loc; O.kpr = kpr;
+	O.groups = (uint32_t)world; O.me = (uint32_t)me; O.nb1_loc = nb1_loc; O.kpr = kpr; O.route = 1;
 	RpPost P{};
 	for (int d = 0; d < world; ++d) { O.E[d] = (uint64_t*)peer_E[d]; O.K[d] = (uint32_t*)peer_K[d]; P.cnt[d] = (uint32_t*)peer_cnt[d]; }
 	if (read_hi > read_lo) {
@@ -1014,10 +1015,10 @@ int bella_b200_mg_route_push(bella_b200_handle* h, uint32_t read_lo, uint32_t re
 		if (g > (uint32_t)h->sms * 2) g = (uint32_t)h->sms * 2;
 		// the strand bit rides in bit 31 of the row ids (panel format): Bstrand == NULL
 		k_rp1<<<g, RP_THREADS, RP_SMEM, h->stream>>>(read_hi, read_lo, 0u, n_kmers, colptr_global_dev, rowids_dev, values_dev, nullptr,
-			shift1, nb1, cap1, h->rp_cur.as<uint32_t>(), O, h->errflag.as<int>());
+			shift1, nb1, cap1, h->mg_rcur.as<uint32_t>(), O, h->errflag.as<int>());
 		LAUNCHED();
 	}
-	k_rp_post<<<grid_for(nb1, 256), 256, 0, h->stream>>>(nb1, cap1, (uint32_t)world, (uint32_t)me, nb1_loc, h->rp_cur.as<uint32_t>(), P);
+	k_rp_post<<<grid_for(nb1, 256), 256, 0, h->stream>>>(nb1, cap1, (uint32_t)world, (uint32_t)me, nb1_loc, h->mg_rcur.as<uint32_t>(), P);
 	LAUNCHED();
 	CK(cudaEventRecord(h->ev[9], h->stream));
 	return BELLA_B200_OK;
@@ -1043,8 +1044,9 @@ int bella_b200_mg_transpose_coarse(bella_b200_handle* h, uint32_t kmer_lo, uint3
 	if (nb1_mine > nb1_loc) return fail(h, BELLA_B200_ERR_ARG, "k-mer range wider than the rank's coarse buckets");
 	h->W = W; h->NB = NB;
 	ENSURE(h->Acolptr, sizeof(uint32_t) * ((size_t)ml + 2));
-	ENSURE(h->Aent, sizeof(uint64_t) * (nnz_cap + 2));
-	ENSURE(h->Ainfo, nnz_cap + 16);
+	const uint64_t rec_max = (uint64_t)world * geom8[5];           // what the slots can hold at most
+	ENSURE(h->Aent, sizeof(uint64_t) * (rec_max + 2));
+	ENSURE(h->Ainfo, rec_max + 16);
 	ENSURE(h->boff, sizeof(uint32_t) * ((size_t)NB + 2));
 	CK(cudaMemsetAsync(cnt_local_dev, 0, sizeof(uint32_t) * (size_t)n, h->stream));
 	if (!ml || !n) {
@@ -1057,16 +1059,31 @@ int bella_b200_mg_transpose_coarse(bella_b200_handle* h, uint32_t kmer_lo, uint3
 	ENSURE(h->bcur, sizeof(uint32_t) * ((size_t)NB + 2) * BCNT_STRIDE);
 	ENSURE(h->part, sizeof(uint64_t) * (size_t)NB * BUCKET_CAP + 64);
 	ENSURE(h->partK, sizeof(uint16_t) * (size_t)NB * BUCKET_CAP + 64);
-	const uint32_t nsb = nb1_mine * (uint32_t)world;
-	ENSURE(h->rp_tiles, sizeof(uint32_t) * ((size_t)nsb + 2));
+	// the received records (one slot of cap1 records per source rank) -> this rank's coarse buckets -> fine buckets
+	const uint32_t capR = cap1, nsbR = (uint32_t)world;
+	const uint64_t capc64 = (((uint64_t)((double)nnz_cap / nb1_mine * 1.3) + 2 * RP_TILE) + 15) & ~15ull;     // nnz_cap: records this rank expects
+	if (capc64 > 0x7FFFFFFFull) return fail(h, BELLA_B200_ERR_RANGE, "coarse transpose bucket too large");
+	const uint32_t capC = (uint32_t)capc64;
+	ENSURE(h->mg_rtiles, sizeof(uint32_t) * ((size_t)nsbR + 2));
+	ENSURE(h->rp_tiles, sizeof(uint32_t) * ((size_t)nb1_mine + 2));
+	ENSURE(h->rp_cur, sizeof(uint32_t) * ((size_t)nb1_mine + 2) * BCNT_STRIDE);
+	ENSURE(h->rp_E, sizeof(uint64_t) * (size_t)nb1_mine * capC + 64);
+	ENSURE(h->rp_K, sizeof(uint32_t) * (size_t)nb1_mine * capC + 64);
+	CK(cudaMemsetAsync(h->rp_cur.p, 0, sizeof(uint32_t) * ((size_t)nb1_mine + 2) * BCNT_STRIDE, h->stream));
 	CK(cudaMemsetAsync(h->bcur.p, 0, sizeof(uint32_t) * ((size_t)NB + 2) * BCNT_STRIDE, h->stream));
+	CK(cudaFuncSetAttribute(k_rp1b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RP_SMEM));
 	CK(cudaFuncSetAttribute(k_rp2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RP_SMEM));
 	CK(cudaFuncSetAttribute(k_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BUCKET_SMEM));
 	(void)l2;
-	k_rp_tiles<<<1, 1024, 0, h->stream>>>(nsb, cap1, cnt_dev, h->rp_tiles.as<uint32_t>());
+	k_rp_tiles<<<1, 1024, 0, h->stream>>>(nsbR, capR, cnt_dev, h->mg_rtiles.as<uint32_t>());
 	LAUNCHED();
-	k_rp2<<<h->sms * 2, RP_THREADS, RP_SMEM, h->stream>>>(shift1, wshift, nsb, (uint32_t)world, cap1, cnt_dev, h->rp_tiles.as<uint32_t>(), 0u, nsb,
-		E_dev, K_dev, h->bcur.as<uint32_t>(), h->part.as<uint64_t>(), h->partK.as<uint16_t>(), h->errflag.as<int>());
+	k_rp1b<<<h->sms * 2, RP_THREADS, RP_SMEM, h->stream>>>(shift1, nb1_mine, nsbR, capR, cnt_dev, h->mg_rtiles.as<uint32_t>(), E_dev, K_dev,
+		capC, h->rp_cur.as<uint32_t>(), h->rp_E.as<uint64_t>(), h->rp_K.as<uint32_t>(), h->errflag.as<int>());
+	LAUNCHED();
+	k_rp_tiles<<<1, 1024, 0, h->stream>>>(nb1_mine, capC, h->rp_cur.as<uint32_t>(), h->rp_tiles.as<uint32_t>());
+	LAUNCHED();
+	k_rp2<<<h->sms * 2, RP_THREADS, RP_SMEM, h->stream>>>(shift1, wshift, nb1_mine, 1u, capC, h->rp_cur.as<uint32_t>(), h->rp_tiles.as<uint32_t>(), 0u, nb1_mine,
+		h->rp_E.as<uint64_t>(), h->rp_K.as<uint32_t>(), h->bcur.as<uint32_t>(), h->part.as<uint64_t>(), h->partK.as<uint16_t>(), h->errflag.as<int>());
 	LAUNCHED();
 	k_bucket_offsets<<<1, 1024, 0, h->stream>>>(0u, NB, h->bcur.as<uint32_t>(), h->boff.as<uint32_t>());
 	LAUNCHED();
@@ -1116,7 +1133,7 @@ int bella_b200_mg_exchange(bella_b200_handle* h, int world, int me, const uint32
 	if (int rc = bella_b200_mg_scatter(h, sendoff_dev, sendbuf_dev)) return rc;
 	MgPeers R{};
 	for (int d = 0; d < world; ++d) R.p[d] = peer_recv[d];
-	k_mg_push<<<h->sms * 4, 256, 0, h->stream>>>((uint32_t)world, sendbuf_dev, (const unsigned long long*)push_dev, R, h->errflag.as<int>());
+	k_mg_push<<<h->sms * 4, 256, 0, h->stream>>>((uint32_t)world, (uint32_t)me, sendbuf_dev, (const unsigned long long*)push_dev, R, h->errflag.as<int>());
 	LAUNCHED();
 	return BELLA_B200_OK;
 }

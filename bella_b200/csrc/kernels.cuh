@@ -240,10 +240,13 @@ __device__ __forceinline__ void rp_reserve(uint32_t* hist, uint32_t* off, uint32
 // Where level 1 writes.  A coarse bucket is a region of `groups` sub-regions of cap1 records, one per writer: on one GPU there
 // is one writer (groups == 1); on several, coarse bucket b belongs to the rank b / nb1_loc that transposes its k-mers, the
 // regions are in that rank's (peer-mapped, NVLink) memory and every rank fills its own sub-region `me`, so the remote
-// stores need no remote cursor -- the cursors stay local and are posted to the owners afterwards (k_rp_post).
+// stores need no remote cursor -- the cursors stay local and are posted to the owners afterwards (k_rp_post).  Measured on
+// 4 GPUs, runs of 18 records (220 coarse buckets per tile) reach a third of the NVLink rate; with route = 1 the pass only
+// splits by destination rank (runs of a thousand records) and the owner runs the coarse level itself (k_rp1b).
 constexpr int MG_MAXW = 8;
 struct RpOut {
 	uint32_t groups, me, nb1_loc, kpr;     // kpr = k-mers per rank = nb1_loc << shift1
+	uint32_t route;                        // 1: the buckets of this pass are the RANKS (bucket = k-mer id / kpr): long runs for the NVLink stores
 	uint64_t* E[MG_MAXW];
 	uint32_t* K[MG_MAXW];
 };
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(RP_THREADS, 2) k_rp1(uint32_t n, uint32_t lo, 
 					const uint32_t st = Bstrand ? (sw[u] >> (j & 7)) & 1u : c >> 31;
 					kv[u] = kid - klo;
 					ev[u] = (uint64_t)i | ((uint64_t)st << 31) | ((uint64_t)pw[u] << 32) | ((uint64_t)(j - j0) << 48);
-					sl[u] = atomicAdd(&hist[kv[u] >> shift1], 1u);
+					sl[u] = atomicAdd(&hist[O.route ? kv[u] / O.kpr : kv[u] >> shift1], 1u);
 				}
 			}
 		}
@@ -307,14 +310,14 @@ __global__ void __launch_bounds__(RP_THREADS, 2) k_rp1(uint32_t n, uint32_t lo, 
 		rp_reserve(hist, off, gbase, nb1, gcur1, BCNT_STRIDE, cap1, err);
 #pragma unroll
 		for (int u = 0; u < RP_ITEMS; ++u)
-			if (sl[u] != 0xFFFFFFFFu) { const uint32_t at = off[kv[u] >> shift1] + sl[u]; SE[at] = ev[u]; SK[at] = kv[u]; }
+			if (sl[u] != 0xFFFFFFFFu) { const uint32_t at = off[O.route ? kv[u] / O.kpr : kv[u] >> shift1] + sl[u]; SE[at] = ev[u]; SK[at] = kv[u]; }
 		__syncthreads();
 		const uint32_t total = off[nb1];
 		for (uint32_t t = tid; t < total; t += RP_THREADS) {
-			const uint32_t k = SK[t], b = k >> shift1;
+			const uint32_t k = SK[t], b = O.route ? k / O.kpr : k >> shift1;
 			const uint32_t g = gbase[b] + (t - off[b]);
 			if (g < cap1) {
-				const uint32_t d = O.groups > 1 ? b / O.nb1_loc : 0u, bl = b - d * O.nb1_loc;
+				const uint32_t d = O.route ? b : O.groups > 1 ? b / O.nb1_loc : 0u, bl = O.route ? 0u : b - d * O.nb1_loc;
 				const size_t at = ((size_t)bl * O.groups + O.me) * cap1 + g;
 				O.E[d][at] = SE[t]; O.K[d][at] = k - d * O.kpr;      // k-mer id relative to the owner's range
 			}
@@ -339,6 +342,65 @@ __global__ void __launch_bounds__(1024) k_rp_tiles(uint32_t nsb, uint32_t cap1, 
 	for (uint32_t c = threadIdx.x; c < nsb; c += blockDim.x) tstart[c] = (min(gcur1[(size_t)c * BCNT_STRIDE], cap1) + RP_TILE - 1) / RP_TILE;
 	__syncthreads();
 	block_excl_scan<uint32_t>(tstart, nsb, s_tmp);
+}
+
+// several GPUs, after the route pass: the records this rank received (one sub-bucket per source rank; k-mer ids relative to
+// this rank's range) -> its coarse buckets.  Same tile loop as k_rp2; the output has level 1's format.
+__global__ void __launch_bounds__(RP_THREADS) k_rp1b(uint32_t shift1, uint32_t nb1, uint32_t nsb, uint32_t cap_in, const uint32_t* __restrict__ cnt_in,
+		const uint32_t* __restrict__ tstart, const uint64_t* __restrict__ Ein, const uint32_t* __restrict__ Kin,
+		uint32_t cap1, uint32_t* __restrict__ gcur1, uint64_t* __restrict__ E1, uint32_t* __restrict__ K1, int* err)
+{
+	extern __shared__ __align__(16) unsigned char rsm[];
+	uint64_t* SE = (uint64_t*)rsm;
+	uint32_t* SK = (uint32_t*)(SE + RP_TILE);
+	uint32_t* hist = SK + RP_TILE;
+	uint32_t* gbase = hist + RP_NBMAX + 2;
+	uint32_t* off = gbase + RP_NBMAX + 2;
+	__shared__ uint32_t s_c;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t ntiles = tstart[nsb];
+	for (uint32_t b = tid; b <= nb1; b += RP_THREADS) hist[b] = 0;
+	for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		if (tid == 0) {
+			uint32_t a = 0, b = nsb;
+			while (b - a > 1) { const uint32_t c = (a + b) >> 1; if (tstart[c] <= tile) a = c; else b = c; }
+			s_c = a;
+		}
+		__syncthreads();
+		const uint32_t sb = s_c;
+		const uint32_t cnt = min(cnt_in[(size_t)sb * BCNT_STRIDE], cap_in), first = (tile - tstart[sb]) * RP_TILE;
+		const uint32_t len = min((uint32_t)RP_TILE, cnt - first);
+		const uint64_t* e1 = Ein + (size_t)sb * cap_in + first;
+		const uint32_t* k1 = Kin + (size_t)sb * cap_in + first;
+		uint64_t ev[RP_ITEMS];
+		uint32_t kv[RP_ITEMS], sl[RP_ITEMS];
+#pragma unroll
+		for (int u = 0; u < RP_ITEMS; ++u) {
+			const uint32_t x = u * RP_THREADS + tid;
+			if (x < len) { ev[u] = e1[x]; kv[u] = k1[x]; }
+		}
+#pragma unroll
+		for (int u = 0; u < RP_ITEMS; ++u) {
+			const uint32_t x = u * RP_THREADS + tid;
+			sl[u] = 0xFFFFFFFFu;
+			if (x < len) {
+				if ((kv[u] >> shift1) >= nb1) { set_err(err, -5); continue; }      // a k-mer outside this rank's range
+				sl[u] = atomicAdd(&hist[kv[u] >> shift1], 1u);
+			}
+		}
+		__syncthreads();
+		rp_reserve(hist, off, gbase, nb1, gcur1, BCNT_STRIDE, cap1, err);
+#pragma unroll
+		for (int u = 0; u < RP_ITEMS; ++u)
+			if (sl[u] != 0xFFFFFFFFu) { const uint32_t at = off[kv[u] >> shift1] + sl[u]; SE[at] = ev[u]; SK[at] = kv[u]; }
+		__syncthreads();
+		const uint32_t total = off[nb1];
+		for (uint32_t t = tid; t < total; t += RP_THREADS) {
+			const uint32_t k = SK[t], b = k >> shift1;
+			const uint32_t g = gbase[b] + (t - off[b]);
+			if (g < cap1) { const size_t at = (size_t)b * cap1 + g; E1[at] = SE[t]; K1[at] = k; }
+		}
+	}
 }
 
 __global__ void __launch_bounds__(RP_THREADS) k_rp2(uint32_t shift1, uint32_t wshift, uint32_t nsb, uint32_t groups, uint32_t cap1, const uint32_t* __restrict__ gcur1,
@@ -1375,11 +1437,12 @@ __global__ void k_mg_plan(uint32_t world, uint32_t me, uint32_t n, const uint32_
 }
 
 // send buffer -> the owners' receive buffers (peer memory): one contiguous block per destination, 16-byte stores
-__global__ void __launch_bounds__(256) k_mg_push(uint32_t world, const uint64_t* __restrict__ send, const unsigned long long* __restrict__ push, const MgPeers recv,
+__global__ void __launch_bounds__(256) k_mg_push(uint32_t world, uint32_t me, const uint64_t* __restrict__ send, const unsigned long long* __restrict__ push, const MgPeers recv,
 		const int* __restrict__ stop)
 {
 	if (*stop) return;
-	for (uint32_t d = 0; d < world; ++d) {
+	for (uint32_t i = 0; i < world; ++i) {
+		const uint32_t d = (me + 1 + i) % world;                    // staggered: at any time every rank receives from ONE sender (no incast)
 		const unsigned long long first = push[3 * d], cnt = push[3 * d + 1], at = push[3 * d + 2];
 		const uint64_t* src = send + first;
 		uint64_t* dst = (uint64_t*)recv.p[d] + at;

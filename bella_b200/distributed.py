@@ -243,6 +243,10 @@ class ShardedOverlapSpGEMM:
             lens = np.diff(inp.B_colptr.astype(np.int64)).astype(np.float64)
             n = inp.n_reads
             w = 1.83 * lens * (np.arange(n - 1, -1, -1, dtype=np.float64) / max(n - 1, 1)) + UNIT_OVERHEAD * (lens > 0)
+            if self.mode == "nvlink":
+                # + what a rank pays per nonzero of its own reads (the route pass), in products: measured on 4 x B200, the route pass
+                # costs 0.6 ms for 18 M nonzeros where group + fold costs 1.0 ms for 16 M products
+                w = w + 0.53 * lens
             pre = np.cumsum(w)
             cuts = [0] + [int(np.searchsorted(pre, pre[-1] * r / self.world)) + 1 for r in range(1, self.world)] + [n]
             cuts = [min(max(c, 0), n) for c in np.maximum.accumulate(cuts)]
@@ -285,13 +289,13 @@ class ShardedOverlapSpGEMM:
         rc = spgemm.lib().bella_b200_mg_geometry(self.n_kmers, nnz_total, world, geom.ctypes.data)
         if rc != 0:
             raise RuntimeError(f"bella_b200_mg_geometry failed: {rc}")
-        # a sub-region holds what ONE rank sends to ONE coarse bucket: sized for the rank with the most nonzeros (the shards
-        # are balanced on products, not on nonzeros)
+        # a slot holds what ONE rank sends to ONE rank: sized for the rank with the most nonzeros (the shards are balanced on
+        # products, not on nonzeros)
         max_nnz = max(b for _, b in self.shapes)
-        geom[5] = (int(1.3 * max_nnz / max(int(geom[2]), 1)) + 2 * 4096 + 15) // 16 * 16
+        geom[5] = (int(1.3 * max_nnz / world) + 2 * 4096 + 15) // 16 * 16
         self.geom = geom
         wshift, shift1, nb1, nb1_loc, kpr, cap1 = (int(x) for x in geom[:6])
-        nsb = nb1_loc * world
+        nsb = world                                              # one slot per source rank
         if not hasattr(self, "cap_recv"):
             # products a rank receives / sends (about flops / world; flops is about nnz for [l,u] = [2,8]); a step that finds them
             # too small says so on every rank (BELLA_B200_ERR_CAPACITY) and _step_nvlink grows them
@@ -311,7 +315,7 @@ class ShardedOverlapSpGEMM:
         self.peer = {k: [b + off for b in base] for k, off in lay.items()}
         self.kr_lo = min(self.rank * kpr, self.n_kmers)
         self.kr_hi = min((self.rank + 1) * kpr, self.n_kmers)
-        self.nnz_cap = nsb * cap1
+        self.nnz_cap = int(1.15 * nnz_total / world) + 4096       # records this rank expects (k-mer ids are uniform)
         self.loc_i32 = lambda name, count: self.sym[lay[name]:lay[name] + 4 * count].view(torch.int32)
         # local work arrays (not symmetric)
         ncols = self.cuts[self.rank + 1] - self.cuts[self.rank]
@@ -537,7 +541,7 @@ def bench_multi(args, w, inp, rank, world, local, METRIC, UNIT, workload, ClockS
     import time
     import os
     dev = torch.device("cuda", local)
-    mode = os.environ.get("BELLA_MG_MODE", "exchange")      # "route" (no all-gather of B) is opt-in until it has been run on 8 GPUs
+    mode = os.environ.get("BELLA_MG_MODE", "nvlink")        # "exchange" / "route" / "replicate": the NCCL-based modes of round 1
     sh = ShardedOverlapSpGEMM(local, mode=mode)
     sh.load_shard(inp, pinned=True)
     stream = torch.cuda.current_stream(dev)
@@ -592,6 +596,24 @@ def bench_multi(args, w, inp, rank, world, local, METRIC, UNIT, workload, ClockS
     e2e_steps = max(2, min(args.steps, 5))
     e2e()
     e2e_ms, res = timed(e2e, e2e_steps)
+    # what was computed: the checksum of every rank's tuples, summed, against the single-GPU result of the same workload
+    # (rank 0 runs the single-GPU path once, outside the timed regions)
+    from .checks import tuple_checksum
+    cs, zc = tuple_checksum(rng[0], res[0], res[1:])
+    allcs = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(allcs, torch.tensor([cs - (1 << 64) if cs >= (1 << 63) else cs, zc], dtype=torch.int64, device=dev))
+    parity = None
+    if rank == 0:
+        from . import spgemm
+        total = sum(int(t[0]) for t in allcs) % (1 << 64)
+        zsum = sum(int(t[1]) for t in allcs)
+        one = spgemm.overlap_spgemm(inp, device=local)
+        ref_cs, ref_z = tuple_checksum(0, one["colptrC"], (one["rowids"], one["count"], one["posH"], one["posV"]))
+        if total != ref_cs or zsum != ref_z:
+            raise SystemExit(f"bench.py: PARITY FAILURE at {world} GPUs: checksum {total:016x} over {zsum} tuples, single GPU {ref_cs:016x} over {ref_z}")
+        parity = f"checksum of the {zsum} tuples of all {world} ranks == single-GPU result of the same workload ({ref_cs:016x})"
+        print("[bench] parity: " + parity, file=sys.stderr, flush=True)
+    dist.barrier()
     d2h = torch.tensor([int(sum(a.nbytes for a in res))], dtype=torch.int64, device=dev)
     h2d = torch.tensor([int(sh.max_bytes)], dtype=torch.int64, device=dev)
     dist.all_reduce(d2h)
@@ -604,11 +626,13 @@ def bench_multi(args, w, inp, rank, world, local, METRIC, UNIT, workload, ClockS
         line = {"metric": METRIC, "value": Zt / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "u16/u32", "data": "synthetic",
-                "config": {"workload": workload, "n_kmers": inp.n_kmers, "nnz_A": inp.nnz, "products": Ft, "output_nnz": Zt,
-                           "parallelism": (f"row-sharded x{world}: all-gather of the B panel, transpose split by k-mer range, all-to-all of the products"
-                                           if mode != "route" else
-                                           f"row-sharded x{world}: all-to-all of k-mer-partitioned records, transpose per k-mer range, all-to-all of the products"),
-                           "l2": "inputs larger than L2, no flush"},
+                "config": {"workload": workload},
+                "workload_stats": {"n_kmers": inp.n_kmers, "nnz_A": inp.nnz, "products": Ft, "output_nnz": Zt, "l2": "inputs larger than L2, no flush",
+                                   "parallelism": {"nvlink": f"row-sharded x{world}: a rank owns the columns of its reads; nonzeros stored into the k-mer owner's "
+                                                             "buckets and product blocks pushed to the column owner over NVLink peer memory, three device barriers, no collective",
+                                                   "route": f"row-sharded x{world}: all-to-all of k-mer-partitioned records, transpose per k-mer range, all-to-all of the products",
+                                                   }.get(mode, f"row-sharded x{world}: all-gather of the B panel, transpose split by k-mer range, all-to-all of the products")},
+                "parity": parity,
                 "clocks": clocks,
                 "e2e": {"value": Zt / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(d2h[0]),
                         "ms_per_step": e2e_ms},
