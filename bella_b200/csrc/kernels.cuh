@@ -653,8 +653,9 @@ __global__ void k_classify_units(uint32_t ucap, const uint32_t* __restrict__ uco
 	for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += gridDim.x * blockDim.x) {
 		const uint32_t f = ucount[u];
 		ucur[u] = uptr[u];
-		// column ranges of about equal product counts (units are ordered by column, so a range is an interval of columns)
-		const uint32_t rg = nrange > 1 ? min(nrange - 1, (uint32_t)((unsigned long long)uptr[u] * nrange / total)) : 0u;
+		// column ranges of about equal product counts (units are ordered by column, so a range is an interval of columns);
+		// a column belongs to the range of its FIRST unit with all its units: the scatter of a range covers whole columns
+		const uint32_t rg = nrange > 1 ? min(nrange - 1, (uint32_t)((unsigned long long)uptr[colinfo[ucol[u]].ubase] * nrange / total)) : 0u;
 		{
 			const uint32_t li = ucol[u];                             // the scatter's per-column cursor: the region of a light column, or the heavy mark
 			ccur[(size_t)li * CCUR_STRIDE] = colinfo[li].sh == 31 ? (unsigned long long)uptr[u] : CCUR_HEAVY;

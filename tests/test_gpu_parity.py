@@ -211,3 +211,17 @@ def test_gpu_one_based_csr_is_refused(small_inputs):
         assert rc == -1
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("nrange", ["2", "4"])
+def test_gpu_scatter_group_pipeline_with_heavy_columns(monkeypatch, nrange):
+    """the scatter | group + fold pipeline over column ranges (on by default only for large inputs) on inputs whose heavy
+    columns are cut into row-range units: a column's units must all be folded after the scatter pass that covers the column"""
+    from bella_b200 import frontend as fe
+    monkeypatch.setenv("BELLA_B200_NRANGE", nrange)
+    inp, ref = golden_util.load("heavy_units")
+    ol.assert_same(gpu_result(inp, False), ref)
+    hifi = fe.synthetic(n_reads=700, read_len=5000, coverage=40.0, err=0.01, seed=13, hi=80)
+    ol.assert_same(gpu_result(hifi, False), ol.oracle_spgemm(hifi))
+    clr = fe.synthetic(n_reads=2500, read_len=6000, seed=77)
+    ol.assert_same(gpu_result(clr, False), ol.oracle_spgemm(clr))
