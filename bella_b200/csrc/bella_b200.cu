@@ -284,7 +284,7 @@ int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32
 				const uint32_t nbk = (uint32_t)(f1 - f0);
 				k_bucket_offsets<<<1, 1024, 0, h->aux_stream>>>((uint32_t)f0, (uint32_t)f1, bcnt, h->boff.as<uint32_t>());
 				LAUNCHED();
-				k_bucket<<<nbk < 148u * 16 ? nbk : 148u * 16, 256, BUCKET_SMEM, h->aux_stream>>>(h->klo, ml, cnt_lo, cnt_hi, wshift, (uint32_t)f0, (uint32_t)f1, NB,
+				k_bucket<<<nbk < (uint32_t)h->sms * 16 ? nbk : (uint32_t)h->sms * 16, 256, BUCKET_SMEM, h->aux_stream>>>(h->klo, ml, cnt_lo, cnt_hi, wshift, (uint32_t)f0, (uint32_t)f1, NB,
 					h->boff.as<uint32_t>(), partE, partK, h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), h->Ainfo.as<uint8_t>(), flop_out, h->errflag.as<int>());
 				LAUNCHED();
 			}
@@ -298,7 +298,7 @@ int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32
 	k_bucket_offsets<<<1, 1024, 0, h->stream>>>(0u, NB, bcnt, h->boff.as<uint32_t>());
 	LAUNCHED();
 	CK(cudaFuncSetAttribute(k_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BUCKET_SMEM));
-	k_bucket<<<NB < 148u * 16 ? NB : 148u * 16, 256, BUCKET_SMEM, h->stream>>>(h->klo, ml, cnt_lo, cnt_hi, wshift, 0u, NB, NB, h->boff.as<uint32_t>(),
+	k_bucket<<<NB < (uint32_t)h->sms * 16 ? NB : (uint32_t)h->sms * 16, 256, BUCKET_SMEM, h->stream>>>(h->klo, ml, cnt_lo, cnt_hi, wshift, 0u, NB, NB, h->boff.as<uint32_t>(),
 		partE, partK, h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), h->Ainfo.as<uint8_t>(), flop_out, h->errflag.as<int>());
 	LAUNCHED();
 	return 0;
@@ -336,7 +336,7 @@ int run_plan(bella_b200_handle* h)
 		h->colinfo.as<ColInfo>(), h->ucol.as<uint32_t>(), h->ucount.as<uint32_t>(), h->meta.as<Meta>(), h->errflag.as<int>());
 	LAUNCHED();
 	if (h->mg_recv) {
-		k_regroup<true><<<148 * 8, 256, 0, h->stream>>>(h->n, h->lo, ncols, (uint32_t)h->mg_world, h->mg_counts, h->mg_segoff, h->mg_recvbase,
+		k_regroup<true><<<h->sms * 8, 256, 0, h->stream>>>(h->n, h->lo, ncols, (uint32_t)h->mg_world, h->mg_counts, h->mg_segoff, h->mg_recvbase,
 			h->mg_recv, h->colinfo.as<ColInfo>(), h->ucount.as<uint32_t>(), nullptr, nullptr, h->meta.as<Meta>(), h->errflag.as<int>());
 	} else {
 		const uint32_t ml = h->khi - h->klo;
@@ -382,10 +382,11 @@ int launch_group(bella_b200_handle* h, const Params& P, int rg, int cls, uint32_
 	CK(cudaFuncSetAttribute(k_group_fold<CAP, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	CK(cudaFuncSetAttribute(k_group_fold<CAP, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	if (count) {
-		uint32_t grid = count < 148u * ctas_per_sm ? count : 148u * ctas_per_sm;
+		const uint32_t resident = (uint32_t)h->sms * ctas_per_sm;
+		uint32_t grid = count < resident ? count : resident;
 		k_group_fold<CAP, NT, false><<<grid, NT, smem, st>>>(P, list, class_count, l1cap, redo, redo_count);
 		LAUNCHED();
-		k_group_fold<CAP, NT, true><<<148, NT, smem, st>>>(P, redo, redo_count, l1cap, nullptr, nullptr);
+		k_group_fold<CAP, NT, true><<<h->sms, NT, smem, st>>>(P, redo, redo_count, l1cap, nullptr, nullptr);
 		LAUNCHED();
 	}
 	return 0;
@@ -476,7 +477,7 @@ int group_and_output(bella_b200_handle* h, bool do_scatter)
 		if (int rc = launch_group<8192, 1024>(h, P, r, 2, cc[2], l1cap, 1, h->aux_stream)) return rc;
 		if (int rc = launch_group<4096, 512>(h, P, r, 1, cc[1], l1cap, 2, h->aux_stream)) return rc;
 		if (cc[3]) {
-			k_huge_pair<<<cc[3] < 148u ? cc[3] : 148u, 1024, 0, h->aux_stream>>>(P, lists + ((size_t)r * (NCLASS + 1) + 3) * ucap, cc[3]);
+			k_huge_pair<<<cc[3] < (uint32_t)h->sms ? cc[3] : (uint32_t)h->sms, 1024, 0, h->aux_stream>>>(P, lists + ((size_t)r * (NCLASS + 1) + 3) * ucap, cc[3]);
 			LAUNCHED();
 		}
 		if (int rc = launch_group<2048, 256>(h, P, r, 0, cc[0], l1cap, 4, h->stream)) return rc;
@@ -949,9 +950,9 @@ int bella_b200_mg_finish(bella_b200_handle* h, uint32_t col_lo, uint32_t col_hi,
 	h->nrange = 1;
 	int rc = plan_loop(h, false);
 	if (!rc && h->flops) {
-		k_regroup<false><<<148 * 8, 256, 0, h->stream>>>(h->n, col_lo, ncols, (uint32_t)world, counts_all_dev, segoff_dev, recvbase_dev, h->mg_recv,
+		k_regroup<false><<<h->sms * 8, 256, 0, h->stream>>>(h->n, col_lo, ncols, (uint32_t)world, counts_all_dev, segoff_dev, recvbase_dev, h->mg_recv,
 			h->colinfo.as<ColInfo>(), nullptr, h->ucur.as<unsigned long long>(), h->raw.as<uint64_t>(), h->meta.as<Meta>(), h->errflag.as<int>());
-		++h->launches;
+		LAUNCHED();
 	}
 	if (!rc) rc = group_and_output(h, false);
 	h->mg_recv = nullptr;
@@ -1087,7 +1088,7 @@ int bella_b200_mg_transpose_coarse(bella_b200_handle* h, uint32_t kmer_lo, uint3
 	LAUNCHED();
 	k_bucket_offsets<<<1, 1024, 0, h->stream>>>(0u, NB, h->bcur.as<uint32_t>(), h->boff.as<uint32_t>());
 	LAUNCHED();
-	k_bucket<<<NB < 148u * 16 ? NB : 148u * 16, 256, BUCKET_SMEM, h->stream>>>(kmer_lo, ml, 0u, n, wshift, 0u, NB, NB, h->boff.as<uint32_t>(),
+	k_bucket<<<NB < (uint32_t)h->sms * 16 ? NB : (uint32_t)h->sms * 16, 256, BUCKET_SMEM, h->stream>>>(kmer_lo, ml, 0u, n, wshift, 0u, NB, NB, h->boff.as<uint32_t>(),
 		h->part.as<uint64_t>(), h->partK.as<uint16_t>(), h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), h->Ainfo.as<uint8_t>(), cnt_local_dev, h->errflag.as<int>());
 	LAUNCHED();
 	CK(cudaEventRecord(h->ev[1], h->stream));
@@ -1186,7 +1187,7 @@ int bella_b200_set_inputs_tuples(bella_b200_handle* h, uint32_t n_kmers, uint32_
 		constexpr int HT = 2048, WARPS = 12;
 		const size_t smem = (size_t)WARPS * 2 * HT * sizeof(uint32_t);
 		CK(cudaFuncSetAttribute(k_merge_duplicates<HT, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		k_merge_duplicates<HT, WARPS><<<148, WARPS * 32, smem, st>>>(n_reads, h->tp_rs.as<uint32_t>(), h->tp_cnt.as<uint32_t>(), h->tp_cp.as<uint32_t>(),
+		k_merge_duplicates<HT, WARPS><<<h->sms, WARPS * 32, smem, st>>>(n_reads, h->tp_rs.as<uint32_t>(), h->tp_cnt.as<uint32_t>(), h->tp_cp.as<uint32_t>(),
 			h->tp_kmer.as<uint32_t>(), h->tp_pos.as<uint16_t>(), h->tp_strand.as<uint8_t>(), h->tp_tmpK.as<uint32_t>(), h->tp_tmpV.as<uint16_t>(),
 			h->tp_merged.as<uint32_t>(), false, nullptr, 0);
 		LAUNCHED();
@@ -1282,7 +1283,7 @@ int bella_b200_mg_route(bella_b200_handle* h, uint32_t n_local, uint32_t read_ba
 	CK(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * 128, h->stream));
 	for (int d = 0; d < world; ++d) send_counts_host[d] = 0;
 	if (!n_local) return BELLA_B200_OK;
-	const int rgrid = n_local < 148u * 8 ? (int)n_local : 148 * 8;
+	const int rgrid = n_local < (uint32_t)h->sms * 8 ? (int)n_local : h->sms * 8;
 	k_route_count<<<rgrid, 256, 0, h->stream>>>(n_local, colptr_local_dev, rowids_dev, kmers_per_rank, (uint32_t)world, counts);
 	LAUNCHED();
 	unsigned long long hc[64];

@@ -211,7 +211,9 @@ void pick_shape(const bella_xdrop* h, int& G, int& T)
 	// the live window is about 2 * xdrop columns wide on real overlaps (xdrop + 9 near the seed), with a tail several
 	// times that; whatever outgrows the chosen shape takes the wide path.  Measured on a B200 (profiles/xdrop_r01.md):
 	// at x = 7 one thread per extension beats every warp shape.
-	if (h->xdrop <= 12) { G = 1; T = 64; }
+	// Round 2, all shapes on the bench batch (60 k pairs, x = 7; profiles/xdrop_r02.md): (3,64) -- the packed thread kernel with
+	// the jobs started longest first -- 38.3 ms, (2,64) 40.0, (1,64) 47.6, the warp shapes 60-115 ms; LOGAN on the same box 1057 ms.
+	if (h->xdrop <= 12) { G = 3; T = 64; }
 	else if (h->xdrop <= 40) { G = 32; T = 2; }
 	else if (h->xdrop <= 100) { G = 32; T = 4; }
 	else { G = 0; T = 0; }
@@ -235,6 +237,8 @@ int run_batch(bella_xdrop* h, uint64_t n_pairs, const uint32_t* d_rows, const ui
 	xd::JobResult* res = (xd::JobResult*)h->res.p;
 	int G, T;
 	pick_shape(h, G, T);
+	// shapes 4 and 5 keep the scores relative to the drop-off limit in 10-bit fields (xdrop.cuh ThreadExtQ): x + 5 must fit
+	if ((G == 4 || G == 5) && h->xdrop > 1018) { G = 0; T = 0; }
 	h->used_lanes = G; h->used_cells = T;
 	const int cap = h->max_len + 3;
 	// wide kernel: up to 4 CTAs per SM, as many as 1 GiB of anti-diagonal scratch allows (3 * cap ints per warp)

@@ -2,7 +2,7 @@
 matrix construction (f2) + overlap SpGEMM (include/bella_b200.h) -> gapped X-drop alignment + accept/reject (f1,
 include/bella_xdrop.h) -> BELLA's output lines (f4, include/overlap.hpp:470-488).  This is src/main.cpp from the k-mer
 counting to the output file (:282-525) with the FASTQ parser left to the caller.  No CPU fallback anywhere.
-The k-mer stage has not run on a B200 yet (see include/bella_kmers.h), so neither has this chain."""
+The whole chain runs on the B200 (tests/test_gpu_rows_f1_f3.py::test_reads_to_overlaps_equals_the_oracle_chain)."""
 import numpy as np
 
 from . import kmers, spgemm, xdrop
@@ -13,6 +13,17 @@ def overlap_reads(seqs, seq_off, names=None, k=17, lower=2, upper=8, bin_size=50
     """-> dict(lines, rows, cols, count, posH, posV, out8, n_kmers, stage_ms)"""
     seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
     seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+    # The strand bit of a nonzero ("the window equals its canonical k-mer") replaces the reference's raw substring comparison
+    # (chain.hpp:35-44) only for upper-case ACGT windows: the k-mer code maps N to G and lower case to upper case
+    # (Kmer.cpp:215-216), so two windows that differ as strings can get the same code and the same bit, and the overlap
+    # estimate, the bins and the count of such a pair would silently differ from BELLA's.  Refuse such reads, as the C++ shim does
+    # (bella_b200/csrc/overlap_b200.hpp); INTEGRATION.md "Reads with N or lower-case bases".
+    ok = np.zeros(256, dtype=bool)
+    ok[list(b"ACGT")] = True
+    if seqs.size and not ok[seqs].all():
+        bad = int(np.flatnonzero(~ok[seqs])[0])
+        raise ValueError(f"read {int(np.searchsorted(seq_off, bad, side='right')) - 1} has the byte {chr(int(seqs[bad]))!r} at offset {bad}: only "
+                         "upper-case ACGT reads are accepted (the strand-bit form of checkstrand is exact for those only)")
     n_reads = len(seq_off) - 1
     lens = np.diff(seq_off.astype(np.int64)).astype(np.uint32)
     kc = kmers.KmerCounter(device)

@@ -36,3 +36,16 @@ def test_chain_finds_the_pairs_of_the_front_end_path():
     np.testing.assert_array_equal(ch["C"].rowids, want.rowids)
     assert ch["inp"].nnz == inp.nnz and ch["inp"].n_kmers == inp.n_kmers
     assert 0 < len(ch["lines"]) <= want.nnz and (ch["out8"][:, 0] >= 17 - 2 * 7).all()     # each side ends within x of its best
+
+
+def test_reads_with_n_or_lower_case_are_refused_before_any_device_call():
+    """the k-mer code maps N -> G and lower case -> upper case, the reference compares raw substrings
+    (chain.hpp:35-44): such reads must fail loudly, not diverge silently.  No GPU is needed to be refused."""
+    import pytest
+    from bella_b200 import pipeline
+    seqs = np.frombuffer(b"ACGTACGTACGTACGTACGTNACGTACGTACGTACGTACGTACGTacgtACGT", dtype=np.uint8)
+    off = np.array([0, 27, len(seqs)], dtype=np.uint64)
+    with pytest.raises(ValueError, match="read 0 has the byte 'N'"):
+        pipeline.overlap_reads(seqs, off)
+    with pytest.raises(ValueError, match="read 1 has the byte 'a'"):
+        pipeline.overlap_reads(seqs[27:], np.array([0, 0, len(seqs) - 27], dtype=np.uint64))     # read 0 is empty, read 1 holds the lower case
