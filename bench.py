@@ -38,9 +38,12 @@ WORKLOAD = dict(n_reads=50000, read_len=10000, coverage=30.0, err=0.15, seed=2, 
 #   3: 200 k CLR reads (the configuration the multi-GPU scaling claim is named on)
 #   5: HiFi, e = 0.005 -- variant (i) of SURVEY.md 8d: coverage 6x with the default [l,u] = [2,8] (at 30x a k-mer of an error-free
 #      read set occurs ~30 times and [2,8] leaves an almost empty matrix); 500 k reads by name, --reads scales it down
-#   1 (E. coli-sim, reads simulated from the reference's own dataset files) and 4 (minimizers) are built by tools/make_config1.py /
-#      not yet: they need files or a front-end option this script does not have
-CONFIGS = {2: WORKLOAD,
+#   1: E. coli-sim -- reads simulated by tools/make_config1.py from the reference's own dataset files (in the build container
+#      only; the packed reads travel in scratch/): refused with a clear message when that file is absent
+#   4 (minimizers, -w 10) needs a front-end option this repository does not have yet
+CONFIG1_READS = os.path.join(ROOT, "scratch", "config1_reads.npz")      # written by tools/make_config1.py (E. coli-sim)
+CONFIGS = {1: dict(WORKLOAD, n_reads=14939, read_len=0, coverage=27.8, seed=1, reads_file=CONFIG1_READS),
+           2: WORKLOAD,
            3: dict(WORKLOAD, n_reads=200000, seed=3),
            5: dict(WORKLOAD, n_reads=500000, coverage=6.0, err=0.005, seed=5)}
 METRIC = "A·Aᵀ output-nnz/s"
@@ -57,6 +60,9 @@ def tuple_checksum(col_lo, colptrC, res):
 
 
 def workload_name(w):
+    if w.get("reads_file"):
+        return (f"E. coli-sim: {w['n_reads']} reads simulated from the reference's dataset/selfSampleData genome at the intervals of "
+                f"dataset/ecsample-truth.txt, e={w['err']}, k={w['k']}, [l,u]=[{w['lo']},{w['hi']}], seed {w['seed']}")
     return (f"synthetic {w['n_reads']} {'HiFi' if w['err'] < 0.02 else 'PacBio'} reads x {w['read_len']} bp, e={w['err']}, k={w['k']}, "
             f"[l,u]=[{w['lo']},{w['hi']}], {w['coverage']:.0f}x, seed {w['seed']}")
 
@@ -64,7 +70,7 @@ def workload_name(w):
 def load_workload(w, need_seqs):
     """Build (or load from the /dev/shm cache shared by both arms and all ranks) the matrices."""
     from bella_b200 import frontend as fe
-    key = "_".join(f"{k}{v}" for k, v in sorted(w.items()))
+    key = "_".join(f"{k}{v}" for k, v in sorted(w.items()) if k != "reads_file")
     cache = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", f"bella_b200_{key}.npz")
     if os.path.exists(cache):
         try:
@@ -74,8 +80,18 @@ def load_workload(w, need_seqs):
         except Exception:
             pass
     t0 = time.time()
-    inp = fe.synthetic(w["n_reads"], w["read_len"], coverage=w["coverage"], err=w["err"], seed=w["seed"], k=w["k"],
-                       lo=w["lo"], hi=w["hi"], bin_size=w["bin_size"])
+    if w.get("reads_file"):
+        if not os.path.exists(w["reads_file"]):
+            raise SystemExit(f"bench.py: {w['reads_file']} is missing -- run tools/make_config1.py in the build container first")
+        z = np.load(w["reads_file"])
+        nb = int(z["n_bases"][0])
+        p = z["packed"]
+        codes = np.stack([p & 3, (p >> 2) & 3, (p >> 4) & 3, (p >> 6) & 3], axis=1).reshape(-1)[:nb]
+        seqs = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+        inp = fe.build_matrices(seqs, z["offs"], w["k"], w["lo"], w["hi"], w["bin_size"])
+    else:
+        inp = fe.synthetic(w["n_reads"], w["read_len"], coverage=w["coverage"], err=w["err"], seed=w["seed"], k=w["k"],
+                           lo=w["lo"], hi=w["hi"], bin_size=w["bin_size"])
     log(f"[bench] front end built A ({inp.n_reads} x {inp.n_kmers}, nnz {inp.nnz}) in {time.time() - t0:.1f}s")
     try:
         tmp = cache + f".{os.getpid()}.tmp.npz"

@@ -62,3 +62,24 @@ def test_full_size_properties_and_oracle_prefix(config2):
     np.testing.assert_array_equal(cnt3, cnt[z0:z1])
     np.testing.assert_array_equal(pH3, pH[z0:z1])
     g.close()
+
+
+def test_config1_ecoli_sim_whole_matrix_against_the_oracle():
+    """BASELINE.json configs[0] as SURVEY.md 8d restates it: E. coli-sim (tools/make_config1.py: reads simulated from the
+    reference's own genome at its own truth intervals).  The packed reads live in scratch/ (git-ignored, travels with the
+    gpurun snapshot); without them the test has nothing to run on.  The WHOLE result is compared with the oracle."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    if not os.path.exists(bench.CONFIG1_READS):
+        pytest.skip("scratch/config1_reads.npz is absent (tools/make_config1.py writes it in the build container)")
+    from bella_b200 import spgemm
+    inp = bench.load_workload(dict(bench.CONFIGS[1]), need_seqs=False)
+    assert inp.n_reads == 14939 and 5.9e6 < inp.n_kmers < 6.1e6 and 15.0e6 < inp.nnz < 15.5e6        # SURVEY.md 8: 14,947 / 6.00 M / 15.24 M
+    r = spgemm.overlap_spgemm(inp, aux=True)
+    got = ol.Result(r["flopC"], r["colptrC"], r["rowids"], r["count"], r["posH"], r["posV"], r["aux"])
+    want = ol.oracle_spgemm(inp)
+    ol.assert_same(got, want)
+    assert 1.70e6 < want.nnz < 1.73e6 and 14.4e6 < r["flops"] < 14.8e6                                 # SURVEY.md 8: Z = 1,713,290, F = 14,606,754
