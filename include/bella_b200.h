@@ -166,10 +166,11 @@ int bella_b200_result_device(bella_b200_handle* h, const uint32_t** colptrC, con
  * nnzC_out / flops_out nullable. */
 int bella_b200_run_resident(bella_b200_handle* h, uint64_t* nnzC_out, uint64_t* flops_out);
 
-/* Timings of the last pass in milliseconds (CUDA events on the handle's stream):
- *   [0] k_partition   [1] k_group_fold (all capacity classes)   [2] output (C's colptr scans + k_compact)
- *   [3] host->device copies   [4] device->host copies   [5] kernels launched (count)
- *   [6] k_bucket + plan kernels   [7] k_scatter */
+/* Timings of the last pass in milliseconds (CUDA events on the handle's streams):
+ *   [0] two-level partition (k_rp1 + k_rp2)   [6] k_bucket + plan kernels
+ *   [1] the scatter | group + fold pipeline (the scatter passes of the later column ranges run beside the group + fold
+ *       kernels of the earlier ones; all capacity classes)   [7] the scatter passes alone, first to last (inside [1])
+ *   [2] output (C's colptr scans + k_compact)   [3] host->device copies   [4] device->host copies   [5] kernels launched (count) */
 int bella_b200_get_timings(bella_b200_handle* h, float* ms8);
 
 /* cudaStream_t of the handle as an opaque pointer (so a caller can order its own work after it). */

@@ -47,9 +47,11 @@ def test_xdrop_matches_oracle(reads, lanes, cells, xdrop):
     want = ol.oracle_align_post(inp, *pairs, xdrop, 0.55, 0.1, -1)
     np.testing.assert_array_equal(got, want)
     st = a.stats()
-    assert st["launches"] == 3 - (st["lanes"] == 0) and st["kernel_ms"] > 0
-    if (lanes, cells) == (-1, -1):
-        assert (st["lanes"], st["cells_per_lane"]) == ((1, 64) if xdrop <= 12 else (32, 2) if xdrop <= 40 else (0, 0))
+    # main kernel + wide kernel + compose (the wide-only path has no main kernel); the shapes that start the longest extensions
+    # first (3 and 5) add the estimate and the sort in front
+    assert 3 - (st["lanes"] == 0) <= st["launches"] <= 8 and st["kernel_ms"] > 0
+    if (lanes, cells) == (-1, -1):      # round 2: (3, 64) measured fastest at x = 7 (profiles/xdrop_r02.md)
+        assert (st["lanes"], st["cells_per_lane"]) == ((3, 64) if xdrop <= 12 else (32, 2) if xdrop <= 40 else (0, 0))
     a.close()
 
 

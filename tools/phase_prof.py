@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 from bella_b200 import _build
-_build.LIB_CUDA = os.path.join(ROOT, "scratch", "libbella_b200_phase.so")
+os.environ["BELLA_B200_LIB"] = os.path.join(ROOT, "scratch", "libbella_b200_phase.so")
 import bench
 from bella_b200 import spgemm
 import torch
@@ -37,8 +37,8 @@ out = (ctypes.c_ulonglong * 32)()
 L.bella_b200_debug_phases(out, 0)
 v = np.array(list(out), dtype=np.float64) / steps
 names = {15: "gf unit params + clear", 0: "gf wait for the bulk load", 1: "gf row bitmap (atomicOr)", 2: "gf popc scan", 3: "gf pair index + slot (atomic_add16)", 4: "gf count scan", 5: "gf placement + multiply",
-         6: "gf rank in pair", 7: "gf fold + pair results", 8: "gf warp path + huge + unit end", 16: "bk load+count", 17: "bk scan", 18: "bk permute", 19: "bk sort+flop", 20: "bk write"}
-gf = sum(v[i] for i in range(9)) + v[15]; bk = sum(v[i] for i in range(16, 21))
+         6: "gf rank in pair", 7: "gf fold + pair results", 8: "gf warp path + huge + unit end", 16: "bk TMA wait + count", 17: "bk scan", 18: "bk group by k-mer", 19: "bk rank by read + write"}
+gf = sum(v[i] for i in range(9)) + v[15]; bk = sum(v[i] for i in range(16, 20))
 res = {"Z": int(Z), "products": int(F), "timings": g.timings()}
 for i, nme in names.items():
     tot = gf if i < 16 else bk
