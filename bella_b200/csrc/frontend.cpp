@@ -133,8 +133,34 @@ void bella_fe_free_buf(void* p) { free(p); }
 
 // Build A, B, strand bits and read lengths from reads.  Returns NULL on error (err_out: -1 bad
 // arguments, -2 a read contains a character other than upper-case ACGT, -3 read longer than 65535).
+// Order of a k-mer under the reference's minimizer sampling (include/minimizer.hpp:23-26): Kmer::rep().hash() = the canonical
+// k-mer packed from the most significant end of one 64-bit word (kmercode/Kmer.cpp:206-222), hashed as 8 bytes with
+// MurmurHash3_x64_128 (seed 313, first 64 bits: kmercode/hash_funcs.c:135-140; the published algorithm, here for len = 8).
+static inline uint64_t rotl64_(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+static inline uint64_t fmix64_(uint64_t k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33; return k; }
+static inline uint64_t kmer_order(uint64_t canon, int k)
+{
+	uint64_t h1 = 313, h2 = 313, k1 = canon << (64 - 2 * k);
+	k1 *= 0x87c37b91114253d5ull; k1 = rotl64_(k1, 31); k1 *= 0x4cf5ad432745937full; h1 ^= k1;
+	h1 ^= 8; h2 ^= 8;
+	h1 += h2; h2 += h1;
+	h1 = fmix64_(h1); h2 = fmix64_(h2);
+	return h1 + h2;
+}
+
+void* bella_fe_build_w(const char* seqs, const uint64_t* offs, uint32_t n_reads, int k, int lo, int hi,
+		int keep_tuples, int nthreads, int window, int* err_out);
+
 void* bella_fe_build(const char* seqs, const uint64_t* offs, uint32_t n_reads, int k, int lo, int hi,
 		int keep_tuples, int nthreads, int* err_out)
+{
+	return bella_fe_build_w(seqs, offs, n_reads, k, lo, hi, keep_tuples, nthreads, 0, err_out);
+}
+
+// window > 0: BELLA's minimizer mode (-w, src/main.cpp:363-388 + MinimizerCount, include/kmercount.hpp:690-832): only the
+// positions getMinimizers samples (include/minimizer.hpp:49-77, robust winnowing) are counted and emitted.
+void* bella_fe_build_w(const char* seqs, const uint64_t* offs, uint32_t n_reads, int k, int lo, int hi,
+		int keep_tuples, int nthreads, int window, int* err_out)
 {
 	int err_dummy; if (!err_out) err_out = &err_dummy;
 	*err_out = 0;
@@ -166,16 +192,49 @@ void* bella_fe_build(const char* seqs, const uint64_t* offs, uint32_t n_reads, i
 		uint32_t len = fe->read_len[r];
 		uint64_t fw = 0, rv = 0;
 		uint32_t valid = 0;
+		if (window <= 0) {
+			for (uint32_t i = 0; i < len; ++i) {
+				int c = base_code(s[i]);
+				if (c < 0) return -2;
+				fw = ((fw << 2) | (uint64_t)c) & kmask;
+				rv = (rv >> 2) | ((uint64_t)(3 - c) << (2 * (k - 1)));
+				if (++valid >= (uint32_t)k) {
+					uint32_t pos = i + 1 - k;
+					bool fwd_is_canon = fw <= rv;
+					emit(fwd_is_canon ? fw : rv, pos, fwd_is_canon);
+				}
+			}
+			return 0;
+		}
+		// minimizer mode: the monotone deque of getMinimizers over the orders of the read's k-mers.  The reference compares the
+		// front's index with `int(i) - window` where window is a size_t, so the difference wraps for i < window and the deque
+		// is emptied: the first `window` k-mers of a read are never sampled.  Reproduced (same unsigned arithmetic).
+		if (len < (uint32_t)k) return 0;
+		const int total = (int)len - k + 1;
+		std::vector<uint64_t> canon(total), ord(total);
+		std::vector<uint8_t> isf(total);
 		for (uint32_t i = 0; i < len; ++i) {
 			int c = base_code(s[i]);
 			if (c < 0) return -2;
 			fw = ((fw << 2) | (uint64_t)c) & kmask;
 			rv = (rv >> 2) | ((uint64_t)(3 - c) << (2 * (k - 1)));
 			if (++valid >= (uint32_t)k) {
-				uint32_t pos = i + 1 - k;
-				bool fwd_is_canon = fw <= rv;
-				emit(fwd_is_canon ? fw : rv, pos, fwd_is_canon);
+				const int p = (int)i + 1 - k;
+				isf[p] = fw <= rv;
+				canon[p] = isf[p] ? fw : rv;
+				ord[p] = kmer_order(canon[p], k);
 			}
+		}
+		std::vector<int> dq(total);
+		int head = 0, tail = 0, last = -1;
+		for (int i = 0; i < total; ++i) {
+			while (tail > head && ord[dq[tail - 1]] > ord[i]) --tail;
+			dq[tail++] = i;
+			while (tail > head && (uint64_t)(int64_t)dq[head] <= (uint64_t)(int64_t)i - (uint64_t)window) {
+				while (tail - head > 1 && ord[dq[head]] == ord[dq[head + 1]]) ++head;      // furtherPop (robust winnowing)
+				++head;
+			}
+			if (tail > head && dq[head] != last) { last = dq[head]; emit(canon[last], (uint32_t)last, (bool)isf[last]); }
 		}
 		return 0;
 	};

@@ -26,6 +26,9 @@ def lib():
         L.bella_fe_build.restype = ctypes.c_void_p
         L.bella_fe_build.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+        L.bella_fe_build_w.restype = ctypes.c_void_p
+        L.bella_fe_build_w.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
         for f, rt in (("bella_fe_n", ctypes.c_uint32), ("bella_fe_m", ctypes.c_uint32),
                       ("bella_fe_nnz", ctypes.c_uint64), ("bella_fe_ntuples", ctypes.c_uint64)):
             getattr(L, f).restype = rt
@@ -109,15 +112,16 @@ def read_fastq(path):
     return names, reads
 
 
-def build_matrices(seqs, offs, k=17, lo=2, hi=8, bin_size=500, keep_tuples=False, nthreads=0, keep_seqs=True):
+def build_matrices(seqs, offs, k=17, lo=2, hi=8, bin_size=500, keep_tuples=False, nthreads=0, keep_seqs=True, window=0):
     """reads -> OverlapInputs (reliable k-mers in [lo,hi], B with the reference's MergeDuplicates
-    order, A = Bᵀ, strand bits, read lengths)."""
+    order, A = Bᵀ, strand bits, read lengths).  window > 0: BELLA's minimizer mode (-w): only the positions the reference's
+    getMinimizers samples (include/minimizer.hpp:49-77) are counted and kept."""
     L = lib()
     seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
     offs = np.ascontiguousarray(offs, dtype=np.uint64)
     n = len(offs) - 1
     err = ctypes.c_int(0)
-    h = L.bella_fe_build(seqs.ctypes.data, offs.ctypes.data, n, k, lo, hi, int(keep_tuples), nthreads, ctypes.byref(err))
+    h = L.bella_fe_build_w(seqs.ctypes.data, offs.ctypes.data, n, k, lo, hi, int(keep_tuples), nthreads, int(window), ctypes.byref(err))
     if not h:
         raise ValueError({-1: "bad arguments", -2: "read contains a character other than upper-case ACGT "
                           "(strand-bit contract, SURVEY 8c)", -3: "read longer than 65535 (u16 positions)",
@@ -149,8 +153,8 @@ def build_matrices(seqs, offs, k=17, lo=2, hi=8, bin_size=500, keep_tuples=False
 
 
 def synthetic(n_reads, read_len, coverage=30.0, err=0.15, split=(0.10, 0.60, 0.30), seed=1, k=17, lo=2, hi=8,
-              bin_size=500, keep_tuples=False, nthreads=0):
+              bin_size=500, keep_tuples=False, nthreads=0, window=0):
     """One call: simulate + build.  genome_len = n*L/coverage."""
     G = max(int(n_reads * read_len / coverage), 2 * read_len + 64 + int(read_len * 1.5) + 64)
     seqs, offs = simulate_reads(G, n_reads, read_len, err, split, seed)
-    return build_matrices(seqs, offs, k, lo, hi, bin_size, keep_tuples, nthreads)
+    return build_matrices(seqs, offs, k, lo, hi, bin_size, keep_tuples, nthreads, window=window)

@@ -40,11 +40,14 @@ WORKLOAD = dict(n_reads=50000, read_len=10000, coverage=30.0, err=0.15, seed=2, 
 #      read set occurs ~30 times and [2,8] leaves an almost empty matrix); 500 k reads by name, --reads scales it down
 #   1: E. coli-sim -- reads simulated by tools/make_config1.py from the reference's own dataset files (in the build container
 #      only; the packed reads travel in scratch/): refused with a clear message when that file is absent
-#   4 (minimizers, -w 10) needs a front-end option this repository does not have yet
+#   4: 1 M ONT-like reads, e = 0.20 (35/25/40 % substitution / insertion / deletion), minimizers -w 10: the front end samples the
+#      k-mer positions as the reference's getMinimizers does (include/minimizer.hpp:49-77; tests/test_oracle_kmers.py pins it to the
+#      reference); 10 Gbases by name, --reads scales it down
 CONFIG1_READS = os.path.join(ROOT, "scratch", "config1_reads.npz")      # written by tools/make_config1.py (E. coli-sim)
 CONFIGS = {1: dict(WORKLOAD, n_reads=14939, read_len=0, coverage=27.8, seed=1, reads_file=CONFIG1_READS),
            2: WORKLOAD,
            3: dict(WORKLOAD, n_reads=200000, seed=3),
+           4: dict(WORKLOAD, n_reads=1000000, err=0.20, split=(0.35, 0.25, 0.40), seed=4, window=10),
            5: dict(WORKLOAD, n_reads=500000, coverage=6.0, err=0.005, seed=5)}
 METRIC = "A·Aᵀ output-nnz/s"
 UNIT = "output-nnz/s"
@@ -63,7 +66,11 @@ def workload_name(w):
     if w.get("reads_file"):
         return (f"E. coli-sim: {w['n_reads']} reads simulated from the reference's dataset/selfSampleData genome at the intervals of "
                 f"dataset/ecsample-truth.txt, e={w['err']}, k={w['k']}, [l,u]=[{w['lo']},{w['hi']}], seed {w['seed']}")
-    return (f"synthetic {w['n_reads']} {'HiFi' if w['err'] < 0.02 else 'PacBio'} reads x {w['read_len']} bp, e={w['err']}, k={w['k']}, "
+    kind = "HiFi" if w["err"] < 0.02 else "ONT" if w.get("window") else "PacBio"
+    if w.get("window"):
+        return (f"synthetic {w['n_reads']} {kind} reads x {w['read_len']} bp, e={w['err']}, k={w['k']}, minimizers w={w['window']}, "
+                f"[l,u]=[{w['lo']},{w['hi']}], {w['coverage']:.0f}x, seed {w['seed']}")
+    return (f"synthetic {w['n_reads']} {kind} reads x {w['read_len']} bp, e={w['err']}, k={w['k']}, "
             f"[l,u]=[{w['lo']},{w['hi']}], {w['coverage']:.0f}x, seed {w['seed']}")
 
 
@@ -91,7 +98,7 @@ def load_workload(w, need_seqs):
         inp = fe.build_matrices(seqs, z["offs"], w["k"], w["lo"], w["hi"], w["bin_size"])
     else:
         inp = fe.synthetic(w["n_reads"], w["read_len"], coverage=w["coverage"], err=w["err"], seed=w["seed"], k=w["k"],
-                           lo=w["lo"], hi=w["hi"], bin_size=w["bin_size"])
+                           lo=w["lo"], hi=w["hi"], bin_size=w["bin_size"], split=tuple(w.get("split", (0.10, 0.60, 0.30))), window=w.get("window", 0))
     log(f"[bench] front end built A ({inp.n_reads} x {inp.n_kmers}, nnz {inp.nnz}) in {time.time() - t0:.1f}s")
     try:
         tmp = cache + f".{os.getpid()}.tmp.npz"

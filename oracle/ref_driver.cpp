@@ -399,6 +399,73 @@ int bella_ref_reliable_occurrences(const char* fastq_path, uint64_t fastq_size, 
 	return n <= cap ? 0 : -1;
 }
 
+// The reference's own minimizer sampling of one read (include/minimizer.hpp:49-77 on the Kmer objects of every position, exactly
+// as src/main.cpp:366-374 builds them).  out: positions, returns their number.
+int bella_ref_minimizers(const char* seq, int len, int kmer_len, int window, int* out, int cap)
+{
+	Kmer::set_k(kmer_len);
+	const std::string s(seq, seq + len);
+	std::vector<Kmer> seqkmers;
+	std::vector<int> seqminimizers;
+	for (int j = 0; j <= len - kmer_len; ++j) {
+		std::string kmerstrfromfastq = s.substr(j, kmer_len);
+		Kmer mykmer(kmerstrfromfastq.c_str(), kmerstrfromfastq.length());
+		seqkmers.emplace_back(mykmer);
+	}
+	getMinimizers((size_t)window, seqkmers, seqminimizers);
+	if ((int)seqminimizers.size() > cap) return -1;
+	for (size_t t = 0; t < seqminimizers.size(); ++t) out[t] = seqminimizers[t];
+	return (int)seqminimizers.size();
+}
+
+// MinimizerCount (include/kmercount.hpp:690-832) on a FASTQ of the reads + the minimizer branch of the tuple emission
+// (src/main.cpp:363-388); outputs as bella_ref_reliable_occurrences.
+int bella_ref_minimizer_occurrences(const char* fastq_path, uint64_t fastq_size, uint32_t n_reads, const char* seqs, const uint64_t* seq_off,
+		int kmer_len, int window, int lower, int upper, uint32_t* out_read, uint16_t* out_pos, uint64_t cap, uint64_t* n_out, uint64_t* n_kmers)
+{
+	Quiet q;
+	const int saved = omp_get_max_threads();
+	omp_set_num_threads(1);
+	BELLApars bpars;
+	bpars.kmerSize = (unsigned short)kmer_len;
+	bpars.windowLen = (size_t)window;
+	bpars.useMinimizer = true;
+	Kmer::set_k(kmer_len);
+	std::vector<filedata> allfiles(1);
+	strncpy(allfiles[0].filename, fastq_path, MAX_FILE_PATH - 1);
+	allfiles[0].filename[MAX_FILE_PATH - 1] = 0;
+	allfiles[0].filesize = fastq_size;
+	CuckooDict<IT> countsreliable;
+	MinimizerCount(allfiles, countsreliable, lower, upper, (size_t)10000000, bpars);
+	omp_set_num_threads(saved);
+	*n_kmers = countsreliable.size();
+	uint64_t n = 0;
+	for (uint32_t r = 0; r < n_reads; ++r) {
+		const std::string seq(seqs + seq_off[r], seqs + seq_off[r + 1]);
+		const int len = (int)seq.length();
+		std::vector<Kmer> seqkmers;
+		std::vector<int> seqminimizers;
+		for (int j = 0; j <= len - kmer_len; ++j) {
+			std::string kmerstrfromfastq = seq.substr(j, kmer_len);
+			Kmer mykmer(kmerstrfromfastq.c_str(), kmerstrfromfastq.length());
+			seqkmers.emplace_back(mykmer);
+		}
+		getMinimizers(bpars.windowLen, seqkmers, seqminimizers);
+		for (auto minpos : seqminimizers) {
+			std::string strminkmer = seq.substr(minpos, kmer_len);
+			Kmer myminkmer(strminkmer.c_str(), strminkmer.length());
+			myminkmer = myminkmer.rep();
+			IT idx;
+			if (countsreliable.find(myminkmer, idx)) {
+				if (n < cap) { out_read[n] = r; out_pos[n] = (uint16_t)minpos; }
+				++n;
+			}
+		}
+	}
+	*n_out = n;
+	return n <= cap ? 0 : -1;
+}
+
 int bella_ref_max_threads(void) { return omp_get_max_threads(); }
 
 } // extern "C"

@@ -226,7 +226,8 @@ def _occurrences(fn, head, inp, k, lower, upper):
     total = int(len(inp.seqs))
     out_read = np.zeros(total, dtype=np.uint32); out_pos = np.zeros(total, dtype=np.uint16)
     n_out, n_kmers = ctypes.c_uint64(0), ctypes.c_uint64(0)
-    rc = fn(*head, ctypes.c_uint32(inp.n_reads), _p(inp.seqs), _p(inp.seq_off), ctypes.c_int(k), ctypes.c_int(lower), ctypes.c_int(upper),
+    kw = [ctypes.c_int(x) for x in k] if isinstance(k, tuple) else [ctypes.c_int(k)]          # (k, window) for the minimizer variants
+    rc = fn(*head, ctypes.c_uint32(inp.n_reads), _p(inp.seqs), _p(inp.seq_off), *kw, ctypes.c_int(lower), ctypes.c_int(upper),
             _p(out_read), _p(out_pos), ctypes.c_uint64(total), ctypes.byref(n_out), ctypes.byref(n_kmers))
     if rc != 0:
         raise RuntimeError(f"reliable k-mer selection failed: {rc}")
@@ -244,6 +245,34 @@ def write_fastq(inp, path):
             s = inp.seqs[int(inp.seq_off[r]):int(inp.seq_off[r + 1])].tobytes()
             f.write(b"@read%d\n" % r + s + b"\n+\n" + b"I" * len(s) + b"\n")
     return os.path.getsize(path)
+
+
+def oracle_minimizers(seq_bytes, k, window):
+    """oracle_minimizers: sampled k-mer positions of one read (numpy int32)"""
+    out = np.zeros(max(len(seq_bytes), 1), dtype=np.int32)
+    n = oracle().oracle_minimizers(ctypes.c_char_p(bytes(seq_bytes)), ctypes.c_int(len(seq_bytes)), ctypes.c_int(k), ctypes.c_int(window), _p(out),
+                                   ctypes.c_int(len(out)))
+    assert n >= 0
+    return out[:n].copy()
+
+
+def ref_minimizers(seq_bytes, k, window):
+    """the reference's getMinimizers (include/minimizer.hpp:49-77) on the read's Kmer objects"""
+    out = np.zeros(max(len(seq_bytes), 1), dtype=np.int32)
+    n = ref().bella_ref_minimizers(ctypes.c_char_p(bytes(seq_bytes)), ctypes.c_int(len(seq_bytes)), ctypes.c_int(k), ctypes.c_int(window), _p(out),
+                                   ctypes.c_int(len(out)))
+    assert n >= 0
+    return out[:n].copy()
+
+
+def oracle_minimizer_occurrences(inp, k, window, lower, upper):
+    return _occurrences(oracle().oracle_minimizer_occurrences, (), inp, (k, window), lower, upper)
+
+
+def ref_minimizer_occurrences(inp, k, window, lower, upper, fastq_path):
+    """the reference's MinimizerCount on a FASTQ of the reads + the minimizer branch of its tuple emission"""
+    size = write_fastq(inp, fastq_path)
+    return _occurrences(ref().bella_ref_minimizer_occurrences, (fastq_path.encode(), ctypes.c_uint64(size)), inp, (k, window), lower, upper)
 
 
 def ref_reliable_occurrences(inp, k, lower, upper, fastq_path):

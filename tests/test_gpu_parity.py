@@ -225,3 +225,12 @@ def test_gpu_scatter_group_pipeline_with_heavy_columns(monkeypatch, nrange):
     ol.assert_same(gpu_result(hifi, False), ol.oracle_spgemm(hifi))
     clr = fe.synthetic(n_reads=2500, read_len=6000, seed=77)
     ol.assert_same(gpu_result(clr, False), ol.oracle_spgemm(clr))
+
+
+def test_gpu_minimizer_sparsified_matrix():
+    """BASELINE.json configs[3]: the read x k-mer matrix of BELLA's minimizer mode (-w 10; only the sparsity pattern changes,
+    include/minimizer.hpp:49-77 through the host front end) -- the SpGEMM must not care"""
+    from bella_b200 import frontend as fe
+    inp = fe.synthetic(n_reads=6000, read_len=8000, err=0.20, split=(0.35, 0.25, 0.40), seed=4, window=10)
+    assert inp.nnz > 100000
+    ol.assert_same(gpu_result(inp, False), ol.oracle_spgemm(inp))

@@ -71,3 +71,54 @@ def test_host_front_end_emits_the_oracle_occurrences():
     np.testing.assert_array_equal(a, b)
     # one id per canonical k-mer: occurrences with the same id carry the same canonical k-mer and vice versa
     assert len(np.unique(t_kmer)) == n_kmers
+
+
+# ---- minimizers (BASELINE.json configs[3], -w): the oracle's restatement against the reference's own functions ----
+@needs_ref
+@pytest.mark.parametrize("window", [10, 5, 32])
+def test_oracle_minimizers_are_the_references(window):
+    """getMinimizers (include/minimizer.hpp:49-77) under Kmer::rep().hash() (MurmurHash3_x64_128 of the packed canonical k-mer,
+    seed 313): positions identical read by read, including the reference's quirk that the first `window` k-mers of a read are
+    never sampled (its range test subtracts a size_t from an int) and reads with repeats (equal orders in one window)."""
+    inp = fe.synthetic(60, 3000, seed=41)
+    rng = np.random.default_rng(7)
+    reads = [bytes(inp.seqs[int(inp.seq_off[r]):int(inp.seq_off[r + 1])]) for r in range(inp.n_reads)]
+    reads += [b"ACGT" * 200, b"A" * 500, bytes(rng.choice(np.frombuffer(b"AC", dtype=np.uint8), 700)), b"ACGTACGTACGTACGTAC", b"ACGTACGTACGTACGTA", b"ACGT"]
+    nonempty = 0
+    for s in reads:
+        want = ol.ref_minimizers(s, 17, window)
+        got = ol.oracle_minimizers(s, 17, window)
+        np.testing.assert_array_equal(got, want)
+        nonempty += len(want) > 0
+        if len(want):
+            assert want.min() >= window                      # the quirk, pinned
+    assert nonempty >= 60
+
+
+@needs_ref
+@pytest.mark.parametrize("window,lower,upper", [(10, 2, 8), (10, 2, 4), (5, 2, 8)])
+def test_oracle_minimizer_selection_is_minimizercounts(tmp_path, window, lower, upper):
+    """MinimizerCount (include/kmercount.hpp:690-832) + the minimizer branch of the tuple emission (src/main.cpp:363-388)"""
+    inp = fe.synthetic(500, 4000, seed=11 + window)
+    want = ol.ref_minimizer_occurrences(inp, 17, window, lower, upper, str(tmp_path / "reads.fastq"))
+    got = ol.oracle_minimizer_occurrences(inp, 17, window, lower, upper)
+    assert got[2] == want[2] and got[2] > 300
+    np.testing.assert_array_equal(got[0], want[0])
+    np.testing.assert_array_equal(got[1], want[1])
+
+
+@pytest.mark.parametrize("window", [10, 5])
+def test_front_end_minimizer_mode_emits_the_oracles_occurrences(window):
+    """the product's host front end (bella_b200/csrc/frontend.cpp, window > 0) against the oracle's minimizer selection (which
+    is pinned against the reference above): same reliable k-mer count, and B holds exactly the selected (read, position)s"""
+    inp = fe.synthetic(500, 4000, seed=23, window=window)
+    reads, pos, nk = ol.oracle_minimizer_occurrences(inp, 17, window, 2, 8)
+    assert inp.n_kmers == nk and nk > 300
+    cols = np.repeat(np.arange(inp.n_reads, dtype=np.uint32), np.diff(inp.B_colptr.astype(np.int64)))
+    got = np.unique(np.stack([cols.astype(np.int64), inp.B_values.astype(np.int64)], axis=1), axis=0)
+    # a k-mer sampled twice in one read keeps its last position in B (MergeDuplicates): compare as sets of (read, k-mer) through positions
+    want = np.unique(np.stack([reads.astype(np.int64), pos.astype(np.int64)], axis=1), axis=0)
+    assert len(got) <= len(want) and len(want) - len(got) <= 0.01 * len(want)
+    assert set(map(tuple, got)) <= set(map(tuple, want))
+    full = fe.synthetic(500, 4000, seed=23)
+    assert 0.1 < inp.nnz / full.nnz < 0.35                  # SURVEY.md 6: -w 10 keeps ~15 % of the nonzeros on E. coli-sim
