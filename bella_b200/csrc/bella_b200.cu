@@ -188,11 +188,10 @@ int rp_geometry(uint64_t ml, uint64_t nnz, uint32_t W_forced, RpGeom* g)
 
 // transpose: B (read-major) -> Aent (k-mer-major, columns sorted by read id) for the k-mers [klo, khi)
 // and the reads >= row_lo, + the product counts of the output columns [cnt_lo, cnt_hi) into flop_out
-int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32_t cnt_hi, uint32_t* flop_out,
-		const uint32_t* rec = nullptr, uint64_t nrec = 0)
+int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32_t cnt_hi, uint32_t* flop_out)
 {
 	const uint32_t n = h->n, ml = h->khi - h->klo;
-	const uint64_t nnz = rec ? nrec : h->nnzB;                     // route mode: the nonzeros are the received records
+	const uint64_t nnz = h->nnzB;
 	const uint32_t ncols = cnt_hi - cnt_lo;
 	ENSURE(h->Acolptr, sizeof(uint32_t) * ((size_t)ml + 2));
 	ENSURE(h->Aent, sizeof(uint64_t) * (nnz + 2));
@@ -206,7 +205,7 @@ int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32
 		return 0;
 	}
 	RpGeom geo;
-	if (rp_geometry(ml, rec ? nnz : (uint64_t)((double)nnz * ml / (h->m ? h->m : 1)), h->W, &geo))
+	if (rp_geometry(ml, (uint64_t)((double)nnz * ml / (h->m ? h->m : 1)), h->W, &geo))
 		return fail(h, BELLA_B200_ERR_RANGE, "%u k-mers are more than the two-level partition addresses", ml);
 	h->W = geo.W;
 	const uint32_t W = geo.W, wshift = geo.wshift, NB = geo.NB;
@@ -220,11 +219,7 @@ int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32
 	uint32_t* bcnt = h->bcur.as<uint32_t>();
 	uint64_t* partE = h->part.as<uint64_t>();
 	uint16_t* partK = h->partK.as<uint16_t>();
-	if (rec) {
-		CK(cudaEventRecord(h->ev[8], h->stream));
-		k_partition_rec<<<grid_for(nrec, 256), 256, 0, h->stream>>>(nrec, rec, h->klo, h->khi, wshift, bcnt, partE, partK, h->errflag.as<int>());
-		LAUNCHED();
-	} else {
+	{
 		const uint32_t l2 = geo.l2, shift1 = geo.shift1, nb1 = geo.nb1;
 		const double share = (double)ml / (double)(h->m ? h->m : 1);           // multi-GPU: only the k-mers [klo, khi) are this handle's
 		const uint32_t groups = 1;                                             // one writer per coarse bucket on one GPU
@@ -294,13 +289,6 @@ int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32
 		CK(cudaStreamWaitEvent(h->stream, h->aux_join, 0));
 		return 0;
 	}
-	CK(cudaEventRecord(h->ev[9], h->stream));
-	k_bucket_offsets<<<1, 1024, 0, h->stream>>>(0u, NB, bcnt, h->boff.as<uint32_t>());
-	LAUNCHED();
-	CK(cudaFuncSetAttribute(k_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BUCKET_SMEM));
-	k_bucket<<<NB < (uint32_t)h->sms * 16 ? NB : (uint32_t)h->sms * 16, 256, BUCKET_SMEM, h->stream>>>(h->klo, ml, cnt_lo, cnt_hi, wshift, 0u, NB, NB, h->boff.as<uint32_t>(),
-		partE, partK, h->Acolptr.as<uint32_t>(), h->Aent.as<uint64_t>(), h->Ainfo.as<uint8_t>(), flop_out, h->errflag.as<int>());
-	LAUNCHED();
 	return 0;
 }
 
@@ -1269,72 +1257,5 @@ int bella_b200_debug_phases(unsigned long long* out32, int reset)
 	return 0;
 }
 #endif
-
-/* route mode (bella_b200/distributed.py, mode "route"): k-mer-partitioned records instead of an all-gather of B */
-int bella_b200_mg_route(bella_b200_handle* h, uint32_t n_local, uint32_t read_base, const uint32_t* colptr_local_dev, const uint32_t* rowids_dev,
-		const uint16_t* values_dev, uint32_t kmers_per_rank, int world, uint32_t* send_dev, uint64_t* send_counts_host)
-{
-	if (!h || world < 1 || world > 64 || !kmers_per_rank || !send_counts_host || (n_local && (!colptr_local_dev || !rowids_dev || !values_dev || !send_dev)))
-		return fail(h, BELLA_B200_ERR_ARG, "bad arguments to bella_b200_mg_route");
-	CK(cudaSetDevice(h->device));
-	ENSURE(h->mg_ucur, sizeof(uint64_t) * 2 * 64 + sizeof(uint64_t) * ((size_t)h->n + 1));
-	unsigned long long* counts = h->mg_ucur.as<unsigned long long>();
-	unsigned long long* cursor = counts + 64;
-	CK(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * 128, h->stream));
-	for (int d = 0; d < world; ++d) send_counts_host[d] = 0;
-	if (!n_local) return BELLA_B200_OK;
-	const int rgrid = n_local < (uint32_t)h->sms * 8 ? (int)n_local : h->sms * 8;
-	k_route_count<<<rgrid, 256, 0, h->stream>>>(n_local, colptr_local_dev, rowids_dev, kmers_per_rank, (uint32_t)world, counts);
-	LAUNCHED();
-	unsigned long long hc[64];
-	CK(cudaMemcpyAsync(hc, counts, sizeof(uint64_t) * world, cudaMemcpyDeviceToHost, h->stream));
-	CK(cudaStreamSynchronize(h->stream));
-	unsigned long long off[64], run = 0;
-	for (int d = 0; d < world; ++d) { off[d] = run; run += hc[d]; send_counts_host[d] = hc[d]; }
-	CK(cudaMemcpyAsync(cursor, off, sizeof(uint64_t) * world, cudaMemcpyHostToDevice, h->stream));
-	k_route_fill<<<rgrid, 256, 0, h->stream>>>(n_local, read_base, colptr_local_dev, rowids_dev, values_dev,
-		kmers_per_rank, (uint32_t)world, cursor, send_dev);
-	LAUNCHED();
-	CK(cudaStreamSynchronize(h->stream));                           // `off` lives on this stack frame
-	return BELLA_B200_OK;
-}
-
-int bella_b200_mg_transpose_records(bella_b200_handle* h, const uint32_t* rec_dev, uint64_t nrec, uint32_t kmer_lo, uint32_t kmer_hi,
-		uint32_t* cnt_local_dev)
-{
-	if (!h || !h->have_inputs) return fail(h, BELLA_B200_ERR_ARG, "set_inputs first");
-	if (kmer_lo > kmer_hi || kmer_hi > h->m || !cnt_local_dev || (nrec && !rec_dev)) return fail(h, BELLA_B200_ERR_ARG, "bad arguments to bella_b200_mg_transpose_records");
-	CK(cudaSetDevice(h->device));
-	h->launches = 0;
-	ENSURE(h->meta, sizeof(Meta));
-	ENSURE(h->errflag, 4 * sizeof(int));
-	h->klo = kmer_lo; h->khi = kmer_hi;
-	h->mg_recv = nullptr;
-	h->symbolic_done = h->numeric_done = false;
-	CK(cudaEventRecord(h->ev[0], h->stream));
-	if (!nrec) {
-		CK(cudaMemsetAsync(cnt_local_dev, 0, sizeof(uint32_t) * (size_t)h->n, h->stream));
-		ENSURE(h->Acolptr, sizeof(uint32_t) * ((size_t)(kmer_hi - kmer_lo) + 2));
-		CK(cudaMemsetAsync(h->Acolptr.p, 0, sizeof(uint32_t) * ((size_t)(kmer_hi - kmer_lo) + 2), h->stream));
-		CK(cudaEventRecord(h->ev[8], h->stream)); CK(cudaEventRecord(h->ev[9], h->stream));
-	}
-	for (; nrec;) {
-		CK(cudaMemsetAsync(h->errflag.p, 0, sizeof(int), h->stream));
-		if (int rc = run_transpose(h, 0, 0, h->n, cnt_local_dev, rec_dev, nrec)) return rc;
-		int e = 0;
-		CK(cudaMemcpyAsync(&e, h->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-		CK(cudaStreamSynchronize(h->stream));
-		if (e == ERR_BUCKET) {
-			if (h->W <= 1) return fail(h, BELLA_B200_ERR_RANGE, "a k-mer occurs in more than %u reads", BUCKET_CAP);
-			h->W = h->W / 2;
-			h->cap_scale *= 1.5;
-			continue;
-		}
-		if (e) return report_device_error(h, e);
-		break;
-	}
-	CK(cudaEventRecord(h->ev[1], h->stream));
-	return BELLA_B200_OK;
-}
 
 } // extern "C"

@@ -1460,100 +1460,6 @@ __global__ void __launch_bounds__(256) k_mg_push(uint32_t world, uint32_t me, co
 	}
 }
 
-// ---- multi-GPU "route" mode: instead of all-gathering B, every GPU sends each of its nonzeros to the GPU that
-// transposes that k-mer range (12-byte records {k-mer id | strand<<31, read id, pos | jrank<<16}) ----
-
-// One CTA per contiguous range of this GPU's reads; warp per read, lanes with the same destination vote together and
-// the CTA keeps its per-destination counters in shared memory, so the few global counters (one per destination GPU)
-// see one atomic per CTA instead of one per warp.
-__device__ __forceinline__ void route_count_cta(uint32_t i0, uint32_t i1, const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ rowids,
-		uint32_t kpr, uint32_t world, uint32_t* s_cnt)
-{
-	const uint32_t w = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31;
-	for (uint32_t i = i0 + w; i < i1; i += nw) {
-		const uint32_t j0 = colptr[i], j1 = colptr[i + 1];
-		for (uint32_t jb = j0; jb < j1; jb += 32) {
-			const uint32_t j = jb + lane;
-			const bool have = j < j1;
-			const uint32_t dest = have ? min((rowids[j] & 0x7FFFFFFFu) / kpr, world - 1) : 0xFFFFFFFFu;
-			const uint32_t act = __ballot_sync(FULL, have);
-			if (have) {
-				const uint32_t same = __match_any_sync(act, dest);
-				if ((uint32_t)(__ffs(same) - 1) == lane) atomicAdd(&s_cnt[dest], (uint32_t)__popc(same));
-			}
-		}
-	}
-}
-
-__global__ void __launch_bounds__(256) k_route_count(uint32_t n_local, const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ rowids,
-		uint32_t kpr, uint32_t world, unsigned long long* __restrict__ counts)
-{
-	__shared__ uint32_t s_cnt[64];
-	if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
-	__syncthreads();
-	const uint32_t i0 = (uint32_t)((uint64_t)n_local * blockIdx.x / gridDim.x), i1 = (uint32_t)((uint64_t)n_local * (blockIdx.x + 1) / gridDim.x);
-	route_count_cta(i0, i1, colptr, rowids, kpr, world, s_cnt);
-	__syncthreads();
-	if (threadIdx.x < world && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
-}
-
-__global__ void __launch_bounds__(256) k_route_fill(uint32_t n_local, uint32_t read_base, const uint32_t* __restrict__ colptr,
-		const uint32_t* __restrict__ rowids, const uint16_t* __restrict__ values, uint32_t kpr, uint32_t world,
-		unsigned long long* __restrict__ cursor, uint32_t* __restrict__ send)
-{
-	__shared__ uint32_t s_cnt[64];
-	__shared__ unsigned long long s_base[64];
-	if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
-	__syncthreads();
-	const uint32_t i0 = (uint32_t)((uint64_t)n_local * blockIdx.x / gridDim.x), i1 = (uint32_t)((uint64_t)n_local * (blockIdx.x + 1) / gridDim.x);
-	route_count_cta(i0, i1, colptr, rowids, kpr, world, s_cnt);           // how much this CTA sends to every destination
-	__syncthreads();
-	if (threadIdx.x < world) {
-		s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]) : 0ull;
-		s_cnt[threadIdx.x] = 0;                                             // becomes the CTA's cursor inside its reservation
-	}
-	__syncthreads();
-	const uint32_t w = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31;
-	for (uint32_t i = i0 + w; i < i1; i += nw) {
-		const uint32_t j0 = colptr[i], j1 = colptr[i + 1];
-		for (uint32_t jb = j0; jb < j1; jb += 32) {
-			const uint32_t j = jb + lane;
-			const bool have = j < j1;
-			const uint32_t c = have ? rowids[j] : 0;
-			const uint32_t dest = have ? min((c & 0x7FFFFFFFu) / kpr, world - 1) : 0xFFFFFFFFu;
-			const uint32_t act = __ballot_sync(FULL, have);
-			if (have) {
-				const uint32_t same = __match_any_sync(act, dest);
-				const uint32_t leader = __ffs(same) - 1;
-				uint32_t off = 0;
-				if (leader == lane) off = atomicAdd(&s_cnt[dest], (uint32_t)__popc(same));
-				off = __shfl_sync(same, off, leader);
-				const unsigned long long q = s_base[dest] + off + __popc(same & ((1u << lane) - 1u));
-				send[3 * q + 0] = c;
-				send[3 * q + 1] = read_base + i;
-				send[3 * q + 2] = (uint32_t)values[j] | ((j - j0) << 16);
-			}
-		}
-	}
-}
-
-// received records -> k-mer buckets (the same fixed-capacity layout k_partition fills)
-__global__ void __launch_bounds__(256) k_partition_rec(uint64_t nrec, const uint32_t* __restrict__ rec, uint32_t klo, uint32_t khi, uint32_t wshift,
-		uint32_t* __restrict__ bcnt, uint64_t* __restrict__ partE, uint16_t* __restrict__ partK, int* err)
-{
-	const uint32_t wmask = (1u << wshift) - 1u;
-	for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < nrec; t += (uint64_t)gridDim.x * blockDim.x) {
-		const uint32_t c = rec[3 * t], kid = c & 0x7FFFFFFFu, rd = rec[3 * t + 1], pj = rec[3 * t + 2];
-		if (kid < klo || kid >= khi) { set_err(err, -5); continue; }
-		const uint32_t b = (kid - klo) >> wshift;
-		const uint32_t q = atomicAdd(&bcnt[(size_t)b * BCNT_STRIDE], 1u);
-		if (q >= BUCKET_CAP) { set_err(err, -6); continue; }
-		const size_t at = (size_t)b * BUCKET_CAP + q;
-		partE[at] = (uint64_t)rd | ((uint64_t)(c >> 31) << 31) | ((uint64_t)(pj & 0xFFFFu) << 32) | ((uint64_t)(pj >> 16) << 48);
-		partK[at] = (uint16_t)((kid - klo) & wmask);
-	}
-}
-
 // ================================ matrix construction (tuples -> B) =========================
 // The reference builds B = CSC(tuples (k-mer id, read id, position), ..., keep-p1, needsort = false)
 // (src/main.cpp:476-480): a stable counting sort of the tuples by read (src/CSC.cpp:432-475), then

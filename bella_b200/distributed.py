@@ -237,7 +237,7 @@ class ShardedOverlapSpGEMM:
 
     def load_shard(self, inp, pinned=False):
         """Take this rank's reads of `inp`, pack the panel and make it device resident."""
-        if self.mode in ("route", "nvlink"):
+        if self.mode == "nvlink":
             # a rank owns the output columns of its own reads: shards balanced on the estimated products + the per-column
             # overhead of the group + fold stage (the same weights the exchange mode balances exactly, but up front)
             lens = np.diff(inp.B_colptr.astype(np.int64)).astype(np.float64)
@@ -267,7 +267,7 @@ class ShardedOverlapSpGEMM:
         self.panel = self.host_panel.to(self.dev)
         if self.mode == "nvlink":
             self._setup_nvlink(inp.n_reads, inp.nnz, n_r, nnz_r)
-        if self.mode in ("route", "nvlink"):
+        if self.mode == "nvlink":
             off, _ = panel_layout(n_r, nnz_r)
             p = self.panel
             self.loc = {"rowids": p[off["rowids"]:off["rowids"] + 4 * nnz_r].view(torch.int32),
@@ -403,8 +403,6 @@ class ShardedOverlapSpGEMM:
         """-> (Z of this rank's columns, products, (col_lo, col_hi)[, host results when fetch=True])"""
         if self.mode == "nvlink":
             return self._step_nvlink(fetch)
-        if self.mode == "route":
-            return self._step_route(fetch)
         if self._profile:
             import time
             torch.cuda.synchronize(self.dev)
@@ -472,65 +470,6 @@ class ShardedOverlapSpGEMM:
         g.numeric_device()
         return int(g.result_nnz()), flops, (lo, hi)
 
-    def _step_route(self, fetch):
-        """No all-gather of B: the nonzeros go to the rank that transposes their k-mer range (all-to-all of 12-byte
-        records), the products to the rank that owns their column (all-to-all of 8-byte records); a rank owns the
-        columns of its own reads, so B's values stay where they are."""
-        if self._profile:
-            import time
-            torch.cuda.synchronize(self.dev)
-            self._t0 = time.perf_counter()
-        g, dev, world, rank = self.g, self.dev, self.world, self.rank
-        r0, r1, n_r = self.r0, self.r1, self.r1 - self.r0
-        n = self.cuts[-1]
-        # read lengths of every read (4 bytes per read) + this rank's local colptr
-        lens_pad = torch.zeros(max(b - a for a, b in zip(self.cuts[:-1], self.cuts[1:])), dtype=torch.int32, device=dev)
-        lens_pad[:n_r] = self.loc["read_len"]
-        gathered = torch.empty((world, lens_pad.numel()), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(gathered.view(-1), lens_pad)
-        read_len = torch.cat([gathered[s, :self.cuts[s + 1] - self.cuts[s]] for s in range(world)])
-        colptr_local = torch.zeros(n_r + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(self.loc["counts"].to(torch.int64), 0, out=colptr_local[1:])
-        colptr_local = colptr_local.to(torch.int32)
-        # the handle sees B through pointers shifted so that the GLOBAL read id indexes colptr
-        g.set_inputs_device(n, self.n_kmers, self.nnz_local, (colptr_local.data_ptr() - 4 * r0, self.loc["rowids"], self.loc["values"]),
-                            read_len, None, self.kmer_size, self.bin_size)
-        kpr = (self.n_kmers + world - 1) // world
-        send = torch.empty(3 * max(self.nnz_local, 1), dtype=torch.int32, device=dev)
-        out_counts = g.mg_route(n_r, r0, colptr_local, self.loc["rowids"], self.loc["values"], kpr, world, send)
-        self._tick("route")
-        oc = torch.tensor(out_counts, dtype=torch.int64, device=dev)
-        ic = torch.empty_like(oc)
-        dist.all_to_all_single(ic, oc)
-        in_counts = [int(x) for x in ic.tolist()]
-        nrec = sum(in_counts)
-        recv = torch.empty(3 * max(nrec, 1), dtype=torch.int32, device=dev)
-        dist.all_to_all_single(recv[:3 * nrec], send[:3 * sum(out_counts)], [3 * x for x in in_counts], [3 * x for x in out_counts])
-        self._tick("all_to_all records")
-        cnt_local = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-        g.mg_transpose_records(recv, nrec, min(rank * kpr, self.n_kmers), min((rank + 1) * kpr, self.n_kmers), cnt_local)
-        self._tick("mg_transpose")
-        counts_all = torch.empty((world, n), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(counts_all.view(-1), cnt_local[:n].contiguous())
-        bounds, in_splits, out_splits, segoff, recvbase, sendoff = exchange_plan(counts_all, rank, fixed_bounds=self.cuts)
-        self._tick("counts+plan")
-        psend = torch.empty(max(sum(out_splits), 1), dtype=torch.int64, device=dev)
-        g.mg_scatter(sendoff, psend)
-        self._tick("mg_scatter")
-        precv = torch.empty(max(sum(in_splits), 1), dtype=torch.int64, device=dev)
-        dist.all_to_all_single(precv[:sum(in_splits)], psend[:sum(out_splits)], in_splits, out_splits)
-        self._tick("all_to_all products")
-        self.keep = (read_len, colptr_local, send, recv, counts_all, segoff, recvbase, psend, precv, cnt_local, sendoff, gathered)
-        g.mg_finish(r0, r1, world, counts_all, segoff, recvbase, precv)
-        self._tick("mg_finish")
-        flops = sum(in_splits)
-        if fetch:
-            colptrC = g.get_colptr(pinned=True)
-            res = g.numeric(pinned=True)
-            return int(colptrC[r1 - r0]), flops, (r0, r1), (colptrC[:r1 - r0 + 1],) + res
-        g.numeric_device()
-        return int(g.result_nnz()), flops, (r0, r1)
-
     def close(self):
         self.g.close()
 
@@ -541,7 +480,7 @@ def bench_multi(args, w, inp, rank, world, local, METRIC, UNIT, workload, ClockS
     import time
     import os
     dev = torch.device("cuda", local)
-    mode = os.environ.get("BELLA_MG_MODE", "nvlink")        # "exchange" / "route" / "replicate": the NCCL-based modes of round 1
+    mode = os.environ.get("BELLA_MG_MODE", "nvlink")        # "exchange" / "replicate": the NCCL-based modes of round 1
     sh = ShardedOverlapSpGEMM(local, mode=mode)
     sh.load_shard(inp, pinned=True)
     stream = torch.cuda.current_stream(dev)
@@ -630,7 +569,6 @@ def bench_multi(args, w, inp, rank, world, local, METRIC, UNIT, workload, ClockS
                 "workload_stats": {"n_kmers": inp.n_kmers, "nnz_A": inp.nnz, "products": Ft, "output_nnz": Zt, "l2": "inputs larger than L2, no flush",
                                    "parallelism": {"nvlink": f"row-sharded x{world}: a rank owns the columns of its reads; nonzeros stored into the k-mer owner's "
                                                              "buckets and product blocks pushed to the column owner over NVLink peer memory, three device barriers, no collective",
-                                                   "route": f"row-sharded x{world}: all-to-all of k-mer-partitioned records, transpose per k-mer range, all-to-all of the products",
                                                    }.get(mode, f"row-sharded x{world}: all-gather of the B panel, transpose split by k-mer range, all-to-all of the products")},
                 "parity": parity,
                 "clocks": clocks,

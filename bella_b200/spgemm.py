@@ -60,8 +60,6 @@ def lib():
         L.bella_b200_mg_scatter.argtypes = [H, vp, vp]
         L.bella_b200_mg_finish.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, vp, vp, vp, vp]
         L.bella_b200_get_colptr.argtypes = [H, vp]
-        L.bella_b200_mg_route.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp, ctypes.c_uint32, ctypes.c_int, vp, ctypes.POINTER(ctypes.c_uint64)]
-        L.bella_b200_mg_transpose_records.argtypes = [H, vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, vp]
         pp = ctypes.POINTER(vp)
         L.bella_b200_mg_geometry.argtypes = [ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int, vp]
         L.bella_b200_mg_route_push.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp, ctypes.c_uint32, vp, ctypes.c_int, ctypes.c_int, pp, pp, pp]
@@ -80,8 +78,7 @@ EXPORTS = ["bella_b200_get_flops", "bella_b200_mg_geometry", "bella_b200_mg_rout
            "bella_b200_numeric", "bella_b200_numeric_aux", "bella_b200_numeric_device",
            "bella_b200_result_device", "bella_b200_run_resident", "bella_b200_get_timings", "bella_b200_stream",
            "bella_b200_set_stream", "bella_b200_mg_transpose", "bella_b200_mg_scatter", "bella_b200_mg_finish",
-           "bella_b200_get_colptr", "bella_b200_set_inputs_tuples", "bella_b200_get_B", "bella_b200_mg_route",
-           "bella_b200_mg_transpose_records"]
+           "bella_b200_get_colptr", "bella_b200_set_inputs_tuples", "bella_b200_get_B"]
 
 
 class BellaB200Error(RuntimeError):
@@ -231,17 +228,6 @@ class OverlapSpGEMM:
     # ---- multi-GPU stages (device tensors / pointers; bella_b200/distributed.py runs the collectives between them) ----
     def mg_transpose(self, kmer_lo, kmer_hi, cnt_local):
         self._check(self._L.bella_b200_mg_transpose(self._h, kmer_lo, kmer_hi, _ptr(cnt_local)), "bella_b200_mg_transpose")
-
-    def mg_route(self, n_local, read_base, colptr_local, rowids, values, kmers_per_rank, world, send):
-        """-> per-destination record counts (python list)"""
-        counts = (ctypes.c_uint64 * world)()
-        self._check(self._L.bella_b200_mg_route(self._h, n_local, read_base, _ptr(colptr_local), _ptr(rowids), _ptr(values), kmers_per_rank,
-                                                world, _ptr(send), counts), "bella_b200_mg_route")
-        return [int(x) for x in counts]
-
-    def mg_transpose_records(self, rec, nrec, kmer_lo, kmer_hi, cnt_local):
-        self._check(self._L.bella_b200_mg_transpose_records(self._h, _ptr(rec), nrec, kmer_lo, kmer_hi, _ptr(cnt_local)),
-                    "bella_b200_mg_transpose_records")
 
     @staticmethod
     def _pp(ptrs):

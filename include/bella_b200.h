@@ -197,14 +197,6 @@ int bella_b200_mg_transpose(bella_b200_handle* h, uint32_t kmer_lo, uint32_t kme
 int bella_b200_mg_scatter(bella_b200_handle* h, const uint64_t* sendoff_dev, uint64_t* sendbuf_dev);
 int bella_b200_mg_finish(bella_b200_handle* h, uint32_t col_lo, uint32_t col_hi, int world, const uint32_t* counts_all_dev,
 		const uint64_t* segoff_dev, const uint64_t* recvbase_dev, const uint64_t* recv_dev);
-/* Route mode (no all-gather of B): mg_route sorts this GPU's nonzeros (reads [read_base, read_base+n_local), local
- * CSC arrays with the strand bit in bit 31 of the row ids) by destination = k-mer id / kmers_per_rank into send_dev as
- * 12-byte records {k-mer id | strand<<31, read id, pos | jrank<<16} and returns the per-destination counts on the host;
- * after the all-to-all, mg_transpose_records is mg_transpose fed with the received records. */
-int bella_b200_mg_route(bella_b200_handle* h, uint32_t n_local, uint32_t read_base, const uint32_t* colptr_local_dev, const uint32_t* rowids_dev,
-		const uint16_t* values_dev, uint32_t kmers_per_rank, int world, uint32_t* send_dev, uint64_t* send_counts_host);
-int bella_b200_mg_transpose_records(bella_b200_handle* h, const uint32_t* rec_dev, uint64_t nrec, uint32_t kmer_lo, uint32_t kmer_hi,
-		uint32_t* cnt_local_dev);
 /* NVLink mode (bella_b200/distributed.py mode "nvlink"): no collective on the data path.  Every rank maps the others'
  * exchange buffers (CUDA peer memory over NVLink / NVSwitch; the Python side allocates them as torch symmetric memory)
  * and the kernels store straight into the owner's memory; between the phases the caller only runs a barrier.
