@@ -66,6 +66,14 @@ struct bella_b200_handle {
 	DevBuf oB_colptr, oB_rowids, oB_values, oB_strand, o_len;
 	// chunked upload of host inputs, overlapped with the transpose (bella_b200_set_inputs)
 	static constexpr int MAX_CHUNKS = 8;
+	// results streamed to the caller's host buffers range by range (bella_b200_set_output_buffers)
+	uint32_t* so_rows = nullptr; uint16_t *so_count = nullptr, *so_posH = nullptr, *so_posV = nullptr;
+	uint64_t so_cap = 0;
+	bool so_done = false;                      // the last symbolic pass delivered the whole result to those buffers
+	float so_ms = 0;
+	cudaStream_t out_stream = nullptr;
+	cudaEvent_t so_main[4]{}, so_aux[4]{}, so_out[4]{}, so_t0 = nullptr, so_t1 = nullptr;
+	uint32_t* so_z = nullptr;                  // pinned: the C offsets of the range boundaries
 	cudaStream_t sc_stream = nullptr;          // the scatter passes of the scatter | group pipeline
 	cudaEvent_t sc_t0 = nullptr, sc_t1 = nullptr;
 	uint32_t nrange = 1;                       // ranges of that pipeline in the current pass (1: multi-GPU finish)
@@ -433,6 +441,7 @@ int group_and_output(bella_b200_handle* h, bool do_scatter)
 	const uint32_t ncols = h->hi - h->lo;
 	const uint32_t U = h->U, ucap = h->ucap;
 	const int R = (int)h->nrange;
+	const bool stream_out = do_scatter && h->so_rows && h->flops && h->U;
 	Params P = make_params(h);
 	CK(cudaEventRecord(h->ev[3], h->stream));
 	// level-1 bitmap words a unit can need: light columns span at most n rows, heavy units at most 2^MAX_SPAN_SHIFT
@@ -469,6 +478,56 @@ int group_and_output(bella_b200_handle* h, bool do_scatter)
 			LAUNCHED();
 		}
 		if (int rc = launch_group<2048, 256>(h, P, r, 0, cc[0], l1cap, 4, h->stream)) return rc;
+		if (stream_out) { CK(cudaEventRecord(h->so_main[r], h->stream)); CK(cudaEventRecord(h->so_aux[r], h->aux_stream)); }
+	}
+	h->so_done = false;
+	if (stream_out) {
+		// The caller's host buffers are known (bella_b200_set_output_buffers): a range of columns is compacted and copied out as
+		// soon as its group + fold kernels are done, while the later ranges still fold.  C's arrays are sized by the product
+		// count (an upper bound of nnz(C)); the offsets of the range boundaries come back through pinned memory.
+		const uint64_t zmax = h->flops + 1;
+		ENSURE(h->rowsC, sizeof(uint32_t) * zmax); ENSURE(h->countC, sizeof(uint16_t) * zmax); ENSURE(h->posH, sizeof(uint16_t) * zmax);
+		ENSURE(h->posV, sizeof(uint16_t) * zmax); ENSURE(h->aux, sizeof(uint16_t) * 3 * zmax);
+		ENSURE(h->unpinned, sizeof(unsigned long long));
+		CK(cudaMemsetAsync(h->unpinned.p, 0, sizeof(unsigned long long), h->out_stream));
+		uint32_t ub[NRANGE + 1];
+		for (int r = 0; r <= R; ++r) ub[r] = r < R ? h->hmeta.range_unit[r] : U;
+		for (int r = R - 1; r >= 0; --r) if (ub[r] > ub[r + 1]) ub[r] = ub[r + 1];      // an empty range starts where the next one does
+		ub[0] = 0;
+		for (int r = 0; r < R; ++r) {
+			CK(cudaStreamWaitEvent(h->out_stream, h->so_main[r], 0));
+			CK(cudaStreamWaitEvent(h->out_stream, h->so_aux[r], 0));
+			if (ub[r + 1] > ub[r]) {
+				k_uoff_range<<<1, 1024, 0, h->out_stream>>>(ub[r], ub[r + 1], h->unnz.as<uint32_t>(), h->uoff.as<uint32_t>());
+				LAUNCHED();
+				k_compact<<<grid_for((uint64_t)(ub[r + 1] - ub[r]) * 32, 256), 256, 0, h->out_stream>>>(ub[r], ub[r + 1], h->uptr.as<uint64_t>(), h->uoff.as<uint32_t>(),
+					h->out.as<uint4>(), h->rowsC.as<uint32_t>(), h->countC.as<uint16_t>(), h->posH.as<uint16_t>(), h->posV.as<uint16_t>(), h->aux.as<uint16_t>(),
+					h->unpinned.as<unsigned long long>());
+				LAUNCHED();
+			}
+			CK(cudaMemcpyAsync(&h->so_z[r + 1], h->uoff.as<uint32_t>() + ub[r + 1], sizeof(uint32_t), cudaMemcpyDeviceToHost, h->out_stream));
+			CK(cudaEventRecord(h->so_out[r], h->out_stream));
+		}
+		h->so_z[0] = 0;
+		bool fits = true;
+		for (int r = 0; r < R; ++r) {
+			// the host waits for range r only (its compaction is done: the offsets are known); the copies go to the copy stream,
+			// which is idle, so they run at once -- beside the group + fold kernels of the later ranges, which are all enqueued
+			CK(cudaEventSynchronize(h->so_out[r]));
+			if (r == 0) CK(cudaEventRecord(h->so_t0, h->copy_stream));
+			const uint64_t z0 = ub[r] ? h->so_z[r] : 0, z1 = h->so_z[r + 1];
+			if (z1 > h->so_cap) fits = false;
+			if (fits && z1 > z0) {
+				cudaStream_t cs = h->copy_stream;
+				CK(cudaMemcpyAsync(h->so_rows + z0, h->rowsC.as<uint32_t>() + z0, sizeof(uint32_t) * (z1 - z0), cudaMemcpyDeviceToHost, cs));
+				CK(cudaMemcpyAsync(h->so_count + z0, h->countC.as<uint16_t>() + z0, sizeof(uint16_t) * (z1 - z0), cudaMemcpyDeviceToHost, cs));
+				CK(cudaMemcpyAsync(h->so_posH + z0, h->posH.as<uint16_t>() + z0, sizeof(uint16_t) * (z1 - z0), cudaMemcpyDeviceToHost, cs));
+				CK(cudaMemcpyAsync(h->so_posV + z0, h->posV.as<uint16_t>() + z0, sizeof(uint16_t) * (z1 - z0), cudaMemcpyDeviceToHost, cs));
+			}
+		}
+		CK(cudaEventRecord(h->so_t1, h->copy_stream));
+		CK(cudaStreamWaitEvent(h->stream, h->so_out[R - 1], 0));     // the scans below rewrite uoff (same values) after the last compaction
+		h->so_done = fits;
 	}
 	CK(cudaEventRecord(h->aux_join, h->aux_stream));
 	CK(cudaStreamWaitEvent(h->stream, h->aux_join, 0));
@@ -490,6 +549,12 @@ int group_and_output(bella_b200_handle* h, bool do_scatter)
 	CK(cudaEventElapsedTime(&h->t_scans, h->ev[4], h->ev[5]));    // scans + colptr
 	h->symbolic_done = true;
 	h->numeric_done = false;
+	if (stream_out) {
+		CK(cudaStreamSynchronize(h->out_stream));
+		CK(cudaStreamSynchronize(h->copy_stream));             // the caller's buffers are complete when the symbolic phase returns
+		h->numeric_done = true;                                 // C's arrays are on the device already (and in the caller's buffers when so_done)
+		CK(cudaEventElapsedTime(&h->so_ms, h->so_t0, h->so_t1));   // first streamed copy to the last, on the copy stream
+	}
 	return 0;
 }
 
@@ -502,6 +567,7 @@ int run_symbolic(bella_b200_handle* h)
 	h->klo = 0; h->khi = h->m;
 	h->mg_recv = nullptr;
 	h->nrange = h->nnzB >= (1u << 22) ? 2u : 1u;                      // two ranges measured best (profiles/README.md); small inputs: one
+	if (h->so_rows && h->nnzB >= (1u << 22)) h->nrange = (uint32_t)NRANGE;      // streamed output: more, smaller ranges leave less of the copy exposed
 	if (const char* e = getenv("BELLA_B200_NRANGE")) { int v = atoi(e); if (v >= 1 && v <= NRANGE) h->nrange = (uint32_t)v; }
 	CK(cudaEventRecord(h->ev[0], h->stream));
 	if (int rc = plan_loop(h, true)) return rc;
@@ -528,7 +594,7 @@ int run_numeric(bella_b200_handle* h)
 	ENSURE(h->unpinned, sizeof(unsigned long long));
 	CK(cudaMemsetAsync(h->unpinned.p, 0, sizeof(unsigned long long), h->stream));
 	if (Z && h->U) {
-		k_compact<<<grid_for((uint64_t)h->U * 32, 256), 256, 0, h->stream>>>(h->U, h->uptr.as<uint64_t>(), h->uoff.as<uint32_t>(), h->out.as<uint4>(),
+		k_compact<<<grid_for((uint64_t)h->U * 32, 256), 256, 0, h->stream>>>(0u, h->U, h->uptr.as<uint64_t>(), h->uoff.as<uint32_t>(), h->out.as<uint4>(),
 			h->rowsC.as<uint32_t>(), h->countC.as<uint16_t>(), h->posH.as<uint16_t>(), h->posV.as<uint16_t>(), h->aux.as<uint16_t>(),
 			h->unpinned.as<unsigned long long>());
 		LAUNCHED();
@@ -586,6 +652,13 @@ int bella_b200_create(bella_b200_handle** out, int device)
 	cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
 	cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
 	cudaStreamCreateWithFlags(&h->sc_stream, cudaStreamNonBlocking);
+	cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking);
+	for (int i = 0; i < 4; ++i) {
+		cudaEventCreateWithFlags(&h->so_main[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->so_aux[i], cudaEventDisableTiming);
+		cudaEventCreateWithFlags(&h->so_out[i], cudaEventDisableTiming);
+	}
+	cudaEventCreate(&h->so_t0); cudaEventCreate(&h->so_t1);
+	cudaHostAlloc((void**)&h->so_z, sizeof(uint32_t) * 16, cudaHostAllocDefault);
 	cudaEventCreate(&h->sc_t0); cudaEventCreate(&h->sc_t1);
 	cudaEventCreateWithFlags(&h->aux_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->aux_join, cudaEventDisableTiming);
 	for (auto& e : h->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -614,6 +687,11 @@ int bella_b200_destroy(bella_b200_handle* h)
 	if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
 	if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
 	if (h->sc_stream) { cudaStreamSynchronize(h->sc_stream); cudaStreamDestroy(h->sc_stream); }
+	if (h->out_stream) { cudaStreamSynchronize(h->out_stream); cudaStreamDestroy(h->out_stream); }
+	for (int i = 0; i < 4; ++i) { if (h->so_main[i]) cudaEventDestroy(h->so_main[i]); if (h->so_aux[i]) cudaEventDestroy(h->so_aux[i]); if (h->so_out[i]) cudaEventDestroy(h->so_out[i]); }
+	if (h->so_t0) cudaEventDestroy(h->so_t0);
+	if (h->so_t1) cudaEventDestroy(h->so_t1);
+	if (h->so_z) cudaFreeHost(h->so_z);
 	if (h->sc_t0) cudaEventDestroy(h->sc_t0);
 	if (h->sc_t1) cudaEventDestroy(h->sc_t1);
 	if (h->aux_fork) cudaEventDestroy(h->aux_fork);
@@ -735,6 +813,7 @@ int bella_b200_symbolic(bella_b200_handle* h, uint64_t* flops, uint32_t* flopC, 
 	CK(cudaEventRecord(h->ev[11], h->stream));
 	CK(cudaStreamSynchronize(h->stream));
 	CK(cudaEventElapsedTime(&h->t_ms[4], h->ev[10], h->ev[11]));
+	if (h->so_done) h->t_ms[4] += h->so_ms;                    // + the result copies that ran beside the fold
 	if (flops) *flops = h->flops;
 	return BELLA_B200_OK;
 }
@@ -765,9 +844,22 @@ static int copy_range(bella_b200_handle* h, uint32_t c0, uint32_t c1, uint64_t* 
 	return 0;
 }
 
+int bella_b200_set_output_buffers(bella_b200_handle* h, uint32_t* rowidsC, uint16_t* count, uint16_t* posH, uint16_t* posV, uint64_t capacity)
+{
+	if (!h) return BELLA_B200_ERR_ARG;
+	if (rowidsC && (!count || !posH || !posV || !capacity)) return fail(h, BELLA_B200_ERR_ARG, "all four output buffers and a capacity are required");
+	h->so_rows = rowidsC; h->so_count = count; h->so_posH = posH; h->so_posV = posV; h->so_cap = rowidsC ? capacity : 0;
+	h->so_done = false;
+	return BELLA_B200_OK;
+}
+
 int bella_b200_numeric(bella_b200_handle* h, uint32_t col_begin, uint32_t col_end,
 		uint32_t* rowidsC, uint16_t* count, uint16_t* posH, uint16_t* posV)
 {
+	// already delivered by the symbolic phase (bella_b200_set_output_buffers): nothing to copy
+	if (h && h->symbolic_done && h->so_done && col_begin == h->lo && col_end == h->hi && rowidsC == h->so_rows && count == h->so_count
+			&& posH == h->so_posH && posV == h->so_posV)
+		return BELLA_B200_OK;
 	if (int rc = bella_b200_numeric_device(h)) return rc;
 	uint64_t off, cnt;
 	if (int rc = copy_range(h, col_begin, col_end, &off, &cnt)) return rc;

@@ -80,6 +80,7 @@ struct Meta {
 	unsigned long long flops;
 	unsigned int class_count[NRANGE][NCLASS + 1];   // per column range (the scatter | group pipeline) and capacity class (+ overflow)
 	unsigned int range_col[NRANGE + 1];      // first local column of every range (ncols when the range is empty)
+	unsigned int range_unit[NRANGE + 1];     // first unit of every range (n_units when the range is empty)
 	unsigned int n_heavy_cols;
 	unsigned int n_units;
 	unsigned int n_refine;
@@ -607,7 +608,7 @@ __global__ void k_units_init(uint32_t ncols, uint32_t ucap, const uint32_t* __re
 	const uint32_t U = ubase[ncols];
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		meta->n_units = U;
-		for (int r = 0; r <= NRANGE; ++r) meta->range_col[r] = ncols;
+		for (int r = 0; r <= NRANGE; ++r) { meta->range_col[r] = ncols; meta->range_unit[r] = U; }
 	}
 	if (U > ucap) { if (blockIdx.x == 0 && threadIdx.x == 0) set_err(err, -7); return; }
 	for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < ncols; li += gridDim.x * blockDim.x) {
@@ -660,6 +661,7 @@ __global__ void k_classify_units(uint32_t ucap, const uint32_t* __restrict__ uco
 			const uint32_t li = ucol[u];                             // the scatter's per-column cursor: the region of a light column, or the heavy mark
 			ccur[(size_t)li * CCUR_STRIDE] = colinfo[li].sh == 31 ? (unsigned long long)uptr[u] : CCUR_HEAVY;
 			atomicMin(&meta->range_col[rg], li);
+			atomicMin(&meta->range_unit[rg], u);
 		}
 		if (!f) continue;
 		int c = f <= CLASS_CAP[0] ? 0 : f <= CLASS_CAP[1] ? 1 : f <= CLASS_CAP[2] ? 2 : 3;
@@ -1586,14 +1588,45 @@ __global__ void k_colptr(uint32_t ncols, const uint32_t* __restrict__ ubase, con
 	for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li <= ncols; li += gridDim.x * blockDim.x) colptrC[li] = uoff[ubase[li]];
 }
 
+// Where the units [u0, u1) start in C: uoff[u] = uoff[u0] + pairs of the units before u (uoff[u0] was left by the launch for the
+// previous range of units; 0 for the first), uoff[u1] = the end.  One CTA; used when the results of a column range are
+// compacted and copied out while the later ranges still fold (bella_b200_set_output_buffers).
+__global__ void __launch_bounds__(1024) k_uoff_range(uint32_t u0, uint32_t u1, const uint32_t* __restrict__ unnz, uint32_t* __restrict__ uoff)
+{
+	__shared__ uint32_t s_w[33];
+	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	uint32_t carry = u0 ? uoff[u0] : 0;
+	if (tid == 0 && !u0) uoff[0] = 0;
+	for (uint32_t base = u0; base < u1; base += 1024) {
+		const uint32_t u = base + tid;
+		const uint32_t x = u < u1 ? unnz[u] : 0;
+		uint32_t v = x;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, v, o); if (lane >= (uint32_t)o) v += y; }
+		if (lane == 31) s_w[wid] = v;
+		__syncthreads();
+		if (wid == 0) {
+			uint32_t w = s_w[lane], ws = w;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, ws, o); if (lane >= (uint32_t)o) ws += y; }
+			s_w[lane] = ws - w;
+			if (lane == 31) s_w[32] = ws;
+		}
+		__syncthreads();
+		if (u < u1) uoff[u + 1] = carry + s_w[wid] + v;
+		carry += s_w[32];
+		__syncthreads();
+	}
+}
+
 // one warp per unit: per-unit pair records -> C (SoA), at the unit's final offset
-__global__ void __launch_bounds__(256) k_compact(uint32_t U, const uint64_t* __restrict__ uptr, const uint32_t* __restrict__ uoff,
+__global__ void __launch_bounds__(256) k_compact(uint32_t u_lo, uint32_t U, const uint64_t* __restrict__ uptr, const uint32_t* __restrict__ uoff,
 		const uint4* __restrict__ out, uint32_t* __restrict__ rowsC, uint16_t* __restrict__ countC, uint16_t* __restrict__ posH,
 		uint16_t* __restrict__ posV, uint16_t* __restrict__ aux, unsigned long long* __restrict__ n_unpinned)
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-	for (uint32_t u = warp; u < U; u += nwarps) {
+	for (uint32_t u = u_lo + warp; u < U; u += nwarps) {              // the units [u_lo, U)
 		const uint32_t g0 = uoff[u], Z = uoff[u + 1] - g0;
 		const uint4* src = out + uptr[u];
 		for (uint32_t p = lane; p < Z; p += 32) {

@@ -482,7 +482,16 @@ def bench_multi(args, w, inp, rank, world, local, METRIC, UNIT, workload, ClockS
     dev = torch.device("cuda", local)
     mode = os.environ.get("BELLA_MG_MODE", "nvlink")        # "exchange" / "replicate": the NCCL-based modes of round 1
     sh = ShardedOverlapSpGEMM(local, mode=mode)
-    sh.load_shard(inp, pinned=True)
+    try:
+        sh.load_shard(inp, pinned=True)
+    except Exception as e:      # noqa: BLE001 -- e.g. peer memory cannot be mapped on this box: every rank fails alike
+        if mode != "nvlink":
+            raise
+        print(f"[bench] rank {rank}: the NVLink mode could not be set up ({type(e).__name__}: {e}); falling back to the NCCL exchange mode",
+              file=sys.stderr, flush=True)
+        mode = "exchange"
+        sh = ShardedOverlapSpGEMM(local, mode=mode)
+        sh.load_shard(inp, pinned=True)
     stream = torch.cuda.current_stream(dev)
 
     def timed(fn, steps):

@@ -46,6 +46,7 @@ def lib():
         L.bella_b200_set_column_range.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32]
         L.bella_b200_symbolic.argtypes = [H, ctypes.POINTER(ctypes.c_uint64), vp, vp]
         L.bella_b200_numeric.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp, vp]
+        L.bella_b200_set_output_buffers.argtypes = [H, vp, vp, vp, vp, ctypes.c_uint64]
         L.bella_b200_numeric_aux.argtypes = [H, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp]
         L.bella_b200_numeric_device.argtypes = [H]
         L.bella_b200_n_unpinned.argtypes = [H, ctypes.POINTER(ctypes.c_uint64)]
@@ -72,7 +73,7 @@ def lib():
     return _lib
 
 
-EXPORTS = ["bella_b200_get_flops", "bella_b200_mg_geometry", "bella_b200_mg_route_push", "bella_b200_mg_transpose_coarse", "bella_b200_mg_post", "bella_b200_mg_exchange",
+EXPORTS = ["bella_b200_set_output_buffers", "bella_b200_get_flops", "bella_b200_mg_geometry", "bella_b200_mg_route_push", "bella_b200_mg_transpose_coarse", "bella_b200_mg_post", "bella_b200_mg_exchange",
            "bella_b200_set_inputs_csr", "bella_b200_n_unpinned", "bella_b200_create", "bella_b200_destroy", "bella_b200_last_error", "bella_b200_set_inputs",
            "bella_b200_set_inputs_device", "bella_b200_set_column_range", "bella_b200_symbolic",
            "bella_b200_numeric", "bella_b200_numeric_aux", "bella_b200_numeric_device",
@@ -187,6 +188,20 @@ class OverlapSpGEMM:
         self._check(self._L.bella_b200_symbolic(self._h, ctypes.byref(flops), _ptr(flopC), _ptr(colptrC)), "bella_b200_symbolic")
         self.flops, self.colptrC = flops.value, colptrC
         return flops.value, flopC, colptrC
+
+    def set_output_buffers(self, capacity):
+        """Register page-locked host buffers of `capacity` entries for the whole result BEFORE symbolic(): the results of a column
+        range are then copied out while the later ranges still fold, and numeric(pinned=True) finds them delivered
+        (include/bella_b200.h bella_b200_set_output_buffers).  capacity = 0 switches it off."""
+        if not capacity:
+            self._check(self._L.bella_b200_set_output_buffers(self._h, None, None, None, None, 0), "bella_b200_set_output_buffers")
+            return
+        for name, dt in (("rows", np.uint32), ("cnt", np.uint16), ("pH", np.uint16), ("pV", np.uint16)):      # the buffers numeric(pinned=True) hands out
+            self._host(name, dt, capacity, True)
+        self._registered = {k: self._pinned[k] for k in ("rows", "cnt", "pH", "pV")}      # kept alive while the library may write to them
+        p = {k: ctypes.c_void_p(t.data_ptr()) for k, t in self._registered.items()}
+        cap = min(t.numel() for t in self._registered.values())
+        self._check(self._L.bella_b200_set_output_buffers(self._h, p["rows"], p["cnt"], p["pH"], p["pV"], cap), "bella_b200_set_output_buffers")
 
     def numeric(self, col_begin=None, col_end=None, aux=False, pinned=False):
         """-> (rowids, count, posH, posV[, aux(nnz,3)]) for global columns [col_begin, col_end).

@@ -330,6 +330,12 @@ def run_b200_arm(args, w):
         pinned[k] = t_
         setattr(hin, k, t_.numpy().view(a.dtype))
 
+    # the caller's (page-locked) result buffers are handed over before the symbolic phase, sized by the result of the resident leg
+    # (a streaming consumer reuses the previous batch's buffers): the results of a column range are then copied out while the
+    # later ranges still fold (bella_b200_set_output_buffers); BELLA_B200_NO_STREAM_OUT=1 measures the plain sequence
+    if not os.environ.get("BELLA_B200_NO_STREAM_OUT"):
+        g.set_output_buffers(int(Z * 1.1) + 1024)
+
     def e2e_step():
         g.set_inputs(hin)
         _, _, colptrC = g.symbolic(want_flopC=False, pinned=True)

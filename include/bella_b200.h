@@ -137,6 +137,15 @@ int bella_b200_symbolic(bella_b200_handle* h, uint64_t* flops, uint32_t* flopC, 
 int bella_b200_numeric(bella_b200_handle* h, uint32_t col_begin, uint32_t col_end,
 		uint32_t* rowidsC, uint16_t* count, uint16_t* posH, uint16_t* posV);
 
+/* Optional, before bella_b200_symbolic: HOST output buffers of `capacity` entries each (page-locked for a truly asynchronous
+ * copy) that the caller will pass to bella_b200_numeric for the handle's WHOLE column range.  The symbolic phase then compacts
+ * and copies the results of a range of columns as soon as that range is folded, while the later ranges still fold, and the
+ * bella_b200_numeric call with these same pointers has nothing left to copy.  The reference sizes its outputs after the symbolic
+ * phase (include/overlap.hpp:716-741); a caller that knows a bound of nnz(C) -- the previous batch's, or the product count --
+ * saves the exposed device->host copy.  A result larger than `capacity` is NOT written: bella_b200_numeric then copies as
+ * usual into whatever it is given.  rowidsC == NULL switches it off. */
+int bella_b200_set_output_buffers(bella_b200_handle* h, uint32_t* rowidsC, uint16_t* count, uint16_t* posH, uint16_t* posV, uint64_t capacity);
+
 /* Optional per-nonzero extras for the same range (HOST, nullable each):
  *   nbins    number of bins of the pair's final value
  *   support  support of the chosen bin            (spmatType_::chain(), common.h:142-149)

@@ -234,3 +234,31 @@ def test_gpu_minimizer_sparsified_matrix():
     inp = fe.synthetic(n_reads=6000, read_len=8000, err=0.20, split=(0.35, 0.25, 0.40), seed=4, window=10)
     assert inp.nnz > 100000
     ol.assert_same(gpu_result(inp, False), ol.oracle_spgemm(inp))
+
+
+@pytest.mark.parametrize("nrange", ["1", "3"])
+def test_gpu_streamed_output_buffers(monkeypatch, medium_inputs, nrange):
+    """bella_b200_set_output_buffers: the results of a column range are copied into the caller's page-locked buffers while the
+    later ranges still fold; numeric() with the same buffers has nothing left to do.  Same bytes as the plain sequence; a
+    capacity that is too small falls back to the plain copy."""
+    from bella_b200 import spgemm
+    monkeypatch.setenv("BELLA_B200_NRANGE", nrange)
+    want = ol.oracle_spgemm(medium_inputs)
+    hifi, href = golden_util.load("heavy_units")
+    for inp, ref, cap in ((medium_inputs, want, want.nnz + 100), (hifi, href, href.nnz + 7), (medium_inputs, want, 10)):
+        g = spgemm.OverlapSpGEMM(0)
+        try:
+            g.set_output_buffers(cap)
+            for _ in range(2):                              # twice: the buffers are reused
+                g.set_inputs(inp)
+                flops, flopC, colptrC = g.symbolic(pinned=True)
+                rows, cnt, pH, pV = g.numeric(pinned=True)
+                np.testing.assert_array_equal(colptrC, ref.colptrC)
+                np.testing.assert_array_equal(rows, ref.rowids)
+                np.testing.assert_array_equal(cnt, ref.count)
+                np.testing.assert_array_equal(pH, ref.posH)
+                np.testing.assert_array_equal(pV, ref.posV)
+            a = g.numeric(aux=True)[4]                      # the device arrays are complete too
+            np.testing.assert_array_equal(a, ref.aux)
+        finally:
+            g.close()
