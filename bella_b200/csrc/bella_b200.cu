@@ -3,13 +3,14 @@
 // kernel-by-kernel roofline.  There is no CPU fallback in this file.
 //
 // Reference behaviour reproduced (bit-exact), by reference file:line:
+//   Transpose()         src/CSC.cpp:289-299           -> k_rp1 + k_rp2 + k_bucket (A derived from B, columns sorted by read)
 //   estimateFLOP        include/overlap.hpp:157-202   -> k_bucket (per-column kept-product count)
 //   estimateNNZ_Hash    include/overlap.hpp:205-276   -> k_group_fold (distinct rows > col, two-level bitmap)
 //   LocalSpGEMM         include/overlap.hpp:281-363   -> k_scatter + k_group_fold (products grouped by pair
 //                                                        in B-column order, then folded)
 //   multiop/overlapop   include/chain.hpp:47-86       -> overlap_estimate()
-//   chainop             include/chain.hpp:100-150     -> fold_short() / fold_coop()
-//   choose()            include/common/common.h:162-170 -> end of fold_short() / fold_coop()
+//   chainop             include/chain.hpp:100-150     -> the fold phases of k_group_fold (thread per product / warp per pair / fold_cta)
+//   choose()            include/common/common.h:162-170 -> the pair results of the same phases
 #include "bella_b200.h"
 
 #include <cuda_runtime.h>
@@ -95,7 +96,7 @@ struct bella_b200_handle {
 	// matrix construction from tuples (bella_b200_set_inputs_tuples)
 	DevBuf tp_kmer, tp_read, tp_pos, tp_strand, tp_rs, tp_re, tp_nruns, tp_cnt, tp_cp, tp_merged, tp_tmpK, tp_tmpV, tp_slab;
 	float t_build_ms = 0;
-	DevBuf boff, bcur, bsize, part, partK, Aent, Ainfo, Acolptr, flop32;
+	DevBuf boff, bcur, part, partK, Aent, Ainfo, Acolptr, flop32;
 	DevBuf rp_cur, rp_tiles, rp_E, rp_K;       // level 1 of the two-level partition: cursors, tile starts, coarse buckets
 	double cap_scale = 1.25;                   // head room of the coarse buckets over the average
 	// plan
@@ -219,7 +220,6 @@ int run_transpose(bella_b200_handle* h, uint32_t row_lo, uint32_t cnt_lo, uint32
 	const uint32_t W = geo.W, wshift = geo.wshift, NB = geo.NB;
 	h->NB = NB;
 	ENSURE(h->bcur, sizeof(uint32_t) * ((size_t)NB + 2) * BCNT_STRIDE);
-	ENSURE(h->bsize, sizeof(uint32_t) * ((size_t)NB + 2));
 	ENSURE(h->boff, sizeof(uint32_t) * ((size_t)NB + 2));
 	ENSURE(h->part, sizeof(uint64_t) * (size_t)NB * BUCKET_CAP + 64);
 	ENSURE(h->partK, sizeof(uint16_t) * (size_t)NB * BUCKET_CAP + 64);
@@ -673,7 +673,7 @@ int bella_b200_destroy(bella_b200_handle* h)
 	if (!h) return BELLA_B200_ERR_ARG;
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->stream);
-	DevBuf* bufs[] = {&h->oB_colptr, &h->oB_rowids, &h->oB_values, &h->oB_strand, &h->o_len, &h->boff, &h->bcur, &h->bsize, &h->part, &h->partK, &h->Ainfo, &h->ccur, &h->rp_cur, &h->rp_tiles, &h->rp_E, &h->rp_K,
+	DevBuf* bufs[] = {&h->oB_colptr, &h->oB_rowids, &h->oB_values, &h->oB_strand, &h->o_len, &h->boff, &h->bcur, &h->part, &h->partK, &h->Ainfo, &h->ccur, &h->rp_cur, &h->rp_tiles, &h->rp_E, &h->rp_K,
 		&h->Aent, &h->Acolptr, &h->flop32, &h->nunits, &h->ubase, &h->shv, &h->refine, &h->colinfo, &h->ucol, &h->ucount,
 		&h->uptr, &h->ucur, &h->lists, &h->redo, &h->unnz, &h->uoff, &h->raw, &h->out, &h->colptrC, &h->rowsC, &h->countC, &h->posH, &h->posV,
 		&h->aux, &h->meta, &h->errflag, &h->cubtmp, &h->unpinned, &h->mg_colinfo, &h->mg_ucur, &h->mg_rcur, &h->mg_rtiles, &h->tp_kmer, &h->tp_read, &h->tp_pos, &h->tp_strand,

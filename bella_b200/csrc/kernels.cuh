@@ -1,31 +1,33 @@
 // kernels.cuh -- device code of the B200 overlap SpGEMM (included once, by bella_b200.cu).
 //
-// The whole path is a chain of "partition into contiguous regions, then finish each region in
-// shared memory" stages, so that every HBM access is either a coalesced stream or a small store
-// to one of a few thousand write frontiers that live in L2 (DESIGN.md has the traffic model):
+// The whole path is a chain of "partition into contiguous regions, then finish each region in shared memory" stages.  A
+// scattered L2 transaction (a cursor atomic with return, a partial-sector store) costs about 12 ps on this chip whatever it
+// is, so wherever the fan-out allows a CTA stages a tile in shared memory, ordered by destination, and global
+// memory sees one cursor atomic per (tile, destination) and coalesced runs:
 //
-//   transpose  k_partition                   B's nonzeros (read-major) -> fixed-capacity buckets of consecutive k-mer ids
-//              k_bucket                      one CTA per bucket: counting sort by k-mer, columns sorted by
-//                                            read id, written as packed entries `Aent` + A's colptr, and the
-//                                            per-output-column product count == estimateFLOP
+//   transpose  k_rp1 / k_rp2                  B's nonzeros (read-major) -> coarse buckets of 2^shift1 k-mers -> fine buckets of
+//                                            2^wshift k-mers (two-level CTA-staged radix partition)
+//              k_bucket                      one CTA per fine bucket (TMA 1-D bulk load): counting sort by k-mer, every entry
+//                                            ranked by read id inside its column, written as packed entries `Aent` (+ `Ainfo`,
+//                                            A's colptr) and the per-output-column product count == estimateFLOP
 //                                            (overlap.hpp:157-202)
 //   plan       k_plan / k_units_init / k_count_units / k_classify_units
-//                                            output columns -> units (a column, or a row range of a heavy
-//                                            column) of at most UNIT_CAP products
-//   scatter    k_scatter                     outer-product expansion on the A side: k-mer column
-//                                            (r0<r1<..) emits the kept products (col r_a, row r_b), a<b,
-//                                            into the unit's region (one 8-byte record per product)
-//   group+fold k_group_fold<CAP,NT,EXACT>    one CTA per unit: region staged into shared memory with one
-//                                            bulk async copy (TMA 1-D), distinct rows through a bitmap (two
-//                                            levels when the unit spans more rows than CAP words cover;
-//                                            == estimateNNZ_Hash, overlap.hpp:205-276), products
-//                                            grouped by pair in B-column order (== LocalSpGEMM's visiting
-//                                            order, overlap.hpp:306-341), then the semiring fold
-//                                            (chain.hpp:74-150) and choose() (common.h:162-170) without
-//                                            leaving shared memory
+//                                            output columns -> units (a column, or a row range of a heavy column) of at most
+//                                            UNIT_CAP products; column ranges of the scatter | group pipeline
+//   scatter    k_scatter                     outer-product expansion on the A side: thread per entry; in its k-mer column
+//                                            (r0<r1<..) entry a emits the kept products (col r_a, row r_b), a<b, into the
+//                                            unit's region (one 8-byte record per product)
+//   group+fold k_group_fold<CAP,NT,EXACT>    one CTA per unit: region staged into shared memory with one bulk async copy (TMA
+//                                            1-D), distinct rows through a bitmap (two levels when the unit spans more rows
+//                                            than CAP words cover; == estimateNNZ_Hash, overlap.hpp:205-276), products grouped
+//                                            by pair, multiplied (overlapop), put in B-column order (== LocalSpGEMM's visiting
+//                                            order, overlap.hpp:306-341) and folded (chain.hpp:74-150, choose():
+//                                            common.h:162-170) without leaving shared memory: short pairs one thread per
+//                                            product, longer pairs one warp per pair
 //              k_huge_pair                   a single pair with more products than fit in shared memory
-//   output     k_colptr / k_compact          per-unit results -> C in CSC order, rows ascending
-//   multi-GPU  k_mg_colinfo / k_mg_sum_counts / k_regroup   send-buffer cursors, summed counts, received segments -> unit regions
+//   output     k_uoff_range / k_colptr / k_compact   per-unit results -> C in CSC order, rows ascending
+//   multi-GPU  k_rp1 (route) / k_rp_post / k_rp1b / k_mg_post / k_mg_plan / k_mg_push / k_regroup   stores into the owner's
+//                                            (peer-mapped) memory over NVLink, exchange planned on the device
 //   build      k_tuple_runs / k_tuple_counts / k_merge_duplicates / k_compact_B   tuples -> B in the reference's
 //                                            MergeDuplicates order (src/CSC.cpp:301-479; "next" row f2)
 #pragma once

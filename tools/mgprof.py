@@ -9,7 +9,7 @@ rank = dist.get_rank()
 if rank != 0: dist.barrier()
 inp = bench.load_workload(dict(bench.WORKLOAD), need_seqs=False)
 if rank == 0: dist.barrier()
-sh = bd.ShardedOverlapSpGEMM(local, mode=os.environ.get("BELLA_MG_MODE","exchange")); sh.load_shard(inp, pinned=True)
+sh = bd.ShardedOverlapSpGEMM(local, mode=os.environ.get("BELLA_MG_MODE","nvlink")); sh.load_shard(inp, pinned=True)
 for _ in range(3): sh.step()
 sh.prof = {}
 for _ in range(5): sh.step()
